@@ -1,0 +1,211 @@
+/*
+ * libspecyolo — C-ABI boundary of the B200-native (sm_100a) Spectrogram-YOLOv11 inference hot path.
+ *
+ * Plain C: raw device pointers, sizes, a CUDA stream handle passed as void*, int status codes.
+ * No torch / C++ types cross this boundary.  Every entry point is asynchronous on `stream`
+ * (nothing synchronises, nothing allocates device memory) so a whole forward can be captured
+ * in a CUDA graph.  All activation tensors are NHWC ("channels last") bf16 unless stated;
+ * a tensor argument is a pointer to its first element plus a *pixel stride* in elements, so a
+ * channel window of a wider concat buffer is passed without a copy.
+ *
+ * Each function names the reference interface (file:line under the upstream repo
+ * httpsLiem/Spectrogram-YOLOv11, a fork of Ultralytics 8.3.70) that it replaces.
+ *
+ * Errors: functions return SPECYOLO_OK or a SPECYOLO_ERR_* code; specyolo_last_error() returns a
+ * thread-local human-readable message.  There is no CPU fallback anywhere behind this header.
+ */
+#ifndef SPECYOLO_H
+#define SPECYOLO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPECYOLO_OK               0
+#define SPECYOLO_ERR_INVALID      1   /* bad argument (shape, alignment, range)          */
+#define SPECYOLO_ERR_CUDA         2   /* CUDA runtime / driver error                     */
+#define SPECYOLO_ERR_UNSUPPORTED  3   /* valid request this build does not implement     */
+
+#define SPECYOLO_ACT_NONE 0
+#define SPECYOLO_ACT_SILU 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* specyolo_last_error(void);
+int         specyolo_version(void);
+/* one-time per-process setup on the current device (constant tables); refuses non-sm_100 devices.
+ * Must be called once before the first specyolo_iq_to_letterbox and outside graph capture. */
+int         specyolo_init(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+uint64_t    specyolo_launch_count(void);
+void        specyolo_reset_launch_count(void);
+
+/* ---- layout plumbing -------------------------------------------------------------------- */
+/* NCHW (fp32 | bf16 | uint8 scaled by 1/255) -> NHWC bf16.
+ * Replaces the dtype/scale step of BasePredictor.preprocess (ultralytics/engine/predictor.py:125-136). */
+#define SPECYOLO_DT_F32  0
+#define SPECYOLO_DT_BF16 1
+#define SPECYOLO_DT_U8   2
+int specyolo_nchw_to_nhwc_bf16(const void* x, int x_dtype, float scale,
+                               int B, int C, int H, int W,
+                               void* y, int y_pixstride, void* stream);
+/* NHWC bf16 window -> NCHW fp32 (debug / drop-in return values such as Detect's raw maps). */
+int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C, int H, int W,
+                                   float* y, void* stream);
+
+/* ---- Conv + BN fold + weight repack ------------------------------------------------------ */
+/* Folds BatchNorm into the conv weights exactly like fuse_conv_and_bn
+ * (ultralytics/utils/torch_utils.py:238-265) and repacks OIHW fp32 -> the K-major bf16 layout the
+ * implicit-GEMM kernel consumes: w_packed[g][n_pad][kh][kw][cin_g], rows n >= cout_g zero.
+ * bn_* may be NULL (plain nn.Conv2d, e.g. the last conv of Detect.cv2/cv3); conv_bias may be NULL.
+ * All pointers are device pointers.  bias_out has groups*n_pad floats. */
+int specyolo_fold_pack_conv(const float* w_oihw, const float* conv_bias,
+                            const float* bn_gamma, const float* bn_beta,
+                            const float* bn_mean, const float* bn_var, float bn_eps,
+                            int cout, int cin_g, int kh, int kw, int groups, int n_pad,
+                            void* w_packed, float* bias_out, void* stream);
+/* n_pad (per-group padded output channels) the kernels expect for a conv of this shape */
+int specyolo_conv_npad(int cout, int groups);
+
+typedef struct {
+    /* input window */
+    const void* x;        /* bf16 NHWC, first element of the channel window            */
+    int B, H, W, Cin;     /* Cin = channels read (all groups)                          */
+    int x_pixstride;      /* elements between consecutive pixels of x                  */
+    int x_upshift;        /* 0, or 1: x is read through a nearest-neighbour x2 upsample
+                             (nn.Upsample folded into the consumer; H,W are the upsampled dims;
+                             1x1 convs only)                                            */
+    /* weights (from specyolo_fold_pack_conv) */
+    const void*  w_packed;
+    const float* bias;
+    int Cout, n_pad;      /* logical output channels; padded rows per group            */
+    int kh, kw, stride, pad, dil, groups;
+    int act;              /* SPECYOLO_ACT_*                                            */
+    /* output window */
+    void* y;              /* bf16 (or fp32 if y_fp32) NHWC window                      */
+    int Ho, Wo;
+    int y_pixstride;
+    int y_fp32;
+    /* optional residual added after the activation (Bottleneck shortcut,
+       ultralytics/nn/modules/block.py:724-726); bf16 NHWC window with Cout channels */
+    const void* residual;
+    int r_pixstride;
+} specyolo_conv_t;
+
+/* y = act(conv(x, W) + b) [+ residual]  — replaces Conv.forward_fuse
+ * (ultralytics/nn/modules/conv.py:81-83) after BaseModel.fuse (ultralytics/nn/tasks.py:223-251).
+ * Dense and grouped convs with Cin/groups % 16 == 0 run on the tcgen05 implicit-GEMM kernel;
+ * depthwise 3x3 and the 3-channel stem run on dedicated CUDA-core kernels. */
+int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream);
+
+/* Stem conv reading the NCHW network input directly (first layer, Cin = 3):
+ * x is NCHW fp32/bf16/u8 (u8 is scaled by 1/255 like predictor.py:133-135), w is fp32
+ * [Cout][3][3][3] *folded* weights (device), output NHWC bf16 with SiLU. */
+int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W,
+                            const float* w_folded_oihw, const float* bias, int Cout,
+                            void* y, int y_pixstride, void* stream);
+
+/* ---- SPPF pooling (ultralytics/nn/modules/block.py:194-198) ------------------------------ */
+/* buf is the 4*c-channel concat buffer whose first c channels hold cv1(x); writes the three
+ * chained MaxPool2d(5,1,2) results into channels [c,2c), [2c,3c), [3c,4c). */
+int specyolo_sppf_pool(void* buf, int B, int H, int W, int c, int pixstride, void* stream);
+
+/* ---- Fusion('ESChannel') (ultralytics/nn/modules/conv.py:2113-2127, GCT :2296-2301,
+ *      WeightedSpatialAttention :1850-1852) ------------------------------------------------ */
+typedef struct {
+    int k;                     /* number of inputs, 2 or 3                              */
+    const void* x[3];          /* bf16 NHWC, c channels each                            */
+    int pixstride[3];
+    int upshift[3];            /* 1: input i is a x2 nearest upsample of a (H/2,W/2) map */
+    int B, H, W, c;
+    const float* alpha;        /* GCT params over k*c channels                          */
+    const float* gamma;
+    const float* beta;
+    float gct_eps;
+    const float* sab_w;        /* [2][3][3] weights of the shared 2->1 3x3 conv         */
+    void* y; int y_pixstride;  /* bf16 NHWC, c channels                                 */
+    float* ws;                 /* workspace, specyolo_fusion_ws_bytes() bytes           */
+} specyolo_fusion_t;
+size_t specyolo_fusion_ws_bytes(int k, int B, int H, int W, int c);
+int    specyolo_fusion_eschannel(const specyolo_fusion_t* a, void* stream);
+
+/* ---- PSA attention core (ultralytics/nn/modules/block.py:1922-1933) ----------------------- */
+/* qkv: bf16 NHWC [B,N,heads*(2*kd+hd)] as written by the qkv 1x1 conv; out[b,n,h*hd+d] =
+ * sum_j softmax_j(q_n.k_j*scale) v_j[d] + pe(v)[n] where pe is the depthwise 3x3 (+folded BN)
+ * positional conv; pe_w is fp32 [heads*hd][3][3], pe_b fp32 [heads*hd]. */
+int specyolo_psa_attention(const void* qkv, int qkv_pixstride, int B, int H, int W,
+                           int heads, int key_dim, int head_dim, float scale,
+                           const float* pe_w, const float* pe_b,
+                           void* out, int out_pixstride, void* stream);
+
+/* ---- Detect decode (ultralytics/nn/modules/head.py:100-131, block.py:80-83 DFL,
+ *      utils/tal.py:334-358 make_anchors/dist2bbox) ---------------------------------------- */
+typedef struct {
+    int nl;                    /* number of levels (3)                                  */
+    const float* logits[4];    /* per level fp32 [B, h*w, no_stride]: 64 box bins then nc cls */
+    int h[4], w[4];
+    float stride[4];
+    int no_stride;             /* floats per anchor row (>= 64+nc)                      */
+    int B, nc, reg_max;        /* reg_max = 16                                          */
+    float* y;                  /* dense fp32 [B, 4+nc, A] (xywh, sigmoid scores); may be NULL */
+    /* fused score-threshold output (may be NULL): anchors with max score > conf_thres,
+       in anchor order inside fixed segments of SPECYOLO_DECODE_SEG anchors:
+       cand[(b*nseg+s)*SEG + i] = {x1,y1,x2,y2,conf,cls}, seg_count[b*nseg+s] = #valid */
+    float conf_thres;
+    float* cand;
+    int*   seg_count;
+} specyolo_decode_t;
+#define SPECYOLO_DECODE_SEG 256
+int specyolo_detect_decode(const specyolo_decode_t* a, void* stream);
+
+/* ---- NMS (ultralytics/utils/ops.py:181-332 + torchvision.ops.nms at ops.py:312) ----------- */
+typedef struct {
+    int B, nc, A;
+    /* input, one of: */
+    const float* prediction;   /* dense [B, 4+nc, A] xywh + scores (ops.py input), or NULL */
+    const float* cand;         /* segmented candidates from specyolo_detect_decode        */
+    const int*   seg_count;
+    float  conf_thres;
+    double iou_thres;          /* compared as double against the fp32 IoU like torchvision's CPU kernel */
+    int    agnostic;
+    int    multi_label;        /* dense input only (ops.py:286-288)                      */
+    int    max_det, max_nms;
+    float  max_wh;
+    const int* classes; int n_classes;   /* optional class filter (ops.py:294-295), device ptr */
+    /* output */
+    float* out;                /* [B, max_det, 6] x1,y1,x2,y2,conf,cls                   */
+    int*   out_count;          /* [B]                                                    */
+    int*   keep_idx;           /* [B, max_det] indices into the post-threshold candidate list
+                                  (the `i` of ops.py:312-313); may be NULL               */
+    int*   n_cand;             /* [B] number of candidates that entered NMS; may be NULL */
+    void*  ws;                 /* workspace, specyolo_nms_ws_bytes() bytes               */
+} specyolo_nms_t;
+size_t specyolo_nms_ws_bytes(int B, int nc, int A, int multi_label);
+int    specyolo_nms(const specyolo_nms_t* a, void* stream);
+
+/* scale_boxes + clip_boxes on the NMS output (ultralytics/utils/ops.py:92-127, 335-354);
+ * out rows [b, i<count[b], 0:4] are rewritten in place.  pad_w/pad_h/gain as computed by the
+ * caller from the reference formula. */
+int specyolo_scale_boxes(float* out, const int* out_count, int B, int max_det,
+                         float gain, float pad_w, float pad_h, float img0_w, float img0_h,
+                         void* stream);
+
+/* ---- IQ -> spectrogram -> letterbox (no reference implementation: README.md:7 only) -------- */
+typedef struct {
+    const float* iq;           /* [B, L] complex64 interleaved (re,im)                   */
+    int B, L;
+    int nfft, hop;             /* nfft = 1024                                            */
+    float db_min, db_max;      /* dBFS range mapped to [0,1]                             */
+    int out_h, out_w;          /* 640, 640                                               */
+    float pad_value;           /* 114/255                                                */
+    void* out;                 /* [B,3,out_h,out_w] NCHW, bf16 or fp32                   */
+    int out_fp32;
+} specyolo_stft_t;
+int specyolo_iq_to_letterbox(const specyolo_stft_t* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECYOLO_H */

@@ -1,0 +1,163 @@
+// extern "C" surface of libspecyolo (see include/specyolo.h): argument validation, dispatch to the
+// kernel launchers, error text.  No logic beyond that lives here.
+#include "common.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+namespace specyolo {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// launchers implemented in the other translation units
+int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream);
+int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream);
+int fold_pack_launch(const float*, const float*, const float*, const float*, const float*, const float*, float,
+                     int, int, int, int, int, int, void*, float*, cudaStream_t);
+int stem_conv_launch(const void*, int, int, int, int, const float*, const float*, int, void*, int, cudaStream_t);
+int nchw_to_nhwc_launch(const void*, int, float, int, int, int, int, void*, int, cudaStream_t);
+int nhwc_to_nchw_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
+int sppf_pool_launch(void*, int, int, int, int, int, cudaStream_t);
+size_t fusion_ws_bytes(int, int, int, int, int);
+int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
+int psa_attention_launch(const void*, int, int, int, int, int, int, int, float, const float*, const float*,
+                         void*, int, cudaStream_t);
+int detect_decode_launch(const specyolo_decode_t*, cudaStream_t);
+size_t nms_ws_bytes(int, int, int, int);
+int nms_launch(const specyolo_nms_t*, cudaStream_t);
+int scale_boxes_launch(float*, const int*, int, int, float, float, float, float, float, cudaStream_t);
+int stft_launch(const specyolo_stft_t*, cudaStream_t);
+int stft_init();
+
+}  // namespace specyolo
+
+using namespace specyolo;
+
+extern "C" {
+
+const char* specyolo_last_error(void) { return g_err; }
+int specyolo_version(void) { return 100; }
+uint64_t specyolo_launch_count(void) { return g_launches.load(); }
+void specyolo_reset_launch_count(void) { g_launches.store(0); }
+
+int specyolo_init(void) {
+    int dev = 0;
+    SY_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SY_CUDA(cudaGetDeviceProperties(&prop, dev));
+    SY_CHECK(prop.major == 10, SPECYOLO_ERR_UNSUPPORTED,
+             "libspecyolo is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return stft_init();
+}
+
+int specyolo_nchw_to_nhwc_bf16(const void* x, int x_dtype, float scale, int B, int C, int H, int W, void* y,
+                               int y_pixstride, void* stream) {
+    SY_CHECK(x && y && B > 0 && C > 0 && H > 0 && W > 0 && y_pixstride >= C, SPECYOLO_ERR_INVALID,
+             "nchw_to_nhwc: bad arguments");
+    return nchw_to_nhwc_launch(x, x_dtype, scale, B, C, H, W, y, y_pixstride, (cudaStream_t)stream);
+}
+
+int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C, int H, int W, float* y,
+                                   void* stream) {
+    SY_CHECK(x && y && B > 0 && C > 0 && H > 0 && W > 0 && x_pixstride >= C, SPECYOLO_ERR_INVALID,
+             "nhwc_to_nchw: bad arguments");
+    return nhwc_to_nchw_launch(x, x_pixstride, B, C, H, W, y, (cudaStream_t)stream);
+}
+
+int specyolo_conv_npad(int cout, int groups) {
+    if (groups <= 0 || cout <= 0 || cout % groups) return -1;
+    const int cg = cout / groups;
+    if (cg == 1) return 1;            // depthwise kernel: one row per group
+    return (cg + 15) / 16 * 16;       // UMMA N granularity for M = 128
+}
+
+int specyolo_fold_pack_conv(const float* w_oihw, const float* conv_bias, const float* bn_gamma,
+                            const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                            int cout, int cin_g, int kh, int kw, int groups, int n_pad, void* w_packed,
+                            float* bias_out, void* stream) {
+    SY_CHECK(w_oihw && w_packed && bias_out, SPECYOLO_ERR_INVALID, "fold_pack: null pointer");
+    SY_CHECK((bn_gamma == nullptr) == (bn_beta == nullptr) && (bn_gamma == nullptr) == (bn_mean == nullptr) &&
+                 (bn_gamma == nullptr) == (bn_var == nullptr),
+             SPECYOLO_ERR_INVALID, "fold_pack: give all BN tensors or none");
+    return fold_pack_launch(w_oihw, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, cout, cin_g, kh, kw,
+                            groups, n_pad, w_packed, bias_out, (cudaStream_t)stream);
+}
+
+int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->w_packed && a->bias && a->y, SPECYOLO_ERR_INVALID, "conv: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0 && a->groups > 0,
+             SPECYOLO_ERR_INVALID, "conv: bad sizes");
+    SY_CHECK(a->kh >= 1 && a->kw >= 1 && a->stride >= 1 && a->dil >= 1 && a->pad >= 0, SPECYOLO_ERR_INVALID,
+             "conv: bad kernel geometry");
+    const int ho = (a->H + 2 * a->pad - a->dil * (a->kh - 1) - 1) / a->stride + 1;
+    const int wo = (a->W + 2 * a->pad - a->dil * (a->kw - 1) - 1) / a->stride + 1;
+    SY_CHECK(ho == a->Ho && wo == a->Wo, SPECYOLO_ERR_INVALID, "conv: Ho/Wo (%d,%d) do not match geometry (%d,%d)",
+             a->Ho, a->Wo, ho, wo);
+    SY_CHECK(a->x_pixstride >= a->Cin && a->y_pixstride >= a->Cout, SPECYOLO_ERR_INVALID, "conv: pixel stride too small");
+    SY_CHECK(a->act == SPECYOLO_ACT_NONE || a->act == SPECYOLO_ACT_SILU, SPECYOLO_ERR_INVALID, "conv: bad act");
+    SY_CHECK(a->x_upshift == 0, SPECYOLO_ERR_UNSUPPORTED, "conv: x_upshift is not implemented");
+    if (a->groups == a->Cin && a->Cin == a->Cout && a->groups > 1)
+        return dwconv3x3_launch(a, (cudaStream_t)stream);
+    return conv_igemm_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,
+                            int Cout, void* y, int y_pixstride, void* stream) {
+    SY_CHECK(x && w && bias && y && B > 0 && H > 0 && W > 0, SPECYOLO_ERR_INVALID, "stem: bad arguments");
+    return stem_conv_launch(x, x_dtype, B, H, W, w, bias, Cout, y, y_pixstride, (cudaStream_t)stream);
+}
+
+int specyolo_sppf_pool(void* buf, int B, int H, int W, int c, int pixstride, void* stream) {
+    SY_CHECK(buf && B > 0 && H > 0 && W > 0 && c > 0, SPECYOLO_ERR_INVALID, "sppf: bad arguments");
+    return sppf_pool_launch(buf, B, H, W, c, pixstride, (cudaStream_t)stream);
+}
+
+size_t specyolo_fusion_ws_bytes(int k, int B, int H, int W, int c) { return fusion_ws_bytes(k, B, H, W, c); }
+int specyolo_fusion_eschannel(const specyolo_fusion_t* a, void* stream) {
+    SY_CHECK(a && a->y && a->alpha && a->gamma && a->beta && a->sab_w, SPECYOLO_ERR_INVALID, "fusion: null pointer");
+    return fusion_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_psa_attention(const void* qkv, int qkv_pixstride, int B, int H, int W, int heads, int key_dim,
+                           int head_dim, float scale, const float* pe_w, const float* pe_b, void* out,
+                           int out_pixstride, void* stream) {
+    SY_CHECK(qkv && pe_w && pe_b && out && B > 0 && H > 0 && W > 0 && heads > 0, SPECYOLO_ERR_INVALID,
+             "psa attention: bad arguments");
+    return psa_attention_launch(qkv, qkv_pixstride, B, H, W, heads, key_dim, head_dim, scale, pe_w, pe_b, out,
+                                out_pixstride, (cudaStream_t)stream);
+}
+
+int specyolo_detect_decode(const specyolo_decode_t* a, void* stream) {
+    SY_CHECK(a && a->B > 0 && a->nc > 0, SPECYOLO_ERR_INVALID, "decode: bad arguments");
+    return detect_decode_launch(a, (cudaStream_t)stream);
+}
+
+size_t specyolo_nms_ws_bytes(int B, int nc, int A, int multi_label) { return nms_ws_bytes(B, nc, A, multi_label); }
+int specyolo_nms(const specyolo_nms_t* a, void* stream) {
+    SY_CHECK(a != nullptr, SPECYOLO_ERR_INVALID, "nms: null argument");
+    return nms_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_scale_boxes(float* out, const int* out_count, int B, int max_det, float gain, float pad_w,
+                         float pad_h, float img0_w, float img0_h, void* stream) {
+    SY_CHECK(out && out_count && B > 0 && max_det > 0 && gain > 0.f, SPECYOLO_ERR_INVALID, "scale_boxes: bad arguments");
+    return scale_boxes_launch(out, out_count, B, max_det, gain, pad_w, pad_h, img0_w, img0_h, (cudaStream_t)stream);
+}
+
+int specyolo_iq_to_letterbox(const specyolo_stft_t* a, void* stream) {
+    SY_CHECK(a && a->iq && a->out && a->B > 0 && a->out_h > 0 && a->out_w > 0, SPECYOLO_ERR_INVALID,
+             "iq_to_letterbox: bad arguments");
+    return stft_launch(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

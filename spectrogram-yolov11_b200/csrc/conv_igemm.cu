@@ -1,0 +1,400 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a.
+//
+//   y[n,oh,ow,co] = act( sum_{ky,kx,ci} x[n, oh*s+ky*d-p, ow*s+kx*d-p, ci] * W[co,ky,kx,ci] + b[co] ) (+ res)
+//
+// GEMM view: M = output pixels (128 per CTA, a TW x TH x TN box of the NHWC output), N = output
+// channels of one group (n_tile <= 256 per CTA), K = taps * Cin_g walked in (tap, 16|32|64-channel) chunks.
+//   * A operand: one TMA 4-D box {kc, TW, TH, TN} of the NHWC input per (tap, channel chunk).  The tap
+//     offset is a coordinate shift, the conv stride is the tensor map's elementStride, padding is TMA
+//     out-of-bounds zero fill.  The box lands in shared memory as 128 K-major rows with the
+//     32/64/128-byte swizzle that the UMMA shared-memory descriptor names.
+//   * B operand: TMA 2-D box {kc, n_tile} of the packed weights [groups*n_pad][taps*Cin_g].
+//   * D: fp32 accumulator in TMEM (n_tile columns x 128 lanes), issued by one thread with
+//     tcgen05.mma.cta_group::1.kind::f16, M=128, N=n_tile, K=16 per instruction.
+//   * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer, warps2-5 = epilogue
+//     (tcgen05.ld -> +bias -> SiLU -> +residual -> bf16/fp32 NHWC store at a channel offset, so
+//     concat buffers are written in place and no torch.cat copy exists).
+//   * Non-persistent: one output tile per CTA; 2+ CTAs/SM overlap one tile's epilogue with the
+//     next tile's main loop.
+//
+// Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:81-83) = cuDNN conv + bias + SiLU.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace specyolo {
+
+struct IgemmParams {
+    int TW, TH, TN;
+    int tiles_w, tiles_h;
+    int Ho, Wo, B;
+    int kh, kw, stride, pad, dil;
+    int kc, cin_chunks, cin_g;
+    int n_tile, n_pad, cout_g;
+    int cps, stages;
+    uint32_t a_chunk_bytes, b_chunk_bytes;
+    uint32_t a_tx_bytes, b_tx_bytes;
+    uint32_t tmem_cols;
+    const float* bias;
+    void* y;
+    int y_pixstride, y_fp32;
+    const __nv_bfloat16* residual;
+    int r_pixstride;
+    int act;
+};
+
+static constexpr int kThreads = 192;
+static constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kThreads)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // 1024-byte aligned operand ring (swizzle-128B atoms repeat every 1024 B)
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t ring_off = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+    uint8_t* ring = smem_raw + ring_off;
+    uint8_t* a_ring = ring;
+    uint8_t* b_ring = ring + (size_t)p.stages * p.cps * p.a_chunk_bytes;
+
+    // tile coordinates
+    const int tile = blockIdx.x;
+    const int tw_i = tile % p.tiles_w;
+    const int th_i = (tile / p.tiles_w) % p.tiles_h;
+    const int tn_i = tile / (p.tiles_w * p.tiles_h);
+    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+    const int nt = blockIdx.y;   // N tile inside the group
+    const int g = blockIdx.z;    // group
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&map_a);
+        ptx::prefetch_tmap(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(&accum_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int taps = p.kh * p.kw;
+    const int total_chunks = taps * p.cin_chunks;
+    const int steps = (total_chunks + p.cps - 1) / p.cps;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int step = 0; step < steps; ++step) {
+                const int stage = step % p.stages;
+                const uint32_t ph = (step / p.stages) & 1;
+                ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+                const int q0 = step * p.cps;
+                const int nch = min(p.cps, total_chunks - q0);
+                ptx::mbar_expect_tx(&full_bar[stage], nch * (p.a_tx_bytes + p.b_tx_bytes));
+                for (int j = 0; j < nch; ++j) {
+                    const int q = q0 + j;
+                    const int tap = q / p.cin_chunks;
+                    const int cc = q - tap * p.cin_chunks;
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    uint8_t* a_dst = a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes;
+                    uint8_t* b_dst = b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes;
+                    ptx::tma_load_4d(a_dst, &map_a, &full_bar[stage], g * p.cin_g + cc * p.kc,
+                                     w0 * p.stride + kx * p.dil - p.pad,
+                                     h0 * p.stride + ky * p.dil - p.pad, n0);
+                    ptx::tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin_g + cc * p.kc,
+                                     g * p.n_pad + nt * p.n_tile);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_tile);
+            const uint32_t row_bytes = p.kc * 2;
+            const int kk = p.kc / 16;
+            uint32_t accumulate = 0;
+            for (int step = 0; step < steps; ++step) {
+                const int stage = step % p.stages;
+                const uint32_t ph = (step / p.stages) & 1;
+                ptx::mbar_wait(&full_bar[stage], ph);
+                ptx::tc_fence_after();
+                const int q0 = step * p.cps;
+                const int nch = min(p.cps, total_chunks - q0);
+                for (int j = 0; j < nch; ++j) {
+                    const uint32_t a_addr =
+                        ptx::smem_u32(a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes);
+                    const uint32_t b_addr =
+                        ptx::smem_u32(b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes);
+                    for (int k = 0; k < kk; ++k) {
+                        const uint64_t da = ptx::umma_smem_desc(a_addr + k * 32, row_bytes);
+                        const uint64_t db = ptx::umma_smem_desc(b_addr + k * 32, row_bytes);
+                        ptx::umma_bf16(tmem_base, da, db, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            }
+            ptx::umma_commit(&accum_bar);             // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int m = quad * 32 + lane;       // accumulator row = pixel inside the tile
+        const int npix = p.TW * p.TH * p.TN;
+        const int tw = m % p.TW;
+        const int th = (m / p.TW) % p.TH;
+        const int tn = m / (p.TW * p.TH);
+        const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+        const bool row_ok = (m < npix) && (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
+        const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
+        const int ch_base = nt * p.n_tile;           // channel offset inside the group
+        const int gch_base = g * p.cout_g + ch_base; // channel offset inside the output window
+        const float* bias = p.bias + g * p.n_pad + ch_base;
+
+        ptx::mbar_wait(&accum_bar, 0);
+        ptx::tc_fence_after();
+
+        const bool y_vec_ok = !p.y_fp32 && (p.y_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
+                              ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool r_vec_ok = p.residual && (p.r_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
+                              ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+
+        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            ptx::tmem_ld_wait();
+            if (!row_ok) continue;
+            const int nvalid = min(16, p.cout_g - (ch_base + c0));
+            if (nvalid <= 0) continue;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float t = __uint_as_float(v[i]) + __ldg(bias + c0 + i);
+                f[i] = (p.act == SPECYOLO_ACT_SILU) ? silu_f(t) : t;
+            }
+            if (p.residual) {
+                const __nv_bfloat16* r = p.residual + pix * p.r_pixstride + gch_base + c0;
+                if (r_vec_ok && nvalid == 16) {
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(r));
+                    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(r) + 1);
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 t = unpack_bf16x2(rr[i]);
+                        f[2 * i] += t.x;
+                        f[2 * i + 1] += t.y;
+                    }
+                } else {
+                    for (int i = 0; i < nvalid; ++i) f[i] += __bfloat162float(r[i]);
+                }
+            }
+            if (p.y_fp32) {
+                float* y = reinterpret_cast<float*>(p.y) + pix * p.y_pixstride + gch_base + c0;
+                for (int i = 0; i < nvalid; ++i) y[i] = f[i];
+            } else {
+                __nv_bfloat16* y =
+                    reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pixstride + gch_base + c0;
+                if (y_vec_ok && nvalid == 16) {
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    reinterpret_cast<uint4*>(y)[0] = o0;
+                    reinterpret_cast<uint4*>(y)[1] = o1;
+                } else {
+                    for (int i = 0; i < nvalid; ++i) y[i] = __float2bfloat16_rn(f[i]);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        }
+    });
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// Pick the output tile (TW,TH,TN), TW*TH*TN <= 128, that needs the fewest CTAs.
+static void choose_tile(int B, int Ho, int Wo, int stride, int& TW, int& TH, int& TN) {
+    long best_tiles = -1;
+    int bw = 1, bh = 1, bn = 1;
+    for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
+        if (tw * stride > 256) break;
+        for (int th = 1; th * tw <= 128 && th <= Ho; ++th) {
+            if (th * stride > 256) break;
+            int tn = 128 / (tw * th);
+            if (tn > B) tn = B;
+            if (tn < 1) continue;
+            // a tile that spans several images must cover whole rows x whole image height only if
+            // it spans them contiguously; the 4-D box makes any (tw,th,tn) legal.
+            const long tiles = (long)ceil_div(Wo, tw) * ceil_div(Ho, th) * ceil_div(B, tn);
+            const bool better = best_tiles < 0 || tiles < best_tiles ||
+                                (tiles == best_tiles && tw > bw);
+            if (better) { best_tiles = tiles; bw = tw; bh = th; bn = tn; }
+        }
+    }
+    TW = bw; TH = bh; TN = bn;
+}
+
+int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
+    EncodeTiledFn encode = get_encode_fn();
+    SY_CHECK(encode != nullptr, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+    const int groups = a->groups;
+    const int cin_g = a->Cin / groups, cout_g = a->Cout / groups;
+    SY_CHECK(a->Cin % groups == 0 && a->Cout % groups == 0, SPECYOLO_ERR_INVALID, "channels not divisible by groups");
+    SY_CHECK(cin_g % 16 == 0, SPECYOLO_ERR_UNSUPPORTED, "igemm conv needs Cin/groups %% 16 == 0 (got %d)", cin_g);
+    SY_CHECK(a->n_pad % 16 == 0 && a->n_pad >= cout_g, SPECYOLO_ERR_INVALID, "bad n_pad %d for cout_g %d", a->n_pad, cout_g);
+    SY_CHECK(a->x_pixstride % 8 == 0, SPECYOLO_ERR_INVALID, "x pixel stride must be a multiple of 8 elements");
+    SY_CHECK((reinterpret_cast<uintptr_t>(a->x) & 15) == 0, SPECYOLO_ERR_INVALID, "x must be 16-byte aligned");
+    SY_CHECK((reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0, SPECYOLO_ERR_INVALID, "w_packed must be 16-byte aligned");
+    SY_CHECK(a->stride >= 1 && a->stride <= 8, SPECYOLO_ERR_INVALID, "stride out of range");
+
+    IgemmParams p{};
+    const int kc = (cin_g % 64 == 0) ? 64 : (cin_g % 32 == 0 ? 32 : 16);
+    p.kc = kc;
+    p.cin_g = cin_g;
+    p.cin_chunks = cin_g / kc;
+    p.kh = a->kh; p.kw = a->kw; p.stride = a->stride; p.pad = a->pad; p.dil = a->dil;
+    p.n_pad = a->n_pad;
+    p.cout_g = cout_g;
+    // N tile: whole padded group if it fits one UMMA, else the largest multiple-of-16 divisor <= 256
+    int n_tile = a->n_pad;
+    if (n_tile > 256) {
+        n_tile = 256;
+        while (a->n_pad % n_tile != 0) n_tile -= 16;
+    }
+    p.n_tile = n_tile;
+
+    // geometry: 1x1/s1/p0 convs run "flat" over all B*H*W pixels
+    const bool flat = (a->kh == 1 && a->kw == 1 && a->stride == 1 && a->pad == 0);
+    int gB, gH, gW, gHo, gWo;
+    if (flat) {
+        gB = 1; gH = 1; gW = a->B * a->H * a->W; gHo = 1; gWo = gW;
+        p.TW = 128; p.TH = 1; p.TN = 1;
+    } else {
+        gB = a->B; gH = a->H; gW = a->W; gHo = a->Ho; gWo = a->Wo;
+        choose_tile(gB, gHo, gWo, a->stride, p.TW, p.TH, p.TN);
+    }
+    p.B = gB; p.Ho = gHo; p.Wo = gWo;
+    p.tiles_w = ceil_div(gWo, p.TW);
+    p.tiles_h = ceil_div(gHo, p.TH);
+    const int tiles_n = ceil_div(gB, p.TN);
+    const long m_tiles = (long)p.tiles_w * p.tiles_h * tiles_n;
+    SY_CHECK(m_tiles > 0 && m_tiles < (1L << 31), SPECYOLO_ERR_INVALID, "bad tile count");
+
+    const int row_bytes = kc * 2;
+    p.cps = 64 / kc;
+    p.a_chunk_bytes = 128u * row_bytes;
+    p.b_chunk_bytes = ((uint32_t)(n_tile * row_bytes) + 1023u) & ~1023u;
+    p.a_tx_bytes = (uint32_t)(p.TW * p.TH * p.TN) * row_bytes;
+    p.b_tx_bytes = (uint32_t)n_tile * row_bytes;
+    const uint32_t stage_bytes = p.cps * (p.a_chunk_bytes + p.b_chunk_bytes);
+    int stages = (int)((96u * 1024u) / stage_bytes);
+    if (stages < 3) stages = 3;
+    if (stages > 6) stages = 6;
+    if (n_tile > 128 && stages < 4) stages = 4;
+    p.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024;
+    SY_CHECK(smem_bytes <= 227 * 1024, SPECYOLO_ERR_INVALID, "smem budget exceeded");
+    uint32_t cols = 32;
+    while (cols < (uint32_t)n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+
+    p.bias = a->bias;
+    p.y = a->y; p.y_pixstride = a->y_pixstride; p.y_fp32 = a->y_fp32;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.r_pixstride = a->r_pixstride;
+    p.act = a->act;
+
+    // ---- tensor maps ----
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t pix_b = (cuuint64_t)a->x_pixstride * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gB};
+        cuuint64_t strides[3] = {pix_b, pix_b * gW, pix_b * gW * gH};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(p.TW * a->stride),
+                             (cuuint32_t)(p.TH * a->stride), (cuuint32_t)p.TN};
+        cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA,
+                 "cuTensorMapEncodeTiled(A) failed (%d): dims %llu,%llu,%llu,%llu box %u,%u,%u,%u",
+                 (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                 (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)a->kh * a->kw * cin_g;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)groups * a->n_pad};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->w_packed),
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
+    }
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024);
+    });
+    SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
+             cudaGetErrorString(attr_err));
+
+    dim3 grid((unsigned)m_tiles, (unsigned)(a->n_pad / n_tile), (unsigned)groups);
+    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+}  // namespace specyolo

@@ -1,0 +1,321 @@
+// CUDA-core kernels around the implicit-GEMM conv: BN fold + weight repack, the 3-channel stem conv,
+// depthwise 3x3, and NCHW<->NHWC layout conversion.  All are HBM-bound streaming kernels: 16-byte
+// vector accesses along the contiguous channel axis, grids sized in multiples of the SM count.
+#include "common.h"
+
+namespace specyolo {
+
+// ------------------------------------------------------------------------------------------------
+// BN fold + repack:  w_packed[g][n][ky][kx][ci] (bf16), rows n >= cout_g are zero.
+// fuse_conv_and_bn (ultralytics/utils/torch_utils.py:238-265):
+//   w' = w * gamma / sqrt(var + eps);  b' = (b_conv) * gamma / sqrt(var+eps) + beta - gamma*mean/sqrt(var+eps)
+// ------------------------------------------------------------------------------------------------
+__global__ void fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                 int cout, int cin_g, int kh, int kw, int groups, int n_pad,
+                                 __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out) {
+    const int cout_g = cout / groups;
+    const int taps = kh * kw;
+    const long per_row = (long)taps * cin_g;
+    const long total = (long)groups * n_pad * per_row;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_g);
+        const int tap = (int)((i / cin_g) % taps);
+        const int n = (int)((i / per_row) % n_pad);
+        const int g = (int)(i / (per_row * n_pad));
+        float v = 0.f;
+        if (n < cout_g) {
+            const int co = g * cout_g + n;
+            const float s = gamma ? gamma[co] / sqrtf(var[co] + eps) : 1.f;
+            // OIHW: ((co*cin_g + ci)*kh + ky)*kw + kx ; tap = ky*kw + kx
+            v = w[((long)co * cin_g + ci) * taps + tap] * s;
+        }
+        wp[i] = __float2bfloat16_rn(v);
+    }
+    const int nb = groups * n_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
+        const int n = i % n_pad, g = i / n_pad;
+        float b = 0.f;
+        if (n < cout_g) {
+            const int co = g * cout_g + n;
+            const float cb = conv_bias ? conv_bias[co] : 0.f;
+            if (gamma) {
+                const float s = gamma[co] / sqrtf(var[co] + eps);
+                b = cb * s + beta[co] - mean[co] * s;
+            } else {
+                b = cb;
+            }
+        }
+        bias_out[i] = b;
+    }
+}
+
+int fold_pack_launch(const float* w, const float* conv_bias, const float* gamma, const float* beta,
+                     const float* mean, const float* var, float eps, int cout, int cin_g, int kh, int kw,
+                     int groups, int n_pad, void* wp, float* bias_out, cudaStream_t stream) {
+    SY_CHECK(cout % groups == 0, SPECYOLO_ERR_INVALID, "cout %% groups != 0");
+    SY_CHECK(n_pad >= cout / groups, SPECYOLO_ERR_INVALID, "n_pad too small");
+    const long total = (long)groups * n_pad * kh * kw * cin_g;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    fold_pack_kernel<<<blocks, 256, 0, stream>>>(w, conv_bias, gamma, beta, mean, var, eps, cout, cin_g, kh,
+                                                 kw, groups, n_pad, reinterpret_cast<__nv_bfloat16*>(wp),
+                                                 bias_out);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: 3x3 stride-2 pad-1 conv on the 3-channel NCHW network input, SiLU, NHWC bf16 output.
+// K = 27 is far too thin for the tensor pipe; the layer is bound by its 3.7x larger output write.
+// One thread produces 8 output channels of one pixel (a 16-byte store); the 27 input taps are read
+// through L1 (each input pixel is shared by ~2.25 outputs x Cout/8 threads).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_in(const T* p, long i);
+template <>
+__device__ __forceinline__ float load_in<float>(const float* p, long i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float load_in<__nv_bfloat16>(const __nv_bfloat16* p, long i) {
+    return __bfloat162float(p[i]);
+}
+template <>
+__device__ __forceinline__ float load_in<uint8_t>(const uint8_t* p, long i) {
+    return (float)__ldg(p + i) * (1.0f / 255.0f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const T* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt,
+                 const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ y, int y_pixstride,
+                 int Ho, int Wo) {
+    extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
+    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+        const int co = i % Cout, k = i / Cout;  // k = ci*9 + ky*3 + kx (OIHW inner order)
+        sw[i] = wgt[co * 27 + k];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
+    __syncthreads();
+    const int cg = Cout / 8;
+    const long total = (long)B * Ho * Wo * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % cg);
+        const long pix = idx / cg;
+        const int ow = (int)(pix % Wo);
+        const int oh = (int)((pix / Wo) % Ho);
+        const int n = (int)(pix / ((long)Wo * Ho));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + c8 * 8 + j];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int ih = oh * 2 + ky - 1;
+                if (ih < 0 || ih >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iw = ow * 2 + kx - 1;
+                    if (iw < 0 || iw >= W) continue;
+                    const float v = load_in<T>(x, (((long)n * 3 + ci) * H + ih) * W + iw);
+                    const float* wr = sw + (ci * 9 + ky * 3 + kx) * Cout + c8 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+                }
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(silu_f(acc[0]), silu_f(acc[1]));
+        o.y = pack_bf16x2(silu_f(acc[2]), silu_f(acc[3]));
+        o.z = pack_bf16x2(silu_f(acc[4]), silu_f(acc[5]));
+        o.w = pack_bf16x2(silu_f(acc[6]), silu_f(acc[7]));
+        *reinterpret_cast<uint4*>(y + pix * y_pixstride + c8 * 8) = o;
+    }
+}
+
+int stem_conv_launch(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,
+                     int Cout, void* y, int y_pixstride, cudaStream_t stream) {
+    SY_CHECK(Cout % 8 == 0 && Cout <= 128, SPECYOLO_ERR_INVALID, "stem Cout must be a multiple of 8 (<=128)");
+    SY_CHECK(y_pixstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, SPECYOLO_ERR_INVALID,
+             "stem output must be 16-byte aligned");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long total = (long)B * Ho * Wo * (Cout / 8);
+    long want = (total + 255) / 256;
+    int blocks = (int)(want < 148L * 16 ? want : 148L * 16);
+    if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)(28 * Cout) * sizeof(float);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+    if (x_dtype == SPECYOLO_DT_F32)
+        stem_conv_kernel<float><<<blocks, 256, smem, stream>>>((const float*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+    else if (x_dtype == SPECYOLO_DT_BF16)
+        stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, stream>>>((const __nv_bfloat16*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+    else if (x_dtype == SPECYOLO_DT_U8)
+        stem_conv_kernel<uint8_t><<<blocks, 256, smem, stream>>>((const uint8_t*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+    else
+        SY_CHECK(false, SPECYOLO_ERR_INVALID, "bad x_dtype %d", x_dtype);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3 stride-1 pad-1 (+bias, optional SiLU): DWConv in Detect.cv3 (head.py:51-52).
+// One thread = 8 channels of one pixel (16-byte loads/stores); weights are packed bf16 [C][3][3][1]
+// by fold_pack (groups=C, cin_g=1, n_pad=1) -> read as wp[c*9 + tap].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int B, int H, int W, int C,
+                 const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias, int act,
+                 __nv_bfloat16* __restrict__ y, int y_pixstride) {
+    const int cg = C / 8;
+    const long total = (long)B * H * W * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % cg);
+        const long pix = idx / cg;
+        const int w = (int)(pix % W);
+        const int h = (int)((pix / W) % H);
+        const long n = pix / ((long)W * H);
+        const int c0 = c8 * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + c0 + j);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ih = h + ky - 1;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iw = w + kx - 1;
+                if (iw < 0 || iw >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                    x + ((n * H + ih) * W + iw) * x_pixstride + c0));
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(vv[j]);
+                    acc[2 * j] = fmaf(f.x, __bfloat162float(wp[(c0 + 2 * j) * 9 + ky * 3 + kx]), acc[2 * j]);
+                    acc[2 * j + 1] = fmaf(f.y, __bfloat162float(wp[(c0 + 2 * j + 1) * 9 + ky * 3 + kx]), acc[2 * j + 1]);
+                }
+            }
+        }
+        if (act == SPECYOLO_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]);
+        o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]);
+        o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(y + pix * y_pixstride + c0) = o;
+    }
+}
+
+int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream) {
+    SY_CHECK(a->Cin == a->Cout && a->groups == a->Cin && a->kh == 3 && a->kw == 3 && a->stride == 1 &&
+                 a->pad == 1 && a->dil == 1,
+             SPECYOLO_ERR_UNSUPPORTED, "depthwise kernel supports 3x3 s1 p1 d1 only");
+    SY_CHECK(a->Cin % 8 == 0 && a->x_pixstride % 8 == 0 && a->y_pixstride % 8 == 0, SPECYOLO_ERR_INVALID,
+             "depthwise needs C, strides multiples of 8");
+    SY_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->y)) & 15) == 0,
+             SPECYOLO_ERR_INVALID, "depthwise needs 16-byte aligned tensors");
+    SY_CHECK(!a->y_fp32 && !a->residual && a->n_pad == 1, SPECYOLO_ERR_UNSUPPORTED,
+             "depthwise: bf16 output, no residual, n_pad==1");
+    const long total = (long)a->B * a->H * a->W * (a->Cin / 8);
+    long want = (total + 255) / 256;
+    int blocks = (int)(want < 148L * 16 ? want : 148L * 16);
+    if (blocks < 1) blocks = 1;
+    dwconv3x3_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->x), a->x_pixstride,
+                                                 a->B, a->H, a->W, a->Cin,
+                                                 reinterpret_cast<const __nv_bfloat16*>(a->w_packed), a->bias,
+                                                 a->act, reinterpret_cast<__nv_bfloat16*>(a->y), a->y_pixstride);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW (f32|bf16|u8) -> NHWC bf16 through a shared-memory transpose tile: reads are coalesced along
+// W, writes along C.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const T* __restrict__ x, float scale, int C, long HW, __nv_bfloat16* __restrict__ y,
+                    int y_pixstride) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long p0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long pp = p0 + tx;
+        float v = 0.f;
+        if (c < C && pp < HW) v = load_in<T>(x, ((long)n * C + c) * HW + pp);
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const long pp = p0 + j;
+        const int c = c0 + tx;
+        if (c < C && pp < HW) y[((long)n * HW + pp) * y_pixstride + c] = __float2bfloat16_rn(tile[tx][j] * scale);
+    }
+}
+int nchw_to_nhwc_launch(const void* x, int x_dtype, float scale, int B, int C, int H, int W, void* y,
+                        int y_pixstride, cudaStream_t stream) {
+    const long HW = (long)H * W;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+    // note: load_in<uint8_t> already applies 1/255; `scale` multiplies on top (pass 1.0 for u8)
+    if (x_dtype == SPECYOLO_DT_F32)
+        nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, scale, C, HW, yy, y_pixstride);
+    else if (x_dtype == SPECYOLO_DT_BF16)
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, scale, C, HW, yy, y_pixstride);
+    else if (x_dtype == SPECYOLO_DT_U8)
+        nchw_to_nhwc_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)x, scale, C, HW, yy, y_pixstride);
+    else
+        SY_CHECK(false, SPECYOLO_ERR_INVALID, "bad x_dtype %d", x_dtype);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int C, long HW,
+                    float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long p0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const long pp = p0 + j;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (c < C && pp < HW) v = __bfloat162float(x[((long)n * HW + pp) * x_pixstride + c]);
+        tile[j][tx] = v;  // [pixel][channel]
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long pp = p0 + tx;
+        if (c < C && pp < HW) y[((long)n * C + c) * HW + pp] = tile[tx][j];
+    }
+}
+
+int nhwc_to_nchw_launch(const void* x, int x_pixstride, int B, int C, int H, int W, float* y,
+                        cudaStream_t stream) {
+    const long HW = (long)H * W;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_pixstride, C, HW, y);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+}  // namespace specyolo

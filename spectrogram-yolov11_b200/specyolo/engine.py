@@ -1,0 +1,250 @@
+"""`YOLO(cfg).predict()` facade, predictor loop and result containers — the host-side mirror of
+ultralytics/engine/model.py:499-558 (Model.predict), engine/predictor.py:118-306 (BasePredictor),
+models/yolo/detect/predict.py:23-73 (DetectionPredictor.postprocess) and engine/results.py (Results / Boxes),
+reduced to what the detection hot path returns.
+
+The whole step (stem -> ... -> Detect head -> fused decode+threshold -> batched NMS) is captured once per
+(input shape, thresholds) in a CUDA graph and replayed: ~170 kernel launches, zero host synchronisation
+inside, one small device->host copy of [B, max_det, 6] + counts at the end.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .nn.tasks import DetectionModel
+
+
+class Boxes:
+    """[n, 6] detections (x1, y1, x2, y2, conf, cls) in original-image pixels (engine/results.py:1015)."""
+
+    def __init__(self, data: torch.Tensor, orig_shape):
+        self.data = data
+        self.orig_shape = orig_shape
+
+    @property
+    def xyxy(self):
+        return self.data[:, :4]
+
+    @property
+    def conf(self):
+        return self.data[:, 4]
+
+    @property
+    def cls(self):
+        return self.data[:, 5]
+
+    @property
+    def xywh(self):
+        b = self.xyxy
+        return torch.cat(((b[:, :2] + b[:, 2:]) / 2, b[:, 2:] - b[:, :2]), 1)
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def cpu(self):
+        return Boxes(self.data.cpu(), self.orig_shape)
+
+    def numpy(self):
+        return Boxes(self.data.cpu().numpy(), self.orig_shape)
+
+
+class Results:
+    """One image's detections (engine/results.py:187).  `orig_img` is kept by reference only when the caller
+    passed host images; tensor sources are not copied back to the host (the reference does, predict.py:37-38)."""
+
+    def __init__(self, orig_shape, boxes: torch.Tensor, names: Dict[int, str], path: str = "", orig_img=None,
+                 speed: Optional[dict] = None):
+        self.orig_shape = orig_shape
+        self.boxes = Boxes(boxes, orig_shape)
+        self.names = names
+        self.path = path
+        self.orig_img = orig_img
+        self.speed = speed or {}
+
+    def __len__(self):
+        return len(self.boxes)
+
+
+class _GraphStep:
+    """A captured forward for one static input signature."""
+
+    def __init__(self, model: DetectionModel, example: torch.Tensor, conf, iou, agnostic, max_det, classes):
+        self.static_in = example.clone()
+        args = dict(conf_thres=conf, iou_thres=iou, agnostic=agnostic, max_det=max_det, classes=classes)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):      # warm-up: lazy weight packing, attribute setup, allocator
+            for _ in range(2):
+                model.detect_fused(self.static_in, **args)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.load().specyolo_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out, self.cnt = model.detect_fused(self.static_in, **args)
+        self.launches = int(_lib.load().specyolo_launch_count() - n0)
+
+    def run(self, x: torch.Tensor):
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out, self.cnt
+
+
+class DetectionPredictor:
+    """preprocess -> inference -> postprocess (engine/predictor.py:221-306), all on the device."""
+
+    def __init__(self, model: DetectionModel, overrides: Optional[dict] = None):
+        self.model = model
+        self.args = dict(conf=0.25, iou=0.7, max_det=300, agnostic_nms=False, classes=None, imgsz=640, half=False,
+                         use_graph=True)
+        self.args.update(overrides or {})
+        self._graphs: Dict[tuple, _GraphStep] = {}
+        self.last_launches = 0
+
+    # -- sources ---------------------------------------------------------------------------------
+    def preprocess(self, source) -> (torch.Tensor, list, list):
+        """Returns (device tensor [B,3,H,W] (fp32/bf16 in 0..1 or uint8), original shapes, host images)."""
+        dev = next(self.model.parameters()).device
+        if isinstance(source, torch.Tensor):
+            # LoadTensor._single_check (data/loaders.py:548-566): BCHW, stride-32 sizes
+            im = source if source.dim() == 4 else source.unsqueeze(0)
+            if im.dim() != 4 or im.shape[1] != 3:
+                raise ValueError(f"WARNING ⚠️ torch.Tensor inputs should be BCHW i.e. shape(1, 3, 640, 640) "
+                                 f"divisible by stride 32. Input shape{tuple(im.shape)} is incompatible.")
+            if im.shape[2] % 32 or im.shape[3] % 32:
+                raise ValueError(f"WARNING ⚠️ torch.Tensor inputs should be BCHW i.e. shape(1, 3, 640, 640) "
+                                 f"divisible by stride 32. Input shape{tuple(im.shape)} is incompatible.")
+            im = im.to(dev, non_blocking=True)
+            return im, [tuple(im.shape[2:])] * im.shape[0], [None] * im.shape[0]
+        if isinstance(source, np.ndarray):
+            source = [source]
+        if isinstance(source, (list, tuple)) and all(isinstance(s, np.ndarray) for s in source):
+            # HWC BGR uint8 images that already have the network size (the letterbox/resize of arbitrary
+            # image files is SURVEY 8(f3), a "next" row; IQ sources are letterboxed by the STFT kernel)
+            shapes = {s.shape for s in source}
+            if len(shapes) != 1:
+                raise ValueError("ndarray sources must share one shape")
+            h, w, c = source[0].shape
+            if c != 3 or h % 32 or w % 32:
+                raise ValueError("ndarray sources must be HWC uint8 with H, W divisible by 32")
+            im = np.stack(source)[..., ::-1].transpose(0, 3, 1, 2)     # BGR->RGB, BHWC->BCHW (predictor.py:129-131)
+            im = torch.from_numpy(np.ascontiguousarray(im)).to(dev, non_blocking=True)
+            return im, [(h, w)] * len(source), list(source)
+        raise TypeError(f"unsupported source type {type(source)}")   # data/build.py:183
+
+    # -- one batch -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer(self, im: torch.Tensor):
+        a = self.args
+        classes = None
+        if a["classes"] is not None:
+            classes = torch.tensor(list(a["classes"]), device=im.device, dtype=torch.int32)
+        if a["use_graph"]:
+            key = (tuple(im.shape), im.dtype, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"],
+                   None if a["classes"] is None else tuple(a["classes"]))
+            step = self._graphs.get(key)
+            if step is None:
+                step = self._graphs[key] = _GraphStep(self.model, im, a["conf"], a["iou"], a["agnostic_nms"],
+                                                      a["max_det"], classes)
+            self.last_launches = step.launches
+            return step.run(im)
+        n0 = _lib.load().specyolo_launch_count()
+        r = self.model.detect_fused(im, conf_thres=a["conf"], iou_thres=a["iou"], agnostic=a["agnostic_nms"],
+                                    max_det=a["max_det"], classes=classes)
+        self.last_launches = int(_lib.load().specyolo_launch_count() - n0)
+        return r
+
+    def __call__(self, source) -> List[Results]:
+        im, shapes, host_imgs = self.preprocess(source)
+        out, cnt = self.infer(im)
+        # postprocess (detect/predict.py:59-73): boxes back to original-image coordinates
+        img1 = tuple(im.shape[2:])
+        if any(s != img1 for s in shapes):
+            raise NotImplementedError("sources must already have the network input size")
+        out_h = out.cpu()                       # single D2H of [B, max_det, 6]
+        counts = cnt.cpu().tolist()
+        return [Results(shapes[b], out_h[b, : counts[b]], self.model.names, orig_img=host_imgs[b])
+                for b in range(im.shape[0])]
+
+
+class YOLO:
+    """`YOLO(cfg_or_weights).predict(source)` (ultralytics/models/yolo/model.py:11, engine/model.py:82-149, 499-558)."""
+
+    def __init__(self, model: Union[str, Path, DetectionModel] = "yolo11s_fusion_sand3_new.yaml", task=None,
+                 verbose=False, nc: Optional[int] = None):
+        if task not in (None, "detect"):
+            raise NotImplementedError(f"task '{task}' is not supported: specyolo implements the detect path only")
+        self.task = "detect"
+        self.overrides: dict = {}
+        self.predictor: Optional[DetectionPredictor] = None
+        if isinstance(model, DetectionModel):
+            self.model = model
+        else:
+            p = Path(str(model))
+            if p.suffix in (".yaml", ".yml"):
+                self.model = DetectionModel(str(p), nc=nc, verbose=verbose)
+            elif p.suffix == ".pt":
+                ck = torch.load(str(p), map_location="cpu", weights_only=True)   # state-dict checkpoints only
+                cfg = ck.get("cfg") if isinstance(ck, dict) else None
+                if cfg is None or "state_dict" not in ck:
+                    raise NotImplementedError("'.pt' must hold {'cfg': yaml name, 'nc': int, 'state_dict': ...}; pickled "
+                                              "nn.Module checkpoints need the reference package to unpickle")
+                self.model = DetectionModel(cfg, nc=ck.get("nc"), verbose=verbose)
+                self.model.load_state_dict(ck["state_dict"])
+            else:
+                raise NotImplementedError(f"unsupported model spec '{model}'")
+        self.model.eval()
+
+    @property
+    def names(self):
+        return self.model.names
+
+    def to(self, device):
+        self.model.to(device)
+        self.predictor = None
+        return self
+
+    def load_state_dict(self, sd, strict=True):
+        r = self.model.load_state_dict(sd, strict=strict)
+        self.predictor = None
+        return r
+
+    def fuse(self):
+        self.model.fuse()
+        return self
+
+    def predict(self, source=None, stream=False, predictor=None, **kwargs) -> List[Results]:
+        if source is None:
+            raise ValueError("source is required (the reference's default assets are not shipped)")
+        if stream:
+            raise NotImplementedError("stream=True generators are outside the hot path")
+        custom = {"conf": 0.25}            # engine/model.py:545
+        args = {**self.overrides, **custom, **kwargs}
+        dev = args.pop("device", None)
+        args.pop("verbose", None)
+        if dev is not None:
+            if str(dev) == "cpu":
+                raise RuntimeError("specyolo has no CPU path; use the reference package for CPU inference")
+            self.model.to(torch.device(dev if isinstance(dev, (str, torch.device)) else f"cuda:{dev}"))
+        elif not next(self.model.parameters()).is_cuda:
+            self.model.to("cuda")
+        if self.predictor is None or any(self.predictor.args.get(k) != v for k, v in args.items()):
+            self.predictor = (predictor or DetectionPredictor)(self.model, args)
+        return self.predictor(source)
+
+    __call__ = predict
+
+    def predict_iq(self, iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0,
+                   db_max: float = 0.0, **kwargs) -> List[Results]:
+        """Raw IQ bursts [B, L] complex64 -> boxes: STFT/letterbox kernel -> detector, all on the device."""
+        if not next(self.model.parameters()).is_cuda:
+            self.model.to("cuda")
+        dev = next(self.model.parameters()).device
+        imgsz = kwargs.pop("imgsz", 640)
+        im = ops.iq_to_letterbox(iq.to(dev, non_blocking=True), nfft, hop, db_min, db_max, (imgsz, imgsz))
+        return self.predict(im, **kwargs)

@@ -1,0 +1,93 @@
+"""Deterministic synthetic weights ("random-init weights of that architecture" for benches and parity
+tests — there is no network for checkpoints).  The recipe follows SURVEY 8(d): BatchNorm running stats
+and affine terms are randomised so the BN fold is exercised, GCT gamma/beta are non-zero so the Fusion
+gates are not the identity they are at init, and the Detect class bias is raised so that a few percent
+of the anchors clear conf=0.25 and NMS has real work.
+
+Everything is generated on the CPU with a seeded torch.Generator, key by key in state_dict order, so the
+same (cfg, seed) gives bit-identical tensors in the build container and on the GPU box.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+
+def synth_state_dict(model: torch.nn.Module, seed: int = 0, cls_bias: float = -2.5) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in model.state_dict().items():
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            t = torch.zeros(shape, dtype=v.dtype)
+        elif k.endswith(".dfl.conv.weight"):
+            t = torch.arange(shape[1], dtype=torch.float32).view(shape)
+        elif k.endswith("bn.running_mean") or k.endswith("bn.bias"):
+            t = torch.randn(shape, generator=g) * 0.1
+        elif k.endswith("bn.running_var") or k.endswith("bn.weight"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif k.endswith(".alpha"):
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif k.endswith(".gamma") or k.endswith(".beta"):
+            t = torch.randn(shape, generator=g) * 0.3
+        elif k.endswith("sab.cv1.weight"):
+            t = torch.randn(shape, generator=g) * 0.5
+        elif k.endswith(".weight") and len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif k.endswith(".bias"):
+            # last conv of a Detect branch: cv2 (box, 64 outputs) or cv3 (classes)
+            is_cls = ".cv3." in k
+            t = torch.randn(shape, generator=g) * 0.1 + (cls_bias if is_cls else 1.0)
+        else:
+            t = torch.randn(shape, generator=g) * 0.1
+        out[k] = t.to(v.dtype)
+    return out
+
+
+def synth_images(batch: int, size: int = 640, seed: int = 0, dtype=torch.float32) -> torch.Tensor:
+    """Spectrogram-like frames: noise floor + a few bright axis-aligned rectangles."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = (torch.randn((batch, 1, size, size), generator=g) * 0.05 + 0.25)
+    for b in range(batch):
+        n = int(torch.randint(4, 13, (1,), generator=g))
+        for _ in range(n):
+            w = int(torch.randint(20, 300, (1,), generator=g))
+            h = int(torch.randint(8, 120, (1,), generator=g))
+            x0 = int(torch.randint(0, size - w, (1,), generator=g))
+            y0 = int(torch.randint(0, size - h, (1,), generator=g))
+            lvl = float(torch.rand((1,), generator=g)) * 0.3 + 0.6
+            x[b, 0, y0:y0 + h, x0:x0 + w] = lvl + torch.randn((h, w), generator=g) * 0.03
+    x = x.clamp_(0, 1).expand(batch, 3, size, size).contiguous()
+    if dtype == torch.uint8:
+        return (x * 255).round().to(torch.uint8)
+    return x.to(dtype)
+
+
+def synth_iq(batch: int, length: int = 1 << 20, seed: int = 0) -> torch.Tensor:
+    """complex64 bursts: complex Gaussian noise + a few band-limited on/off carriers."""
+    out = torch.empty((batch, length), dtype=torch.complex64)
+    t = torch.arange(length, dtype=torch.float64)
+    for b in range(batch):
+        g = torch.Generator().manual_seed(1000 + seed * 7919 + b)
+        x = torch.complex(torch.randn(length, generator=g, dtype=torch.float64),
+                          torch.randn(length, generator=g, dtype=torch.float64)) * (0.1 / math.sqrt(2))
+        n = int(torch.randint(2, 7, (1,), generator=g))
+        for _ in range(n):
+            fc = (float(torch.rand((1,), generator=g)) - 0.5) * 0.9
+            bw = float(torch.rand((1,), generator=g)) * 0.19 + 0.01
+            t0 = int(torch.randint(0, length // 2, (1,), generator=g))
+            dur = int(torch.randint(length // 16, length // 2, (1,), generator=g))
+            amp = 10 ** (float(torch.rand((1,), generator=g)) * 1.0 - 0.5) * 0.1
+            # band-limited noise-like carrier: sum of a few tones inside the band
+            seg = torch.zeros(dur, dtype=torch.complex128)
+            tt = t[:dur]
+            for _k in range(8):
+                f = fc + (float(torch.rand((1,), generator=g)) - 0.5) * bw
+                ph = float(torch.rand((1,), generator=g)) * 2 * math.pi
+                seg += torch.exp(1j * (2 * math.pi * f * tt + ph))
+            x[t0:t0 + dur] += seg[: max(0, min(dur, length - t0))] * (amp / math.sqrt(8))
+        out[b] = x.to(torch.complex64)
+    return out

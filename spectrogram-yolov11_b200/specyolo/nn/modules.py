@@ -1,0 +1,488 @@
+"""B200 versions of the reference's operator blocks — same class names, constructor signatures,
+sub-module names and state_dict keys as ultralytics.nn.modules (so reference checkpoints / state
+dicts load unchanged), but every forward runs libspecyolo kernels on NHWC bf16 feature maps.
+
+torch.nn.Conv2d / BatchNorm2d instances are used purely as parameter containers (their forward is
+never called): BatchNorm is folded into the conv and the weights are repacked for the tcgen05
+implicit-GEMM kernel on first use (`Conv.packed()`), the device-side equivalent of
+BaseModel.fuse() (ultralytics/nn/tasks.py:223-251).
+
+Concats never materialise as copies inside a block: each block allocates its concat buffer once per
+call and hands channel-slice views to the producing convs (`out=`).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+BN_EPS = 1e-3  # initialize_weights (ultralytics/utils/torch_utils.py:410-420)
+
+
+def autopad(k, p=None, d=1):
+    """Same-shape padding (ultralytics/nn/modules/conv.py:56-62)."""
+    if isinstance(k, (tuple, list)):
+        k = k[0]
+    if d > 1:
+        k = d * (k - 1) + 1
+    return k // 2 if p is None else p
+
+
+def _as_fmap(x: torch.Tensor) -> torch.Tensor:
+    """Accept what reference callers pass (NCHW fp32/bf16/uint8) and bring it to NHWC bf16."""
+    if x.dtype == torch.bfloat16 and x.dim() == 4 and (x.stride(1) == 1 or x.shape[1] == 1):
+        return x
+    return ops.to_nhwc_bf16(x)
+
+
+class Conv(nn.Module):
+    """Conv2d + BatchNorm2d + SiLU (ultralytics/nn/modules/conv.py:65-83), run as one fused kernel."""
+
+    default_act = nn.SiLU()
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
+        super().__init__()
+        if isinstance(k, (tuple, list)):   # C2f passes k=((3, 3), (3, 3)); only square kernels exist on the path
+            assert k[0] == k[1]
+            k = k[0]
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p, d), groups=g, dilation=d, bias=False)
+        self.bn = nn.BatchNorm2d(c2, eps=BN_EPS, momentum=0.03)
+        if not (act is True or act is False or isinstance(act, (nn.SiLU, nn.Identity))):
+            raise NotImplementedError("specyolo Conv supports SiLU or no activation")
+        self.act = nn.SiLU() if (act is True or isinstance(act, nn.SiLU)) else nn.Identity()
+        self._packed: Optional[ops.PackedConv] = None
+
+    # -- weight prep ---------------------------------------------------------------------------
+    def packed(self) -> ops.PackedConv:
+        if self._packed is None:
+            c = self.conv
+            self._packed = ops.fold_pack(
+                c.weight, None, (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var),
+                self.bn.eps, c.stride[0], c.padding[0], c.dilation[0], c.groups, isinstance(self.act, nn.SiLU))
+        return self._packed
+
+    def invalidate(self):
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None  # parameters moved / cast: repack lazily
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    # -- forward -------------------------------------------------------------------------------
+    def forward(self, x, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None):
+        if self.conv.in_channels == 3 and self.conv.groups == 1 and x.dim() == 4 and x.stride(1) != 1:
+            return ops.stem_conv(x, self.packed(), out)  # NCHW network input straight into the stem
+        return ops.conv2d(_as_fmap(x), self.packed(), out, residual)
+
+    forward_fuse = forward
+
+
+class DWConv(Conv):
+    """Depth-wise conv (conv.py:687-692)."""
+
+    def __init__(self, c1, c2, k=1, s=1, d=1, act=True):
+        super().__init__(c1, c2, k, s, g=math.gcd(c1, c2), d=d, act=act)
+
+
+class DDWConv(nn.Module):
+    """Grouped (g=8) dilated strided conv followed by a 1x1 conv (conv.py:694-710)."""
+
+    def __init__(self, c1, c2, k=3, s=2, d=1, act=True):
+        super().__init__()
+        self.conv1 = Conv(c1, c2, k, s, g=8, d=d, act=act)
+        self.kz = k
+        self.conv2 = Conv(c2, c2, k=1, s=1)
+
+    def forward(self, x, out=None):
+        return self.conv2(self.conv1(x), out=out)
+
+
+class Bottleneck(nn.Module):
+    """Two convs with an optional shortcut added in the second conv's epilogue (block.py:713-726)."""
+
+    def __init__(self, c1, c2, shortcut=True, g=1, k=(3, 3), e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0], 1)
+        self.cv2 = Conv(c_, c2, k[1], 1, g=g)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x, out=None):
+        return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
+
+
+class C3(nn.Module):
+    """CSP bottleneck with 3 convs (block.py:490-504); concat buffer written in place."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=((1, 1), (3, 3)), e=1.0) for _ in range(n)))
+        self.c_ = c_
+
+    def forward(self, x, out=None):
+        x = _as_fmap(x)
+        B, _, H, W = x.shape
+        cat = ops.new_act(B, 2 * self.c_, H, W, x.device)
+        t = self.cv1(x)
+        last = len(self.m) - 1
+        for j, m in enumerate(self.m):
+            t = m(t, out=cat[:, : self.c_] if j == last else None)
+        if last < 0:
+            cat[:, : self.c_].copy_(t)
+        self.cv2(x, out=cat[:, self.c_:])
+        return self.cv3(cat, out=out)
+
+
+class C3k(C3):
+    """C3 with k x k bottlenecks (block.py:1672-1680)."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, k=3):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        c_ = int(c2 * e)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=(k, k), e=1.0) for _ in range(n)))
+
+
+class C2f(nn.Module):
+    """CSP bottleneck with 2 convs and n inner blocks (block.py:444-464)."""
+
+    def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5):
+        super().__init__()
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
+        self.n = n
+
+    def forward(self, x, out=None):
+        x = _as_fmap(x)
+        B, _, H, W = x.shape
+        c = self.c
+        cat = ops.new_act(B, (2 + len(self.m)) * c, H, W, x.device)
+        self.cv1(x, out=cat[:, : 2 * c])           # the two chunks of cv1 are the first 2c channels
+        for j, m in enumerate(self.m):
+            m(cat[:, (1 + j) * c: (2 + j) * c], out=cat[:, (2 + j) * c: (3 + j) * c])
+        return self.cv2(cat, out=out)
+
+
+class C3k2(C2f):
+    """C2f whose inner blocks are C3k or Bottleneck (block.py:1659-1671)."""
+
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, g=1, shortcut=True):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        self.m = nn.ModuleList(
+            C3k(self.c, self.c, 2, shortcut, g) if c3k else Bottleneck(self.c, self.c, shortcut, g) for _ in range(n))
+
+
+class SPPF(nn.Module):
+    """cv1 -> 3 chained 5x5 max-pools -> cat -> cv2 (block.py:179-198)."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        if k != 5:
+            raise NotImplementedError("SPPF kernel is specialised for k=5")
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.c_ = c_
+
+    def forward(self, x, out=None):
+        x = _as_fmap(x)
+        B, _, H, W = x.shape
+        cat = ops.new_act(B, 4 * self.c_, H, W, x.device)
+        self.cv1(x, out=cat[:, : self.c_])
+        ops.sppf_pool(cat, self.c_)
+        return self.cv2(cat, out=out)
+
+
+class Attention(nn.Module):
+    """Multi-head self-attention over the H*W tokens + depthwise positional conv (block.py:1878-1933)."""
+
+    def __init__(self, dim, num_heads=8, attn_ratio=0.5):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.key_dim = int(self.head_dim * attn_ratio)
+        self.scale = self.key_dim ** -0.5
+        nh_kd = self.key_dim * num_heads
+        h = dim + nh_kd * 2
+        self.qkv = Conv(dim, h, 1, act=False)
+        self.proj = Conv(dim, dim, 1, act=False)
+        self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
+        self._pe_f32 = None
+
+    def _pe_weights(self):
+        if self._pe_f32 is None or self._pe_f32[0].device != self.pe.conv.weight.device:
+            bn = self.pe.bn
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = (self.pe.conv.weight.detach().float().view(-1, 9) * s[:, None]).contiguous()
+            b = (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
+            self._pe_f32 = (w, b)
+        return self._pe_f32
+
+    def _apply(self, fn, *a, **k):
+        self._pe_f32 = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._pe_f32 = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def forward(self, x, out=None, residual=None):
+        qkv = self.qkv(x)
+        pe_w, pe_b = self._pe_weights()
+        y = ops.psa_attention(qkv, self.num_heads, self.key_dim, self.head_dim, self.scale, pe_w, pe_b)
+        return self.proj(y, out=out, residual=residual)
+
+
+class PSABlock(nn.Module):
+    """x + attn(x); x + ffn(x) (block.py:1973-2007); both residual adds live in conv epilogues."""
+
+    def __init__(self, c, attn_ratio=0.5, num_heads=4, shortcut=True):
+        super().__init__()
+        self.attn = Attention(c, attn_ratio=attn_ratio, num_heads=num_heads)
+        self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
+        self.add = shortcut
+
+    def forward(self, x, out=None):
+        x = self.attn(x, residual=x if self.add else None)
+        return self.ffn[1](self.ffn[0](x), out=out, residual=x if self.add else None)
+
+
+class C2PSA(nn.Module):
+    """cv1 -> split(a, b) -> b = PSABlocks(b) -> cv2(cat(a, b)) (block.py:2100-2139)."""
+
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=self.c // 64) for _ in range(n)))
+
+    def forward(self, x, out=None):
+        x = _as_fmap(x)
+        B, _, H, W = x.shape
+        cat = ops.new_act(B, 2 * self.c, H, W, x.device)
+        self.cv1(x, out=cat)
+        b = cat[:, self.c:]
+        last = len(self.m) - 1
+        for j, m in enumerate(self.m):
+            b = m(b, out=cat[:, self.c:] if j == last else None)   # last block overwrites b in place
+        return self.cv2(cat, out=out)
+
+
+class Concat(nn.Module):
+    """torch.cat along channels (conv.py:1810-1820) — used by the stock YOLO11 necks."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, xs: Sequence[torch.Tensor]):
+        xs = [_as_fmap(x) for x in xs]
+        B, _, H, W = xs[0].shape
+        out = ops.new_act(B, sum(x.shape[1] for x in xs), H, W, xs[0].device)
+        o = 0
+        for x in xs:
+            out[:, o: o + x.shape[1]].copy_(x)   # plumbing copy (torch); the fusion cfg has no Concat
+            o += x.shape[1]
+        return out
+
+
+class Upsample2x(nn.Module):
+    """nn.Upsample(None, 2, 'nearest').  In the Spectrogram cfg the only consumer is Fusion, which reads
+    through the upsample by index math, so this module just tags its input (no kernel, no bytes)."""
+
+    def __init__(self, size=None, scale_factor=2, mode="nearest"):
+        super().__init__()
+        if size is not None or scale_factor != 2 or mode != "nearest":
+            raise NotImplementedError("only x2 nearest upsampling is on the hot path")
+
+    def forward(self, x):
+        return UpsampledView(_as_fmap(x))
+
+
+class UpsampledView:
+    """Lazy x2 nearest-neighbour upsample of an NHWC feature map."""
+
+    def __init__(self, src: torch.Tensor):
+        self.src = src
+
+    @property
+    def shape(self):
+        B, C, H, W = self.src.shape
+        return torch.Size((B, C, 2 * H, 2 * W))
+
+    def materialise(self) -> torch.Tensor:
+        s = self.src
+        B, C, H, W = s.shape
+        out = ops.new_act(B, C, 2 * H, 2 * W, s.device)
+        v = out.permute(0, 2, 3, 1).view(B, H, 2, W, 2, C)
+        v.copy_(s.permute(0, 2, 3, 1)[:, :, None, :, None, :].expand(B, H, 2, W, 2, C))
+        return out
+
+
+class GCT(nn.Module):
+    """Parameter container for the gated channel transformation (conv.py:2284-2301)."""
+
+    def __init__(self, num_channels, epsilon=1e-5, mode="l2", after_relu=False):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, num_channels, 1, 1))
+        self.gamma = nn.Parameter(torch.zeros(1, num_channels, 1, 1))
+        self.beta = nn.Parameter(torch.zeros(1, num_channels, 1, 1))
+        self.epsilon = epsilon
+
+
+class WeightedSpatialAttention(nn.Module):
+    """Parameter container for the 2->1 spatial-attention conv (conv.py:1839-1852)."""
+
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        assert kernel_size in {3, 7}
+        self.cv1 = nn.Conv2d(2, 1, kernel_size, padding=kernel_size // 2, bias=False)
+
+
+class Fusion(nn.Module):
+    """Fusion('ESChannel') (conv.py:1854-1937, 2113-2127): GCT gate over the concatenated inputs plus a
+    shared spatial-attention gate per input, summed — two HBM-bound kernels, no concat, no upsample copy."""
+
+    def __init__(self, inc_list, fusion="ESChannel", c1=128):
+        super().__init__()
+        if fusion != "ESChannel":
+            raise NotImplementedError("only Fusion('ESChannel') is reachable from the target configs")
+        self.fusion = fusion
+        self.sab = WeightedSpatialAttention(3)
+        self.gsc2 = GCT(c1 * 2)
+        self.gsc3 = GCT(c1 * 3)
+
+    def forward(self, xs, out=None):
+        srcs, ups = [], []
+        for x in xs:
+            if isinstance(x, UpsampledView):
+                srcs.append(x.src)
+                ups.append(1)
+            else:
+                srcs.append(_as_fmap(x))
+                ups.append(0)
+        g = self.gsc2 if len(xs) == 2 else self.gsc3
+        return ops.fusion_eschannel(srcs, ups, g.alpha.detach().float().contiguous(), g.gamma.detach().float().contiguous(),
+                                    g.beta.detach().float().contiguous(), g.epsilon,
+                                    self.sab.cv1.weight.detach().float().contiguous(), out)
+
+
+class DFL(nn.Module):
+    """Parameter container kept for state_dict parity (block.py:65-83); the expectation over the 16 bins is
+    computed inside the fused decode kernel."""
+
+    def __init__(self, c1=16):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, 1, 1, bias=False).requires_grad_(False)
+        self.conv.weight.data[:] = torch.arange(c1, dtype=torch.float).view(1, c1, 1, 1)
+        self.c1 = c1
+
+
+class _HeadConv(nn.Conv2d):
+    """Plain nn.Conv2d(c, n, 1) with bias ending each Detect branch; fp32 output into the decode buffer."""
+
+    _packed = None
+
+    def packed(self):
+        if self._packed is None:
+            self._packed = ops.fold_pack(self.weight, self.bias, None, 0.0, 1, 0, 1, 1, act=False)
+        return self._packed
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+
+class Detect(nn.Module):
+    """YOLO Detect head (ultralytics/nn/modules/head.py:21-172).
+
+    forward(list of 3 maps) -> (y [B, 4+nc, A] fp32, [raw maps [B, no, h, w] fp32]) in eval mode, like
+    the reference.  The last 1x1 conv of every branch writes fp32 logits straight into the
+    [B, h*w, no_stride] buffer that the fused decode kernel reads.
+    """
+
+    dynamic = False
+    export = False
+    format = None
+    end2end = False
+    max_det = 300
+    shape = None
+    anchors = torch.empty(0)
+    strides = torch.empty(0)
+    legacy = False
+
+    def __init__(self, nc=80, ch=()):
+        super().__init__()
+        self.nc = nc
+        self.nl = len(ch)
+        self.reg_max = 16
+        self.no = nc + self.reg_max * 4
+        self.stride = torch.zeros(self.nl)
+        c2, c3 = max((16, ch[0] // 4, self.reg_max * 4)), max(ch[0], min(self.nc, 100))
+        self.cv2 = nn.ModuleList(
+            nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), _HeadConv(c2, 4 * self.reg_max, 1)) for x in ch)
+        self.cv3 = (
+            nn.ModuleList(nn.Sequential(Conv(x, c3, 3), Conv(c3, c3, 3), _HeadConv(c3, self.nc, 1)) for x in ch)
+            if self.legacy
+            else nn.ModuleList(
+                nn.Sequential(
+                    nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)),
+                    nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)),
+                    _HeadConv(c3, self.nc, 1),
+                )
+                for x in ch
+            )
+        )
+        self.dfl = DFL(self.reg_max)
+        self.no_stride = (self.no + 3) // 4 * 4
+
+    def bias_init(self):
+        """head.py:133-144."""
+        for a, b, s in zip(self.cv2, self.cv3, self.stride):
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)
+
+    def head_logits(self, xs: Sequence[torch.Tensor]):
+        """Runs the cv2 / cv3 branches; returns per-level fp32 [B, h*w, no_stride] buffers and (h, w)."""
+        bufs, hw = [], []
+        for i, x in enumerate(xs):
+            x = _as_fmap(x)
+            B, _, H, W = x.shape
+            buf = torch.empty((B, H * W, self.no_stride), device=x.device, dtype=torch.float32)
+            view = buf.view(B, H, W, self.no_stride).permute(0, 3, 1, 2)   # [B, no_stride, H, W], NHWC memory
+            t = self.cv2[i][1](self.cv2[i][0](x))
+            ops.conv2d(t, self.cv2[i][2].packed(), out=view[:, : 4 * self.reg_max], out_fp32=True)
+            if self.legacy:
+                t = self.cv3[i][1](self.cv3[i][0](x))
+            else:
+                t = self.cv3[i][0][1](self.cv3[i][0][0](x))
+                t = self.cv3[i][1][1](self.cv3[i][1][0](t))
+            ops.conv2d(t, self.cv3[i][2].packed(), out=view[:, 4 * self.reg_max: self.no], out_fp32=True)
+            bufs.append(buf)
+            hw.append((H, W))
+        return bufs, hw
+
+    def forward(self, xs: List[torch.Tensor]):
+        bufs, hw = self.head_logits(xs)
+        y, _, _ = ops.detect_decode(bufs, hw, [float(s) for s in self.stride], self.nc, want_dense=True)
+        raw = [b.view(b.shape[0], h, w, self.no_stride)[..., : self.no].permute(0, 3, 1, 2) for b, (h, w) in zip(bufs, hw)]
+        return y if self.export else (y, raw)

@@ -1,0 +1,210 @@
+"""YAML -> layer graph -> forward interpreter: the host-side mirror of ultralytics/nn/tasks.py
+(parse_model :963-1168, DetectionModel :329-375, BaseModel._predict_once :161-188, fuse :223-251)
+restricted to the modules of the Spectrogram-YOLOv11 and stock YOLO11 detection configs.
+
+Differences by design: there is no CPU forward at build time (the reference probes strides with a
+256x256 CPU forward, tasks.py:365 — here they follow from the graph), and `fuse()` folds BatchNorm and
+repacks weights on the device for the tcgen05 kernels instead of rewriting nn.Conv2d modules.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import math
+import re
+from copy import deepcopy
+from pathlib import Path
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import yaml
+
+from .. import ops
+from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, Concat, Conv, DDWConv, Detect, DWConv, Fusion,
+                      Upsample2x, UpsampledView)
+
+CFG_DIR = Path(__file__).resolve().parent.parent / "cfg"
+
+_MODULES = {m.__name__: m for m in (Conv, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA, Concat, Fusion,
+                                    Detect)}
+_BASE = {Conv, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA}
+_REPEAT = {C2f, C3, C3k, C3k2, C2PSA}
+_STRIDE2 = {Conv, DWConv, DDWConv}
+
+
+def make_divisible(x, divisor):
+    return math.ceil(x / divisor) * divisor
+
+
+def guess_model_scale(path) -> str:
+    """Scale letter embedded in the file name, e.g. yolo11s_fusion_sand3_new.yaml -> 's' (tasks.py:1187-1202)."""
+    m = re.search(r"yolo[v]?\d+([nslmx])", Path(path).stem)
+    return m.group(1) if m else ""
+
+
+def yaml_model_load(path) -> dict:
+    """Resolve 'yolo11s_fusion_sand3_new.yaml' -> cfg/yolo11_fusion_sand3_new.yaml + scale (tasks.py:1171-1184)."""
+    path = Path(path)
+    unified = re.sub(r"(\d+)([nslmx])(.+)?$", r"\1\3", path.stem)
+    candidates = [path, path.with_name(unified + path.suffix), CFG_DIR / path.name, CFG_DIR / (unified + ".yaml")]
+    for c in candidates:
+        if c.is_file():
+            d = yaml.safe_load(c.read_text())
+            d["scale"] = guess_model_scale(path)
+            d["yaml_file"] = str(path)
+            return d
+    raise FileNotFoundError(f"model config '{path}' not found (searched {[str(c) for c in candidates]})")
+
+
+def parse_model(d: dict, ch: int, verbose: bool = False):
+    """Build the nn.Sequential of blocks and the save list; also returns each layer's cumulative stride."""
+    legacy = True
+    max_channels = float("inf")
+    nc, scales = d.get("nc"), d.get("scales")
+    depth, width = d.get("depth_multiple", 1.0), d.get("width_multiple", 1.0)
+    scale = d.get("scale")
+    if scales:
+        if not scale:
+            scale = tuple(scales.keys())[0]
+        depth, width, max_channels = scales[scale]
+    chans = [ch]
+    strides_in = [1]
+    layers, save, lstride = [], [], []
+    c2 = ch
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        args = list(args)
+        if m == "nn.Upsample":
+            mod = Upsample2x
+        elif m in _MODULES:
+            mod = _MODULES[m]
+        else:
+            raise NotImplementedError(f"module '{m}' is outside the hot path this package implements")
+        for j, a in enumerate(args):
+            if isinstance(a, str):
+                with contextlib.suppress(ValueError, SyntaxError):
+                    args[j] = nc if a == "nc" else ast.literal_eval(a)
+        n = n_ = max(round(n * depth), 1) if n > 1 else n
+        fin = f if isinstance(f, int) else f[0]
+        s_in = strides_in[fin] if fin != -1 else strides_in[-1]
+        s_out = s_in
+        if mod in _BASE:
+            c1, c2 = chans[f], args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if mod in _REPEAT:
+                args.insert(2, n)
+                n = 1
+            if mod is C3k2:
+                legacy = False
+                if scale in "mlx":
+                    args[3] = True
+            if mod in _STRIDE2:
+                s = args[3] if len(args) > 3 else (1 if mod is not DDWConv else 2)
+                s_out = s_in * s
+        elif mod is Upsample2x:
+            c2 = chans[f]
+            s_out = s_in // 2
+        elif mod is Concat:
+            c2 = sum(chans[x] for x in f)
+        elif mod is Fusion:
+            c2 = chans[f[0]]
+            args = [[chans[x] for x in f], "ESChannel"]   # tasks.py:1132-1135
+        elif mod is Detect:
+            args.append([chans[x] for x in f])
+            Detect.legacy = legacy
+        m_ = nn.Sequential(*(mod(*args) for _ in range(n))) if n > 1 else mod(*args)
+        m_.np = sum(x.numel() for x in m_.parameters())
+        m_.i, m_.f, m_.type = i, f, m
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(m_)
+        if i == 0:
+            chans, strides_in = [], []
+        chans.append(c2)
+        strides_in.append(s_out)
+        lstride.append(s_out)
+        if verbose:
+            print(f"{i:>3}{str(f):>20}{n_:>3}{m_.np:10.0f}  {m:<20}{str(args):<30}")
+    return nn.Sequential(*layers), sorted(save), lstride
+
+
+class DetectionModel(nn.Module):
+    """Detection model built from a YAML (ultralytics/nn/tasks.py:329-375)."""
+
+    def __init__(self, cfg="yolo11s_fusion_sand3_new.yaml", ch=3, nc=None, verbose=False):
+        super().__init__()
+        self.yaml = cfg if isinstance(cfg, dict) else yaml_model_load(cfg)
+        ch = self.yaml["ch"] = self.yaml.get("ch", ch)
+        if nc and nc != self.yaml["nc"]:
+            self.yaml["nc"] = nc
+        self.model, self.save, lstride = parse_model(deepcopy(self.yaml), ch=ch, verbose=verbose)
+        self.names = {i: f"{i}" for i in range(self.yaml["nc"])}
+        self.inplace = True
+        self.end2end = False
+        m = self.model[-1]
+        if isinstance(m, Detect):
+            m.stride = torch.tensor([float(lstride[x]) for x in m.f])
+            self.stride = m.stride
+            m.bias_init()
+        else:
+            self.stride = torch.tensor([32.0])
+        self.task = "detect"
+
+    # ---- weight prep ---------------------------------------------------------------------------
+    def fuse(self, verbose=False):
+        """Fold BN + repack every conv now (otherwise done lazily on first forward)."""
+        for m in self.modules():
+            if hasattr(m, "packed"):
+                m.packed()
+        return self
+
+    def is_fused(self, thresh=10):
+        return all(getattr(m, "_packed", 1) is not None for m in self.modules())
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x, *args, **kwargs):
+        return self.predict(x, *args, **kwargs)
+
+    def predict(self, x, profile=False, visualize=False, augment=False, embed=None):
+        if augment or visualize or embed or profile:
+            raise NotImplementedError("augment / visualize / embed / profile are outside the hot path")
+        return self._predict_once(x)
+
+    def _run_trunk(self, x):
+        """All layers except Detect; returns the list of Detect inputs."""
+        y = []
+        for m in self.model[:-1]:
+            if m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            if isinstance(x, UpsampledView) and not isinstance(m, Fusion):
+                x = x.materialise()
+            if isinstance(m, Concat):
+                x = [t.materialise() if isinstance(t, UpsampledView) else t for t in x]
+            x = m(x)
+            y.append(x if m.i in self.save else None)
+        det = self.model[-1]
+        return [x if j == -1 else y[j] for j in det.f]
+
+    def _predict_once(self, x):
+        """tasks.py:161-188 — the layer interpreter."""
+        if not x.is_cuda:
+            raise RuntimeError("specyolo runs on a CUDA device (B200); there is no CPU fallback")
+        feats = self._run_trunk(x)
+        return self.model[-1](feats)
+
+    @torch.no_grad()
+    def detect_fused(self, x, conf_thres=0.25, iou_thres=0.7, agnostic=False, max_det=300, max_nms=30000,
+                     max_wh=7680.0, classes: Optional[torch.Tensor] = None):
+        """Trunk -> head logits -> fused decode+threshold -> batched NMS, never materialising the dense
+        [B, 4+nc, A] prediction.  Returns device tensors (out [B,max_det,6], count [B])."""
+        det: Detect = self.model[-1]
+        feats = self._run_trunk(x)
+        bufs, hw = det.head_logits(feats)
+        _, cand, seg = ops.detect_decode(bufs, hw, [float(s) for s in det.stride], det.nc, want_dense=False,
+                                         conf_thres=conf_thres)
+        A = sum(h * w for h, w in hw)
+        out, cnt, _, _ = ops.nms(cand=cand, seg_count=seg, B=bufs[0].shape[0], nc=det.nc, A=A, conf_thres=conf_thres,
+                                 iou_thres=iou_thres, agnostic=agnostic, max_det=max_det, max_nms=max_nms,
+                                 max_wh=max_wh, classes=classes)
+        return out, cnt

@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C-ABI: unpack torch tensors into pointers / strides and call
+libspecyolo on the current CUDA stream.  PyTorch is plumbing only (allocation, streams).
+
+Activation convention: a feature map is a bf16 tensor of logical shape [B, C, H, W] whose memory is
+NHWC ("channels last", stride(1) == 1).  A channel slice of a wider buffer is a valid feature map,
+which is how concat buffers are written in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, DecodeArgs, FusionArgs, NmsArgs, StftArgs, check
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def new_act(B: int, Cc: int, H: int, W: int, device, dtype=torch.bfloat16) -> torch.Tensor:
+    """Uninitialised [B,C,H,W] feature map with NHWC memory."""
+    return torch.empty((B, H, W, Cc), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def nhwc_meta(t: torch.Tensor):
+    """(B, C, H, W, pixel stride) of an NHWC-memory feature map; raises if the layout is anything else."""
+    if t.dim() != 4 or not t.is_cuda:
+        raise ValueError(f"expected a 4-D CUDA feature map, got {tuple(t.shape)} on {t.device}")
+    B, Cc, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    pix = sw if W > 1 else (sh if H > 1 else (sb if B > 1 else Cc))
+    ok = (sc == 1 or Cc == 1) and (W == 1 or sw == pix) and (H == 1 or sh == W * pix) and (B == 1 or sb == H * W * pix)
+    if not ok or pix < Cc:
+        raise ValueError(f"feature map is not NHWC-contiguous: shape {tuple(t.shape)} strides {t.stride()}")
+    return B, Cc, H, W, pix
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.uint8: _lib.DT_U8}
+
+
+def to_nhwc_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW-contiguous fp32 / bf16 / uint8 (scaled by 1/255) -> NHWC bf16 feature map."""
+    _lib.init_device()
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported input dtype {x.dtype}")
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = new_act(B, Cc, H, W, x.device)
+    _, _, _, _, pix = nhwc_meta(out)
+    check(_lib.load().specyolo_nchw_to_nhwc_bf16(x.data_ptr(), _DT[x.dtype], 1.0, B, Cc, H, W, out.data_ptr(), pix,
+                                                 _lib.stream_ptr()))
+    return out
+
+
+def to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    """NHWC bf16 feature map -> NCHW-contiguous fp32 tensor."""
+    B, Cc, H, W, pix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("to_nchw_f32 expects bf16")
+    y = torch.empty((B, Cc, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().specyolo_nhwc_bf16_to_nchw_f32(x.data_ptr(), pix, B, Cc, H, W, y.data_ptr(), _lib.stream_ptr()))
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# conv
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PackedConv:
+    """BN-folded, repacked conv weights (device) + geometry."""
+    w: torch.Tensor          # bf16 [groups*n_pad, kh*kw*cin_g]
+    bias: torch.Tensor       # fp32 [groups*n_pad]
+    cin: int
+    cout: int
+    k: int
+    s: int
+    p: int
+    d: int
+    g: int
+    n_pad: int
+    act: int
+    w_folded_f32: Optional[torch.Tensor] = None   # stem only: fp32 OIHW folded weights
+
+    def out_hw(self, H: int, W: int):
+        ke = self.d * (self.k - 1) + 1
+        return (H + 2 * self.p - ke) // self.s + 1, (W + 2 * self.p - ke) // self.s + 1
+
+
+def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optional[Sequence[torch.Tensor]],
+              eps: float, stride: int, pad: int, dil: int, groups: int, act: bool) -> PackedConv:
+    """fuse_conv_and_bn + repack on the device (specyolo_fold_pack_conv).  `bn` = (gamma, beta, mean, var)."""
+    _lib.init_device()
+    lib = _lib.load()
+    w = weight.detach().to(torch.float32).contiguous()
+    if not w.is_cuda:
+        raise ValueError("fold_pack: weights must live on the CUDA device")
+    cout, cin_g, kh, kw = w.shape
+    if kh != kw:
+        raise ValueError("square kernels only")
+    n_pad = lib.specyolo_conv_npad(cout, groups)
+    if n_pad <= 0:
+        raise ValueError("bad conv shape")
+    wp = torch.empty((groups * n_pad, kh * kw * cin_g), device=w.device, dtype=torch.bfloat16)
+    bias = torch.empty((groups * n_pad,), device=w.device, dtype=torch.float32)
+    bnt = [None] * 4 if bn is None else [t.detach().to(torch.float32).contiguous() for t in bn]
+    cb = None if conv_bias is None else conv_bias.detach().to(torch.float32).contiguous()
+    check(lib.specyolo_fold_pack_conv(w.data_ptr(), _p(cb), _p(bnt[0]), _p(bnt[1]), _p(bnt[2]), _p(bnt[3]),
+                                      float(eps), cout, cin_g, kh, kw, groups, n_pad, wp.data_ptr(), bias.data_ptr(),
+                                      _lib.stream_ptr()))
+    pc = PackedConv(wp, bias, cin_g * groups, cout, kh, stride, pad, dil, groups, n_pad,
+                    _lib.ACT_SILU if act else _lib.ACT_NONE)
+    if cin_g * groups == 3:  # stem: CUDA-core kernel consumes folded fp32 OIHW weights
+        if bn is not None:
+            scale = bnt[0] / torch.sqrt(bnt[3] + eps)
+            pc.w_folded_f32 = (w * scale.view(-1, 1, 1, 1)).contiguous()
+        else:
+            pc.w_folded_f32 = w
+    return pc
+
+
+def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out_fp32: bool = False) -> torch.Tensor:
+    """y = act(conv(x) + b) [+ residual] on NHWC feature maps (specyolo_conv2d_bias_act)."""
+    B, Cin, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("conv2d expects a bf16 feature map")
+    if Cin != pc.cin:
+        raise ValueError(f"conv2d: input has {Cin} channels, weights expect {pc.cin}")
+    Ho, Wo = pc.out_hw(H, W)
+    if out is None:
+        out = new_act(B, pc.cout, Ho, Wo, x.device, torch.float32 if out_fp32 else torch.bfloat16)
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, pc.cout, Ho, Wo):
+        raise ValueError(f"conv2d: out shape {tuple(out.shape)} != {(B, pc.cout, Ho, Wo)}")
+    if out.dtype != (torch.float32 if out_fp32 else torch.bfloat16):
+        raise TypeError("conv2d: out dtype mismatch")
+    a = ConvArgs()
+    a.x, a.B, a.H, a.W, a.Cin, a.x_pixstride, a.x_upshift = x.data_ptr(), B, H, W, Cin, xpix, 0
+    a.w_packed, a.bias, a.Cout, a.n_pad = pc.w.data_ptr(), pc.bias.data_ptr(), pc.cout, pc.n_pad
+    a.kh = a.kw = pc.k
+    a.stride, a.pad, a.dil, a.groups, a.act = pc.s, pc.p, pc.d, pc.g, pc.act
+    a.y, a.Ho, a.Wo, a.y_pixstride, a.y_fp32 = out.data_ptr(), Ho, Wo, ypix, int(out_fp32)
+    if residual is not None:
+        rB, rC, rH, rW, rpix = nhwc_meta(residual)
+        if (rB, rC, rH, rW) != (B, pc.cout, Ho, Wo) or residual.dtype != torch.bfloat16:
+            raise ValueError("conv2d: residual shape/dtype mismatch")
+        a.residual, a.r_pixstride = residual.data_ptr(), rpix
+    else:
+        a.residual, a.r_pixstride = None, 0
+    check(_lib.load().specyolo_conv2d_bias_act(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3-channel 3x3/s2 stem reading the NCHW network input (fp32 | bf16 | uint8/255)."""
+    _lib.init_device()
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported input dtype {x.dtype}")
+    if pc.w_folded_f32 is None or pc.k != 3 or pc.s != 2 or pc.p != 1 or pc.act != _lib.ACT_SILU:
+        raise ValueError("stem_conv: weights are not a 3->C 3x3/s2 SiLU stem")
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    Ho, Wo = pc.out_hw(H, W)
+    if out is None:
+        out = new_act(B, pc.cout, Ho, Wo, x.device)
+    _, _, _, _, ypix = nhwc_meta(out)
+    check(_lib.load().specyolo_stem_conv3x3s2(x.data_ptr(), _DT[x.dtype], B, H, W, pc.w_folded_f32.data_ptr(),
+                                              pc.bias.data_ptr(), pc.cout, out.data_ptr(), ypix, _lib.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# neck glue
+# ----------------------------------------------------------------------------------------------
+def sppf_pool(buf: torch.Tensor, c: int) -> None:
+    """Fill channels [c,4c) of the SPPF concat buffer with the three chained 5x5 max-pools of [0,c)."""
+    B, Cc, H, W, pix = nhwc_meta(buf)
+    if Cc != 4 * c:
+        raise ValueError("sppf_pool: buffer must have 4*c channels")
+    check(_lib.load().specyolo_sppf_pool(buf.data_ptr(), B, H, W, c, pix, _lib.stream_ptr()))
+
+
+def fusion_eschannel(xs: Sequence[torch.Tensor], upshift: Sequence[int], alpha: torch.Tensor, gamma: torch.Tensor,
+                     beta: torch.Tensor, eps: float, sab_w: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fusion('ESChannel'); inputs flagged in `upshift` are read through a x2 nearest upsample."""
+    k = len(xs)
+    metas = [nhwc_meta(x) for x in xs]
+    B, c = metas[0][0], metas[0][1]
+    H, W = metas[0][2] << upshift[0], metas[0][3] << upshift[0]
+    for m, u in zip(metas, upshift):
+        if (m[0], m[1], m[2] << u, m[3] << u) != (B, c, H, W):
+            raise ValueError("fusion: input shapes differ")
+    if out is None:
+        out = new_act(B, c, H, W, xs[0].device)
+    lib = _lib.load()
+    ws = torch.empty(lib.specyolo_fusion_ws_bytes(k, B, H, W, c), device=xs[0].device, dtype=torch.uint8)
+    a = FusionArgs()
+    a.k = k
+    for i in range(k):
+        a.x[i], a.pixstride[i], a.upshift[i] = xs[i].data_ptr(), metas[i][4], int(upshift[i])
+    a.B, a.H, a.W, a.c = B, H, W, c
+    a.alpha, a.gamma, a.beta, a.gct_eps = alpha.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps)
+    a.sab_w = sab_w.data_ptr()
+    a.y, a.y_pixstride = out.data_ptr(), nhwc_meta(out)[4]
+    a.ws = ws.data_ptr()
+    check(lib.specyolo_fusion_eschannel(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def psa_attention(qkv: torch.Tensor, heads: int, key_dim: int, head_dim: int, scale: float, pe_w: torch.Tensor,
+                  pe_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, Cc, H, W, pix = nhwc_meta(qkv)
+    if Cc != heads * (2 * key_dim + head_dim):
+        raise ValueError("psa_attention: qkv channel count mismatch")
+    if out is None:
+        out = new_act(B, heads * head_dim, H, W, qkv.device)
+    check(_lib.load().specyolo_psa_attention(qkv.data_ptr(), pix, B, H, W, heads, key_dim, head_dim, float(scale),
+                                             pe_w.data_ptr(), pe_b.data_ptr(), out.data_ptr(), nhwc_meta(out)[4],
+                                             _lib.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# head
+# ----------------------------------------------------------------------------------------------
+def num_segments(A: int) -> int:
+    return (A + _lib.DECODE_SEG - 1) // _lib.DECODE_SEG
+
+
+def detect_decode(logits: Sequence[torch.Tensor], hw: Sequence[tuple], strides: Sequence[float], nc: int,
+                  want_dense: bool = True, conf_thres: Optional[float] = None):
+    """Fused DFL + dist2bbox + sigmoid (+ score threshold).
+
+    logits[l]: fp32 [B, h*w, no_stride] (64 DFL bins then nc class logits per anchor).
+    Returns (y_dense [B,4+nc,A] or None, cand [B,nseg,256,6] or None, seg_count [B,nseg] or None).
+    """
+    _lib.init_device()
+    B, _, no_stride = logits[0].shape
+    A = sum(h * w for h, w in hw)
+    dev = logits[0].device
+    a = DecodeArgs()
+    a.nl = len(logits)
+    for i, (t, (h, w), s) in enumerate(zip(logits, hw, strides)):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != (B, h * w, no_stride):
+            raise ValueError("detect_decode: logits must be contiguous fp32 [B, h*w, no_stride]")
+        a.logits[i], a.h[i], a.w[i], a.stride[i] = t.data_ptr(), h, w, float(s)
+    a.no_stride, a.B, a.nc, a.reg_max = no_stride, B, nc, 16
+    y = torch.empty((B, 4 + nc, A), device=dev, dtype=torch.float32) if want_dense else None
+    cand = seg = None
+    if conf_thres is not None:
+        nseg = num_segments(A)
+        cand = torch.empty((B, nseg, _lib.DECODE_SEG, 6), device=dev, dtype=torch.float32)
+        seg = torch.empty((B, nseg), device=dev, dtype=torch.int32)
+    a.y, a.conf_thres, a.cand, a.seg_count = _p(y), float(conf_thres or 0.0), _p(cand), _p(seg)
+    check(_lib.load().specyolo_detect_decode(C.byref(a), _lib.stream_ptr()))
+    return y, cand, seg
+
+
+def nms(prediction: Optional[torch.Tensor] = None, cand: Optional[torch.Tensor] = None,
+        seg_count: Optional[torch.Tensor] = None, *, B: int, nc: int, A: int, conf_thres: float, iou_thres: float,
+        agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
+        max_wh: float = 7680.0, classes: Optional[torch.Tensor] = None):
+    """Batched NMS; returns (out [B,max_det,6], count [B], keep_idx [B,max_det], n_cand [B]) on device."""
+    _lib.init_device()
+    lib = _lib.load()
+    dev = (prediction if prediction is not None else cand).device
+    out = torch.zeros((B, max_det, 6), device=dev, dtype=torch.float32)
+    cnt = torch.empty((B,), device=dev, dtype=torch.int32)
+    keep = torch.zeros((B, max_det), device=dev, dtype=torch.int32)
+    ncand = torch.empty((B,), device=dev, dtype=torch.int32)
+    ml = bool(multi_label and nc > 1)
+    ws = torch.empty(lib.specyolo_nms_ws_bytes(B, nc, A, int(ml)), device=dev, dtype=torch.uint8)
+    a = NmsArgs()
+    a.B, a.nc, a.A = B, nc, A
+    a.prediction, a.cand, a.seg_count = _p(prediction), _p(cand), _p(seg_count)
+    a.conf_thres, a.iou_thres = float(conf_thres), float(iou_thres)
+    a.agnostic, a.multi_label, a.max_det, a.max_nms, a.max_wh = int(agnostic), int(ml), max_det, max_nms, float(max_wh)
+    a.classes, a.n_classes = _p(classes), 0 if classes is None else classes.numel()
+    a.out, a.out_count, a.keep_idx, a.n_cand, a.ws = out.data_ptr(), cnt.data_ptr(), keep.data_ptr(), ncand.data_ptr(), ws.data_ptr()
+    check(lib.specyolo_nms(C.byref(a), _lib.stream_ptr()))
+    return out, cnt, keep, ncand
+
+
+def scale_boxes_(out: torch.Tensor, cnt: torch.Tensor, img1_shape, img0_shape) -> None:
+    """In-place scale_boxes + clip_boxes on the NMS output (ops.py:92-127 geometry)."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_w = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+    pad_h = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    B, max_det, _ = out.shape
+    check(_lib.load().specyolo_scale_boxes(out.data_ptr(), cnt.data_ptr(), B, max_det, float(gain), float(pad_w),
+                                           float(pad_h), float(img0_shape[1]), float(img0_shape[0]),
+                                           _lib.stream_ptr()))
+
+
+# ----------------------------------------------------------------------------------------------
+# front end
+# ----------------------------------------------------------------------------------------------
+def iq_to_letterbox(iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0, db_max: float = 0.0,
+                    out_hw=(640, 640), pad_value: float = 114.0 / 255.0, out_dtype=torch.bfloat16,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """complex64 bursts [B, L] -> letterboxed spectrogram images [B, 3, H, W] (NCHW) in [0,1]."""
+    _lib.init_device()
+    if iq.dtype == torch.complex64:
+        iq = torch.view_as_real(iq)
+    if iq.dtype != torch.float32 or iq.dim() != 3 or iq.shape[-1] != 2 or not iq.is_contiguous():
+        raise ValueError("iq must be complex64 [B, L] (or float32 [B, L, 2]), contiguous")
+    B, L, _ = iq.shape
+    if out is None:
+        out = torch.empty((B, 3, out_hw[0], out_hw[1]), device=iq.device, dtype=out_dtype)
+    a = StftArgs()
+    a.iq, a.B, a.L, a.nfft, a.hop = iq.data_ptr(), B, L, nfft, hop
+    a.db_min, a.db_max, a.out_h, a.out_w, a.pad_value = db_min, db_max, out_hw[0], out_hw[1], pad_value
+    a.out, a.out_fp32 = out.data_ptr(), int(out.dtype == torch.float32)
+    check(_lib.load().specyolo_iq_to_letterbox(C.byref(a), _lib.stream_ptr()))
+    return out

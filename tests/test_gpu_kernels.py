@@ -1,0 +1,380 @@
+"""Kernel-level parity on the B200 (pytest -m gpu): every libspecyolo kernel, called through the C-ABI
+(ctypes wrappers in specyolo.ops), against the CPU oracle / a plain fp32 restatement of the same op on
+identical inputs.  Tolerances are stated per test: bf16 operands + bf16 outputs bound conv outputs to
+~2^-8 relative; fp32 kernels (decode, STFT) are compared at 1e-3 px / 1e-4; NMS is bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _rel_err(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _fmap(x_nchw_f32):
+    """fp32 NCHW (cpu) -> NHWC bf16 feature map on the GPU via plain torch (test plumbing)."""
+    return x_nchw_f32.to(DEV).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_layout_roundtrip(lib):
+    from specyolo import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((2, 37, 9, 13), generator=g)
+    y = ops.to_nhwc_bf16(x.to(DEV))
+    assert y.shape == x.shape and y.stride(1) == 1
+    back = ops.to_nchw_f32(y).cpu()
+    assert torch.equal(back, _bf(x))
+    u8 = (x * 255).to(torch.uint8)
+    y8 = ops.to_nchw_f32(ops.to_nhwc_bf16(u8.to(DEV))).cpu()
+    assert torch.allclose(y8, _bf(u8.float() / 255), atol=4e-3)
+
+
+CONV_CASES = [
+    # cin, cout, k, s, d, g, B, H, W, act, residual
+    (64, 64, 1, 1, 1, 1, 2, 40, 40, True, False),
+    (96, 128, 1, 1, 1, 1, 2, 20, 20, True, False),      # kc = 32
+    (16, 32, 1, 1, 1, 1, 1, 24, 24, True, False),       # kc = 16
+    (512, 512, 1, 1, 1, 1, 2, 20, 20, True, False),     # two N tiles
+    (1024, 512, 1, 1, 1, 1, 1, 20, 20, True, False),    # long K
+    (128, 2, 1, 1, 1, 1, 2, 20, 20, False, False),      # nc=2 head conv (n_pad 16)
+    (128, 80, 1, 1, 1, 1, 1, 20, 20, False, False),
+    (32, 16, 3, 1, 1, 1, 2, 32, 32, True, False),
+    (16, 32, 3, 1, 1, 1, 2, 32, 32, True, True),        # bottleneck cv2 + shortcut
+    (64, 64, 3, 1, 1, 1, 3, 20, 20, True, True),        # tile spans images
+    (128, 128, 3, 1, 1, 1, 2, 40, 40, True, False),
+    (32, 64, 3, 2, 1, 1, 2, 64, 64, True, False),       # stride 2
+    (128, 128, 3, 2, 1, 1, 2, 80, 80, True, False),
+    (256, 512, 3, 2, 1, 1, 2, 40, 40, True, False),
+    (128, 128, 7, 2, 2, 8, 2, 32, 32, True, False),     # DDWConv.conv1 (layer 11)
+    (256, 128, 3, 2, 2, 8, 2, 40, 40, True, False),     # DDWConv.conv1 (layer 13)
+    (64, 64, 3, 1, 1, 1, 1, 7, 9, True, False),         # ragged spatial size
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,d,g,B,H,W,act,res", CONV_CASES)
+def test_conv_igemm(lib, cin, cout, k, s, d, g, B, H, W, act, res):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(cin * 131 + cout * 7 + k)
+    x = torch.randn((B, cin, H, W), generator=gen)
+    w = torch.randn((cout, cin // g, k, k), generator=gen) * math.sqrt(2.0 / (cin // g * k * k))
+    gamma = torch.rand(cout, generator=gen) + 0.5
+    beta = torch.randn(cout, generator=gen) * 0.1
+    mean = torch.randn(cout, generator=gen) * 0.1
+    var = torch.rand(cout, generator=gen) + 0.5
+    eps = 1e-3
+    ke = d * (k - 1) + 1
+    p = ke // 2
+    pc = ops.fold_pack(w.to(DEV), None, [t.to(DEV) for t in (gamma, beta, mean, var)], eps, s, p, d, g, act)
+    xf = _fmap(x)
+    Ho, Wo = pc.out_hw(H, W)
+    r = torch.randn((B, cout, Ho, Wo), generator=gen) if res else None
+    rf = _fmap(r) if res else None
+    y = ops.conv2d(xf, pc, residual=rf)
+    torch.cuda.synchronize()
+    # reference: fp32 conv on the bf16-rounded operands (what the tensor core multiplies)
+    scale = gamma / torch.sqrt(var + eps)
+    wf = _bf(w * scale.view(-1, 1, 1, 1))
+    bf = beta - mean * scale
+    ref = F.conv2d(_bf(x), wf, bf, s, p, d, g)
+    if act:
+        ref = F.silu(ref)
+    if res:
+        ref = ref + _bf(r)
+    got = y.float().cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 1.5e-2 * ref.abs() + 1.5e-2
+    assert bool((err <= tol).all()), f"max err {err.max().item()} rel {_rel_err(got, ref)}"
+    assert _rel_err(got, ref) < 6e-3
+
+
+def test_conv_concat_slices(lib):
+    """Input read from / output written into channel windows of wider NHWC buffers."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(5)
+    B, H, W = 2, 20, 20
+    big_in = torch.randn((B, 192, H, W), generator=gen)
+    w = torch.randn((64, 64, 3, 3), generator=gen) * 0.05
+    pc = ops.fold_pack(w.to(DEV), torch.randn(64, generator=gen).to(DEV) * 0.1, None, 0.0, 1, 1, 1, 1, True)
+    fin = _fmap(big_in)
+    out_big = ops.new_act(B, 256, H, W, DEV)
+    out_big.zero_()
+    ops.conv2d(fin[:, 64:128], pc, out=out_big[:, 128:192])
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(_bf(big_in[:, 64:128]), _bf(w), pc.bias[:64].cpu(), 1, 1))
+    got = out_big.float().cpu()
+    assert torch.count_nonzero(got[:, :128]) == 0 and torch.count_nonzero(got[:, 192:]) == 0
+    assert _rel_err(got[:, 128:192], ref) < 6e-3
+
+
+def test_conv_fp32_out(lib):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(6)
+    B, H, W, no_stride = 2, 10, 10, 68
+    x = torch.randn((B, 64, H, W), generator=gen)
+    w = torch.randn((64, 64, 1, 1), generator=gen) * 0.1
+    b = torch.randn(64, generator=gen)
+    pc = ops.fold_pack(w.to(DEV), b.to(DEV), None, 0.0, 1, 0, 1, 1, False)
+    buf = torch.zeros((B, H * W, no_stride), device=DEV)
+    view = buf.view(B, H, W, no_stride).permute(0, 3, 1, 2)
+    ops.conv2d(_fmap(x), pc, out=view[:, :64], out_fp32=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(_bf(x), _bf(w), b)
+    got = view[:, :64].cpu()
+    assert torch.allclose(got, ref, atol=2e-3, rtol=2e-3)
+    assert torch.count_nonzero(buf[..., 64:]) == 0
+
+
+def test_stem_conv(lib):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(7)
+    x = torch.rand((2, 3, 64, 96), generator=gen)
+    w = torch.randn((32, 3, 3, 3), generator=gen) * 0.2
+    bn = [torch.rand(32, generator=gen) + 0.5, torch.randn(32, generator=gen) * 0.1,
+          torch.randn(32, generator=gen) * 0.1, torch.rand(32, generator=gen) + 0.5]
+    pc = ops.fold_pack(w.to(DEV), None, [t.to(DEV) for t in bn], 1e-3, 2, 1, 1, 1, True)
+    scale = bn[0] / torch.sqrt(bn[3] + 1e-3)
+    ref = F.silu(F.conv2d(x, w * scale.view(-1, 1, 1, 1), bn[1] - bn[2] * scale, 2, 1))
+    y = ops.stem_conv(x.to(DEV), pc).float().cpu()
+    assert _rel_err(y, ref) < 5e-3
+    u8 = (x * 255).round().to(torch.uint8)
+    y8 = ops.stem_conv(u8.to(DEV), pc).float().cpu()
+    ref8 = F.silu(F.conv2d(u8.float() / 255, w * scale.view(-1, 1, 1, 1), bn[1] - bn[2] * scale, 2, 1))
+    assert _rel_err(y8, ref8) < 5e-3
+
+
+def test_depthwise(lib):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn((2, 128, 20, 20), generator=gen)
+    w = torch.randn((128, 1, 3, 3), generator=gen) * 0.3
+    bn = [torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.1,
+          torch.randn(128, generator=gen) * 0.1, torch.rand(128, generator=gen) + 0.5]
+    for act in (True, False):
+        pc = ops.fold_pack(w.to(DEV), None, [t.to(DEV) for t in bn], 1e-3, 1, 1, 1, 128, act)
+        scale = bn[0] / torch.sqrt(bn[3] + 1e-3)
+        ref = F.conv2d(_bf(x), _bf(w * scale.view(-1, 1, 1, 1)), bn[1] - bn[2] * scale, 1, 1, 1, 128)
+        ref = F.silu(ref) if act else ref
+        y = ops.conv2d(_fmap(x), pc).float().cpu()
+        assert _rel_err(y, ref) < 5e-3
+
+
+def test_sppf_pool(lib):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(9)
+    c, B, H, W = 32, 2, 20, 20
+    y0 = torch.randn((B, c, H, W), generator=gen)
+    buf = ops.new_act(B, 4 * c, H, W, DEV)
+    buf.zero_()
+    buf[:, :c].copy_(y0.to(DEV))
+    ops.sppf_pool(buf, c)
+    y = [_bf(y0)]
+    for _ in range(3):
+        y.append(F.max_pool2d(y[-1], 5, 1, 2))
+    assert torch.equal(buf.float().cpu(), torch.cat(y, 1))     # max of bf16 values is exact
+
+
+@pytest.mark.parametrize("k,H,W,up", [(3, 16, 16, (1, 0, 0)), (2, 10, 10, (0, 0)), (3, 40, 40, (0, 0, 0))])
+def test_fusion_eschannel(lib, k, H, W, up):
+    from oracle.yolo_ref import Ref
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(10 + k)
+    B, c = 2, 128
+    xs = [torch.randn((B, c, H >> u, W >> u), generator=gen) for u in up]
+    sd = {"f.gsc%d.alpha" % k: torch.rand((1, k * c, 1, 1), generator=gen) * 0.5 + 0.75,
+          "f.gsc%d.gamma" % k: torch.randn((1, k * c, 1, 1), generator=gen) * 0.3,
+          "f.gsc%d.beta" % k: torch.randn((1, k * c, 1, 1), generator=gen) * 0.3,
+          "f.sab.cv1.weight": torch.randn((1, 2, 3, 3), generator=gen) * 0.5}
+    xs_full = [F.interpolate(_bf(x), scale_factor=2, mode="nearest") if u else _bf(x) for x, u in zip(xs, up)]
+    ref = Ref(sd).fusion(xs_full, "f")
+    got = ops.fusion_eschannel([_fmap(x) for x in xs], list(up), sd["f.gsc%d.alpha" % k].to(DEV),
+                               sd["f.gsc%d.gamma" % k].to(DEV), sd["f.gsc%d.beta" % k].to(DEV), 1e-5,
+                               sd["f.sab.cv1.weight"].to(DEV)).float().cpu()
+    assert _rel_err(got, ref) < 5e-3
+
+
+@pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2)])
+def test_psa_attention(lib, H, W, heads):
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(11)
+    B, kd, hd = 2, 32, 64
+    C = heads * hd
+    qkv = torch.randn((B, heads * (2 * kd + hd), H, W), generator=gen)
+    pe_w = torch.randn((C, 9), generator=gen) * 0.2
+    pe_b = torch.randn((C,), generator=gen) * 0.1
+    scale = kd ** -0.5
+    got = ops.psa_attention(_fmap(qkv), heads, kd, hd, scale, pe_w.to(DEV), pe_b.to(DEV)).float().cpu()
+    # block.py:1922-1933
+    N = H * W
+    q, k, v = _bf(qkv).view(B, heads, 2 * kd + hd, N).split([kd, kd, hd], dim=2)
+    attn = ((q.transpose(-2, -1) @ k) * scale).softmax(dim=-1)
+    ref = (v @ attn.transpose(-2, -1)).view(B, C, H, W) + F.conv2d(v.reshape(B, C, H, W), pe_w.view(C, 1, 3, 3), pe_b, 1, 1, 1, C)
+    assert _rel_err(got, ref) < 6e-3
+
+
+def _rand_head_logits(gen, B, hw, nc, no_stride):
+    bufs = []
+    for (h, w) in hw:
+        t = torch.zeros((B, h * w, no_stride))
+        t[..., :64] = torch.randn((B, h * w, 64), generator=gen) * 2.0
+        t[..., 64:64 + nc] = torch.randn((B, h * w, nc), generator=gen) * 1.5 - 2.0
+        bufs.append(t)
+    return bufs
+
+
+@pytest.mark.parametrize("nc,hw", [(2, [(80, 80), (40, 40), (20, 20)]), (80, [(16, 12), (8, 6), (4, 3)])])
+def test_detect_decode(lib, nc, hw):
+    from oracle import yolo_ref
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(12)
+    B = 2
+    no = 64 + nc
+    no_stride = (no + 3) // 4 * 4
+    bufs = _rand_head_logits(gen, B, hw, nc, no_stride)
+    strides = [8.0, 16.0, 32.0]
+    raw = [b[..., :no].view(B, h, w, no).permute(0, 3, 1, 2).contiguous() for b, (h, w) in zip(bufs, hw)]
+    ref = yolo_ref.detect_decode(raw, strides, nc)
+    conf = 0.25
+    y, cand, seg = ops.detect_decode([b.to(DEV) for b in bufs], hw, strides, nc, want_dense=True, conf_thres=conf)
+    y = y.cpu()
+    # fp32 kernel vs fp32 oracle on identical logits: 1e-3 px on boxes, 1e-6 on scores
+    assert torch.allclose(y[:, :4], ref[:, :4], atol=1e-3, rtol=0)
+    assert torch.allclose(y[:, 4:], ref[:, 4:], atol=1e-6, rtol=0)
+    # fused candidates == thresholding the kernel's own dense output, in anchor order
+    A = y.shape[2]
+    cand, seg = cand.cpu(), seg.cpu()
+    for b in range(B):
+        sc, cl = y[b, 4:].max(0)
+        idx = torch.nonzero(sc > conf).flatten()
+        rows = torch.cat([cand[b, s, : seg[b, s]] for s in range(seg.shape[1])])
+        assert rows.shape[0] == idx.numel()
+        xy, wh = y[b, :2, idx].T, y[b, 2:4, idx].T / 2
+        exp = torch.cat((xy - wh, xy + wh, sc[idx, None], cl[idx, None].float()), 1)
+        assert torch.equal(rows, exp)
+
+
+def _nms_inputs(gen, B, nc, A, dup=True):
+    xy = torch.rand((B, 2, A), generator=gen) * 600 + 20
+    wh = torch.rand((B, 2, A), generator=gen) * 192 + 8
+    scores = torch.distributions.Beta(0.5, 8.0).sample((B, nc, A))
+    pred = torch.cat((xy, wh, scores), 1).float()
+    if dup:   # exact score ties and duplicated boxes
+        pred[:, :, 1::7] = pred[:, :, 0:-1:7][:, :, : pred[:, :, 1::7].shape[2]]
+    return pred
+
+
+@pytest.mark.parametrize("nc,A,conf,iou,agn,ml", [
+    (2, 8400, 0.25, 0.7, False, False),
+    (2, 8400, 0.05, 0.45, False, False),
+    (80, 2100, 0.1, 0.7, False, False),
+    (80, 2100, 0.1, 0.5, True, False),
+    (3, 3000, 0.02, 0.6, False, True),       # multi_label (validation path)
+    (2, 8400, 0.001, 0.7, False, False),     # thousands of candidates -> global-memory sort path
+])
+def test_nms_bit_exact(lib, nc, A, conf, iou, agn, ml):
+    from oracle import nms_ref
+    from specyolo.utils.ops import non_max_suppression
+
+    gen = torch.Generator().manual_seed(13 + nc + A)
+    torch.manual_seed(13 + nc + A)
+    B = 3
+    pred = _nms_inputs(gen, B, nc, A)
+    ref, ref_idx = nms_ref.non_max_suppression(pred.numpy(), conf, iou, agnostic=agn, multi_label=ml, return_indices=True)
+    got, got_idx = non_max_suppression(pred.to(DEV), conf, iou, agnostic=agn, multi_label=ml, return_idxs=True)
+    for b in range(B):
+        g = got[b].cpu().numpy()
+        assert g.shape == ref[b].shape, (g.shape, ref[b].shape)
+        assert np.array_equal(got_idx[b].cpu().numpy(), ref_idx[b])        # keep indices: exact
+        assert np.array_equal(g, ref[b])                                   # boxes, conf, cls: bit-exact
+
+
+def test_nms_vs_torchvision(lib):
+    """Same inputs through the reference's own third-party kernel (torchvision CPU nms)."""
+    torchvision = pytest.importorskip("torchvision")
+    from specyolo.utils.ops import non_max_suppression
+
+    gen = torch.Generator().manual_seed(99)
+    torch.manual_seed(99)
+    pred = _nms_inputs(gen, 2, 1, 4000)
+    conf, iou = 0.05, 0.5
+    got, idx = non_max_suppression(pred.to(DEV), conf, iou, return_idxs=True)
+    for b in range(2):
+        x = pred[b].T
+        m = x[:, 4] > conf
+        x = x[m]
+        boxes = torch.cat((x[:, :2] - x[:, 2:4] / 2, x[:, :2] + x[:, 2:4] / 2), 1)
+        keep = torchvision.ops.nms(boxes, x[:, 4], iou)[:300]
+        assert torch.equal(idx[b].cpu(), keep)
+
+
+def test_nms_edge_cases(lib):
+    from specyolo.utils.ops import non_max_suppression
+
+    pred = torch.zeros((2, 6, 100))
+    pred[:, 2:4] = 10
+    out = non_max_suppression(pred.to(DEV), 0.25, 0.7)
+    assert all(o.shape == (0, 6) for o in out)                    # no candidate at all
+    # boxes exactly at the IoU threshold: IoU = 1/3 with thr = 1/3 -> NOT > thr in fp32/double compare
+    p = torch.zeros((1, 5, 2))
+    p[0, :, 0] = torch.tensor([10.0, 10.0, 20.0, 20.0, 0.9])
+    p[0, :, 1] = torch.tensor([20.0, 10.0, 20.0, 20.0, 0.8])      # overlap 10x20 of two 20x20 boxes: IoU = 1/3
+    from oracle import nms_ref
+    for thr in (1.0 / 3.0, 0.33, 0.34):
+        ref = nms_ref.non_max_suppression(p.numpy(), 0.25, thr)
+        got = non_max_suppression(p.to(DEV), 0.25, thr)
+        assert got[0].shape[0] == ref[0].shape[0]
+    with pytest.raises(AssertionError):
+        non_max_suppression(p.to(DEV), 1.5, 0.5)
+
+
+def test_stft_letterbox(lib):
+    from oracle import stft_ref
+    from specyolo import ops
+    from specyolo.nn.init import synth_iq
+
+    iq = synth_iq(2, 1 << 16, seed=3)           # 2^16 samples -> 1024 x 253 spectrogram (up-sampled in time)
+    ref = stft_ref.iq_to_letterbox(iq.numpy(), out_hw=(640, 640))
+    got = ops.iq_to_letterbox(iq.to(DEV), out_dtype=torch.float32).cpu().numpy()
+    assert got.shape == ref.shape
+    # fp32 FFT + log vs float64 spec: 1e-4 on the [0,1] image, a few px at steep edges excepted
+    err = np.abs(got - ref)
+    assert err.max() < 5e-3 and np.mean(err > 1e-4) < 1e-3, (err.max(), np.mean(err > 1e-4))
+    got_bf = ops.iq_to_letterbox(iq.to(DEV), out_dtype=torch.bfloat16).float().cpu().numpy()
+    assert np.abs(got_bf - ref).max() < 8e-3
+
+
+def test_stft_letterbox_full_burst(lib):
+    """North-star geometry: 2^20 samples, hop 256 -> 1024 x 4093 -> 160 x 640 band."""
+    from oracle import stft_ref
+    from specyolo import ops
+    from specyolo.nn.init import synth_iq
+
+    iq = synth_iq(1, 1 << 20, seed=4)
+    ref = stft_ref.iq_to_letterbox(iq.numpy(), out_hw=(640, 640))
+    got = ops.iq_to_letterbox(iq.to(DEV), out_dtype=torch.float32).cpu().numpy()
+    err = np.abs(got - ref)
+    assert err.max() < 5e-3 and np.mean(err > 1e-4) < 1e-3, (err.max(), np.mean(err > 1e-4))
+    assert np.all(got[0, :, :240] == np.float32(114.0 / 255.0)) and np.all(got[0, :, 400:] == np.float32(114.0 / 255.0))
