@@ -23,6 +23,15 @@ def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "ultralytics"))
 
 
+def _lenient(factory):
+    """module-level __getattr__ that never answers dunder lookups (inspect.getmodule probes __file__)."""
+    def _ga(k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return factory()
+    return _ga
+
+
 def _stub(name: str, attrs: dict | None = None, package: bool = True) -> types.ModuleType:
     m = types.ModuleType(name)
     m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None, is_package=package)
@@ -45,6 +54,8 @@ def _install_stubs() -> None:
             return self
 
         def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
             return _Anything()
 
     if "matplotlib" not in sys.modules:
@@ -53,9 +64,9 @@ def _install_stubs() -> None:
         except ImportError:
             mpl = _stub("matplotlib", {"use": lambda *a, **k: None, "rc": lambda *a, **k: None,
                                        "rcParams": {}, "get_backend": lambda: "agg", "__version__": "0.0"})
-            mpl.pyplot = _stub("matplotlib.pyplot", {"__getattr__": lambda k: _Anything()}, package=False)
-            mpl.font_manager = _stub("matplotlib.font_manager", {"__getattr__": lambda k: _Anything()}, package=False)
-            mpl.colors = _stub("matplotlib.colors", {"__getattr__": lambda k: _Anything()}, package=False)
+            mpl.pyplot = _stub("matplotlib.pyplot", {"__getattr__": _lenient(_Anything)}, package=False)
+            mpl.font_manager = _stub("matplotlib.font_manager", {"__getattr__": _lenient(_Anything)}, package=False)
+            mpl.colors = _stub("matplotlib.colors", {"__getattr__": _lenient(_Anything)}, package=False)
     if "thop" not in sys.modules:
         try:
             import thop  # noqa: F401
@@ -77,14 +88,14 @@ def _install_stubs() -> None:
             timm = _stub("timm")
             _stub("timm.layers", {"DropPath": DropPath, "trunc_normal_": _noop, "to_2tuple": lambda x: (x, x),
                                   "make_divisible": lambda v, d=8, *a, **k: int(v + d / 2) // d * d,
-                                  "get_act_layer": lambda *a, **k: nn.ReLU, "__getattr__": lambda k: _Anything})
-            _stub("timm.models", {"__getattr__": lambda k: _Anything})
+                                  "get_act_layer": lambda *a, **k: nn.ReLU, "__getattr__": _lenient(lambda: _Anything)})
+            _stub("timm.models", {"__getattr__": _lenient(lambda: _Anything)})
             _stub("timm.models.layers", {"DropPath": DropPath, "trunc_normal_": _noop, "to_2tuple": lambda x: (x, x),
-                                         "__getattr__": lambda k: _Anything})
+                                         "__getattr__": _lenient(lambda: _Anything)})
             for sub in ("create_act", "create_conv2d", "helpers", "mlp", "norm", "drop", "weight_init", "conv_bn_act"):
-                _stub(f"timm.layers.{sub}", {"__getattr__": lambda k: _Anything, "DropPath": DropPath,
+                _stub(f"timm.layers.{sub}", {"__getattr__": _lenient(lambda: _Anything), "DropPath": DropPath,
                                              "trunc_normal_": _noop}, package=False)
-                _stub(f"timm.models.layers.{sub}", {"__getattr__": lambda k: _Anything}, package=False)
+                _stub(f"timm.models.layers.{sub}", {"__getattr__": _lenient(lambda: _Anything)}, package=False)
 
 
 _ref = None

@@ -47,6 +47,7 @@ struct IgemmParams {
 
 static constexpr int kThreads = 192;
 static constexpr int kMaxStages = 8;
+static constexpr int kMaxDynSmem = 200 * 1024;  // opt-in limit is 227 KB minus the static barriers
 
 __global__ void __launch_bounds__(kThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -340,7 +341,7 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     if (n_tile > 128 && stages < 4) stages = 4;
     p.stages = stages;
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024;
-    SY_CHECK(smem_bytes <= 227 * 1024, SPECYOLO_ERR_INVALID, "smem budget exceeded");
+    SY_CHECK(smem_bytes <= (size_t)kMaxDynSmem, SPECYOLO_ERR_INVALID, "smem budget exceeded");
     uint32_t cols = 32;
     while (cols < (uint32_t)n_tile) cols <<= 1;
     p.tmem_cols = cols;
@@ -385,7 +386,7 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
         attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024);
+                                        kMaxDynSmem);
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
              cudaGetErrorString(attr_err));
