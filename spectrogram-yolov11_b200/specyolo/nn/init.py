@@ -9,14 +9,28 @@ same (cfg, seed) gives bit-identical tensors in the build container and on the G
 """
 from __future__ import annotations
 
+import json
 import math
+from pathlib import Path
 from typing import Dict
 
 import torch
 
 
-def synth_state_dict(model: torch.nn.Module, seed: int = 0, cls_bias: float = -2.5) -> Dict[str, torch.Tensor]:
+def _load_scales(model) -> Dict[str, float]:
+    """Per-conv RMS table measured offline by tools/calibrate_synth.py (plain data, cfg/<name>.synth.json)."""
+    name = Path(str(getattr(model, "yaml", {}).get("yaml_file", ""))).stem
+    f = Path(__file__).resolve().parent.parent / "cfg" / f"{name}.synth.json"
+    return json.loads(f.read_text()) if name and f.is_file() else {}
+
+
+def synth_state_dict(model: torch.nn.Module, seed: int = 0, cls_bias: float | None = None,
+                     calibrated: bool = True) -> Dict[str, torch.Tensor]:
+    if cls_bias is None:   # ~1-3 % of the anchors clear conf=0.25 for 2 classes as for 80
+        nc = int(getattr(model, "yaml", {}).get("nc", 2))
+        cls_bias = -2.4 - 0.45 * math.log(max(nc, 2) / 2.0)
     g = torch.Generator().manual_seed(seed)
+    scales = _load_scales(model) if calibrated else {}
     out: Dict[str, torch.Tensor] = {}
     for k, v in model.state_dict().items():
         shape = tuple(v.shape)
@@ -43,6 +57,14 @@ def synth_state_dict(model: torch.nn.Module, seed: int = 0, cls_bias: float = -2
             t = torch.randn(shape, generator=g) * 0.1 + (cls_bias if is_cls else 1.0)
         else:
             t = torch.randn(shape, generator=g) * 0.1
+        # BatchNorm running stats follow the measured RMS of the conv output (what training would give);
+        # the last conv of each Detect branch is normalised to unit-RMS logits (x1.5 for the DFL bins)
+        if k.endswith("bn.running_var") and k[: -len(".bn.running_var")] in scales:
+            t = t * scales[k[: -len(".bn.running_var")]] ** 2
+        elif k.endswith("bn.running_mean") and k[: -len(".bn.running_mean")] in scales:
+            t = t * scales[k[: -len(".bn.running_mean")]]
+        elif k.endswith(".2.weight") and k[: -len(".weight")] in scales:
+            t = t * ((1.5 if ".cv2." in k else 1.0) / scales[k[: -len(".weight")]])
         out[k] = t.to(v.dtype)
     return out
 

@@ -1,0 +1,148 @@
+"""End-to-end parity on the B200 (pytest -m gpu): the whole detector (29 layers, ~110 kernel launches)
+against the CPU oracle (fp32 restatement of the reference, pinned to the real reference by
+tests/golden/model_*.npz) on the same seeded weights and inputs.
+
+Tolerances: the reference's own half-precision precedent is check_amp's atol=0.5 on [x1,y1,x2,y2,conf,cls]
+(ultralytics/utils/checks.py:691-699).  Here: per-layer activations rel-L2 <= 3e-2 (bf16 storage between
+~60 chained convs), decoded boxes <= 1.0 px at 640 px scale on anchors whose score clears 0.05, scores
+<= 0.03 absolute; NMS indices exact on identical inputs (tests/test_gpu_kernels.py).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+CFG = ROOT / "spectrogram-yolov11_b200" / "specyolo" / "cfg"
+GOLD = ROOT / "tests" / "golden"
+
+
+def _build(cfg, nc, seed):
+    import specyolo
+    from specyolo.nn.init import synth_state_dict
+
+    m = specyolo.DetectionModel(cfg, nc=nc)
+    sd = synth_state_dict(m, seed=seed)
+    m.load_state_dict(sd)
+    return m.eval().to("cuda"), sd
+
+
+def _oracle(cfg_file, scale, nc, sd, x, layers=False):
+    from oracle import yolo_ref
+
+    d = yaml.safe_load((CFG / cfg_file).read_text())
+    g = yolo_ref.parse_graph(d, scale, nc)
+    with torch.no_grad():
+        return yolo_ref.forward(g, sd, x, return_layers=layers)
+
+
+@pytest.mark.parametrize("name,cfg,cfg_file,scale,nc", [
+    ("specyolo_s", "yolo11s_fusion_sand3_new.yaml", "yolo11_fusion_sand3_new.yaml", "s", 2),
+    ("yolo11n", "yolo11n.yaml", "yolo11.yaml", "n", 80),
+])
+def test_model_vs_golden_reference(lib, name, cfg, cfg_file, scale, nc):
+    """CUDA path vs outputs of the REAL reference (fixture) on the fixture's input and seeded weights."""
+    z = np.load(GOLD / f"model_{name}.npz")
+    model, sd = _build(cfg, nc, int(z["seed"]))
+    x = torch.from_numpy(z["x"])
+    y, raw = model(x.cuda())
+    y = y.cpu()
+    ref = torch.from_numpy(z["y"])
+    assert y.shape == ref.shape
+    for i, r in enumerate(raw):
+        rr = torch.from_numpy(z[f"raw{i}"])
+        rel = ((r.cpu() - rr).norm() / rr.norm()).item()
+        assert rel < 4e-2, f"raw head map {i}: rel-L2 {rel}"
+    dsc = (y[:, 4:] - ref[:, 4:]).abs().max().item()
+    assert dsc < 0.05, f"scores differ by {dsc}"
+    dbox = (y[:, :4] - ref[:, :4]).abs().max().item()
+    assert dbox < 1.5, f"boxes differ by {dbox} px"
+
+
+def test_layers_vs_oracle(lib):
+    """Layer-by-layer activations of the Spectrogram cfg at 256x256, batch 2."""
+    from specyolo import ops
+    from specyolo.nn.init import synth_images
+    from specyolo.nn.modules import UpsampledView
+
+    cfg, nc = "yolo11s_fusion_sand3_new.yaml", 2
+    model, sd = _build(cfg, nc, 0)
+    x = synth_images(2, 256, seed=2)
+    (y_ref, raw_ref), layers_ref = _oracle("yolo11_fusion_sand3_new.yaml", "s", nc, sd, x, layers=True)
+    # run the trunk keeping every layer output
+    outs, t = [], x.cuda()
+    for m in model.model[:-1]:
+        if m.f != -1:
+            t = outs[m.f] if isinstance(m.f, int) else [t if j == -1 else outs[j] for j in m.f]
+        t = m(t)
+        outs.append(t)
+    worst = 0.0
+    for i, (o, r) in enumerate(zip(outs, layers_ref)):
+        if isinstance(o, UpsampledView):
+            o = o.materialise()
+        got = ops.to_nchw_f32(o).cpu()
+        rel = ((got - r).norm() / r.norm()).item()
+        worst = max(worst, rel)
+        assert rel < 3e-2, f"layer {i} ({model.model[i].type}): rel-L2 {rel}"
+    y, raw = model(x.cuda())
+    y = y.cpu()
+    keep = y_ref[:, 4:].amax(1) > 0.05
+    dbox = (y[:, :4] - y_ref[:, :4]).abs().permute(0, 2, 1)[keep].max().item()
+    dsc = (y[:, 4:] - y_ref[:, 4:]).abs().max().item()
+    assert dbox < 1.0 and dsc < 0.03, (dbox, dsc, worst)
+
+
+def test_predict_api_and_fused_path(lib):
+    """YOLO(cfg).predict(tensor): CUDA-graph replay == eager fused path == model() + non_max_suppression."""
+    import specyolo
+    from specyolo.nn.init import synth_images, synth_state_dict
+    from specyolo.utils.ops import non_max_suppression
+
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    x = synth_images(4, 320, seed=5).cuda()
+    res_graph = yolo.predict(x, conf=0.25, iou=0.7)
+    res_graph2 = yolo.predict(x, conf=0.25, iou=0.7)            # replay
+    res_eager = yolo.predict(x, conf=0.25, iou=0.7, use_graph=False)
+    y, _ = yolo.model(x)
+    dense = non_max_suppression(y, 0.25, 0.7)
+    assert len(res_graph) == 4
+    for a, b, c, d in zip(res_graph, res_graph2, res_eager, dense):
+        assert torch.equal(a.boxes.data, b.boxes.data)
+        assert torch.equal(a.boxes.data, c.boxes.data)
+        assert torch.equal(a.boxes.data, d.cpu())
+        assert a.boxes.data.shape[1] == 6 and a.orig_shape == (320, 320)
+    # uint8 HWC BGR ndarray source (predictor.py:125-136 path)
+    img = (synth_images(1, 320, seed=6)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)[..., ::-1]
+    r = yolo.predict([np.ascontiguousarray(img)], conf=0.25)
+    assert len(r) == 1 and r[0].orig_img is not None
+    with pytest.raises(ValueError):
+        yolo.predict(torch.zeros(1, 3, 100, 100))                # not stride-32 (loaders.py:554-562)
+    with pytest.raises(RuntimeError):
+        yolo.predict(x, device="cpu")
+
+
+def test_iq_to_boxes(lib):
+    """Raw IQ -> STFT kernel -> detector -> NMS, vs the oracle chain on the kernel's own spectrogram."""
+    import specyolo
+    from oracle import nms_ref
+    from specyolo.nn.init import synth_iq, synth_state_dict
+
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    sd = synth_state_dict(yolo.model, seed=0)
+    yolo.load_state_dict(sd)
+    yolo.to("cuda")
+    iq = synth_iq(2, 1 << 18, seed=9)
+    res = yolo.predict_iq(iq, conf=0.25, iou=0.7, imgsz=640)
+    img = specyolo.ops.iq_to_letterbox(iq.cuda(), out_hw=(640, 640))
+    y, _ = yolo.model(img)
+    ref = nms_ref.non_max_suppression(y.cpu().numpy(), 0.25, 0.7)
+    for r, e in zip(res, ref):
+        assert np.array_equal(r.boxes.data.numpy(), e)
+    y_ref, _ = _oracle("yolo11_fusion_sand3_new.yaml", "s", 2, sd, img.float().cpu())
+    assert (y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max().item() < 0.05
