@@ -28,7 +28,9 @@ namespace specyolo {
 
 struct IgemmParams {
     int TW, TH, TN;
-    int tiles_w, tiles_h;
+    int tiles_w, tiles_h, tiles_n;
+    int n_tiles, groups;
+    int total_tiles;
     int Ho, Wo, B;
     int kh, kw, stride, pad, dil;
     int kc, cin_chunks, cin_g;
@@ -48,15 +50,49 @@ struct IgemmParams {
 static constexpr int kThreads = 192;
 static constexpr int kMaxStages = 8;
 static constexpr int kMaxDynSmem = 200 * 1024;  // opt-in limit is 227 KB minus the static barriers
+static constexpr int kMaxBias = 1024;           // groups * n_pad floats staged in shared memory
 
+struct TileCoord {
+    int w0, h0, n0, nt, g;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+    // N tile fastest, then group, then the spatial tile: neighbouring CTAs share the same A box in L2
+    TileCoord t;
+    t.nt = tile % p.n_tiles;
+    int r = tile / p.n_tiles;
+    t.g = r % p.groups;
+    r /= p.groups;
+    const int tw_i = r % p.tiles_w;
+    r /= p.tiles_w;
+    const int th_i = r % p.tiles_h;
+    const int tn_i = r / p.tiles_h;
+    t.w0 = tw_i * p.TW;
+    t.h0 = th_i * p.TH;
+    t.n0 = tn_i * p.TN;
+    return t;
+}
+
+// SiLU with one MUFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx error ~2^-11, below bf16 resolution)
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// Persistent, warp-specialised: every CTA walks tiles blockIdx.x, +gridDim.x, ...; the TMA ring keeps
+// streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile
+// i overlaps the loads and MMAs of tile i+1.
 __global__ void __launch_bounds__(kThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float bias_s[kMaxBias];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -68,15 +104,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint8_t* a_ring = ring;
     uint8_t* b_ring = ring + (size_t)p.stages * p.cps * p.a_chunk_bytes;
 
-    // tile coordinates
-    const int tile = blockIdx.x;
-    const int tw_i = tile % p.tiles_w;
-    const int th_i = (tile / p.tiles_w) % p.tiles_h;
-    const int tn_i = tile / (p.tiles_w * p.tiles_h);
-    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
-    const int nt = blockIdx.y;   // N tile inside the group
-    const int g = blockIdx.z;    // group
-
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_b);
@@ -84,10 +111,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
-        ptx::mbar_init(&accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&tmem_full_bar[b], 1);
+            ptx::mbar_init(&tmem_empty_bar[b], 4);   // one arrival per epilogue warp
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.groups * p.n_pad; i += kThreads) bias_s[i] = p.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -100,25 +131,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int step = 0; step < steps; ++step) {
-                const int stage = step % p.stages;
-                const uint32_t ph = (step / p.stages) & 1;
-                ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
-                const int q0 = step * p.cps;
-                const int nch = min(p.cps, total_chunks - q0);
-                ptx::mbar_expect_tx(&full_bar[stage], nch * (p.a_tx_bytes + p.b_tx_bytes));
-                for (int j = 0; j < nch; ++j) {
-                    const int q = q0 + j;
-                    const int tap = q / p.cin_chunks;
-                    const int cc = q - tap * p.cin_chunks;
-                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                    uint8_t* a_dst = a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes;
-                    uint8_t* b_dst = b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes;
-                    ptx::tma_load_4d(a_dst, &map_a, &full_bar[stage], g * p.cin_g + cc * p.kc,
-                                     w0 * p.stride + kx * p.dil - p.pad,
-                                     h0 * p.stride + ky * p.dil - p.pad, n0);
-                    ptx::tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin_g + cc * p.kc,
-                                     g * p.n_pad + nt * p.n_tile);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                for (int step = 0; step < steps; ++step, ++it) {
+                    const int stage = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    const int q0 = step * p.cps;
+                    const int nch = min(p.cps, total_chunks - q0);
+                    ptx::mbar_expect_tx(&full_bar[stage], nch * (p.a_tx_bytes + p.b_tx_bytes));
+                    for (int j = 0; j < nch; ++j) {
+                        const int q = q0 + j;
+                        const int tap = q / p.cin_chunks;
+                        const int cc = q - tap * p.cin_chunks;
+                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                        uint8_t* a_dst = a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes;
+                        uint8_t* b_dst = b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes;
+                        ptx::tma_load_4d(a_dst, &map_a, &full_bar[stage], tc.g * p.cin_g + cc * p.kc,
+                                         tc.w0 * p.stride + kx * p.dil - p.pad,
+                                         tc.h0 * p.stride + ky * p.dil - p.pad, tc.n0);
+                        ptx::tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin_g + cc * p.kc,
+                                         tc.g * p.n_pad + tc.nt * p.n_tile);
+                    }
                 }
             }
         }
@@ -128,29 +163,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_tile);
             const uint32_t row_bytes = p.kc * 2;
             const int kk = p.kc / 16;
-            uint32_t accumulate = 0;
-            for (int step = 0; step < steps; ++step) {
-                const int stage = step % p.stages;
-                const uint32_t ph = (step / p.stages) & 1;
-                ptx::mbar_wait(&full_bar[stage], ph);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                const uint32_t bph = (tl >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[buf], bph ^ 1u);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
-                const int q0 = step * p.cps;
-                const int nch = min(p.cps, total_chunks - q0);
-                for (int j = 0; j < nch; ++j) {
-                    const uint32_t a_addr =
-                        ptx::smem_u32(a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes);
-                    const uint32_t b_addr =
-                        ptx::smem_u32(b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes);
-                    for (int k = 0; k < kk; ++k) {
-                        const uint64_t da = ptx::umma_smem_desc(a_addr + k * 32, row_bytes);
-                        const uint64_t db = ptx::umma_smem_desc(b_addr + k * 32, row_bytes);
-                        ptx::umma_bf16(tmem_base, da, db, idesc, accumulate);
-                        accumulate = 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.n_tile);
+                uint32_t accumulate = 0;
+                for (int step = 0; step < steps; ++step, ++it) {
+                    const int stage = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    ptx::mbar_wait(&full_bar[stage], ph);
+                    ptx::tc_fence_after();
+                    const int q0 = step * p.cps;
+                    const int nch = min(p.cps, total_chunks - q0);
+                    for (int j = 0; j < nch; ++j) {
+                        const uint32_t a_addr =
+                            ptx::smem_u32(a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes);
+                        const uint32_t b_addr =
+                            ptx::smem_u32(b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes);
+                        for (int k = 0; k < kk; ++k) {
+                            const uint64_t da = ptx::umma_smem_desc(a_addr + k * 32, row_bytes);
+                            const uint64_t db = ptx::umma_smem_desc(b_addr + k * 32, row_bytes);
+                            ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
+                            accumulate = 1;
+                        }
                     }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                 }
-                ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                ptx::umma_commit(&tmem_full_bar[buf]);    // accumulator complete
             }
-            ptx::umma_commit(&accum_bar);             // accumulator complete
         }
         __syncwarp();
     } else {
@@ -161,68 +204,97 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int tw = m % p.TW;
         const int th = (m / p.TW) % p.TH;
         const int tn = m / (p.TW * p.TH);
-        const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
-        const bool row_ok = (m < npix) && (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
-        const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
-        const int ch_base = nt * p.n_tile;           // channel offset inside the group
-        const int gch_base = g * p.cout_g + ch_base; // channel offset inside the output window
-        const float* bias = p.bias + g * p.n_pad + ch_base;
+        const bool silu = p.act == SPECYOLO_ACT_SILU;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            const TileCoord tc = decode_tile(p, tile);
+            const int buf = tl & 1;
+            const uint32_t bph = (tl >> 1) & 1;
+            const int ow = tc.w0 + tw, oh = tc.h0 + th, on = tc.n0 + tn;
+            const bool row_ok = (m < npix) && (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
+            const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
+            const int ch_base = tc.nt * p.n_tile;             // channel offset inside the group
+            const int gch_base = tc.g * p.cout_g + ch_base;   // channel offset inside the output window
+            const float* bias = bias_s + tc.g * p.n_pad + ch_base;
+            const bool y_vec_ok = !p.y_fp32 && (p.y_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
+                                  ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+            const bool r_vec_ok = p.residual && (p.r_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
+                                  ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
 
-        ptx::mbar_wait(&accum_bar, 0);
-        ptx::tc_fence_after();
+            ptx::mbar_wait(&tmem_full_bar[buf], bph);
+            ptx::tc_fence_after();
 
-        const bool y_vec_ok = !p.y_fp32 && (p.y_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
-                              ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-        const bool r_vec_ok = p.residual && (p.r_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
-                              ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            ptx::tmem_ld_wait();
-            if (!row_ok) continue;
-            const int nvalid = min(16, p.cout_g - (ch_base + c0));
-            if (nvalid <= 0) continue;
-            float f[16];
+            uint32_t va[16], vb[16];
+            ptx::tmem_ld16(t_addr, va);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float t = __uint_as_float(v[i]) + __ldg(bias + c0 + i);
-                f[i] = (p.act == SPECYOLO_ACT_SILU) ? silu_f(t) : t;
-            }
-            if (p.residual) {
-                const __nv_bfloat16* r = p.residual + pix * p.r_pixstride + gch_base + c0;
-                if (r_vec_ok && nvalid == 16) {
-                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(r));
-                    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(r) + 1);
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 t = unpack_bf16x2(rr[i]);
-                        f[2 * i] += t.x;
-                        f[2 * i + 1] += t.y;
+                for (int half = 0; half < 2; ++half) {
+                    const int c = c0 + half * 16;
+                    if (c >= p.n_tile) break;
+                    uint32_t(&v)[16] = half ? vb : va;
+                    uint32_t(&vn)[16] = half ? va : vb;
+                    // residual for this chunk: issue the loads before waiting on TMEM
+                    const int nvalid = min(16, p.cout_g - (ch_base + c));
+                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+                    const bool res_vec = r_vec_ok && row_ok && nvalid == 16;
+                    if (res_vec) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.r_pixstride + gch_base + c);
+                        r0 = __ldg(rp);
+                        r1 = __ldg(rp + 1);
                     }
-                } else {
-                    for (int i = 0; i < nvalid; ++i) f[i] += __bfloat162float(r[i]);
+                    ptx::tmem_ld_wait();                               // v is ready
+                    if (c + 16 < p.n_tile) ptx::tmem_ld16(t_addr + (uint32_t)(c + 16), vn);   // prefetch next
+                    if (!row_ok || nvalid <= 0) continue;
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float t = __uint_as_float(v[i]) + bias[c + i];
+                        f[i] = silu ? silu_tanh(t) : t;
+                    }
+                    if (p.residual) {
+                        if (res_vec) {
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 t = unpack_bf16x2(rr[i]);
+                                f[2 * i] += t.x;
+                                f[2 * i + 1] += t.y;
+                            }
+                        } else {
+                            const __nv_bfloat16* r = p.residual + pix * p.r_pixstride + gch_base + c;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) f[i] += __bfloat162float(r[i]);
+                        }
+                    }
+                    if (p.y_fp32) {
+                        float* y = reinterpret_cast<float*>(p.y) + pix * p.y_pixstride + gch_base + c;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < nvalid) y[i] = f[i];
+                    } else {
+                        __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pixstride + gch_base + c;
+                        if (y_vec_ok && nvalid == 16) {
+                            uint4 o0, o1;
+                            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                            reinterpret_cast<uint4*>(y)[0] = o0;
+                            reinterpret_cast<uint4*>(y)[1] = o1;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) y[i] = __float2bfloat16_rn(f[i]);
+                        }
+                    }
                 }
             }
-            if (p.y_fp32) {
-                float* y = reinterpret_cast<float*>(p.y) + pix * p.y_pixstride + gch_base + c0;
-                for (int i = 0; i < nvalid; ++i) y[i] = f[i];
-            } else {
-                __nv_bfloat16* y =
-                    reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pixstride + gch_base + c0;
-                if (y_vec_ok && nvalid == 16) {
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                    reinterpret_cast<uint4*>(y)[0] = o0;
-                    reinterpret_cast<uint4*>(y)[1] = o1;
-                } else {
-                    for (int i = 0; i < nvalid; ++i) y[i] = __float2bfloat16_rn(f[i]);
-                }
-            }
+            // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
         }
     }
 
@@ -324,9 +396,13 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     p.B = gB; p.Ho = gHo; p.Wo = gWo;
     p.tiles_w = ceil_div(gWo, p.TW);
     p.tiles_h = ceil_div(gHo, p.TH);
-    const int tiles_n = ceil_div(gB, p.TN);
-    const long m_tiles = (long)p.tiles_w * p.tiles_h * tiles_n;
-    SY_CHECK(m_tiles > 0 && m_tiles < (1L << 31), SPECYOLO_ERR_INVALID, "bad tile count");
+    p.tiles_n = ceil_div(gB, p.TN);
+    p.n_tiles = a->n_pad / n_tile;
+    p.groups = groups;
+    const long total_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * groups;
+    SY_CHECK(total_tiles > 0 && total_tiles < (1L << 30), SPECYOLO_ERR_INVALID, "bad tile count");
+    p.total_tiles = (int)total_tiles;
+    SY_CHECK(groups * a->n_pad <= kMaxBias, SPECYOLO_ERR_UNSUPPORTED, "too many output channels (%d)", groups * a->n_pad);
 
     const int row_bytes = kc * 2;
     p.cps = 64 / kc;
@@ -335,16 +411,19 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     p.a_tx_bytes = (uint32_t)(p.TW * p.TH * p.TN) * row_bytes;
     p.b_tx_bytes = (uint32_t)n_tile * row_bytes;
     const uint32_t stage_bytes = p.cps * (p.a_chunk_bytes + p.b_chunk_bytes);
-    int stages = (int)((96u * 1024u) / stage_bytes);
-    if (stages < 3) stages = 3;
-    if (stages > 6) stages = 6;
-    if (n_tile > 128 && stages < 4) stages = 4;
+    // two persistent CTAs per SM when the double-buffered accumulators of both fit TMEM (2*2*n_tile <= 512):
+    // ring <= ~100 KB each; otherwise one CTA per SM with a deeper ring
+    uint32_t cols = 32;
+    while (cols < 2u * (uint32_t)n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+    const int occ = (cols <= 256) ? 2 : 1;
+    const uint32_t ring_budget = (occ == 2) ? 100u * 1024u : 190u * 1024u;
+    int stages = (int)(ring_budget / stage_bytes);
+    if (stages < 2) stages = 2;
+    if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024;
     SY_CHECK(smem_bytes <= (size_t)kMaxDynSmem, SPECYOLO_ERR_INVALID, "smem budget exceeded");
-    uint32_t cols = 32;
-    while (cols < (uint32_t)n_tile) cols <<= 1;
-    p.tmem_cols = cols;
 
     p.bias = a->bias;
     p.y = a->y; p.y_pixstride = a->y_pixstride; p.y_fp32 = a->y_fp32;
@@ -391,7 +470,14 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
              cudaGetErrorString(attr_err));
 
-    dim3 grid((unsigned)m_tiles, (unsigned)(a->n_pad / n_tile), (unsigned)groups);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SY_CUDA(cudaGetDevice(&dev));
+        SY_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long resident = (long)num_sms * occ;
+    const unsigned grid = (unsigned)(total_tiles < resident ? total_tiles : resident);
     conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
     SY_LAUNCH_CHECK();
     count_launch();
