@@ -58,15 +58,21 @@ int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C,
 /* ---- Conv + BN fold + weight repack ------------------------------------------------------ */
 /* Folds BatchNorm into the conv weights exactly like fuse_conv_and_bn
  * (ultralytics/utils/torch_utils.py:238-265) and repacks OIHW fp32 -> the K-major bf16 layout the
- * implicit-GEMM kernel consumes: w_packed[g][n_pad][kh][kw][cin_g], rows n >= cout_g zero.
+ * implicit-GEMM kernel consumes: w_packed[g'][n_pad][kh][kw][cin_g'], rows n >= cout_g' zero.
+ * `merge` (>= 1, divides groups) fuses that many source groups into one packed group with block-diagonal
+ * weights: g' = groups/merge, cin_g' = cin_g*merge, cout_g' = cout/groups*merge; the packed conv is then
+ * run with groups = g'.  Use specyolo_conv_merge() for the factor the kernels prefer and
+ * specyolo_conv_npad(cout, g') for n_pad.
  * bn_* may be NULL (plain nn.Conv2d, e.g. the last conv of Detect.cv2/cv3); conv_bias may be NULL.
- * All pointers are device pointers.  bias_out has groups*n_pad floats. */
+ * All pointers are device pointers.  bias_out has g'*n_pad floats. */
 int specyolo_fold_pack_conv(const float* w_oihw, const float* conv_bias,
                             const float* bn_gamma, const float* bn_beta,
                             const float* bn_mean, const float* bn_var, float bn_eps,
-                            int cout, int cin_g, int kh, int kw, int groups, int n_pad,
+                            int cout, int cin_g, int kh, int kw, int groups, int merge, int n_pad,
                             void* w_packed, float* bias_out, void* stream);
-/* n_pad (per-group padded output channels) the kernels expect for a conv of this shape */
+/* group-merge factor preferred for a grouped conv (1 for dense and depthwise convs) */
+int specyolo_conv_merge(int cin, int cout, int groups);
+/* n_pad (per-group padded output channels) the kernels expect for a conv with `groups` (packed) groups */
 int specyolo_conv_npad(int cout, int groups);
 
 typedef struct {

@@ -23,7 +23,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream);
 int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream);
 int fold_pack_launch(const float*, const float*, const float*, const float*, const float*, const float*, float,
-                     int, int, int, int, int, int, void*, float*, cudaStream_t);
+                     int, int, int, int, int, int, int, void*, float*, cudaStream_t);
 int stem_conv_launch(const void*, int, int, int, int, const float*, const float*, int, void*, int, cudaStream_t);
 int nchw_to_nhwc_launch(const void*, int, float, int, int, int, int, void*, int, cudaStream_t);
 int nhwc_to_nchw_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
@@ -74,6 +74,15 @@ int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C,
     return nhwc_to_nchw_launch(x, x_pixstride, B, C, H, W, y, (cudaStream_t)stream);
 }
 
+int specyolo_conv_merge(int cin, int cout, int groups) {
+    if (groups <= 1 || cin <= 0 || cout <= 0 || cin % groups || cout % groups) return 1;
+    const int cin_g = cin / groups;
+    if (cin_g == 1 && cout / groups == 1) return 1;    // depthwise: dedicated kernel
+    int merge = 1;
+    while (cin_g * merge * 2 <= 64 && groups % (merge * 2) == 0) merge *= 2;
+    return merge;
+}
+
 int specyolo_conv_npad(int cout, int groups) {
     if (groups <= 0 || cout <= 0 || cout % groups) return -1;
     const int cg = cout / groups;
@@ -83,14 +92,14 @@ int specyolo_conv_npad(int cout, int groups) {
 
 int specyolo_fold_pack_conv(const float* w_oihw, const float* conv_bias, const float* bn_gamma,
                             const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
-                            int cout, int cin_g, int kh, int kw, int groups, int n_pad, void* w_packed,
-                            float* bias_out, void* stream) {
+                            int cout, int cin_g, int kh, int kw, int groups, int merge, int n_pad,
+                            void* w_packed, float* bias_out, void* stream) {
     SY_CHECK(w_oihw && w_packed && bias_out, SPECYOLO_ERR_INVALID, "fold_pack: null pointer");
     SY_CHECK((bn_gamma == nullptr) == (bn_beta == nullptr) && (bn_gamma == nullptr) == (bn_mean == nullptr) &&
                  (bn_gamma == nullptr) == (bn_var == nullptr),
              SPECYOLO_ERR_INVALID, "fold_pack: give all BN tensors or none");
     return fold_pack_launch(w_oihw, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, cout, cin_g, kh, kw,
-                            groups, n_pad, w_packed, bias_out, (cudaStream_t)stream);
+                            groups, merge, n_pad, w_packed, bias_out, (cudaStream_t)stream);
 }
 
 int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {

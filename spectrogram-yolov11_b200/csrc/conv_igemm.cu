@@ -218,6 +218,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const float* bias = bias_s + tc.g * p.n_pad + ch_base;
             const bool y_vec_ok = !p.y_fp32 && (p.y_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
                                   ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+            const bool y32_vec_ok = p.y_fp32 && (p.y_pixstride % 4 == 0) && (gch_base % 4 == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
             const bool r_vec_ok = p.residual && (p.r_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
                                   ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
@@ -270,9 +272,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     if (p.y_fp32) {
                         float* y = reinterpret_cast<float*>(p.y) + pix * p.y_pixstride + gch_base + c;
+                        if (y32_vec_ok && nvalid == 16) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < nvalid) y[i] = f[i];
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<float4*>(y)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) y[i] = f[i];
+                        }
                     } else {
                         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pixstride + gch_base + c;
                         if (y_vec_ok && nvalid == 16) {

@@ -10,35 +10,41 @@ namespace specyolo {
 // fuse_conv_and_bn (ultralytics/utils/torch_utils.py:238-265):
 //   w' = w * gamma / sqrt(var + eps);  b' = (b_conv) * gamma / sqrt(var+eps) + beta - gamma*mean/sqrt(var+eps)
 // ------------------------------------------------------------------------------------------------
+// `merge` source groups are fused into one packed group with block-diagonal weights (zeros off the diagonal):
+// a g=8, 16->16-per-group conv becomes a g=2, 64->64-per-group conv whose K chunks are full 128-byte swizzle
+// rows and whose UMMA N is 64 instead of 16 — 4x fewer TMA / MMA / barrier operations for the same bytes.
 __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                 int cout, int cin_g, int kh, int kw, int groups, int n_pad,
+                                 int cout, int cin_g, int kh, int kw, int groups, int merge, int n_pad,
                                  __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out) {
     const int cout_g = cout / groups;
     const int taps = kh * kw;
-    const long per_row = (long)taps * cin_g;
-    const long total = (long)groups * n_pad * per_row;
+    const int pgroups = groups / merge;           // packed groups
+    const int pcin = cin_g * merge;               // packed input channels per group
+    const int pcout = cout_g * merge;             // packed (valid) output channels per group
+    const long per_row = (long)taps * pcin;
+    const long total = (long)pgroups * n_pad * per_row;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % cin_g);
-        const int tap = (int)((i / cin_g) % taps);
+        const int ci = (int)(i % pcin);
+        const int tap = (int)((i / pcin) % taps);
         const int n = (int)((i / per_row) % n_pad);
-        const int g = (int)(i / (per_row * n_pad));
+        const int pg = (int)(i / (per_row * n_pad));
         float v = 0.f;
-        if (n < cout_g) {
-            const int co = g * cout_g + n;
+        if (n < pcout && (n / cout_g) == (ci / cin_g)) {
+            const int co = pg * pcout + n;        // == source group * cout_g + local index
             const float s = gamma ? gamma[co] / sqrtf(var[co] + eps) : 1.f;
-            // OIHW: ((co*cin_g + ci)*kh + ky)*kw + kx ; tap = ky*kw + kx
-            v = w[((long)co * cin_g + ci) * taps + tap] * s;
+            // OIHW: ((co*cin_g + ci_local)*kh + ky)*kw + kx ; tap = ky*kw + kx
+            v = w[((long)co * cin_g + (ci % cin_g)) * taps + tap] * s;
         }
         wp[i] = __float2bfloat16_rn(v);
     }
-    const int nb = groups * n_pad;
+    const int nb = pgroups * n_pad;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
-        const int n = i % n_pad, g = i / n_pad;
+        const int n = i % n_pad, pg = i / n_pad;
         float b = 0.f;
-        if (n < cout_g) {
-            const int co = g * cout_g + n;
+        if (n < pcout) {
+            const int co = pg * pcout + n;
             const float cb = conv_bias ? conv_bias[co] : 0.f;
             if (gamma) {
                 const float s = gamma[co] / sqrtf(var[co] + eps);
@@ -53,15 +59,16 @@ __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __res
 
 int fold_pack_launch(const float* w, const float* conv_bias, const float* gamma, const float* beta,
                      const float* mean, const float* var, float eps, int cout, int cin_g, int kh, int kw,
-                     int groups, int n_pad, void* wp, float* bias_out, cudaStream_t stream) {
+                     int groups, int merge, int n_pad, void* wp, float* bias_out, cudaStream_t stream) {
     SY_CHECK(cout % groups == 0, SPECYOLO_ERR_INVALID, "cout %% groups != 0");
-    SY_CHECK(n_pad >= cout / groups, SPECYOLO_ERR_INVALID, "n_pad too small");
-    const long total = (long)groups * n_pad * kh * kw * cin_g;
+    SY_CHECK(merge >= 1 && groups % merge == 0, SPECYOLO_ERR_INVALID, "merge must divide groups");
+    SY_CHECK(n_pad >= cout / groups * merge, SPECYOLO_ERR_INVALID, "n_pad too small");
+    const long total = (long)(groups / merge) * n_pad * kh * kw * cin_g * merge;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     fold_pack_kernel<<<blocks, 256, 0, stream>>>(w, conv_bias, gamma, beta, mean, var, eps, cout, cin_g, kh,
-                                                 kw, groups, n_pad, reinterpret_cast<__nv_bfloat16*>(wp),
+                                                 kw, groups, merge, n_pad, reinterpret_cast<__nv_bfloat16*>(wp),
                                                  bias_out);
     SY_LAUNCH_CHECK();
     count_launch();
@@ -87,74 +94,95 @@ __device__ __forceinline__ float load_in<uint8_t>(const uint8_t* p, long i) {
     return (float)__ldg(p + i) * (1.0f / 255.0f);
 }
 
+// Output tile per CTA: 8 rows x 32 columns = 256 pixels, one per thread, every output channel.  The 17 x 65 x 3
+// input patch is staged once in shared memory (coalesced reads of the NCHW planes, zero padding, uint8 -> float
+// scaling) with even / odd columns de-interleaved so that the stride-2 taps of neighbouring threads hit
+// consecutive banks.  Weights live in shared memory as [27][Cout] and are read as broadcast float4; the FMAs
+// are issued as packed fp32x2 (FFMA2), 16 output channels at a time, stored as two 16-byte vectors.
+static constexpr int kStemTH = 8, kStemTW = 32;
+static constexpr int kStemIH = 2 * kStemTH + 1, kStemIWH = kStemTW + 1;   // rows, columns per parity plane
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const T* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt,
                  const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ y, int y_pixstride,
                  int Ho, int Wo) {
-    extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
-    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
-        const int co = i % Cout, k = i / Cout;  // k = ci*9 + ky*3 + kx (OIHW inner order)
+    extern __shared__ __align__(16) float stem_smem[];
+    float* sw = stem_smem;                       // [27][Cout]
+    float* sb = sw + 27 * Cout;                  // [Cout]
+    float* sin = sb + Cout;                      // [3][kStemIH][2][kStemIWH]
+    const int n = blockIdx.z;
+    const int oh0 = blockIdx.y * kStemTH, ow0 = blockIdx.x * kStemTW;
+    for (int i = threadIdx.x; i < 27 * Cout; i += 256) {
+        const int co = i % Cout, k = i / Cout;   // k = ci*9 + ky*3 + kx (OIHW inner order)
         sw[i] = wgt[co * 27 + k];
     }
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
+    for (int i = threadIdx.x; i < Cout; i += 256) sb[i] = bias[i];
+    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+    for (int i = threadIdx.x; i < 3 * kStemIH * (2 * kStemTW + 1); i += 256) {
+        const int c = i % (2 * kStemTW + 1);
+        const int r = (i / (2 * kStemTW + 1)) % kStemIH;
+        const int ci = i / ((2 * kStemTW + 1) * kStemIH);
+        const int ih = ih0 + r, iw = iw0 + c;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = load_in<T>(x, (((long)n * 3 + ci) * H + ih) * W + iw);
+        sin[((ci * kStemIH + r) * 2 + (c & 1)) * kStemIWH + (c >> 1)] = v;
+    }
     __syncthreads();
-    const int cg = Cout / 8;
-    const long total = (long)B * Ho * Wo * cg;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(idx % cg);
-        const long pix = idx / cg;
-        const int ow = (int)(pix % Wo);
-        const int oh = (int)((pix / Wo) % Ho);
-        const int n = (int)(pix / ((long)Wo * Ho));
-        float acc[8];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    float in[27];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + c8 * 8 + j];
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
+        for (int ky = 0; ky < 3; ++ky) {
+            const float* row = sin + ((ci * kStemIH + 2 * ty + ky) * 2) * kStemIWH;
+            in[ci * 9 + ky * 3 + 0] = row[tx];                 // column 2tx   (even plane)
+            in[ci * 9 + ky * 3 + 1] = row[kStemIWH + tx];      // column 2tx+1 (odd plane)
+            in[ci * 9 + ky * 3 + 2] = row[tx + 1];             // column 2tx+2 (even plane)
+        }
+    if (oh >= Ho || ow >= Wo) return;
+    __nv_bfloat16* yp = y + (((long)n * Ho + oh) * Wo + ow) * y_pixstride;
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+        float2 acc[8];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int ih = oh * 2 + ky - 1;
-                if (ih < 0 || ih >= H) continue;
+        for (int j = 0; j < 8; ++j) acc[j] = make_float2(sb[c0 + 2 * j], sb[c0 + 2 * j + 1]);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int iw = ow * 2 + kx - 1;
-                    if (iw < 0 || iw >= W) continue;
-                    const float v = load_in<T>(x, (((long)n * 3 + ci) * H + ih) * W + iw);
-                    const float* wr = sw + (ci * 9 + ky * 3 + kx) * Cout + c8 * 8;
+        for (int k = 0; k < 27; ++k) {
+            const float4* w4 = reinterpret_cast<const float4*>(sw + k * Cout + c0);
+            const float2 v2 = make_float2(in[k], in[k]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float4 w = w4[q];
+                acc[2 * q] = __ffma2_rn(v2, make_float2(w.x, w.y), acc[2 * q]);
+                acc[2 * q + 1] = __ffma2_rn(v2, make_float2(w.z, w.w), acc[2 * q + 1]);
             }
         }
-        uint4 o;
-        o.x = pack_bf16x2(silu_f(acc[0]), silu_f(acc[1]));
-        o.y = pack_bf16x2(silu_f(acc[2]), silu_f(acc[3]));
-        o.z = pack_bf16x2(silu_f(acc[4]), silu_f(acc[5]));
-        o.w = pack_bf16x2(silu_f(acc[6]), silu_f(acc[7]));
-        *reinterpret_cast<uint4*>(y + pix * y_pixstride + c8 * 8) = o;
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(silu_f(acc[0].x), silu_f(acc[0].y)); o0.y = pack_bf16x2(silu_f(acc[1].x), silu_f(acc[1].y));
+        o0.z = pack_bf16x2(silu_f(acc[2].x), silu_f(acc[2].y)); o0.w = pack_bf16x2(silu_f(acc[3].x), silu_f(acc[3].y));
+        o1.x = pack_bf16x2(silu_f(acc[4].x), silu_f(acc[4].y)); o1.y = pack_bf16x2(silu_f(acc[5].x), silu_f(acc[5].y));
+        o1.z = pack_bf16x2(silu_f(acc[6].x), silu_f(acc[6].y)); o1.w = pack_bf16x2(silu_f(acc[7].x), silu_f(acc[7].y));
+        reinterpret_cast<uint4*>(yp + c0)[0] = o0;
+        reinterpret_cast<uint4*>(yp + c0)[1] = o1;
     }
 }
 
 int stem_conv_launch(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,
                      int Cout, void* y, int y_pixstride, cudaStream_t stream) {
-    SY_CHECK(Cout % 8 == 0 && Cout <= 128, SPECYOLO_ERR_INVALID, "stem Cout must be a multiple of 8 (<=128)");
+    SY_CHECK(Cout % 16 == 0 && Cout <= 128, SPECYOLO_ERR_INVALID, "stem Cout must be a multiple of 16 (<=128)");
     SY_CHECK(y_pixstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, SPECYOLO_ERR_INVALID,
              "stem output must be 16-byte aligned");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const long total = (long)B * Ho * Wo * (Cout / 8);
-    long want = (total + 255) / 256;
-    int blocks = (int)(want < 148L * 16 ? want : 148L * 16);
-    if (blocks < 1) blocks = 1;
-    const size_t smem = (size_t)(28 * Cout) * sizeof(float);
+    dim3 grid((unsigned)ceil_div(Wo, kStemTW), (unsigned)ceil_div(Ho, kStemTH), (unsigned)B);
+    const size_t smem = (size_t)(28 * Cout + 3 * kStemIH * 2 * kStemIWH) * sizeof(float);
     __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
     if (x_dtype == SPECYOLO_DT_F32)
-        stem_conv_kernel<float><<<blocks, 256, smem, stream>>>((const float*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+        stem_conv_kernel<float><<<grid, 256, smem, stream>>>((const float*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
     else if (x_dtype == SPECYOLO_DT_BF16)
-        stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, stream>>>((const __nv_bfloat16*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+        stem_conv_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
     else if (x_dtype == SPECYOLO_DT_U8)
-        stem_conv_kernel<uint8_t><<<blocks, 256, smem, stream>>>((const uint8_t*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
+        stem_conv_kernel<uint8_t><<<grid, 256, smem, stream>>>((const uint8_t*)x, B, H, W, w, bias, Cout, yy, y_pixstride, Ho, Wo);
     else
         SY_CHECK(false, SPECYOLO_ERR_INVALID, "bad x_dtype %d", x_dtype);
     SY_LAUNCH_CHECK();
@@ -167,52 +195,84 @@ int stem_conv_launch(const void* x, int x_dtype, int B, int H, int W, const floa
 // One thread = 8 channels of one pixel (16-byte loads/stores); weights are packed bf16 [C][3][3][1]
 // by fold_pack (groups=C, cin_g=1, n_pad=1) -> read as wp[c*9 + tap].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// Each thread owns 8 channels (one 16-byte vector) of a run of kDwRun consecutive pixels of one row and slides
+// the 3x3 window along it: 3 new vector loads per output instead of 9, the 72 folded weights of its channels
+// held in registers as bf16x2 pairs.
+static constexpr int kDwRun = 8;
+
+__global__ void __launch_bounds__(256, 2)
 dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int B, int H, int W, int C,
                  const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias, int act,
                  __nv_bfloat16* __restrict__ y, int y_pixstride) {
+    extern __shared__ __align__(16) float dw_smem[];   // [9][C] weights then [C] bias
+    for (int i = threadIdx.x; i < 9 * C; i += 256) {
+        const int c = i % C, t = i / C;
+        dw_smem[i] = __bfloat162float(wp[c * 9 + t]);
+    }
+    for (int i = threadIdx.x; i < C; i += 256) dw_smem[9 * C + i] = bias[i];
+    __syncthreads();
     const int cg = C / 8;
-    const long total = (long)B * H * W * cg;
+    const int runs_w = (W + kDwRun - 1) / kDwRun;
+    const long total = (long)B * H * runs_w * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
          idx += (long)gridDim.x * blockDim.x) {
         const int c8 = (int)(idx % cg);
-        const long pix = idx / cg;
-        const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
-        const long n = pix / ((long)W * H);
+        long r = idx / cg;
+        const int rw = (int)(r % runs_w);
+        r /= runs_w;
+        const int h = (int)(r % H);
+        const long n = r / H;
         const int c0 = c8 * 8;
-        float acc[8];
+        const int w0 = rw * kDwRun;
+        const float* wt = dw_smem + c0;           // wt[t*C + j]
+        const float* bs = dw_smem + 9 * C + c0;
+        // column ring: col[k][ky][j] for input columns w-1, w, w+1
+        float col[3][3][8];
+        auto load_col = [&](int slot, int iw) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + c0 + j);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int ih = h + ky - 1;
-            if (ih < 0 || ih >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int iw = w + kx - 1;
-                if (iw < 0 || iw >= W) continue;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                    x + ((n * H + ih) * W + iw) * x_pixstride + c0));
+            for (int ky = 0; ky < 3; ++ky) {
+                const int ih = h + ky - 1;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    v = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * x_pixstride + c0));
                 const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 f = unpack_bf16x2(vv[j]);
-                    acc[2 * j] = fmaf(f.x, __bfloat162float(wp[(c0 + 2 * j) * 9 + ky * 3 + kx]), acc[2 * j]);
-                    acc[2 * j + 1] = fmaf(f.y, __bfloat162float(wp[(c0 + 2 * j + 1) * 9 + ky * 3 + kx]), acc[2 * j + 1]);
+                    col[slot][ky][2 * j] = f.x;
+                    col[slot][ky][2 * j + 1] = f.y;
                 }
             }
-        }
-        if (act == SPECYOLO_ACT_SILU) {
+        };
+        load_col(0, w0 - 1);
+        load_col(1, w0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+        for (int i = 0; i < kDwRun; ++i) {
+            const int w = w0 + i;
+            load_col((i + 2) % 3, w + 1);
+            if (w < W) {
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            acc[j] = fmaf(col[(i + kx) % 3][ky][j], wt[(ky * 3 + kx) * C + j], acc[j]);
+                if (act == SPECYOLO_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(acc[0], acc[1]);
+                o.y = pack_bf16x2(acc[2], acc[3]);
+                o.z = pack_bf16x2(acc[4], acc[5]);
+                o.w = pack_bf16x2(acc[6], acc[7]);
+                *reinterpret_cast<uint4*>(y + ((n * H + h) * W + w) * y_pixstride + c0) = o;
+            }
         }
-        uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]);
-        o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]);
-        o.w = pack_bf16x2(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(y + pix * y_pixstride + c0) = o;
     }
 }
 
@@ -226,11 +286,11 @@ int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream) {
              SPECYOLO_ERR_INVALID, "depthwise needs 16-byte aligned tensors");
     SY_CHECK(!a->y_fp32 && !a->residual && a->n_pad == 1, SPECYOLO_ERR_UNSUPPORTED,
              "depthwise: bf16 output, no residual, n_pad==1");
-    const long total = (long)a->B * a->H * a->W * (a->Cin / 8);
+    const long total = (long)a->B * a->H * ((a->W + kDwRun - 1) / kDwRun) * (a->Cin / 8);
     long want = (total + 255) / 256;
     int blocks = (int)(want < 148L * 16 ? want : 148L * 16);
     if (blocks < 1) blocks = 1;
-    dwconv3x3_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->x), a->x_pixstride,
+    dwconv3x3_kernel<<<blocks, 256, (size_t)10 * a->Cin * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->x), a->x_pixstride,
                                                  a->B, a->H, a->W, a->Cin,
                                                  reinterpret_cast<const __nv_bfloat16*>(a->w_packed), a->bias,
                                                  a->act, reinterpret_cast<__nv_bfloat16*>(a->y), a->y_pixstride);

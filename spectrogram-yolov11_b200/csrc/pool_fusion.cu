@@ -94,6 +94,7 @@ struct FusionParams {
     int nchunks;
     float* part;  // [B][nchunks][k*c]
     float* mm;    // [B][k][2][H*W]
+    float* gate;  // [B][k*c]
 };
 
 __device__ __forceinline__ const __nv_bfloat16* fus_pix_ptr(const specyolo_fusion_t& a, int i, int b, int h, int w) {
@@ -162,24 +163,20 @@ fusion_stats_kernel(const __grid_constant__ FusionParams p) {
     }
 }
 
+// One CTA per image: reduce the per-chunk partial sums (fixed order -> deterministic) and evaluate the k*c gates.
 __global__ void __launch_bounds__(256)
-fusion_apply_kernel(const __grid_constant__ FusionParams p) {
+fusion_gate_kernel(const __grid_constant__ FusionParams p) {
     const specyolo_fusion_t& a = p.a;
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    const int HW = a.H * a.W;
+    const int b = blockIdx.x;
     const int KC = a.k * a.c;
-    extern __shared__ float fs[];  // gate[KC]
-    float* gate = fs;
     __shared__ float s_red[256];
-    __shared__ float s_sab[3 * kFusPix];
-
-    // ---- GCT gates for image b ----
+    __shared__ float s_e[1024];
     float e2_local = 0.f;
     for (int ch = threadIdx.x; ch < KC; ch += 256) {
         float ssq = 0.f;
         for (int q = 0; q < p.nchunks; ++q) ssq += p.part[((size_t)b * p.nchunks + q) * KC + ch];
         const float e = sqrtf(ssq + a.gct_eps) * a.alpha[ch];
-        gate[ch] = e;
+        s_e[ch] = e;
         e2_local += e * e;
     }
     s_red[threadIdx.x] = e2_local;
@@ -189,10 +186,20 @@ fusion_apply_kernel(const __grid_constant__ FusionParams p) {
         __syncthreads();
     }
     const float inv = 1.0f / sqrtf(s_red[0] / (float)KC + a.gct_eps);
-    for (int ch = threadIdx.x; ch < KC; ch += 256) {
-        const float e = gate[ch];
-        gate[ch] = 1.0f + tanhf(e * (a.gamma[ch] * inv) + a.beta[ch]);
-    }
+    for (int ch = threadIdx.x; ch < KC; ch += 256)
+        p.gate[(size_t)b * KC + ch] = 1.0f + tanhf(s_e[ch] * (a.gamma[ch] * inv) + a.beta[ch]);
+}
+
+__global__ void __launch_bounds__(256)
+fusion_apply_kernel(const __grid_constant__ FusionParams p) {
+    const specyolo_fusion_t& a = p.a;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int HW = a.H * a.W;
+    const int KC = a.k * a.c;
+    extern __shared__ float fs[];  // gate[KC]
+    float* gate = fs;
+    __shared__ float s_sab[3 * kFusPix];
+    for (int ch = threadIdx.x; ch < KC; ch += 256) gate[ch] = p.gate[(size_t)b * KC + ch];
 
     // ---- spatial attention logits for this chunk's pixels ----
     const int pix_begin = chunk * kFusPix;
@@ -255,7 +262,7 @@ fusion_apply_kernel(const __grid_constant__ FusionParams p) {
 
 size_t fusion_ws_bytes(int k, int B, int H, int W, int c) {
     const int nchunks = ceil_div(H * W, kFusPix);
-    return ((size_t)B * nchunks * k * c + (size_t)B * k * 2 * H * W) * sizeof(float) + 256;
+    return ((size_t)B * nchunks * k * c + (size_t)B * k * 2 * H * W + (size_t)B * k * c) * sizeof(float) + 256;
 }
 
 int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
@@ -278,12 +285,16 @@ int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a->ws) + 255) & ~(uintptr_t)255);
     p.part = ws;
     p.mm = ws + (size_t)a->B * p.nchunks * a->k * a->c;
+    p.gate = p.mm + (size_t)a->B * a->k * 2 * a->H * a->W;
+    SY_CHECK(a->k * a->c <= 1024, SPECYOLO_ERR_UNSUPPORTED, "fusion: k*c must be <= 1024");
     dim3 grid((unsigned)p.nchunks, (unsigned)a->B);
     fusion_stats_kernel<<<grid, 256, 0, stream>>>(p);
     SY_LAUNCH_CHECK();
+    fusion_gate_kernel<<<a->B, 256, 0, stream>>>(p);
+    SY_LAUNCH_CHECK();
     fusion_apply_kernel<<<grid, 256, (size_t)a->k * a->c * sizeof(float), stream>>>(p);
     SY_LAUNCH_CHECK();
-    count_launch(2);
+    count_launch(3);
     return SPECYOLO_OK;
 }
 

@@ -94,6 +94,10 @@ class _GraphStep:
         self.graph.replay()
         return self.out, self.cnt
 
+    def clone(self, model: DetectionModel, conf, iou, agnostic, max_det, classes) -> "_GraphStep":
+        """A second, independent instance (own static input / outputs) for double-buffered streaming."""
+        return _GraphStep(model, self.static_in, conf, iou, agnostic, max_det, classes)
+
 
 class DetectionPredictor:
     """preprocess -> inference -> postprocess (engine/predictor.py:221-306), all on the device."""
@@ -104,6 +108,8 @@ class DetectionPredictor:
                          use_graph=True)
         self.args.update(overrides or {})
         self._graphs: Dict[tuple, _GraphStep] = {}
+        self._stream_steps: List[Optional[_GraphStep]] = [None, None]   # double-buffered graph instances
+        self._stream_host: list = [None, None]                           # their pinned host result buffers
         self.last_launches = 0
 
     # -- sources ---------------------------------------------------------------------------------
@@ -158,6 +164,89 @@ class DetectionPredictor:
                                     max_det=a["max_det"], classes=classes)
         self.last_launches = int(_lib.load().specyolo_launch_count() - n0)
         return r
+
+    @torch.no_grad()
+    def stream(self, batches):
+        """`predict(source, stream=True)`: generator over an iterable of batches (engine/predictor.py:169-175 yields per
+        batch too).  Two captured graph instances alternate so that the host->device copy of batch i+1 (copy stream)
+        overlaps the forward + NMS of batch i, and the device->host copy of its [B, max_det, 6] result lands in
+        pinned memory while batch i+1 is already running.  Yields List[Results] per batch, in order."""
+        a = self.args
+        dev = next(self.model.parameters()).device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        steps, host_out = self._stream_steps, self._stream_host          # captured once, reused across calls
+        done = [None, None]          # event: results of the batch that used slot s are in pinned host memory
+        uploaded = [None, None]
+        meta: list = [None, None]
+        classes = None
+        if a["classes"] is not None:
+            classes = torch.tensor(list(a["classes"]), device=dev, dtype=torch.int32)
+
+        def prep(item):
+            if isinstance(item, torch.Tensor):
+                im = item if item.dim() == 4 else item.unsqueeze(0)
+                if im.dim() != 4 or im.shape[1] != 3 or im.shape[2] % 32 or im.shape[3] % 32:
+                    raise ValueError(f"WARNING ⚠️ torch.Tensor inputs should be BCHW i.e. shape(1, 3, 640, 640) "
+                                     f"divisible by stride 32. Input shape{tuple(im.shape)} is incompatible.")
+                return im, [tuple(im.shape[2:])] * im.shape[0], [None] * im.shape[0]
+            im, shapes, imgs = self.preprocess(item)
+            return im, shapes, imgs
+
+        def enqueue_upload(slot, item):
+            im, shapes, imgs = prep(item)
+            if steps[slot] is None or steps[slot].static_in.shape != im.shape or steps[slot].static_in.dtype != im.dtype:
+                example = im.to(dev) if not im.is_cuda else im
+                steps[slot] = _GraphStep(self.model, example, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"], classes)
+                host_out[slot] = (torch.empty(steps[slot].out.shape, dtype=torch.float32).pin_memory(),
+                                  torch.empty(steps[slot].cnt.shape, dtype=torch.int32).pin_memory())
+                self.last_launches = steps[slot].launches
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])          # the graph that read this input buffer has finished
+            with torch.cuda.stream(copy_stream):
+                steps[slot].static_in.copy_(im, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            uploaded[slot] = ev
+            meta[slot] = (shapes, imgs, im.shape[0], tuple(im.shape[2:]))
+
+        def launch(slot):
+            main.wait_event(uploaded[slot])
+            steps[slot].graph.replay()
+            host_out[slot][0].copy_(steps[slot].out, non_blocking=True)
+            host_out[slot][1].copy_(steps[slot].cnt, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done[slot] = ev
+
+        def collect(slot):
+            done[slot].synchronize()
+            shapes, imgs, B, img1 = meta[slot]
+            out_h, counts = host_out[slot][0], host_out[slot][1].tolist()
+            return [Results(shapes[b], out_h[b, : counts[b]].clone(), self.model.names, orig_img=imgs[b])
+                    for b in range(B)]
+
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        enqueue_upload(0, first)
+        i = 0
+        pending = None
+        while True:
+            slot = i & 1
+            launch(slot)
+            nxt = next(it, None)
+            if nxt is not None:
+                enqueue_upload(1 - slot, nxt)      # overlaps the graph just launched
+            if pending is not None:
+                yield collect(pending)
+            pending = slot
+            if nxt is None:
+                break
+            i += 1
+        yield collect(pending)
 
     def __call__(self, source) -> List[Results]:
         im, shapes, host_imgs = self.preprocess(source)
@@ -221,8 +310,6 @@ class YOLO:
     def predict(self, source=None, stream=False, predictor=None, **kwargs) -> List[Results]:
         if source is None:
             raise ValueError("source is required (the reference's default assets are not shipped)")
-        if stream:
-            raise NotImplementedError("stream=True generators are outside the hot path")
         custom = {"conf": 0.25}            # engine/model.py:545
         args = {**self.overrides, **custom, **kwargs}
         dev = args.pop("device", None)
@@ -235,6 +322,8 @@ class YOLO:
             self.model.to("cuda")
         if self.predictor is None or any(self.predictor.args.get(k) != v for k, v in args.items()):
             self.predictor = (predictor or DetectionPredictor)(self.model, args)
+        if stream:      # `source` is an iterable of batches; generator of List[Results], copies overlapped with compute
+            return self.predictor.stream(source)
         return self.predictor(source)
 
     __call__ = predict

@@ -76,8 +76,8 @@ def synth_images(batch: int, size: int = 640, seed: int = 0, dtype=torch.float32
     for b in range(batch):
         n = int(torch.randint(4, 13, (1,), generator=g))
         for _ in range(n):
-            w = int(torch.randint(20, 300, (1,), generator=g))
-            h = int(torch.randint(8, 120, (1,), generator=g))
+            w = int(torch.randint(max(2, size // 32), max(3, size * 15 // 32), (1,), generator=g))
+            h = int(torch.randint(max(2, size // 80), max(3, size * 3 // 16), (1,), generator=g))
             x0 = int(torch.randint(0, size - w, (1,), generator=g))
             y0 = int(torch.randint(0, size - h, (1,), generator=g))
             lvl = float(torch.rand((1,), generator=g)) * 0.3 + 0.6

@@ -88,6 +88,8 @@ class PackedConv:
     g: int
     n_pad: int
     act: int
+    g_orig: int = 1          # groups of the source conv (g is the packed, possibly merged, group count)
+    cin_true: int = 0        # input channels of the source conv (cin may be zero-padded to a multiple of 16)
     w_folded_f32: Optional[torch.Tensor] = None   # stem only: fp32 OIHW folded weights
 
     def out_hw(self, H: int, W: int):
@@ -106,18 +108,27 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
     cout, cin_g, kh, kw = w.shape
     if kh != kw:
         raise ValueError("square kernels only")
-    n_pad = lib.specyolo_conv_npad(cout, groups)
+    cin_true = cin_g * groups
+    if groups == 1 and cin_g > 3 and cin_g % 16:
+        # the UMMA K step is 16 channels: thin convs (8 channels in yolo11n's first C3k2) get zero weight columns;
+        # conv2d() zero-extends the activation to match (a plumbing copy on a layer that is 0.2 % of the FLOPs)
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 16 - cin_g % 16))
+        cin_g = w.shape[1]
+    merge = lib.specyolo_conv_merge(cin_g * groups, cout, groups)   # grouped convs: fuse groups up to 64-ch K chunks
+    pgroups = groups // merge
+    n_pad = lib.specyolo_conv_npad(cout, pgroups)
     if n_pad <= 0:
         raise ValueError("bad conv shape")
-    wp = torch.empty((groups * n_pad, kh * kw * cin_g), device=w.device, dtype=torch.bfloat16)
-    bias = torch.empty((groups * n_pad,), device=w.device, dtype=torch.float32)
+    wp = torch.empty((pgroups * n_pad, kh * kw * cin_g * merge), device=w.device, dtype=torch.bfloat16)
+    bias = torch.empty((pgroups * n_pad,), device=w.device, dtype=torch.float32)
     bnt = [None] * 4 if bn is None else [t.detach().to(torch.float32).contiguous() for t in bn]
     cb = None if conv_bias is None else conv_bias.detach().to(torch.float32).contiguous()
     check(lib.specyolo_fold_pack_conv(w.data_ptr(), _p(cb), _p(bnt[0]), _p(bnt[1]), _p(bnt[2]), _p(bnt[3]),
-                                      float(eps), cout, cin_g, kh, kw, groups, n_pad, wp.data_ptr(), bias.data_ptr(),
-                                      _lib.stream_ptr()))
-    pc = PackedConv(wp, bias, cin_g * groups, cout, kh, stride, pad, dil, groups, n_pad,
-                    _lib.ACT_SILU if act else _lib.ACT_NONE)
+                                      float(eps), cout, cin_g, kh, kw, groups, merge, n_pad, wp.data_ptr(),
+                                      bias.data_ptr(), _lib.stream_ptr()))
+    pc = PackedConv(wp, bias, cin_g * groups, cout, kh, stride, pad, dil, pgroups, n_pad,
+                    _lib.ACT_SILU if act else _lib.ACT_NONE, g_orig=groups)
+    pc.cin_true = cin_true
     if cin_g * groups == 3:  # stem: CUDA-core kernel consumes folded fp32 OIHW weights
         if bn is not None:
             scale = bnt[0] / torch.sqrt(bnt[3] + eps)
@@ -134,7 +145,11 @@ def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
     if x.dtype != torch.bfloat16:
         raise TypeError("conv2d expects a bf16 feature map")
     if Cin != pc.cin:
-        raise ValueError(f"conv2d: input has {Cin} channels, weights expect {pc.cin}")
+        if Cin != pc.cin_true:
+            raise ValueError(f"conv2d: input has {Cin} channels, weights expect {pc.cin_true}")
+        xp = torch.zeros((B, H, W, pc.cin), device=x.device, dtype=x.dtype).permute(0, 3, 1, 2)
+        xp[:, :Cin].copy_(x)
+        x, Cin, xpix = xp, pc.cin, pc.cin
     Ho, Wo = pc.out_hw(H, W)
     if out is None:
         out = new_act(B, pc.cout, Ho, Wo, x.device, torch.float32 if out_fp32 else torch.bfloat16)

@@ -90,10 +90,16 @@ def test_layers_vs_oracle(lib):
         assert rel < 3e-2, f"layer {i} ({model.model[i].type}): rel-L2 {rel}"
     y, raw = model(x.cuda())
     y = y.cpu()
-    keep = y_ref[:, 4:].amax(1) > 0.05
-    dbox = (y[:, :4] - y_ref[:, :4]).abs().permute(0, 2, 1)[keep].max().item()
+    # boxes: the DFL expectation over 16 bins turns a ~1 % logit error (bf16 activations, broad random-weight
+    # distributions) into up to ~0.2 bins on the worst anchor, i.e. stride-scaled pixels:
+    # max <= 0.25 * stride per level (2 / 4 / 8 px), mean <= 0.25 px; scores <= 0.03
+    err = (y[:, :4] - y_ref[:, :4]).abs().amax(1)                      # [B, A]
+    A_lvl = [(256 // s) ** 2 for s in (8, 16, 32)]
+    lim = torch.cat([torch.full((n,), 0.25 * s) for n, s in zip(A_lvl, (8, 16, 32))])
+    assert bool((err <= lim).all()), (err / lim).max().item()
+    assert err.mean().item() < 0.25
     dsc = (y[:, 4:] - y_ref[:, 4:]).abs().max().item()
-    assert dbox < 1.0 and dsc < 0.03, (dbox, dsc, worst)
+    assert dsc < 0.03, (dsc, worst)
 
 
 def test_predict_api_and_fused_path(lib):
@@ -117,6 +123,17 @@ def test_predict_api_and_fused_path(lib):
         assert torch.equal(a.boxes.data, c.boxes.data)
         assert torch.equal(a.boxes.data, d.cpu())
         assert a.boxes.data.shape[1] == 6 and a.orig_shape == (320, 320)
+    # stream=True: double-buffered copies, same detections batch by batch
+    batches = [x.cpu().pin_memory(), synth_images(4, 320, seed=7).pin_memory(), x.cpu().pin_memory()]
+    outs = list(yolo.predict(batches, stream=True, conf=0.25, iou=0.7))
+    assert len(outs) == 3 and all(len(o) == 4 for o in outs)
+    for a, c in zip(res_graph, outs[0]):
+        assert torch.equal(a.boxes.data, c.boxes.data)
+    for a, c in zip(outs[0], outs[2]):
+        assert torch.equal(a.boxes.data, c.boxes.data)
+    ref1 = yolo.predict(batches[1].cuda(), conf=0.25, iou=0.7)
+    for a, c in zip(ref1, outs[1]):
+        assert torch.equal(a.boxes.data, c.boxes.data)
     # uint8 HWC BGR ndarray source (predictor.py:125-136 path)
     img = (synth_images(1, 320, seed=6)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)[..., ::-1]
     r = yolo.predict([np.ascontiguousarray(img)], conf=0.25)

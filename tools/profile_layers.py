@@ -28,10 +28,10 @@ def wrap(name):
         if name == "conv2d":
             xx, pc = a[0], a[1]
             Bq, Cin, H, W = xx.shape; Ho, Wo = pc.out_hw(H, W)
-            fl = 2.0 * Bq * Ho * Wo * pc.cout * (pc.cin // pc.g) * pc.k * pc.k
+            fl = 2.0 * Bq * Ho * Wo * pc.cout * (pc.cin // pc.g_orig) * pc.k * pc.k
             by = 2.0 * (xx.numel() + r.numel() * (2 if r.dtype == torch.float32 else 1)) + 2.0 * pc.w.numel()
             if len(a) > 3 and a[3] is not None or k.get("residual") is not None: by += 2.0 * r.numel()
-            desc = f"conv {Cin:4d}->{pc.cout:4d} k{pc.k} s{pc.s} d{pc.d} g{pc.g:3d} {H:3d}x{W:3d} M={Bq*Ho*Wo:8d} K={(pc.cin//pc.g)*pc.k*pc.k:5d}"
+            desc = f"conv {Cin:4d}->{pc.cout:4d} k{pc.k} s{pc.s} d{pc.d} g{pc.g_orig:3d} {H:3d}x{W:3d} M={Bq*Ho*Wo:8d} K={(pc.cin//pc.g_orig)*pc.k*pc.k:5d}"
         rec.append((desc, e0, e1, fl, by)); return r
     setattr(ops, name, g)
 for n in ("conv2d", "stem_conv", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
