@@ -1,0 +1,75 @@
+"""One-process-per-GPU plumbing for the sharded inference path: images / bursts are independent
+units, so a global batch is split contiguously across ranks, every rank runs its own replica of the detector
+on its shard, and nothing crosses NVLink on the data path.  torch.distributed (NCCL on GPUs, gloo in the CPU
+tests) is used only for the barrier around a timed region, the max-over-ranks of the elapsed time and the
+gather of per-rank detection counts.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank() -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) as set by torch.distributed.run; (0, 1, 0) when run directly."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of `n_items` owned by `rank`; the first n_items % world ranks get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def init(backend: str | None = None, device: torch.device | None = None) -> Tuple[int, int]:
+    """Initialise the default process group from the environment when WORLD_SIZE > 1. Returns (rank, world)."""
+    rank, world, _ = env_rank()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return rank, world
+
+
+def barrier() -> None:
+    if dist.is_initialized():
+        dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_counts(counts: torch.Tensor) -> List[torch.Tensor]:
+    """Per-image detection counts of every rank, in global image order (rank 0's shard first)."""
+    if not dist.is_initialized():
+        return [counts]
+    world = dist.get_world_size()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=counts.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([counts.numel()], dtype=torch.int64, device=counts.device))
+    mx = int(max(int(s) for s in sizes))
+    pad = torch.zeros(mx, dtype=counts.dtype, device=counts.device)
+    pad[: counts.numel()] = counts
+    outs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return [o[: int(s)] for o, s in zip(outs, sizes)]
