@@ -180,12 +180,14 @@ def stage_roofline(model, x_dev, peaks):
     wrap("detect_decode", None, lambda r, logits, *a, **k: 4.0 * sum(t.numel() for t in logits))
     wrap("nms", None, None)
     # modules bind `ops.<fn>` at call time through the module attribute, so patching ops is enough
+    ops.CONCURRENT = False          # time every kernel alone (the graph runs independent branches concurrently)
     try:
         torch.cuda.synchronize()
         torch.cuda._sleep(int(4e8))
         model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
         torch.cuda.synchronize()
     finally:
+        ops.CONCURRENT = True
         for n, f in orig.items():
             setattr(ops, n, f)
     agg = {}

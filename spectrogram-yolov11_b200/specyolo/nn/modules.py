@@ -462,23 +462,33 @@ class Detect(nn.Module):
             b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)
 
     def head_logits(self, xs: Sequence[torch.Tensor]):
-        """Runs the cv2 / cv3 branches; returns per-level fp32 [B, h*w, no_stride] buffers and (h, w)."""
-        bufs, hw = [], []
-        for i, x in enumerate(xs):
-            x = _as_fmap(x)
+        """Runs the cv2 / cv3 branches; returns per-level fp32 [B, h*w, no_stride] buffers and (h, w).
+        The 2 x nl branches are independent chains of small convs: they run as parallel streams."""
+        bufs, hw, views, fns = [], [], [], []
+        xs = [_as_fmap(x) for x in xs]
+        for x in xs:
             B, _, H, W = x.shape
             buf = torch.empty((B, H * W, self.no_stride), device=x.device, dtype=torch.float32)
-            view = buf.view(B, H, W, self.no_stride).permute(0, 3, 1, 2)   # [B, no_stride, H, W], NHWC memory
-            t = self.cv2[i][1](self.cv2[i][0](x))
-            ops.conv2d(t, self.cv2[i][2].packed(), out=view[:, : 4 * self.reg_max], out_fp32=True)
-            if self.legacy:
-                t = self.cv3[i][1](self.cv3[i][0](x))
-            else:
-                t = self.cv3[i][0][1](self.cv3[i][0][0](x))
-                t = self.cv3[i][1][1](self.cv3[i][1][0](t))
-            ops.conv2d(t, self.cv3[i][2].packed(), out=view[:, 4 * self.reg_max: self.no], out_fp32=True)
+            views.append(buf.view(B, H, W, self.no_stride).permute(0, 3, 1, 2))   # [B, no_stride, H, W], NHWC memory
             bufs.append(buf)
             hw.append((H, W))
+
+        def box_branch(i):
+            t = self.cv2[i][1](self.cv2[i][0](xs[i]))
+            ops.conv2d(t, self.cv2[i][2].packed(), out=views[i][:, : 4 * self.reg_max], out_fp32=True)
+
+        def cls_branch(i):
+            if self.legacy:
+                t = self.cv3[i][1](self.cv3[i][0](xs[i]))
+            else:
+                t = self.cv3[i][0][1](self.cv3[i][0][0](xs[i]))
+                t = self.cv3[i][1][1](self.cv3[i][1][0](t))
+            ops.conv2d(t, self.cv3[i][2].packed(), out=views[i][:, 4 * self.reg_max: self.no], out_fp32=True)
+
+        for i in range(len(xs)):
+            fns.append(lambda i=i: box_branch(i))
+            fns.append(lambda i=i: cls_branch(i))
+        ops.run_concurrently(fns)
         return bufs, hw
 
     def forward(self, xs: List[torch.Tensor]):

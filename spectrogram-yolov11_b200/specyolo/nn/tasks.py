@@ -171,10 +171,45 @@ class DetectionModel(nn.Module):
             raise NotImplementedError("augment / visualize / embed / profile are outside the hot path")
         return self._predict_once(x)
 
+    def _parallel_groups(self):
+        """Runs of consecutive trunk layers that read only earlier saved outputs (never each other or the running
+        `x`), e.g. the five lateral / DDWConv layers 11-15 of the Spectrogram cfg: they can run concurrently."""
+        if getattr(self, "_groups", None) is None:
+            groups, i, n = {}, 0, len(self.model) - 1
+            while i < n:
+                f = self.model[i].f
+                if isinstance(f, int) and f != -1:
+                    j = i
+                    while j + 1 < n:
+                        fn = self.model[j + 1].f
+                        if isinstance(fn, int) and fn != -1 and fn % (j + 1) < i:
+                            j += 1
+                        else:
+                            break
+                    if j > i and f % i < i:
+                        groups[i] = j
+                        i = j + 1
+                        continue
+                i += 1
+            self._groups = groups
+        return self._groups
+
     def _run_trunk(self, x):
         """All layers except Detect; returns the list of Detect inputs."""
         y = []
-        for m in self.model[:-1]:
+        groups = self._parallel_groups()
+        layers = list(self.model[:-1])
+        i = 0
+        while i < len(layers):
+            m = layers[i]
+            if i in groups:                     # independent layers: fork / join on side streams
+                j = groups[i]
+                outs = ops.run_concurrently([lambda m=layers[k]: m(y[m.f]) for k in range(i, j + 1)])
+                for k, o in zip(range(i, j + 1), outs):
+                    y.append(o if layers[k].i in self.save or k == j else None)
+                x = outs[-1]
+                i = j + 1
+                continue
             if m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             if isinstance(x, UpsampledView) and not isinstance(m, Fusion):
@@ -183,6 +218,7 @@ class DetectionModel(nn.Module):
                 x = [t.materialise() if isinstance(t, UpsampledView) else t for t in x]
             x = m(x)
             y.append(x if m.i in self.save else None)
+            i += 1
         det = self.model[-1]
         return [x if j == -1 else y[j] for j in det.f]
 

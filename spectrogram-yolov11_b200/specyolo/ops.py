@@ -41,6 +41,55 @@ def nhwc_meta(t: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------------------------
+# concurrency: independent chains of small kernels on side streams (fork / join)
+# ----------------------------------------------------------------------------------------------
+_side_streams: dict = {}
+CONCURRENT = True     # bench.py's per-kernel timing pass switches this off so kernels are timed alone
+
+
+def run_concurrently(fns):
+    """Run independent callables on separate CUDA streams, forked from and joined back into the current stream.
+
+    The small layers of the neck and the six Detect branches are 200-3200 tiles each — not enough to fill 148 SMs
+    alone — and they do not depend on each other, so they are issued as parallel branches (under CUDA-graph
+    capture this becomes a fork/join in the graph).  Returns the list of results; tensors inside them are marked as
+    used by the joining stream so the caching allocator cannot recycle them early.
+    """
+    if len(fns) <= 1 or not CONCURRENT:
+        return [f() for f in fns]
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    pool = _side_streams.setdefault(dev.index, [])
+    while len(pool) < len(fns) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    fork = cur.record_event()
+    results, joins = [None] * len(fns), []
+    for i, f in enumerate(fns):
+        if i == 0:
+            continue
+        st = pool[i - 1]
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            results[i] = f()
+            joins.append(st.record_event())
+    results[0] = fns[0]()           # first chain stays on the current stream
+    for ev in joins:
+        cur.wait_event(ev)
+
+    def mark(o):
+        if isinstance(o, torch.Tensor):
+            o.record_stream(cur)
+        elif isinstance(o, (list, tuple)):
+            for t in o:
+                mark(t)
+        elif hasattr(o, "src") and isinstance(getattr(o, "src"), torch.Tensor):
+            o.src.record_stream(cur)
+    for r in results[1:]:
+        mark(r)
+    return results
+
+
+# ----------------------------------------------------------------------------------------------
 # layout
 # ----------------------------------------------------------------------------------------------
 _DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.uint8: _lib.DT_U8}

@@ -19,6 +19,7 @@ yolo.load_state_dict(synth_state_dict(yolo.model, seed=0)); yolo.to("cuda"); yol
 x = synth_images(B, imgsz, seed=0, dtype=torch.uint8).cuda()
 rec = []
 orig = {}
+ops.CONCURRENT = False
 def wrap(name):
     f = getattr(ops, name); orig[name] = f
     def g(*a, **k):
