@@ -70,8 +70,9 @@ int specyolo_fold_pack_conv(const float* w_oihw, const float* conv_bias,
                             const float* bn_mean, const float* bn_var, float bn_eps,
                             int cout, int cin_g, int kh, int kw, int groups, int merge, int n_pad,
                             void* w_packed, float* bias_out, void* stream);
-/* group-merge factor preferred for a grouped conv (1 for dense and depthwise convs) */
-int specyolo_conv_merge(int cin, int cout, int groups);
+/* group-merge factor preferred for a grouped conv with a k x k kernel of the given stride / padding / dilation
+ * (1 for dense and depthwise convs, and for grouped convs the halo-tile kernel runs group by group) */
+int specyolo_conv_merge(int cin, int cout, int groups, int k, int stride, int pad, int dil);
 /* n_pad (per-group padded output channels) the kernels expect for a conv with `groups` (packed) groups */
 int specyolo_conv_npad(int cout, int groups);
 
@@ -102,7 +103,8 @@ typedef struct {
 
 /* y = act(conv(x, W) + b) [+ residual]  — replaces Conv.forward_fuse
  * (ultralytics/nn/modules/conv.py:81-83) after BaseModel.fuse (ultralytics/nn/tasks.py:223-251).
- * Dense and grouped convs with Cin/groups % 16 == 0 run on the tcgen05 implicit-GEMM kernel;
+ * Dense and grouped convs with Cin/groups % 16 == 0 run on the tcgen05 implicit-GEMM kernels (k x k convs whose
+ * weights fit in shared memory on the halo-tile variant, everything else on the per-tap variant);
  * depthwise 3x3 and the 3-channel stem run on dedicated CUDA-core kernels. */
 int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream);
 

@@ -21,6 +21,8 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 // launchers implemented in the other translation units
 int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream);
+int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream);
+bool conv_halo_geometry_ok(int kh, int kw, int stride, int pad, int dil);
 int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream);
 int fold_pack_launch(const float*, const float*, const float*, const float*, const float*, const float*, float,
                      int, int, int, int, int, int, int, void*, float*, cudaStream_t);
@@ -74,10 +76,12 @@ int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C,
     return nhwc_to_nchw_launch(x, x_pixstride, B, C, H, W, y, (cudaStream_t)stream);
 }
 
-int specyolo_conv_merge(int cin, int cout, int groups) {
+int specyolo_conv_merge(int cin, int cout, int groups, int k, int stride, int pad, int dil) {
     if (groups <= 1 || cin <= 0 || cout <= 0 || cin % groups || cout % groups) return 1;
     const int cin_g = cin / groups;
     if (cin_g == 1 && cout / groups == 1) return 1;    // depthwise: dedicated kernel
+    // the halo kernel multiplies every group by its own weight box (UMMA N = cout_g): nothing to merge
+    if (cin_g % 16 == 0 && conv_halo_geometry_ok(k, k, stride, pad, dil)) return 1;
     int merge = 1;
     while (cin_g * merge * 2 <= 64 && groups % (merge * 2) == 0) merge *= 2;
     return merge;
@@ -117,6 +121,8 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
     SY_CHECK(a->x_upshift == 0, SPECYOLO_ERR_UNSUPPORTED, "conv: x_upshift is not implemented");
     if (a->groups == a->Cin && a->Cin == a->Cout && a->groups > 1)
         return dwconv3x3_launch(a, (cudaStream_t)stream);
+    const int r = conv_halo_try_launch(a, (cudaStream_t)stream);   // k x k convs with resident weights
+    if (r >= 0) return r;
     return conv_igemm_launch(a, (cudaStream_t)stream);
 }
 

@@ -44,6 +44,21 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Division by a launch-time constant without the ~100-cycle integer-divide sequence: the single-thread TMA / MMA
+// issue loops are latency chains, so every runtime `/` or `%` in them costs more than the instruction they feed.
+// q = (n * m) >> 40 with m = ceil(2^40 / d) is exact while n * d < 2^40 (checked by the launchers).
+struct FastDiv {
+    uint64_t m;
+    uint32_t d;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    f.m = ((1ull << 40) + d - 1) / d;
+    return f;
+}
+static inline bool fastdiv_ok(uint64_t n_max, uint32_t d) { return n_max * (uint64_t)d < (1ull << 40); }
+
 // Launch counter (bench.py reports gpu_launches from it).
 void count_launch(int n = 1);
 
@@ -52,10 +67,27 @@ void count_launch(int n = 1);
 #ifdef __CUDACC__
 namespace specyolo {
 
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+    return (uint32_t)(((uint64_t)n * f.m) >> 40);
+}
+// n -> (n / d, n % d)
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+    q = fdiv(n, f);
+    r = n - q * f.d;
+}
+
 __device__ __forceinline__ float silu_f(float x) {
     // x * sigmoid(x); __expf error is far below bf16 output resolution
     return __fdividef(x, 1.0f + __expf(-x));
 }
+// SiLU with one MUFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx error ~2^-11, below bf16 resolution)
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -1,0 +1,449 @@
+// Halo-tile implicit-GEMM convolution for sm_100a: k x k convs (k >= 2) whose weights fit in shared memory.
+//
+// The per-tap kernel in conv_igemm.cu issues one TMA box per (tap, channel chunk), so a 3x3 conv pulls its input
+// through the L2 -> SM fabric nine times (a 7x7: 49 times) — that fabric, not HBM or the tensor pipe, bounds every
+// small-channel k x k layer of the network.  Here each CTA
+//   * loads its weights ONCE (all taps, all channel chunks of its groups) and keeps them resident in shared memory
+//     while it walks its share of the output tiles (persistent CTA), and
+//   * loads, per output tile and 64-channel chunk, ONE input box that already contains the halo:
+//     (16 + (k-1)d) x (8 + (k-1)d) pixels for a 16 x 8 output tile.  The box lands as consecutive K-major rows
+//     (one row per pixel, TMA swizzle).  The A operand of tap (ky,kx) is the SAME box read through a UMMA
+//     shared-memory descriptor whose start address is shifted by (ky*d*halo_w + kx*d) rows and whose 8-row-group
+//     stride (SBO) is halo_w rows: row group g of the 128-row operand = the 8 pixels of output row g.  The
+//     swizzle is a function of the absolute shared-memory address, so a shifted, non-1024-aligned start is legal
+//     (tests/cuda/umma_shift_probe.cu checks this on the device).
+// Input traffic drops from taps x to ~1.4 x (3x3) / ~2.4 x (7x7) of the tensor.
+//
+// Strided convs whose taps all fall on one sub-lattice (stride s, dilation and padding multiples of s — DDWConv's
+// k7/s2/d2/p6 and k3/s2/d2/p2, ultralytics/nn/modules/conv.py:694-710) are the same problem on the s-subsampled
+// input: the TMA tensor map's elementStrides do the subsampling.
+//
+// Grouped convs are NOT merged to block-diagonal weights here: a 64-channel A box holds 64/cin_g groups, and each
+// group's 16-channel K step multiplies its own [n_pad x cin_g] weight box into its own TMEM column range
+// (UMMA N = n_pad = 16 for DDWConv) — no multiplications by zero.
+//
+// Warp roles as in conv_igemm.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue;
+// the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the loads / MMAs of tile i+1.
+//
+// Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:81-83) for the k x k layers.
+#include "common.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "epilogue.cuh"
+
+#include <cstdlib>
+
+namespace specyolo {
+
+struct HaloParams {
+    int tiles_w, tiles_h;        // 8-wide x 16-high output tiles per image
+    int B, Ho, Wo;
+    int spatial_tiles;           // B * tiles_h * tiles_w
+    FastDiv d_img, d_tw;         // tile -> (image, tile row, tile column)
+    FastDiv d_cin_g, d_npad;     // channel -> (group, channel in group); accumulator column -> (group, column in group)
+    int kcb_log2;
+    uint32_t tap_a16[49];        // A start-address shift of every tap, 16-byte units
+    int gsplit;                  // CTAs with blockIdx.x % gsplit == s own channel split s
+    int kw, taps;
+    int dil, pad, sub;           // dilation / padding on the subsampled lattice; lattice step (TMA element stride)
+    int halo_w;                  // pixels (= smem rows) per halo line
+    int kc_box, boxes;           // channels per A box; A boxes per tile
+    int cin_g, kc_b, bchunks;    // weight boxes: kc_b channels wide, bchunks per (group, tap)
+    int groups_cta, n_pad, cout_g, cin_cta;
+    int ncols;                   // accumulator columns per tile = groups_cta * n_pad
+    uint32_t a_row_bytes, b_row_bytes;
+    uint32_t a_stage_bytes, a_tx_bytes, b_box_bytes, b_total_bytes, b_region_bytes;
+    int stages;
+    uint32_t tmem_cols;
+    const float* bias;
+    void* y;
+    int y_pixstride, y_fp32;
+    const __nv_bfloat16* residual;
+    int r_pixstride;
+    int act;
+};
+
+static constexpr int kHaloThreads = kConvThreads;
+static constexpr int kHaloTW = 8, kHaloTH = 16;
+static constexpr int kHaloMaxStages = 8;
+static constexpr int kHaloMaxBias = 1024;
+static constexpr int kHaloMaxDynSmem = 222 * 1024;
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;
+    d |= layout << 61;
+    return d;
+}
+
+template <bool kSilu, bool kRes, bool kFp32>
+__global__ void __launch_bounds__(kHaloThreads)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[kHaloMaxBias];
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
+    const int split = blockIdx.x % p.gsplit;
+    const int cta = blockIdx.x / p.gsplit;
+    const int ctas = gridDim.x / p.gsplit;
+
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t off = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+    uint8_t* b_s = smem_raw + off;                  // resident weights
+    uint8_t* a_ring = b_s + p.b_region_bytes;       // halo boxes
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&map_a);
+        ptx::prefetch_tmap(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&tmem_full_bar[b], 1);
+            ptx::mbar_init(&tmem_empty_bar[b], kEpiWarps);
+        }
+        ptx::mbar_init(&w_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    {
+        const float* bsrc = p.bias + (size_t)split * p.ncols;
+        for (int i = threadIdx.x; i < p.ncols; i += kHaloThreads) bias_s[i] = (kSilu ? 0.5f : 1.0f) * bsrc[i];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        // all lanes walk the loops converged (uniform datapath); the elected lane issues
+        {
+            const bool leader = ptx::elect_one();
+            // resident weights: every (group, tap, chunk) box of this CTA's channel split, once
+            if (leader) ptx::mbar_expect_tx(&w_bar, p.b_total_bytes);
+            {
+                uint8_t* dst = b_s;
+                for (int gl = 0; gl < p.groups_cta; ++gl) {
+                    const int row = (split * p.groups_cta + gl) * p.n_pad;
+                    int kcol = 0;
+                    for (int i = 0; i < p.taps * p.bchunks; ++i) {          // (tap, chunk) boxes are consecutive K columns
+                        if (leader) ptx::tma_load_2d(dst, &map_b, &w_bar, kcol, row);
+                        dst += p.b_box_bytes;
+                        kcol += p.kc_b;
+                    }
+                }
+            }
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int tile = cta; tile < p.spatial_tiles; tile += ctas) {
+                uint32_t n, r, th_i, tw_i;
+                fdivmod((uint32_t)tile, p.d_img, n, r);
+                fdivmod(r, p.d_tw, th_i, tw_i);
+                const int w0 = ((int)tw_i * kHaloTW - p.pad) * p.sub;
+                const int h0 = ((int)th_i * kHaloTH - p.pad) * p.sub;
+                int ch = split * p.cin_cta;
+                for (int box = 0; box < p.boxes; ++box) {
+                    ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    if (leader) {
+                        ptx::mbar_expect_tx(&full_bar[stage], p.a_tx_bytes);
+                        ptx::tma_load_4d(a_ring + (size_t)stage * p.a_stage_bytes, &map_a, &full_bar[stage], ch, w0, h0,
+                                         (int)n);
+                    }
+                    ch += p.kc_box;
+                    if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // All lanes walk the loops converged so that descriptors live in uniform registers; the elected lane issues.
+        // No runtime divisions: K step outermost (group / weight-box lookup once per step), taps innermost.
+        {
+            const bool leader = ptx::elect_one();
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_pad);
+            const uint64_t a_hi = halo_desc(0, (uint32_t)p.halo_w * p.a_row_bytes, p.a_row_bytes);
+            const uint64_t b_hi = halo_desc(0, 8u * p.b_row_bytes, p.b_row_bytes);
+            const uint32_t a_ring16 = ptx::smem_u32(a_ring) >> 4, b_base16 = ptx::smem_u32(b_s) >> 4;
+            const uint32_t b_box16 = p.b_box_bytes >> 4;
+            const uint32_t b_tap16 = (uint32_t)p.bchunks * b_box16;       // next tap of the same (group, chunk)
+            const uint32_t b_grp16 = (uint32_t)p.taps * b_tap16;          // next group
+            const int ksteps = p.kc_box / 16;
+            ptx::mbar_wait(&w_bar, 0);
+            ptx::tc_fence_after();
+            int stage = 0;
+            uint32_t ph = 0, tl = 0;
+            for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+                const uint32_t buf = tl & 1u;
+                const uint32_t bph = (tl >> 1) & 1u;
+                ptx::mbar_wait(&tmem_empty_bar[buf], bph ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.ncols;
+                for (int box = 0; box < p.boxes; ++box) {
+                    ptx::mbar_wait(&full_bar[stage], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a16 = a_ring16 + (((uint32_t)stage * p.a_stage_bytes) >> 4);
+                    for (int k = 0; k < ksteps; ++k) {
+                        uint32_t gl, cio;
+                        fdivmod((uint32_t)(box * p.kc_box + k * 16), p.d_cin_g, gl, cio);   // channel inside the split
+                        const uint32_t bc = cio >> p.kcb_log2;
+                        const uint32_t kb = (cio - (bc << p.kcb_log2)) >> 4;
+                        uint32_t b16 = b_base16 + gl * b_grp16 + bc * b_box16 + 2u * kb;
+                        const uint32_t a16k = a16 + 2u * (uint32_t)k;
+                        const uint32_t d_col = d_tmem + gl * (uint32_t)p.n_pad;
+                        uint32_t accumulate = cio == 0 ? 0u : 1u;         // first K step of this group
+                        for (int tap = 0; tap < p.taps; ++tap) {
+                            if (leader)
+                                ptx::umma_bf16(d_col, a_hi | (uint64_t)(a16k + p.tap_a16[tap]), b_hi | (uint64_t)b16, idesc,
+                                               accumulate);
+                            accumulate = 1u;
+                            b16 += b_tap16;
+                        }
+                    }
+                    if (leader) ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+                }
+                if (leader) ptx::umma_commit(&tmem_full_bar[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..9, see epilogue.cuh) =====================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int tw = m & (kHaloTW - 1), th = m >> 3;
+        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
+        EpiCols ec;
+        ec.ncols = p.ncols;
+        ec.n_pad = p.n_pad;
+        ec.d_npad = p.d_npad;
+        ec.cout_g = p.cout_g;
+        ec.within0 = 0;
+        ec.gch0 = split * p.groups_cta * p.cout_g;
+        uint32_t tl = 0;
+        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            uint32_t n, r, th_i, tw_i;
+            fdivmod((uint32_t)tile, p.d_img, n, r);
+            fdivmod(r, p.d_tw, th_i, tw_i);
+            const uint32_t buf = tl & 1u;
+            const uint32_t bph = (tl >> 1) & 1u;
+            const int ow = (int)tw_i * kHaloTW + tw, oh = (int)th_i * kHaloTH + th;
+            const bool row_ok = (ow < p.Wo) && (oh < p.Ho);
+            const size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.ncols;
+
+            ptx::mbar_wait(&tmem_full_bar[buf], bph);
+            ptx::tc_fence_after();
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int halo_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = std::getenv("SPECYOLO_HALO");   // 0 disables the halo path (A/B measurements)
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
+}
+
+// Geometry test shared with fold_pack's merge decision: can this conv run on the halo kernel at all?
+// (the weights-fit test needs n_pad and is done in conv_halo_plan)
+bool conv_halo_geometry_ok(int kh, int kw, int stride, int pad, int dil) {
+    if (!halo_mode()) return false;
+    if (kh != kw || kh < 2 || kh > 7) return false;
+    if (stride < 1 || stride > 2) return false;
+    if (dil % stride || pad % stride) return false;
+    return true;
+}
+
+struct HaloPlan {
+    HaloParams p;
+    size_t smem_bytes;
+    int occ;
+    unsigned grid;
+};
+
+// Returns true and fills `plan` when the conv is eligible for the halo kernel.
+static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
+    if (!conv_halo_geometry_ok(a->kh, a->kw, a->stride, a->pad, a->dil)) return false;
+    const int groups = a->groups;
+    if (a->Cin % groups || a->Cout % groups) return false;
+    const int cin_g = a->Cin / groups, cout_g = a->Cout / groups;
+    if (cin_g % 16 || a->n_pad % 16 || a->n_pad < cout_g || a->n_pad > 256) return false;
+    if (a->x_pixstride % 8 || (reinterpret_cast<uintptr_t>(a->x) & 15)) return false;
+
+    HaloParams p{};
+    p.sub = a->stride;
+    p.dil = a->dil / p.sub;
+    p.pad = a->pad / p.sub;
+    p.kw = a->kw;
+    p.taps = a->kh * a->kw;
+    p.halo_w = kHaloTW + (a->kw - 1) * p.dil;
+    const int halo_h = kHaloTH + (a->kh - 1) * p.dil;
+    if (p.halo_w * p.sub > 256 || halo_h * p.sub > 256) return false;
+    p.cin_g = cin_g;
+    p.cout_g = cout_g;
+    p.n_pad = a->n_pad;
+    p.kc_b = (cin_g % 64 == 0) ? 64 : (cin_g % 32 == 0 ? 32 : 16);
+    p.bchunks = cin_g / p.kc_b;
+    p.b_row_bytes = (uint32_t)p.kc_b * 2;
+    p.b_box_bytes = (uint32_t)p.n_pad * p.b_row_bytes;
+
+    // channel split across CTAs: the smallest that lets the weights stay resident beside a >= 3-deep halo ring
+    // (a 2-deep ring is accepted only if no split reaches 3)
+    bool found = false;
+    int best_stages = 0;
+    for (int gs = 1; gs <= groups && groups % gs == 0 && best_stages < 3; gs *= 2) {
+        const int gcta = groups / gs;
+        const int cin_cta = gcta * cin_g;
+        // one A box spans several whole groups when the groups are thinner than 64 channels
+        const int kc_box = (gcta > 1 && cin_g < 64 && 64 % cin_g == 0 && cin_cta % 64 == 0) ? 64 : p.kc_b;
+        const int ncols = gcta * p.n_pad;
+        if (ncols > 256) continue;
+        const uint32_t a_row = (uint32_t)kc_box * 2;
+        const uint32_t a_tx = (uint32_t)(p.halo_w * halo_h) * a_row;
+        const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
+        const uint32_t b_total = (uint32_t)(gcta * p.taps * p.bchunks) * p.b_box_bytes;
+        const uint32_t b_region = (b_total + 1023u) & ~1023u;
+        if (b_total >= (1u << 20)) continue;                      // mbarrier tx-count limit
+        const long avail = (long)kHaloMaxDynSmem - 1024 - (long)b_region;
+        if (avail < 2L * a_stage) continue;
+        int stages = (int)(avail / a_stage);
+        // two CTAs per SM when everything fits twice: more epilogue warps per SM for the thin-K layers
+        int occ = 1;
+        uint32_t cols = 32;
+        while (cols < 2u * (uint32_t)ncols) cols <<= 1;
+        const long half = 110L * 1024 - 1024 - (long)b_region;
+        if (cols <= 256 && half >= 3L * a_stage) {
+            occ = 2;
+            stages = (int)(half / a_stage);
+        }
+        if (stages > kHaloMaxStages) stages = kHaloMaxStages;
+        if (stages <= best_stages) continue;
+        best_stages = stages;
+        found = true;
+        p.gsplit = gs;
+        p.groups_cta = gcta;
+        p.cin_cta = cin_cta;
+        p.kc_box = kc_box;
+        p.boxes = cin_cta / kc_box;
+        p.ncols = ncols;
+        p.a_row_bytes = a_row;
+        p.a_tx_bytes = a_tx;
+        p.a_stage_bytes = a_stage;
+        p.b_total_bytes = b_total;
+        p.b_region_bytes = b_region;
+        p.stages = stages;
+        p.tmem_cols = cols;
+        plan.occ = occ;
+        plan.smem_bytes = 1024 + (size_t)b_region + (size_t)stages * a_stage;
+    }
+    if (!found) return false;
+
+    p.B = a->B; p.Ho = a->Ho; p.Wo = a->Wo;
+    p.tiles_w = ceil_div(a->Wo, kHaloTW);
+    p.tiles_h = ceil_div(a->Ho, kHaloTH);
+    const long spatial = (long)a->B * p.tiles_w * p.tiles_h;
+    if (spatial <= 0 || spatial >= (1L << 30)) return false;
+    p.spatial_tiles = (int)spatial;
+    p.d_img = make_fastdiv((uint32_t)(p.tiles_w * p.tiles_h));
+    p.d_tw = make_fastdiv((uint32_t)p.tiles_w);
+    p.d_cin_g = make_fastdiv((uint32_t)cin_g);
+    p.d_npad = make_fastdiv((uint32_t)p.n_pad);
+    p.kcb_log2 = p.kc_b == 64 ? 6 : (p.kc_b == 32 ? 5 : 4);
+    if (!fastdiv_ok((uint64_t)spatial, (uint32_t)(p.tiles_w * p.tiles_h)) || p.taps > 49) return false;
+    for (int t = 0; t < p.taps; ++t)
+        p.tap_a16[t] = ((uint32_t)(((t / p.kw) * p.halo_w + (t % p.kw)) * p.dil) * p.a_row_bytes) >> 4;
+    p.bias = a->bias;
+    p.y = a->y; p.y_pixstride = a->y_pixstride; p.y_fp32 = a->y_fp32;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.r_pixstride = a->r_pixstride;
+    p.act = a->act;
+    plan.p = p;
+    const long resident = (long)sm_count() * plan.occ / p.gsplit;           // CTAs per split
+    const long per_split = spatial < resident ? spatial : (resident < 1 ? 1 : resident);
+    plan.grid = (unsigned)(per_split * p.gsplit);
+    return true;
+}
+
+// Returns SPECYOLO_OK after launching, or -1 when the conv is not eligible (caller falls through to the per-tap kernel).
+int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
+    HaloPlan plan{};
+    if (!conv_halo_plan(a, plan)) return -1;
+    EncodeTiledFn encode = get_encode_fn();
+    SY_CHECK(encode != nullptr, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const HaloParams& p = plan.p;
+    const int halo_h = kHaloTH + (a->kh - 1) * p.dil;
+
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t pix_b = (cuuint64_t)a->x_pixstride * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {pix_b, pix_b * a->W, pix_b * a->W * a->H};
+        cuuint32_t box[4] = {(cuuint32_t)p.kc_box, (cuuint32_t)(p.halo_w * p.sub), (cuuint32_t)(halo_h * p.sub), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.sub, (cuuint32_t)p.sub, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.a_row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo A) failed (%d): box %u,%u,%u", (int)r,
+                 box[0], box[1], box[2]);
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)p.taps * p.cin_g;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)a->groups * a->n_pad};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.kc_b, (cuuint32_t)p.n_pad};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->w_packed), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.b_row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo B) failed (%d)", (int)r);
+    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const HaloParams);
+    static const KernelFn kernels[8] = {
+        conv_halo_kernel<false, false, false>, conv_halo_kernel<false, false, true>,
+        conv_halo_kernel<false, true, false>,  conv_halo_kernel<false, true, true>,
+        conv_halo_kernel<true, false, false>,  conv_halo_kernel<true, false, true>,
+        conv_halo_kernel<true, true, false>,   conv_halo_kernel<true, true, true>};
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        for (KernelFn k : kernels) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloMaxDynSmem);
+            if (e != cudaSuccess) attr_err = e;
+        }
+    });
+    SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
+    kernel<<<plan.grid, kHaloThreads, plan.smem_bytes, stream>>>(map_a, map_b, p);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+}  // namespace specyolo

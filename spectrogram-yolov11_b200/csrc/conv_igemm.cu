@@ -20,6 +20,8 @@
 // Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:81-83) = cuDNN conv + bias + SiLU.
 #include "common.h"
 #include "ptx.cuh"
+#include "tma_host.h"
+#include "epilogue.cuh"
 
 #include <cuda.h>
 #include <mutex>
@@ -30,6 +32,8 @@ struct IgemmParams {
     int TW, TH, TN;
     int tiles_w, tiles_h, tiles_n;
     int n_tiles, groups;
+    FastDiv d_ntiles, d_groups, d_tw, d_th;   // tile index -> (nt, g, tw_i, th_i, tn_i)
+    FastDiv d_TW, d_TWTH;                      // accumulator row -> (tw, th, tn)
     int total_tiles;
     int Ho, Wo, B;
     int kh, kw, stride, pad, dil;
@@ -47,7 +51,7 @@ struct IgemmParams {
     int act;
 };
 
-static constexpr int kThreads = 192;
+static constexpr int kThreads = kConvThreads;
 static constexpr int kMaxStages = 8;
 static constexpr int kMaxDynSmem = 200 * 1024;  // opt-in limit is 227 KB minus the static barriers
 static constexpr int kMaxBias = 1024;           // groups * n_pad floats staged in shared memory
@@ -58,31 +62,23 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
     // N tile fastest, then group, then the spatial tile: neighbouring CTAs share the same A box in L2
     TileCoord t;
-    t.nt = tile % p.n_tiles;
-    int r = tile / p.n_tiles;
-    t.g = r % p.groups;
-    r /= p.groups;
-    const int tw_i = r % p.tiles_w;
-    r /= p.tiles_w;
-    const int th_i = r % p.tiles_h;
-    const int tn_i = r / p.tiles_h;
-    t.w0 = tw_i * p.TW;
-    t.h0 = th_i * p.TH;
-    t.n0 = tn_i * p.TN;
+    uint32_t r, nt, g, tw_i, th_i;
+    fdivmod((uint32_t)tile, p.d_ntiles, r, nt);
+    fdivmod(r, p.d_groups, r, g);
+    fdivmod(r, p.d_tw, r, tw_i);
+    fdivmod(r, p.d_th, r, th_i);
+    t.nt = (int)nt;
+    t.g = (int)g;
+    t.w0 = (int)tw_i * p.TW;
+    t.h0 = (int)th_i * p.TH;
+    t.n0 = (int)r * p.TN;
     return t;
-}
-
-// SiLU with one MUFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx error ~2^-11, below bf16 resolution)
-__device__ __forceinline__ float silu_tanh(float x) {
-    const float h = 0.5f * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
 }
 
 // Persistent, warp-specialised: every CTA walks tiles blockIdx.x, +gridDim.x, ...; the TMA ring keeps
 // streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile
 // i overlaps the loads and MMAs of tile i+1.
+template <bool kSilu, bool kRes, bool kFp32>
 __global__ void __launch_bounds__(kThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ IgemmParams p) {
@@ -92,9 +88,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float bias_s[kMaxBias];
+    __shared__ __align__(16) float bias_s[kMaxBias];
 
-    const int warp = threadIdx.x >> 5;
+    // warp index made warp-uniform for the compiler: the role loops below then run on the uniform datapath and
+    // feed UTMALDG / UTCHMMA (which take uniform registers) without a per-instruction R2UR round trip
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
     // 1024-byte aligned operand ring (swizzle-128B atoms repeat every 1024 B)
@@ -113,12 +111,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&tmem_full_bar[b], 1);
-            ptx::mbar_init(&tmem_empty_bar[b], 4);   // one arrival per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[b], kEpiWarps);   // one arrival per epilogue warp
         }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.groups * p.n_pad; i += kThreads) bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.groups * p.n_pad; i += kThreads) bias_s[i] = (kSilu ? 0.5f : 1.0f) * p.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -130,176 +128,120 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int it = 0;
+        // All 32 lanes walk the loops converged (uniform control flow, no runtime divisions: the issue stream is
+        // one long latency chain); the elected lane issues the TMA instructions.
+        {
+            const bool leader = ptx::elect_one();
+            int stage = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile);
-                for (int step = 0; step < steps; ++step, ++it) {
-                    const int stage = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
+                const int ca = tc.g * p.cin_g;
+                const int cw = tc.w0 * p.stride - p.pad, chh = tc.h0 * p.stride - p.pad;
+                const int bn = tc.g * p.n_pad + tc.nt * p.n_tile;
+                int ky = 0, kx = 0, cc = 0, kb = 0;       // running (tap row, tap column, channel chunk, weight K offset)
+                int left = total_chunks;
+                for (int step = 0; step < steps; ++step) {
                     ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
-                    const int q0 = step * p.cps;
-                    const int nch = min(p.cps, total_chunks - q0);
-                    ptx::mbar_expect_tx(&full_bar[stage], nch * (p.a_tx_bytes + p.b_tx_bytes));
+                    const int nch = min(p.cps, left);
+                    left -= nch;
+                    if (leader) ptx::mbar_expect_tx(&full_bar[stage], nch * (p.a_tx_bytes + p.b_tx_bytes));
+                    uint8_t* a_dst = a_ring + (size_t)(stage * p.cps) * p.a_chunk_bytes;
+                    uint8_t* b_dst = b_ring + (size_t)(stage * p.cps) * p.b_chunk_bytes;
                     for (int j = 0; j < nch; ++j) {
-                        const int q = q0 + j;
-                        const int tap = q / p.cin_chunks;
-                        const int cc = q - tap * p.cin_chunks;
-                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                        uint8_t* a_dst = a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes;
-                        uint8_t* b_dst = b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes;
-                        ptx::tma_load_4d(a_dst, &map_a, &full_bar[stage], tc.g * p.cin_g + cc * p.kc,
-                                         tc.w0 * p.stride + kx * p.dil - p.pad,
-                                         tc.h0 * p.stride + ky * p.dil - p.pad, tc.n0);
-                        ptx::tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin_g + cc * p.kc,
-                                         tc.g * p.n_pad + tc.nt * p.n_tile);
+                        if (leader) {
+                            ptx::tma_load_4d(a_dst, &map_a, &full_bar[stage], ca + cc * p.kc, cw + kx * p.dil,
+                                             chh + ky * p.dil, tc.n0);
+                            ptx::tma_load_2d(b_dst, &map_b, &full_bar[stage], kb, bn);
+                        }
+                        a_dst += p.a_chunk_bytes;
+                        b_dst += p.b_chunk_bytes;
+                        kb += p.kc;
+                        if (++cc == p.cin_chunks) {
+                            cc = 0;
+                            if (++kx == p.kw) { kx = 0; ++ky; }
+                        }
                     }
+                    if (++stage == p.stages) { stage = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
+            const bool leader = ptx::elect_one();
             const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_tile);
             const uint32_t row_bytes = p.kc * 2;
             const int kk = p.kc / 16;
-            int it = 0, tl = 0;
+            const uint64_t desc_hi = ptx::umma_smem_desc(0, row_bytes);    // everything but the start address
+            const uint32_t a_ring_addr = ptx::smem_u32(a_ring), b_ring_addr = ptx::smem_u32(b_ring);
+            int stage = 0;
+            uint32_t ph = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-                const int buf = tl & 1;
-                const uint32_t bph = (tl >> 1) & 1;
+                const uint32_t buf = tl & 1u;
+                const uint32_t bph = (tl >> 1) & 1u;
                 ptx::mbar_wait(&tmem_empty_bar[buf], bph ^ 1u);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.n_tile);
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.n_tile;
                 uint32_t accumulate = 0;
-                for (int step = 0; step < steps; ++step, ++it) {
-                    const int stage = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
+                int left = total_chunks;
+                for (int step = 0; step < steps; ++step) {
                     ptx::mbar_wait(&full_bar[stage], ph);
                     ptx::tc_fence_after();
-                    const int q0 = step * p.cps;
-                    const int nch = min(p.cps, total_chunks - q0);
+                    const int nch = min(p.cps, left);
+                    left -= nch;
+                    // descriptor start-address fields (16-byte units) of the first chunk of this stage
+                    uint32_t a16 = (a_ring_addr + (uint32_t)(stage * p.cps) * p.a_chunk_bytes) >> 4;
+                    uint32_t b16 = (b_ring_addr + (uint32_t)(stage * p.cps) * p.b_chunk_bytes) >> 4;
                     for (int j = 0; j < nch; ++j) {
-                        const uint32_t a_addr =
-                            ptx::smem_u32(a_ring + (size_t)(stage * p.cps + j) * p.a_chunk_bytes);
-                        const uint32_t b_addr =
-                            ptx::smem_u32(b_ring + (size_t)(stage * p.cps + j) * p.b_chunk_bytes);
                         for (int k = 0; k < kk; ++k) {
-                            const uint64_t da = ptx::umma_smem_desc(a_addr + k * 32, row_bytes);
-                            const uint64_t db = ptx::umma_smem_desc(b_addr + k * 32, row_bytes);
-                            ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
+                            if (leader)
+                                ptx::umma_bf16(d_tmem, desc_hi | (uint64_t)(a16 + 2u * k), desc_hi | (uint64_t)(b16 + 2u * k),
+                                               idesc, accumulate);
                             accumulate = 1;
                         }
+                        a16 += p.a_chunk_bytes >> 4;
+                        b16 += p.b_chunk_bytes >> 4;
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (leader) ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; ph ^= 1u; }
                 }
-                ptx::umma_commit(&tmem_full_bar[buf]);    // accumulator complete
+                if (leader) ptx::umma_commit(&tmem_full_bar[buf]);    // accumulator complete
             }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9, see epilogue.cuh) =====================
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;     // which half of the tile's column chunks
         const int m = quad * 32 + lane;       // accumulator row = pixel inside the tile
         const int npix = p.TW * p.TH * p.TN;
-        const int tw = m % p.TW;
-        const int th = (m / p.TW) % p.TH;
-        const int tn = m / (p.TW * p.TH);
-        const bool silu = p.act == SPECYOLO_ACT_SILU;
-        int tl = 0;
+        uint32_t tn_u, th_u, tw_u, rem_u;
+        fdivmod((uint32_t)m, p.d_TWTH, tn_u, rem_u);
+        fdivmod(rem_u, p.d_TW, th_u, tw_u);
+        const int tw = (int)tw_u, th = (int)th_u, tn = (int)tn_u;
+        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
+        EpiCols ec;
+        ec.ncols = p.n_tile;
+        ec.n_pad = 1 << 20;                   // the tile is a slice of ONE group: column -> (0, within0 + column)
+        ec.d_npad = FastDiv{1ull << 20, 1u << 20};
+        ec.cout_g = p.cout_g;
+        uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
             const TileCoord tc = decode_tile(p, tile);
-            const int buf = tl & 1;
-            const uint32_t bph = (tl >> 1) & 1;
+            const uint32_t buf = tl & 1u;
+            const uint32_t bph = (tl >> 1) & 1u;
             const int ow = tc.w0 + tw, oh = tc.h0 + th, on = tc.n0 + tn;
             const bool row_ok = (m < npix) && (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
             const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
-            const int ch_base = tc.nt * p.n_tile;             // channel offset inside the group
-            const int gch_base = tc.g * p.cout_g + ch_base;   // channel offset inside the output window
-            const float* bias = bias_s + tc.g * p.n_pad + ch_base;
-            const bool y_vec_ok = !p.y_fp32 && (p.y_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
-                                  ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-            const bool y32_vec_ok = p.y_fp32 && (p.y_pixstride % 4 == 0) && (gch_base % 4 == 0) &&
-                                    ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-            const bool r_vec_ok = p.residual && (p.r_pixstride % 8 == 0) && (gch_base % 8 == 0) &&
-                                  ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.n_tile);
+            ec.within0 = tc.nt * p.n_tile;            // channel offset inside the group
+            ec.gch0 = tc.g * p.cout_g;                // group offset inside the output window
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.n_tile;
 
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
             ptx::tc_fence_after();
-
-            uint32_t va[16], vb[16];
-            ptx::tmem_ld16(t_addr, va);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c = c0 + half * 16;
-                    if (c >= p.n_tile) break;
-                    uint32_t(&v)[16] = half ? vb : va;
-                    uint32_t(&vn)[16] = half ? va : vb;
-                    // residual for this chunk: issue the loads before waiting on TMEM
-                    const int nvalid = min(16, p.cout_g - (ch_base + c));
-                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-                    const bool res_vec = r_vec_ok && row_ok && nvalid == 16;
-                    if (res_vec) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.r_pixstride + gch_base + c);
-                        r0 = __ldg(rp);
-                        r1 = __ldg(rp + 1);
-                    }
-                    ptx::tmem_ld_wait();                               // v is ready
-                    if (c + 16 < p.n_tile) ptx::tmem_ld16(t_addr + (uint32_t)(c + 16), vn);   // prefetch next
-                    if (!row_ok || nvalid <= 0) continue;
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float t = __uint_as_float(v[i]) + bias[c + i];
-                        f[i] = silu ? silu_tanh(t) : t;
-                    }
-                    if (p.residual) {
-                        if (res_vec) {
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 t = unpack_bf16x2(rr[i]);
-                                f[2 * i] += t.x;
-                                f[2 * i + 1] += t.y;
-                            }
-                        } else {
-                            const __nv_bfloat16* r = p.residual + pix * p.r_pixstride + gch_base + c;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < nvalid) f[i] += __bfloat162float(r[i]);
-                        }
-                    }
-                    if (p.y_fp32) {
-                        float* y = reinterpret_cast<float*>(p.y) + pix * p.y_pixstride + gch_base + c;
-                        if (y32_vec_ok && nvalid == 16) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                reinterpret_cast<float4*>(y)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < nvalid) y[i] = f[i];
-                        }
-                    } else {
-                        __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pixstride + gch_base + c;
-                        if (y_vec_ok && nvalid == 16) {
-                            uint4 o0, o1;
-                            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                            reinterpret_cast<uint4*>(y)[0] = o0;
-                            reinterpret_cast<uint4*>(y)[1] = o1;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < nvalid) y[i] = __float2bfloat16_rn(f[i]);
-                        }
-                    }
-                }
-            }
-            // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s + tc.g * p.n_pad + ec.within0, eo, pix, row_ok, half);
+            // all TMEM reads of this accumulator are complete (wait::ld inside): hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
@@ -314,31 +256,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
-                cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess) {
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-        }
-    });
-    return fn;
-}
-
-static CUtensorMapSwizzle swizzle_for(int row_bytes) {
-    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
 // Pick the output tile (TW,TH,TN), TW*TH*TN <= 128, that needs the fewest CTAs.
 static void choose_tile(int B, int Ho, int Wo, int stride, int& TW, int& TH, int& TN) {
     long best_tiles = -1;
@@ -410,6 +327,17 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     const long total_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * groups;
     SY_CHECK(total_tiles > 0 && total_tiles < (1L << 30), SPECYOLO_ERR_INVALID, "bad tile count");
     p.total_tiles = (int)total_tiles;
+    p.d_ntiles = make_fastdiv((uint32_t)p.n_tiles);
+    p.d_groups = make_fastdiv((uint32_t)groups);
+    p.d_tw = make_fastdiv((uint32_t)p.tiles_w);
+    p.d_th = make_fastdiv((uint32_t)p.tiles_h);
+    p.d_TW = make_fastdiv((uint32_t)p.TW);
+    p.d_TWTH = make_fastdiv((uint32_t)(p.TW * p.TH));
+    {
+        uint32_t dmax = 128;
+        for (int d : {p.n_tiles, groups, p.tiles_w, p.tiles_h}) dmax = (uint32_t)d > dmax ? (uint32_t)d : dmax;
+        SY_CHECK(fastdiv_ok((uint64_t)total_tiles, dmax), SPECYOLO_ERR_UNSUPPORTED, "too many tiles for the fast tile decode");
+    }
     SY_CHECK(groups * a->n_pad <= kMaxBias, SPECYOLO_ERR_UNSUPPORTED, "too many output channels (%d)", groups * a->n_pad);
 
     const int row_bytes = kc * 2;
@@ -469,24 +397,27 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
     }
 
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const IgemmParams);
+    static const KernelFn kernels[8] = {
+        conv_igemm_kernel<false, false, false>, conv_igemm_kernel<false, false, true>,
+        conv_igemm_kernel<false, true, false>,  conv_igemm_kernel<false, true, true>,
+        conv_igemm_kernel<true, false, false>,  conv_igemm_kernel<true, false, true>,
+        conv_igemm_kernel<true, true, false>,   conv_igemm_kernel<true, true, true>};
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kMaxDynSmem);
+        for (KernelFn k : kernels) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+            if (e != cudaSuccess) attr_err = e;
+        }
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
              cudaGetErrorString(attr_err));
 
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        SY_CUDA(cudaGetDevice(&dev));
-        SY_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const long resident = (long)num_sms * occ;
+    const long resident = (long)sm_count() * occ;
     const unsigned grid = (unsigned)(total_tiles < resident ? total_tiles : resident);
-    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+    const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
+    kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

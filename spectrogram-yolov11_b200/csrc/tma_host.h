@@ -1,0 +1,46 @@
+// Host-side TMA helpers shared by the implicit-GEMM launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+
+namespace specyolo {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        }
+    });
+    return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n = 148;
+    }
+    return n;
+}
+
+}  // namespace specyolo

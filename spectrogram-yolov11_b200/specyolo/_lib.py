@@ -90,7 +90,7 @@ SIGNATURES = {
                                                  C.c_void_p, C.c_void_p]),
     "specyolo_fold_pack_conv": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 7 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "specyolo_conv_merge": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "specyolo_conv_merge": (C.c_int, [C.c_int] * 7),
     "specyolo_conv_npad": (C.c_int, [C.c_int, C.c_int]),
     "specyolo_conv2d_bias_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "specyolo_stem_conv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -163,7 +163,7 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
         # conv2d() zero-extends the activation to match (a plumbing copy on a layer that is 0.2 % of the FLOPs)
         w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 16 - cin_g % 16))
         cin_g = w.shape[1]
-    merge = lib.specyolo_conv_merge(cin_g * groups, cout, groups)   # grouped convs: fuse groups up to 64-ch K chunks
+    merge = lib.specyolo_conv_merge(cin_g * groups, cout, groups, kh, stride, pad, dil)   # grouped convs on the per-tap kernel: fuse groups up to 64-ch K chunks
     pgroups = groups // merge
     n_pad = lib.specyolo_conv_npad(cout, pgroups)
     if n_pad <= 0:

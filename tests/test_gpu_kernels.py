@@ -62,6 +62,13 @@ CONV_CASES = [
     (128, 128, 7, 2, 2, 8, 2, 32, 32, True, False),     # DDWConv.conv1 (layer 11)
     (256, 128, 3, 2, 2, 8, 2, 40, 40, True, False),     # DDWConv.conv1 (layer 13)
     (64, 64, 3, 1, 1, 1, 1, 7, 9, True, False),         # ragged spatial size
+    # halo-tile kernel: resident weights, one halo box per tile, taps as shifted UMMA descriptors
+    (128, 64, 3, 1, 1, 1, 2, 24, 40, True, False),      # two 64-channel weight chunks per tap
+    (64, 32, 3, 1, 1, 1, 16, 64, 64, True, True),       # 512 tiles: every persistent CTA walks several
+    (32, 32, 3, 1, 2, 1, 2, 20, 20, True, False),       # dilation 2, stride 1
+    (32, 48, 5, 1, 1, 1, 1, 19, 21, True, False),       # 5x5, Cout not a multiple of 16... of 32
+    (64, 64, 7, 2, 2, 4, 2, 36, 28, True, False),       # grouped, sub-lattice stride 2
+    (128, 128, 3, 1, 1, 1, 2, 20, 20, True, True),      # weights too large to stay resident: per-tap kernel
 ]
 
 
