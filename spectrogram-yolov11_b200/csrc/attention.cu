@@ -1,163 +1,284 @@
-// PSA attention core of C2PSA (ultralytics/nn/modules/block.py:1922-1933):
+// PSA attention core of C2PSA (ultralytics/nn/modules/block.py:1922-1933) on tcgen05 / TMEM:
 //   q,k,v = qkv.view(B, heads, 2*kd+hd, N).split([kd,kd,hd], 2)
 //   attn = softmax((q^T k) * scale, -1);  x = v @ attn^T  + pe(v)      (pe = depthwise 3x3 + folded BN)
-// The reference materialises the B x heads x N x N matrix through two cuBLAS bmm and a softmax
-// kernel; here the scores never leave the SM (online softmax, flash style).
+// The reference materialises the B x heads x N x N matrix through two cuBLAS bmm and a softmax kernel; here the
+// scores live in TMEM and the probabilities in shared memory only.
 //
-// v1 maps the work onto CUDA cores: N is 400 (640^2) or 1600 (1280^2) tokens with kd = 32, hd = 64,
-// i.e. 0.12 GFLOP of the 19 GFLOP per image.  CTA = 64 queries of one (image, head); 4 threads share
-// a query, each walking a quarter of the keys of every 64-key tile staged in shared memory, with
-// private running (max, sum, acc[hd]) merged by shuffles at the end.
+// CTA = 128 queries of one (image, head); kd = 32, hd = 64 (every YOLO11 scale).  Keys / values stream through a
+// 2-stage TMA ring in blocks of 128 tokens read straight from the NHWC qkv tensor (3-D tensor map {channel, token,
+// image}: tokens past N are zero-filled and masked).  Two sweeps over the keys, so any N works (400 tokens at 640^2,
+// 1600 at 1280^2) without rescaling an accumulator:
+//   sweep 1:  S = Q K_j^T  (UMMA 128x128x32, fp32 in TMEM)  ->  row maximum m
+//   sweep 2:  S = Q K_j^T again -> P = exp2((S - m) * scale*log2e) as bf16, written to shared memory in the
+//             K-major SWIZZLE_128B operand layout, row sums l accumulated in fp32;
+//             O += P V_j  (UMMA 128x64x128; V_j is the [token][channel] tile as TMA wrote it = an MN-major B operand)
+//   end:      x = O / l + pe(v) -> bf16 NHWC store.  pe(v) (9 taps x 64 channels per token) is read from L2.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 softmax / epilogue (one query row per
+// thread: TMEM lane = row, so the row reductions need no shuffles).  TMEM: 128 (S) + 64 (O) columns -> two CTAs
+// per SM overlap one tile's softmax with the other's MMAs.
 #include "common.h"
+#include "ptx.cuh"
+#include "tma_host.h"
 
 namespace specyolo {
 
-static constexpr int kAttQ = 64;    // queries per CTA
-static constexpr int kAttK = 64;    // keys per smem tile
 static constexpr int KD = 32, HD = 64;
+static constexpr int kAttThreads = 192;
+static constexpr int kAttQ = 128;            // queries per CTA (UMMA M)
+static constexpr int kAttKB = 128;           // keys per block
+static constexpr uint32_t kQBytes = kAttQ * KD * 2;        // 8 KB, 64-byte rows, SWIZZLE_64B
+static constexpr uint32_t kKBytes = kAttKB * KD * 2;       // 8 KB
+static constexpr uint32_t kVBytes = kAttKB * HD * 2;       // 16 KB, 128-byte rows, SWIZZLE_128B
+static constexpr uint32_t kPBytes = kAttQ * kAttKB * 2;    // 32 KB: two [128 rows x 64 keys] K-major SW128 chunks
+static constexpr uint32_t kAttSmem = 1024 + kQBytes + 2 * (kKBytes + kVBytes) + kPBytes;   // 89 KB
+static constexpr uint32_t kAttTmemCols = 256;              // S at column 0, O at column 128
 
-__global__ void __launch_bounds__(256)
-psa_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_pixstride, int H, int W, int heads,
-                     float scale_log2e, const float* __restrict__ pe_w, const float* __restrict__ pe_b,
-                     __nv_bfloat16* __restrict__ out, int out_pixstride) {
-    const int N = H * W;
-    const int b = blockIdx.z, head = blockIdx.y;
-    const int q0 = blockIdx.x * kAttQ;
-    const int tid = threadIdx.x;
-    const int ql = tid >> 2;       // local query
-    const int part = tid & 3;      // key quarter
-    const int qi = q0 + ql;
-    const int per_head = 2 * KD + HD;
-    const __nv_bfloat16* base = qkv + (size_t)b * N * qkv_pixstride + head * per_head;
+struct AttParams {
+    int N, H, W, heads, nblk;
+    float scale_log2e;
+    const __nv_bfloat16* qkv;
+    int qkv_pixstride;
+    const float* pe_w;
+    const float* pe_b;
+    __nv_bfloat16* out;
+    int out_pixstride;
+};
 
-    __shared__ __align__(16) __nv_bfloat16 sK[kAttK][KD + 8];   // +8 pad: rows 80 B apart
-    __shared__ __align__(16) __nv_bfloat16 sV[kAttK][HD + 8];
+__global__ void __launch_bounds__(kAttThreads)
+psa_attention_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
+                     const __grid_constant__ AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_empty, p_full, p_empty, o_full;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float pe_ws[9 * HD];    // [tap][d]
+    __shared__ __align__(16) float pe_bs[HD];
 
-    // query row in registers, pre-scaled by scale*log2(e) so that exp2f can be used
-    float q[KD];
-    if (qi < N) {
-        const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)qi * qkv_pixstride);
-#pragma unroll
-        for (int i = 0; i < KD / 8; ++i) {
-            const uint4 u = __ldg(qp + i);
-            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(uu[j]);
-                q[i * 8 + 2 * j] = f.x * scale_log2e;
-                q[i * 8 + 2 * j + 1] = f.y * scale_log2e;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kAttQ, head = blockIdx.y, b = blockIdx.z;
+    const int ch0 = head * (2 * KD + HD);
+
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* q_s = base;
+    uint8_t* k_s = q_s + kQBytes;                 // 2 stages
+    uint8_t* v_s = k_s + 2 * kKBytes;             // 2 stages
+    uint8_t* p_s = v_s + 2 * kVBytes;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&map_qk);
+        ptx::prefetch_tmap(&map_v);
+        ptx::mbar_init(&q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&kv_full[s], 1);
+            ptx::mbar_init(&kv_empty[s], 1);
+        }
+        ptx::mbar_init(&s_full, 1);
+        ptx::mbar_init(&s_empty, 4);
+        ptx::mbar_init(&p_full, 4);
+        ptx::mbar_init(&p_empty, 1);
+        ptx::mbar_init(&o_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, kAttTmemCols);
+    for (int i = threadIdx.x; i < 9 * HD; i += kAttThreads) {
+        const int tap = i / HD, d = i - tap * HD;
+        pe_ws[i] = p.pe_w[(head * HD + d) * 9 + tap];
+    }
+    for (int i = threadIdx.x; i < HD; i += kAttThreads) pe_bs[i] = p.pe_b[head * HD + i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+    const int nblk = p.nblk;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const bool leader = ptx::elect_one();
+        if (leader) {
+            ptx::mbar_expect_tx(&q_full, kQBytes);
+            ptx::tma_load_3d(q_s, &map_qk, &q_full, ch0, q0, b);
+        }
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int j = 0; j < nblk; ++j) {
+                ptx::mbar_wait(&kv_empty[stage], ph ^ 1u);
+                if (leader) {
+                    ptx::mbar_expect_tx(&kv_full[stage], sweep ? kKBytes + kVBytes : kKBytes);
+                    ptx::tma_load_3d(k_s + stage * kKBytes, &map_qk, &kv_full[stage], ch0 + KD, j * kAttKB, b);
+                    if (sweep) ptx::tma_load_3d(v_s + stage * kVBytes, &map_v, &kv_full[stage], ch0 + 2 * KD, j * kAttKB, b);
+                }
+                if (++stage == 2) { stage = 0; ph ^= 1u; }
             }
         }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc_s = ptx::umma_idesc_bf16(128, kAttKB);
+        const uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, HD);
+        const uint64_t dq = ptx::umma_desc(ptx::smem_u32(q_s), 0, 8 * 64, 64);
+        const uint64_t dp = ptx::umma_desc(ptx::smem_u32(p_s), 0, 8 * 128, 128);
+        ptx::mbar_wait(&q_full, 0);
+        int stage = 0;
+        uint32_t ph = 0, s_ph = 0, p_ph = 0;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int j = 0; j < nblk; ++j) {
+                ptx::mbar_wait(&kv_full[stage], ph);
+                ptx::mbar_wait(&s_empty, s_ph ^ 1u);          // softmax warps have read the previous S
+                s_ph ^= 1u;
+                ptx::tc_fence_after();
+                const uint64_t dk = ptx::umma_desc(ptx::smem_u32(k_s + stage * kKBytes), 0, 8 * 64, 64);
+                if (leader) {
+                    ptx::umma_bf16(tmem_s, dq, dk, idesc_s, 0u);
+                    ptx::umma_bf16(tmem_s, dq + 2, dk + 2, idesc_s, 1u);        // K step 2: +32 bytes
+                    ptx::umma_commit(&s_full);
+                }
+                if (sweep) {
+                    ptx::mbar_wait(&p_full, p_ph);             // P_j is in shared memory
+                    p_ph ^= 1u;
+                    ptx::tc_fence_after();
+                    const uint64_t dv = ptx::umma_desc(ptx::smem_u32(v_s + stage * kVBytes), 0, 8 * 128, 128);
+                    if (leader) {
+#pragma unroll
+                        for (int kk = 0; kk < kAttKB / 16; ++kk) {
+                            // A: 16 keys = 32 bytes inside the 64-key chunk kk/4; B: 16 token rows = 2048 bytes
+                            const uint64_t da = dp + (uint64_t)(((kk >> 2) * (kAttQ * 128) + (kk & 3) * 32) >> 4);
+                            ptx::umma_bf16(tmem_o, da, dv + (uint64_t)((kk * 2048) >> 4), idesc_o, (j | kk) ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&p_empty);
+                    }
+                }
+                if (leader) ptx::umma_commit(&kv_empty[stage]);
+                if (++stage == 2) { stage = 0; ph ^= 1u; }
+            }
+        }
+        if (leader) ptx::umma_commit(&o_full);
     } else {
+        // ===================== softmax / epilogue (warps 2..5) =====================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                       // query inside the tile = TMEM lane
+        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+        const float c = p.scale_log2e;
+        uint32_t s_ph = 0, pe_ph = 0;
+        float m = -INFINITY, l = 0.f;
+        // ---- sweep 1: row maximum ----
+        for (int j = 0; j < nblk; ++j) {
+            ptx::mbar_wait(&s_full, s_ph);
+            s_ph ^= 1u;
+            ptx::tc_fence_after();
+            const int kvalid = min(kAttKB, p.N - j * kAttKB);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kAttKB; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld32(tmem_s + t_lane + c0, v);
+                ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < KD; ++i) q[i] = 0.f;
-    }
-
-    float m = -INFINITY, l = 0.f;
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-
-    for (int k0 = 0; k0 < N; k0 += kAttK) {
-        __syncthreads();
-        // stage K (64 x 32) and V (64 x 64) tiles: 16-byte vectors
-        for (int i = tid; i < kAttK * (KD / 8); i += 256) {
-            const int r = i / (KD / 8), c = i % (KD / 8);
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (k0 + r < N) u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(k0 + r) * qkv_pixstride + KD) + c);
-            *reinterpret_cast<uint4*>(&sK[r][c * 8]) = u;
-        }
-        for (int i = tid; i < kAttK * (HD / 8); i += 256) {
-            const int r = i / (HD / 8), c = i % (HD / 8);
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (k0 + r < N) u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(k0 + r) * qkv_pixstride + 2 * KD) + c);
-            *reinterpret_cast<uint4*>(&sV[r][c * 8]) = u;
-        }
-        __syncthreads();
-        const int kend = min(kAttK, N - k0);
-        for (int j = part; j < kend; j += 4) {
-            float s = 0.f;
-            const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(&sK[j][0]);
-#pragma unroll
-            for (int i = 0; i < KD / 2; ++i) {
-                const float2 f = __bfloat1622float2(kr[i]);
-                s = fmaf(q[2 * i], f.x, s);
-                s = fmaf(q[2 * i + 1], f.y, s);
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < kvalid) m = fmaxf(m, __uint_as_float(v[i]));
             }
-            const float mn = fmaxf(m, s);
-            const float corr = exp2f(m - mn);   // m = -inf on first key -> 0
-            const float pj = exp2f(s - mn);
-            l = l * corr + pj;
-            const __nv_bfloat162* vr = reinterpret_cast<const __nv_bfloat162*>(&sV[j][0]);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&s_empty);
+        }
+        const float mc = m * c;
+        // ---- sweep 2: P = exp2(S*c - m*c) -> shared memory (bf16, UMMA A layout), l = row sum ----
+        uint8_t* p_row = p_s + row * 128;
+        const uint32_t sw = (uint32_t)(row & 7);
+        for (int j = 0; j < nblk; ++j) {
+            ptx::mbar_wait(&s_full, s_ph);
+            s_ph ^= 1u;
+            ptx::mbar_wait(&p_empty, pe_ph ^ 1u);               // previous P·V has finished reading P
+            pe_ph ^= 1u;
+            ptx::tc_fence_after();
+            const int kvalid = min(kAttKB, p.N - j * kAttKB);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kAttKB; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld32(tmem_s + t_lane + c0, v);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
 #pragma unroll
-            for (int d = 0; d < HD / 2; ++d) {
-                const float2 f = __bfloat1622float2(vr[d]);
-                acc[2 * d] = fmaf(acc[2 * d], corr, pj * f.x);
-                acc[2 * d + 1] = fmaf(acc[2 * d + 1], corr, pj * f.y);
+                for (int i = 0; i < 16; ++i) {
+                    float e0 = exp2f(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+                    float e1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+                    if (c0 + 2 * i >= kvalid) e0 = 0.f;
+                    if (c0 + 2 * i + 1 >= kvalid) e1 = 0.f;
+                    // the sum uses the bf16-rounded probabilities the tensor core will multiply
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(e0, e1);
+                    const float2 pf = __bfloat1622float2(pb);
+                    l += pf.x + pf.y;
+                    pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
+                }
+                // 32 keys = 4 x 16-byte units of this row; unit index inside the 64-key chunk is swizzled by row % 8
+                uint8_t* chunk = p_row + (c0 >> 6) * (kAttQ * 128);
+                const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ sw) << 4)) =
+                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
             }
-            m = mn;
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async();                           // generic-proxy writes of P -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(&s_empty);
+                ptx::mbar_arrive(&p_full);
+            }
         }
-    }
-    // merge the 4 partial softmax states of a query (lanes 4q..4q+3)
+        // ---- epilogue: O / l + pe(v) ----
+        ptx::mbar_wait(&o_full, 0);
+        ptx::tc_fence_after();
+        const int qi = q0 + row;
+        const float inv_l = 1.0f / l;
+        const int h = qi / p.W, w = qi - h * p.W;
+        const __nv_bfloat16* vbase = p.qkv + (size_t)b * p.N * p.qkv_pixstride + ch0 + 2 * KD;
+        __nv_bfloat16* op = p.out + ((size_t)b * p.N + qi) * p.out_pixstride + head * HD;
+#pragma unroll 1
+        for (int d0 = 0; d0 < HD; d0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld16(tmem_o + t_lane + d0, v);
+            ptx::tmem_ld_wait();
+            if (qi >= p.N) continue;
+            float res[16];
 #pragma unroll
-    for (int off = 1; off < 4; off <<= 1) {
-        const float mo = __shfl_xor_sync(0xffffffffu, m, off);
-        const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-        const float mn = fmaxf(m, mo);
-        const float c0 = (m == -INFINITY) ? 0.f : exp2f(m - mn);
-        const float c1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-        l = l * c0 + lo * c1;
+            for (int i = 0; i < 16; ++i) res[i] = fmaf(__uint_as_float(v[i]), inv_l, pe_bs[d0 + i]);
+            for (int ky = 0; ky < 3; ++ky) {
+                const int hh = h + ky - 1;
+                if (hh < 0 || hh >= p.H) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ww = w + kx - 1;
+                    if (ww < 0 || ww >= p.W) continue;
+                    const uint4* vp = reinterpret_cast<const uint4*>(vbase + (size_t)(hh * p.W + ww) * p.qkv_pixstride + d0);
+                    const float* wt = pe_ws + (ky * 3 + kx) * HD + d0;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) {
-            const float ao = __shfl_xor_sync(0xffffffffu, acc[d], off);
-            acc[d] = acc[d] * c0 + ao * c1;
-        }
-        m = mn;
-    }
-    if (qi >= N) return;
-    // each of the 4 threads finishes 16 of the 64 head channels: + pe(v) (depthwise 3x3) and store
-    const float inv_l = 1.0f / l;
-    const int h = qi / W, w = qi % W;
-    const int dbase = part * 16;
-    float res[16];
+                    for (int half = 0; half < 2; ++half) {
+                        const uint4 u = __ldg(vp + half);
+                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-        // static indexing of acc[] requires the unrolled select below
-        float a = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp)
-            if (pp == part) a = acc[pp * 16 + d];
-        res[d] = a * inv_l + __ldg(pe_b + head * HD + dbase + d);
-    }
-    for (int ky = 0; ky < 3; ++ky) {
-        const int hh = h + ky - 1;
-        if (hh < 0 || hh >= H) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ww = w + kx - 1;
-            if (ww < 0 || ww >= W) continue;
-            const uint4* vp = reinterpret_cast<const uint4*>(base + (size_t)(hh * W + ww) * qkv_pixstride + 2 * KD + dbase);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint4 u = __ldg(vp + half);
-                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16x2(uu[j]);
-                    const int d = half * 8 + 2 * j;
-                    res[d] = fmaf(f.x, __ldg(pe_w + (head * HD + dbase + d) * 9 + ky * 3 + kx), res[d]);
-                    res[d + 1] = fmaf(f.y, __ldg(pe_w + (head * HD + dbase + d + 1) * 9 + ky * 3 + kx), res[d + 1]);
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float2 f = unpack_bf16x2(uu[jj]);
+                            const int d = half * 8 + 2 * jj;
+                            res[d] = fmaf(f.x, wt[d], res[d]);
+                            res[d + 1] = fmaf(f.y, wt[d + 1], res[d + 1]);
+                        }
+                    }
                 }
             }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(res[0], res[1]);   o0.y = pack_bf16x2(res[2], res[3]);
+            o0.z = pack_bf16x2(res[4], res[5]);   o0.w = pack_bf16x2(res[6], res[7]);
+            o1.x = pack_bf16x2(res[8], res[9]);   o1.y = pack_bf16x2(res[10], res[11]);
+            o1.z = pack_bf16x2(res[12], res[13]); o1.w = pack_bf16x2(res[14], res[15]);
+            reinterpret_cast<uint4*>(op + d0)[0] = o0;
+            reinterpret_cast<uint4*>(op + d0)[1] = o1;
         }
     }
-    __nv_bfloat16* op = out + ((size_t)b * N + qi) * out_pixstride + head * HD + dbase;
-    uint4 o0, o1;
-    o0.x = pack_bf16x2(res[0], res[1]);   o0.y = pack_bf16x2(res[2], res[3]);
-    o0.z = pack_bf16x2(res[4], res[5]);   o0.w = pack_bf16x2(res[6], res[7]);
-    o1.x = pack_bf16x2(res[8], res[9]);   o1.y = pack_bf16x2(res[10], res[11]);
-    o1.z = pack_bf16x2(res[12], res[13]); o1.w = pack_bf16x2(res[14], res[15]);
-    reinterpret_cast<uint4*>(op)[0] = o0;
-    reinterpret_cast<uint4*>(op)[1] = o1;
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kAttTmemCols);
 }
 
 int psa_attention_launch(const void* qkv, int qkv_pixstride, int B, int H, int W, int heads, int key_dim,
@@ -168,12 +289,48 @@ int psa_attention_launch(const void* qkv, int qkv_pixstride, int B, int H, int W
     SY_CHECK(qkv_pixstride % 8 == 0 && out_pixstride % 8 == 0 &&
                  ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
              SPECYOLO_ERR_INVALID, "psa attention: tensors must be 16-byte aligned");
+    SY_CHECK(qkv_pixstride >= heads * (2 * KD + HD), SPECYOLO_ERR_INVALID, "psa attention: qkv pixel stride too small");
+    EncodeTiledFn encode = get_encode_fn();
+    SY_CHECK(encode != nullptr, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const int N = H * W;
+    AttParams p{};
+    p.N = N; p.H = H; p.W = W; p.heads = heads;
+    p.nblk = ceil_div(N, kAttKB);
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    p.qkv_pixstride = qkv_pixstride;
+    p.pe_w = pe_w; p.pe_b = pe_b;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.out_pixstride = out_pixstride;
+
+    // 3-D views {channel, token, image} of the NHWC qkv tensor: 32-channel boxes for Q / K, 64-channel boxes for V
+    CUtensorMap map_qk, map_v;
+    const cuuint64_t pix_b = (cuuint64_t)qkv_pixstride * 2;
+    cuuint64_t dims[3] = {(cuuint64_t)heads * (2 * KD + HD), (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {pix_b, pix_b * N};
+    cuuint32_t estr[3] = {1, 1, 1};
+    {
+        cuuint32_t box[3] = {KD, kAttKB, 1};
+        CUresult r = encode(&map_qk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(attention Q/K) failed (%d)", (int)r);
+    }
+    {
+        cuuint32_t box[3] = {HD, kAttKB, 1};
+        CUresult r = encode(&map_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(attention V) failed (%d)", (int)r);
+    }
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(psa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem);
+    });
+    SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     dim3 grid((unsigned)ceil_div(N, kAttQ), (unsigned)heads, (unsigned)B);
-    const float scale_log2e = scale * 1.4426950408889634f;
-    psa_attention_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), qkv_pixstride, H, W,
-                                                   heads, scale_log2e, pe_w, pe_b,
-                                                   reinterpret_cast<__nv_bfloat16*>(out), out_pixstride);
+    psa_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(map_qk, map_v, p);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

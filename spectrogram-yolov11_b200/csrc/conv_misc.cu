@@ -2,6 +2,8 @@
 // depthwise 3x3, and NCHW<->NHWC layout conversion.  All are HBM-bound streaming kernels: 16-byte
 // vector accesses along the contiguous channel axis, grids sized in multiples of the SM count.
 #include "common.h"
+#include "tma_host.h"
+#include <cstdlib>
 
 namespace specyolo {
 
@@ -195,82 +197,87 @@ int stem_conv_launch(const void* x, int x_dtype, int B, int H, int W, const floa
 // One thread = 8 channels of one pixel (16-byte loads/stores); weights are packed bf16 [C][3][3][1]
 // by fold_pack (groups=C, cin_g=1, n_pad=1) -> read as wp[c*9 + tap].
 // ------------------------------------------------------------------------------------------------
-// Each thread owns 8 channels (one 16-byte vector) of a run of kDwRun consecutive pixels of one row and slides
-// the 3x3 window along it: 3 new vector loads per output instead of 9, the 72 folded weights of its channels
-// held in registers as bf16x2 pairs.
-static constexpr int kDwRun = 8;
-
-__global__ void __launch_bounds__(256, 2)
+// Each thread owns 4 channels (one 8-byte vector; a warp covers 128 contiguous channels = one 256-byte pixel row) of
+// a run of kDwRun consecutive pixels of one image row and slides the 3x3 window along it: 3 new vector loads per
+// output instead of 9.  The 36 folded weights + 4 biases of its channels live in REGISTERS (fp32) — with them in
+// shared memory every FMA needed its own LDS and the kernel ran at 14 % of HBM bandwidth, LSU-bound.
+template <int kDwRun, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int B, int H, int W, int C,
                  const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias, int act,
-                 __nv_bfloat16* __restrict__ y, int y_pixstride) {
-    extern __shared__ __align__(16) float dw_smem[];   // [9][C] weights then [C] bias
-    for (int i = threadIdx.x; i < 9 * C; i += 256) {
-        const int c = i % C, t = i / C;
-        dw_smem[i] = __bfloat162float(wp[c * 9 + t]);
-    }
-    for (int i = threadIdx.x; i < C; i += 256) dw_smem[9 * C + i] = bias[i];
-    __syncthreads();
-    const int cg = C / 8;
-    const int runs_w = (W + kDwRun - 1) / kDwRun;
-    const long total = (long)B * H * runs_w * cg;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(idx % cg);
-        long r = idx / cg;
-        const int rw = (int)(r % runs_w);
-        r /= runs_w;
-        const int h = (int)(r % H);
-        const long n = r / H;
-        const int c0 = c8 * 8;
-        const int w0 = rw * kDwRun;
-        const float* wt = dw_smem + c0;           // wt[t*C + j]
-        const float* bs = dw_smem + 9 * C + c0;
-        // column ring: col[k][ky][j] for input columns w-1, w, w+1
-        float col[3][3][8];
-        auto load_col = [&](int slot, int iw) {
+                 __nv_bfloat16* __restrict__ y, int y_pixstride, FastDiv d_cg, FastDiv d_runs, FastDiv d_h,
+                 uint32_t total) {
+    float wt[9][4], bs[4];
+    uint32_t cached = 0xffffffffu;
+    // persistent grid: every thread walks many runs and keeps its channels (the grid stride is a multiple of C/4
+    // whenever C/4 divides 256), so the weights are fetched once per thread, not once per run
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t r, c4, rw, h, n;
+        fdivmod(idx, d_cg, r, c4);
+        fdivmod(r, d_runs, r, rw);
+        fdivmod(r, d_h, n, h);
+        const int c0 = (int)c4 * 4;
+        if (c4 != cached) {
+            cached = c4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bs[j] = bias[c0 + j];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wt[t][j] = __bfloat162float(wp[(c0 + j) * 9 + t]);
+            }
+        }
+        const int w0 = (int)rw * kDwRun;
+        // the whole 3 x (run + 2) input window is requested up front (independent 8-byte loads in flight: enough
+        // outstanding bytes per SM to cover HBM latency), kept packed, and unpacked column by column
+        uint2 win[3][kDwRun + 2];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ih = (int)h + ky - 1;
+            const bool row_ok = ih >= 0 && ih < H;
+            const __nv_bfloat16* rowp = x + (((size_t)n * H + (row_ok ? ih : 0)) * W) * x_pixstride + c0;
+#pragma unroll
+            for (int i = 0; i < kDwRun + 2; ++i) {
+                const int iw = w0 + i - 1;
+                win[ky][i] = (row_ok && iw >= 0 && iw < W)
+                                 ? __ldg(reinterpret_cast<const uint2*>(rowp + (size_t)iw * x_pixstride))
+                                 : make_uint2(0, 0);
+            }
+        }
+        float col[3][3][4];        // ring of unpacked columns w-1, w, w+1
+        auto unpack_col = [&](int slot, int i) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                const int ih = h + ky - 1;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-                    v = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * x_pixstride + c0));
-                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16x2(vv[j]);
-                    col[slot][ky][2 * j] = f.x;
-                    col[slot][ky][2 * j + 1] = f.y;
-                }
+                const float2 f0 = unpack_bf16x2(win[ky][i].x), f1 = unpack_bf16x2(win[ky][i].y);
+                col[slot][ky][0] = f0.x; col[slot][ky][1] = f0.y;
+                col[slot][ky][2] = f1.x; col[slot][ky][3] = f1.y;
             }
         };
-        load_col(0, w0 - 1);
-        load_col(1, w0);
+        unpack_col(0, 0);
+        unpack_col(1, 1);
+        __nv_bfloat16* yrow = y + (((size_t)n * H + h) * W) * y_pixstride + c0;
 #pragma unroll
         for (int i = 0; i < kDwRun; ++i) {
             const int w = w0 + i;
-            load_col((i + 2) % 3, w + 1);
+            unpack_col((i + 2) % 3, i + 2);
             if (w < W) {
-                float acc[8];
+                float acc[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+                for (int j = 0; j < 4; ++j) acc[j] = bs[j];
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            acc[j] = fmaf(col[(i + kx) % 3][ky][j], wt[(ky * 3 + kx) * C + j], acc[j]);
+                        for (int j = 0; j < 4; ++j)
+                            acc[j] = fmaf(col[(i + kx) % 3][ky][j], wt[ky * 3 + kx][j], acc[j]);
                 if (act == SPECYOLO_ACT_SILU) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+                    for (int j = 0; j < 4; ++j) acc[j] = silu_tanh(acc[j]);
                 }
-                uint4 o;
+                uint2 o;
                 o.x = pack_bf16x2(acc[0], acc[1]);
                 o.y = pack_bf16x2(acc[2], acc[3]);
-                o.z = pack_bf16x2(acc[4], acc[5]);
-                o.w = pack_bf16x2(acc[6], acc[7]);
-                *reinterpret_cast<uint4*>(y + ((n * H + h) * W + w) * y_pixstride + c0) = o;
+                *reinterpret_cast<uint2*>(yrow + (size_t)w * y_pixstride) = o;
             }
         }
     }
@@ -280,20 +287,34 @@ int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     SY_CHECK(a->Cin == a->Cout && a->groups == a->Cin && a->kh == 3 && a->kw == 3 && a->stride == 1 &&
                  a->pad == 1 && a->dil == 1,
              SPECYOLO_ERR_UNSUPPORTED, "depthwise kernel supports 3x3 s1 p1 d1 only");
-    SY_CHECK(a->Cin % 8 == 0 && a->x_pixstride % 8 == 0 && a->y_pixstride % 8 == 0, SPECYOLO_ERR_INVALID,
-             "depthwise needs C, strides multiples of 8");
-    SY_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->y)) & 15) == 0,
-             SPECYOLO_ERR_INVALID, "depthwise needs 16-byte aligned tensors");
+    SY_CHECK(a->Cin % 4 == 0 && a->x_pixstride % 4 == 0 && a->y_pixstride % 4 == 0, SPECYOLO_ERR_INVALID,
+             "depthwise needs C, strides multiples of 4");
+    SY_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->y)) & 7) == 0,
+             SPECYOLO_ERR_INVALID, "depthwise needs 8-byte aligned tensors");
     SY_CHECK(!a->y_fp32 && !a->residual && a->n_pad == 1, SPECYOLO_ERR_UNSUPPORTED,
              "depthwise: bf16 output, no residual, n_pad==1");
-    const long total = (long)a->B * a->H * ((a->W + kDwRun - 1) / kDwRun) * (a->Cin / 8);
-    long want = (total + 255) / 256;
-    int blocks = (int)(want < 148L * 16 ? want : 148L * 16);
-    if (blocks < 1) blocks = 1;
-    dwconv3x3_kernel<<<blocks, 256, (size_t)10 * a->Cin * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->x), a->x_pixstride,
-                                                 a->B, a->H, a->W, a->Cin,
-                                                 reinterpret_cast<const __nv_bfloat16*>(a->w_packed), a->bias,
-                                                 a->act, reinterpret_cast<__nv_bfloat16*>(a->y), a->y_pixstride);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("SPECYOLO_DW"); variant = e ? atoi(e) : 0; }
+    const int run = variant == 1 ? 8 : 4;
+    const int cg = a->Cin / 4;
+    const int runs_w = (a->W + run - 1) / run;
+    const long total = (long)a->B * a->H * runs_w * cg;
+    SY_CHECK(total < (1L << 31) && fastdiv_ok((uint64_t)total, (uint32_t)(cg > a->H ? cg : a->H)) &&
+                 fastdiv_ok((uint64_t)total, (uint32_t)runs_w),
+             SPECYOLO_ERR_UNSUPPORTED, "depthwise: tensor too large");
+    const long want = (total + 255) / 256;
+    const long cap = (long)sm_count() * (variant == 1 ? 1 : 2);
+    const int blocks = (int)(want < cap ? want : cap);
+    const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(a->x);
+    const __nv_bfloat16* ww = reinterpret_cast<const __nv_bfloat16*>(a->w_packed);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(a->y);
+    const FastDiv d_cg = make_fastdiv((uint32_t)cg), d_runs = make_fastdiv((uint32_t)runs_w), d_h = make_fastdiv((uint32_t)a->H);
+    if (variant == 1)
+        dwconv3x3_kernel<8, 1><<<blocks, 256, 0, stream>>>(xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
+                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total);
+    else
+        dwconv3x3_kernel<4, 2><<<blocks, 256, 0, stream>>>(xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
+                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

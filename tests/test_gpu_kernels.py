@@ -185,6 +185,20 @@ def test_depthwise(lib):
         assert _rel_err(y, ref) < 5e-3
 
 
+def test_depthwise_ragged(lib):
+    """C not a multiple of the warp's 128-channel span, W not a multiple of the run length."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(18)
+    x = torch.randn((3, 80, 11, 13), generator=gen)
+    w = torch.randn((80, 1, 3, 3), generator=gen) * 0.3
+    b = torch.randn(80, generator=gen) * 0.1
+    pc = ops.fold_pack(w.to(DEV), b.to(DEV), None, 0.0, 1, 1, 1, 80, True)
+    ref = F.silu(F.conv2d(_bf(x), _bf(w), b, 1, 1, 1, 80))
+    y = ops.conv2d(_fmap(x), pc).float().cpu()
+    assert _rel_err(y, ref) < 5e-3
+
+
 def test_sppf_pool(lib):
     from specyolo import ops
 
