@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -166,14 +166,15 @@ def stage_roofline(model, x_dev, peaks):
     def conv_flops(x, pc, *a, **k):
         B, _, H, W = x.shape
         Ho, Wo = pc.out_hw(H, W)
-        return 2.0 * B * Ho * Wo * pc.cout * (pc.cin // pc.g_orig) * pc.k * pc.k   # algorithmic (source groups)
+        kk = pc.alg_k or (pc.cin // pc.g_orig) * pc.k * pc.k                       # algorithmic (source groups, no padding)
+        return 2.0 * B * Ho * Wo * pc.cout * kk
 
     def conv_bytes(r, x, pc, *a, **k):
         B, Cin, H, W = x.shape
         return 2.0 * (B * Cin * H * W + r.numel()) + 2.0 * pc.w.numel()
 
     wrap("conv2d", conv_flops, conv_bytes)
-    wrap("stem_conv", None, lambda r, x, pc, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel())
+    wrap("stem_space_to_depth", None, lambda r, x, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel())
     wrap("sppf_pool", None, lambda r, buf, c: 2.0 * buf.numel())
     wrap("fusion_eschannel", None, lambda r, xs, *a, **k: 2.0 * (2 * sum(t.numel() for t in xs) + r.numel()))
     wrap("psa_attention", None, lambda r, qkv, *a, **k: 2.0 * (qkv.numel() + r.numel()))
@@ -181,22 +182,29 @@ def stage_roofline(model, x_dev, peaks):
     wrap("nms", None, None)
     # modules bind `ops.<fn>` at call time through the module attribute, so patching ops is enough
     ops.CONCURRENT = False          # time every kernel alone (the graph runs independent branches concurrently)
+    reps = 3
     try:
-        torch.cuda.synchronize()
-        torch.cuda._sleep(int(4e8))
-        model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
+        for _ in range(2):          # warm the eager path (caching allocator: a cudaMalloc would serialise the host)
+            model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
+        rec.clear()
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(4e8))
+            model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
         torch.cuda.synchronize()
     finally:
         ops.CONCURRENT = True
         for n, f in orig.items():
             setattr(ops, n, f)
     agg = {}
-    for name, e0, e1, fl, by in rec:
+    for name, e0, e1, fl, by in rec:                 # per-step averages over `reps` eager passes
         a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-        a[0] += e0.elapsed_time(e1) * 1e-3
-        a[1] += fl
-        a[2] += by
+        a[0] += e0.elapsed_time(e1) * 1e-3 / reps
+        a[1] += fl / reps
+        a[2] += by / reps
         a[3] += 1
+    for a in agg.values():
+        a[3] //= reps
     total = sum(a[0] for a in agg.values())
     stages = {}
     for name, (t, fl, by, n) in agg.items():
@@ -323,7 +331,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="specyolo", choices=["specyolo", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")

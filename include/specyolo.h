@@ -92,7 +92,7 @@ typedef struct {
     int act;              /* SPECYOLO_ACT_*                                            */
     /* output window */
     void* y;              /* bf16 (or fp32 if y_fp32) NHWC window                      */
-    int Ho, Wo;
+    int Ho, Wo;           /* output size; may be smaller than the geometry gives (far-edge rows/columns skipped) */
     int y_pixstride;
     int y_fp32;
     /* optional residual added after the activation (Bottleneck shortcut,
@@ -114,6 +114,13 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream);
 int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W,
                             const float* w_folded_oihw, const float* bias, int Cout,
                             void* y, int y_pixstride, void* stream);
+
+/* Tensor-core route of the same layer: 2x2 space-to-depth of the NCHW input into an NHWC bf16 tensor
+ * y[b, Y, X, (dy*2+dx)*3 + c] = x[b, c, 2Y+dy, 2X+dx] (channels 12..15 zero; uint8 stored unscaled).  The stem is then
+ * specyolo_conv2d_bias_act with a 2x2 / stride-1 / pad-1 kernel over 16 channels and Ho = H/2, Wo = W/2 (the caller
+ * repacks the 3x3 weights: tap (ty,tx), channel (dy,dx,c) <- w[c][2ty+dy-1][2tx+dx-1], times 1/255 for uint8). */
+int specyolo_stem_space_to_depth(const void* x, int x_dtype, int B, int H, int W,
+                                 void* y, int y_pixstride, void* stream);
 
 /* ---- SPPF pooling (ultralytics/nn/modules/block.py:194-198) ------------------------------ */
 /* buf is the 4*c-channel concat buffer whose first c channels hold cv1(x); writes the three

@@ -27,6 +27,7 @@ int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream);
 int fold_pack_launch(const float*, const float*, const float*, const float*, const float*, const float*, float,
                      int, int, int, int, int, int, int, void*, float*, cudaStream_t);
 int stem_conv_launch(const void*, int, int, int, int, const float*, const float*, int, void*, int, cudaStream_t);
+int stem_s2d_launch(const void*, int, int, int, int, void*, int, cudaStream_t);
 int nchw_to_nhwc_launch(const void*, int, float, int, int, int, int, void*, int, cudaStream_t);
 int nhwc_to_nchw_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
 int sppf_pool_launch(void*, int, int, int, int, int, cudaStream_t);
@@ -114,8 +115,10 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
              "conv: bad kernel geometry");
     const int ho = (a->H + 2 * a->pad - a->dil * (a->kh - 1) - 1) / a->stride + 1;
     const int wo = (a->W + 2 * a->pad - a->dil * (a->kw - 1) - 1) / a->stride + 1;
-    SY_CHECK(ho == a->Ho && wo == a->Wo, SPECYOLO_ERR_INVALID, "conv: Ho/Wo (%d,%d) do not match geometry (%d,%d)",
-             a->Ho, a->Wo, ho, wo);
+    // Ho/Wo may be SMALLER than the full output: the bottom rows / right columns are then not computed (a conv with
+    // less padding at the far edge, e.g. the 2x2 space-to-depth form of the stem)
+    SY_CHECK(a->Ho >= 1 && a->Wo >= 1 && a->Ho <= ho && a->Wo <= wo, SPECYOLO_ERR_INVALID,
+             "conv: Ho/Wo (%d,%d) exceed the geometry (%d,%d)", a->Ho, a->Wo, ho, wo);
     SY_CHECK(a->x_pixstride >= a->Cin && a->y_pixstride >= a->Cout, SPECYOLO_ERR_INVALID, "conv: pixel stride too small");
     SY_CHECK(a->act == SPECYOLO_ACT_NONE || a->act == SPECYOLO_ACT_SILU, SPECYOLO_ERR_INVALID, "conv: bad act");
     SY_CHECK(a->x_upshift == 0, SPECYOLO_ERR_UNSUPPORTED, "conv: x_upshift is not implemented");
@@ -130,6 +133,11 @@ int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W, con
                             int Cout, void* y, int y_pixstride, void* stream) {
     SY_CHECK(x && w && bias && y && B > 0 && H > 0 && W > 0, SPECYOLO_ERR_INVALID, "stem: bad arguments");
     return stem_conv_launch(x, x_dtype, B, H, W, w, bias, Cout, y, y_pixstride, (cudaStream_t)stream);
+}
+
+int specyolo_stem_space_to_depth(const void* x, int x_dtype, int B, int H, int W, void* y, int y_pixstride, void* stream) {
+    SY_CHECK(x && y && B > 0 && H > 0 && W > 0, SPECYOLO_ERR_INVALID, "stem s2d: bad arguments");
+    return stem_s2d_launch(x, x_dtype, B, H, W, y, y_pixstride, (cudaStream_t)stream);
 }
 
 int specyolo_sppf_pool(void* buf, int B, int H, int W, int c, int pixstride, void* stream) {

@@ -193,6 +193,76 @@ int stem_conv_launch(const void* x, int x_dtype, int B, int H, int W, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem, tensor-core route: space-to-depth.  A 3x3 / stride-2 / pad-1 conv over 3 channels equals a 2x2 / stride-1
+// conv (taps at block offsets -1, 0) over the 2x2-blocked image with 12 channels (dy, dx, c); padded to 16 channels
+// that is a K = 64 implicit GEMM the tcgen05 kernels run at HBM speed, instead of 27 FMAs per output on CUDA cores.
+// This kernel writes the blocked NHWC bf16 tensor y[b, Y, X, (dy*2+dx)*3 + c] = x[b, c, 2Y+dy, 2X+dx]; uint8 input is
+// stored as its integer value (exact in bf16; the 1/255 of predictor.py:133-135 is folded into the weights).
+// One thread per output pixel: 32-byte (2 x 16 B) stores, 2-element loads that coalesce along the row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_raw(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_raw<float>(const float* p, size_t i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float load_raw<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+template <>
+__device__ __forceinline__ float load_raw<uint8_t>(const uint8_t* p, size_t i) { return (float)__ldg(p + i); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_s2d_kernel(const T* __restrict__ x, int B, int H, int W, __nv_bfloat16* __restrict__ y, int y_pixstride) {
+    const int Wo = W >> 1, Ho = H >> 1;
+    const size_t total = (size_t)B * Ho * Wo;
+    const size_t plane = (size_t)H * W;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(idx % Wo);
+        const size_t r = idx / Wo;
+        const int Y = (int)(r % Ho);
+        const size_t n = r / Ho;
+        float v[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const size_t off = (n * 3 + c) * plane + (size_t)(2 * Y + dy) * W + 2 * X;
+                v[(dy * 2 + 0) * 3 + c] = load_raw<T>(x, off);
+                v[(dy * 2 + 1) * 3 + c] = load_raw<T>(x, off + 1);
+            }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+        o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+        o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+        o1.z = 0u;                        o1.w = 0u;
+        uint4* yp = reinterpret_cast<uint4*>(y + idx * y_pixstride);
+        yp[0] = o0;
+        yp[1] = o1;
+    }
+}
+
+int stem_s2d_launch(const void* x, int x_dtype, int B, int H, int W, void* y, int y_pixstride, cudaStream_t stream) {
+    SY_CHECK(H % 2 == 0 && W % 2 == 0, SPECYOLO_ERR_INVALID, "stem space-to-depth needs even H and W");
+    SY_CHECK(y_pixstride >= 16 && y_pixstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, SPECYOLO_ERR_INVALID,
+             "stem space-to-depth output must be a 16-byte aligned NHWC window of >= 16 channels");
+    const size_t total = (size_t)B * (H / 2) * (W / 2);
+    size_t want = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+    if (x_dtype == SPECYOLO_DT_F32)
+        stem_s2d_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, B, H, W, yy, y_pixstride);
+    else if (x_dtype == SPECYOLO_DT_BF16)
+        stem_s2d_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, B, H, W, yy, y_pixstride);
+    else if (x_dtype == SPECYOLO_DT_U8)
+        stem_s2d_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t*)x, B, H, W, yy, y_pixstride);
+    else
+        SY_CHECK(false, SPECYOLO_ERR_INVALID, "bad x_dtype %d", x_dtype);
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Depthwise 3x3 stride-1 pad-1 (+bias, optional SiLU): DWConv in Detect.cv3 (head.py:51-52).
 // One thread = 8 channels of one pixel (16-byte loads/stores); weights are packed bf16 [C][3][3][1]
 // by fold_pack (groups=C, cin_g=1, n_pad=1) -> read as wp[c*9 + tap].

@@ -95,6 +95,8 @@ SIGNATURES = {
     "specyolo_conv2d_bias_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "specyolo_stem_conv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "specyolo_stem_space_to_depth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_void_p]),
     "specyolo_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "specyolo_fusion_ws_bytes": (C.c_size_t, [C.c_int] * 5),
     "specyolo_fusion_eschannel": (C.c_int, [C.POINTER(FusionArgs), C.c_void_p]),

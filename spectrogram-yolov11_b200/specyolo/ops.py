@@ -140,10 +140,13 @@ class PackedConv:
     g_orig: int = 1          # groups of the source conv (g is the packed, possibly merged, group count)
     cin_true: int = 0        # input channels of the source conv (cin may be zero-padded to a multiple of 16)
     w_folded_f32: Optional[torch.Tensor] = None   # stem only: fp32 OIHW folded weights
+    alg_k: int = 0           # algorithmic reduction length when it differs from cin/g*k*k (space-to-depth stem: 27)
+    trim: int = 0            # far-edge output rows / columns that are not computed (space-to-depth stem: 1)
+    s2d: Optional[dict] = None   # stem only: {"u8": PackedConv, "f": PackedConv} 2x2 convs over the blocked image
 
     def out_hw(self, H: int, W: int):
         ke = self.d * (self.k - 1) + 1
-        return (H + 2 * self.p - ke) // self.s + 1, (W + 2 * self.p - ke) // self.s + 1
+        return (H + 2 * self.p - ke) // self.s + 1 - self.trim, (W + 2 * self.p - ke) // self.s + 1 - self.trim
 
 
 def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optional[Sequence[torch.Tensor]],
@@ -184,6 +187,23 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
             pc.w_folded_f32 = (w * scale.view(-1, 1, 1, 1)).contiguous()
         else:
             pc.w_folded_f32 = w
+        if kh == 3 and stride == 2 and pad == 1 and dil == 1 and groups == 1 and cin_g == 3:
+            # tensor-core route: the same conv as a 2x2 / stride-1 conv over the 2x2-blocked (space-to-depth) image
+            w2 = torch.zeros((cout, 16, 2, 2), device=w.device, dtype=torch.float32)
+            for ty in range(2):
+                for tx in range(2):
+                    for dy in range(2):
+                        for dx in range(2):
+                            ky, kx = 2 * ty + dy - 1, 2 * tx + dx - 1
+                            if 0 <= ky < 3 and 0 <= kx < 3:
+                                c0 = (dy * 2 + dx) * 3
+                                w2[:, c0:c0 + 3, ty, tx] = w[:, :, ky, kx]
+            pc.s2d = {}
+            for key, scale in (("u8", 1.0 / 255.0), ("f", 1.0)):
+                q = fold_pack(w2 * scale, conv_bias, bn, eps, 1, 1, 1, 1, act)
+                q.trim = 1
+                q.alg_k = 27
+                pc.s2d[key] = q
     return pc
 
 
@@ -224,6 +244,15 @@ def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
     return out
 
 
+def stem_space_to_depth(x: torch.Tensor) -> torch.Tensor:
+    """NCHW network input (fp32 | bf16 | uint8) -> 2x2-blocked NHWC bf16 [B, 16, H/2, W/2] (specyolo_stem_space_to_depth)."""
+    B, _, H, W = x.shape
+    blocked = new_act(B, 16, H // 2, W // 2, x.device)
+    check(_lib.load().specyolo_stem_space_to_depth(x.data_ptr(), _DT[x.dtype], B, H, W, blocked.data_ptr(), 16,
+                                                   _lib.stream_ptr()))
+    return blocked
+
+
 def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3-channel 3x3/s2 stem reading the NCHW network input (fp32 | bf16 | uint8/255)."""
     _lib.init_device()
@@ -233,6 +262,9 @@ def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = Non
         raise ValueError("stem_conv: weights are not a 3->C 3x3/s2 SiLU stem")
     x = x.contiguous()
     B, Cin, H, W = x.shape
+    if pc.s2d is not None and H % 2 == 0 and W % 2 == 0:
+        # tensor-core route: space-to-depth (one streaming pass) + a K = 64 implicit GEMM
+        return conv2d(stem_space_to_depth(x), pc.s2d["u8" if x.dtype == torch.uint8 else "f"], out=out)
     Ho, Wo = pc.out_hw(H, W)
     if out is None:
         out = new_act(B, pc.cout, Ho, Wo, x.device)

@@ -35,7 +35,7 @@ def wrap(name):
             desc = f"conv {Cin:4d}->{pc.cout:4d} k{pc.k} s{pc.s} d{pc.d} g{pc.g_orig:3d} {H:3d}x{W:3d} M={Bq*Ho*Wo:8d} K={(pc.cin//pc.g_orig)*pc.k*pc.k:5d}"
         rec.append((desc, e0, e1, fl, by)); return r
     setattr(ops, name, g)
-for n in ("conv2d", "stem_conv", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
+for n in ("conv2d", "stem_space_to_depth", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
     wrap(n)
 for _ in range(2):
     yolo.model.detect_fused(x)
