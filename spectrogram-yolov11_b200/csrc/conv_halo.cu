@@ -61,6 +61,9 @@ struct HaloParams {
     const __nv_bfloat16* residual;
     int r_pixstride;
     int act;
+    // TMA-store epilogue (store_bw == 0: direct stores)
+    int store_bw;
+    uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
 static constexpr int kHaloThreads = kConvThreads;
@@ -82,7 +85,7 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes,
 template <bool kSilu, bool kRes, bool kFp32>
 __global__ void __launch_bounds__(kHaloThreads)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ HaloParams p) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kHaloMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kHaloMaxStages];
@@ -106,6 +109,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_b);
+        if (p.store_bw) ptx::prefetch_tmap(&map_y);
         for (int s = 0; s < p.stages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -226,6 +230,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int m = quad * 32 + lane;
         const int tw = m & (kHaloTW - 1), th = m >> 3;
         EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
+        EpiStage st;
+        st.enabled = p.store_bw != 0;
+        st.buf = a_ring + p.ring_bytes + (uint32_t)half * 128u * p.store_row_bytes;
+        st.map_y = &map_y;
+        st.bw = p.store_bw;
+        st.row_bytes = p.store_row_bytes;
+        st.swz_mask = p.store_swz_mask;
+        st.bar_id = 1 + half;
+        st.issuer = (warp == 2 + 4 * half) && lane == 0;
+        st.m = m;
         EpiCols ec;
         ec.ncols = p.ncols;
         ec.n_pad = p.n_pad;
@@ -247,11 +261,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
             ptx::tc_fence_after();
-            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half);
+            st.c0 = ec.gch0;
+            st.c1 = (int)tw_i * kHaloTW; st.c2 = (int)th_i * kHaloTH; st.c3 = (int)n;
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (st.enabled && st.issuer) ptx::bulk_wait_read0();   // staging must outlive the last store's read
     }
 
     ptx::tc_fence_before();
@@ -331,15 +348,27 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         const uint32_t b_total = (uint32_t)(gcta * p.taps * p.bchunks) * p.b_box_bytes;
         const uint32_t b_region = (b_total + 1023u) & ~1023u;
         if (b_total >= (1u << 20)) continue;                      // mbarrier tx-count limit
-        const long avail = (long)kHaloMaxDynSmem - 1024 - (long)b_region;
+        // TMA-store staging (two halves x 128 rows x box row): only when the columns map to consecutive channels
+        const int es = a->y_fp32 ? 4 : 2;
+        int store_bw = epi_stage_box_cols(ncols, es);
+        if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * es) % 16 ||
+            (gcta > 1 && cout_g != p.n_pad) || env_flag("SPECYOLO_NO_TMA_STORE"))
+            store_bw = 0;
+        uint32_t stage_out = store_bw ? 2u * 128u * (uint32_t)(store_bw * es) : 0u;
+        if ((long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out < 3L * a_stage) {   // keep a 3-deep ring
+            store_bw = 0;
+            stage_out = 0;
+        }
+        const long avail = (long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out;
         if (avail < 2L * a_stage) continue;
         int stages = (int)(avail / a_stage);
         // two CTAs per SM when everything fits twice: more epilogue warps per SM for the thin-K layers
         int occ = 1;
         uint32_t cols = 32;
         while (cols < 2u * (uint32_t)ncols) cols <<= 1;
-        const long half = 110L * 1024 - 1024 - (long)b_region;
-        if (cols <= 256 && half >= 3L * a_stage) {
+        // (228 KB per SM, ~5.5 KB of static + reserved shared memory per CTA: two CTAs fit with <= 108 KB dynamic each)
+        const long half = 108L * 1024 - 1024 - (long)b_region - (long)stage_out;
+        if (cols <= 256 && half >= 2L * a_stage) {
             occ = 2;
             stages = (int)(half / a_stage);
         }
@@ -361,7 +390,11 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         p.stages = stages;
         p.tmem_cols = cols;
         plan.occ = occ;
-        plan.smem_bytes = 1024 + (size_t)b_region + (size_t)stages * a_stage;
+        plan.smem_bytes = 1024 + (size_t)b_region + (size_t)stages * a_stage + stage_out;
+        p.store_bw = store_bw;
+        p.store_row_bytes = (uint32_t)(store_bw * es);
+        p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
+        p.ring_bytes = (uint32_t)stages * a_stage;
     }
     if (!found) return false;
 
@@ -424,7 +457,20 @@ int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo B) failed (%d)", (int)r);
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const HaloParams);
+    CUtensorMap map_y = map_b;      // placeholder when the direct-store epilogue is used
+    if (p.store_bw) {
+        const int es = a->y_fp32 ? 4 : 2;
+        const cuuint64_t pix_b = (cuuint64_t)a->y_pixstride * es;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)a->Wo, (cuuint64_t)a->Ho, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {pix_b, pix_b * a->Wo, pix_b * a->Wo * a->Ho};
+        cuuint32_t box[4] = {(cuuint32_t)p.store_bw, (cuuint32_t)kHaloTW, (cuuint32_t)kHaloTH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_y, a->y_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->y,
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.store_row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo Y) failed (%d)", (int)r);
+    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams);
     static const KernelFn kernels[8] = {
         conv_halo_kernel<false, false, false>, conv_halo_kernel<false, false, true>,
         conv_halo_kernel<false, true, false>,  conv_halo_kernel<false, true, true>,
@@ -440,7 +486,7 @@ int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
-    kernel<<<plan.grid, kHaloThreads, plan.smem_bytes, stream>>>(map_a, map_b, p);
+    kernel<<<plan.grid, kHaloThreads, plan.smem_bytes, stream>>>(map_a, map_b, map_y, p);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

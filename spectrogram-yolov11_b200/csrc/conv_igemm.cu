@@ -49,6 +49,9 @@ struct IgemmParams {
     const __nv_bfloat16* residual;
     int r_pixstride;
     int act;
+    // TMA-store epilogue (store_bw == 0: direct stores)
+    int store_bw;
+    uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
 static constexpr int kThreads = kConvThreads;
@@ -81,7 +84,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
 template <bool kSilu, bool kRes, bool kFp32>
 __global__ void __launch_bounds__(kThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ IgemmParams p) {
+                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -105,6 +108,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_b);
+        if (p.store_bw) ptx::prefetch_tmap(&map_y);
         for (int s = 0; s < p.stages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -221,6 +225,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         fdivmod(rem_u, p.d_TW, th_u, tw_u);
         const int tw = (int)tw_u, th = (int)th_u, tn = (int)tn_u;
         EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
+        EpiStage st;
+        st.enabled = p.store_bw != 0;
+        st.buf = ring + p.ring_bytes + (uint32_t)half * 128u * p.store_row_bytes;     // 1024-aligned: ring_bytes is
+        st.map_y = &map_y;
+        st.bw = p.store_bw;
+        st.row_bytes = p.store_row_bytes;
+        st.swz_mask = p.store_swz_mask;
+        st.bar_id = 1 + half;
+        st.issuer = (warp == 2 + 4 * half) && lane == 0;
+        st.m = m;
         EpiCols ec;
         ec.ncols = p.n_tile;
         ec.n_pad = 1 << 20;                   // the tile is a slice of ONE group: column -> (0, within0 + column)
@@ -240,12 +254,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
             ptx::tc_fence_after();
-            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s + tc.g * p.n_pad + ec.within0, eo, pix, row_ok, half);
+            st.c0 = ec.gch0 + ec.within0;
+            st.c1 = tc.w0; st.c2 = tc.h0; st.c3 = tc.n0;
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s + tc.g * p.n_pad + ec.within0, eo, pix, row_ok, half, lane, st);
             // all TMEM reads of this accumulator are complete (wait::ld inside): hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (st.enabled && st.issuer) ptx::bulk_wait_read0();   // staging must outlive the last store's read
     }
 
     ptx::tc_fence_before();
@@ -353,12 +370,24 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     while (cols < 2u * (uint32_t)n_tile) cols <<= 1;
     p.tmem_cols = cols;
     const int occ = (cols <= 256) ? 2 : 1;
-    const uint32_t ring_budget = (occ == 2) ? 100u * 1024u : 190u * 1024u;
+    // TMA-store epilogue: needs a 16-byte aligned output window whose pixel stride is a multiple of 16 bytes, and
+    // accumulator columns that map to consecutive channels (no per-group padding between groups)
+    const int es = a->y_fp32 ? 4 : 2;
+    int store_bw = epi_stage_box_cols(n_tile, es);
+    if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * es) % 16 || (groups > 1 && cout_g != a->n_pad) ||
+        env_flag("SPECYOLO_NO_TMA_STORE"))
+        store_bw = 0;
+    const uint32_t stage_out_bytes = store_bw ? 2u * 128u * (uint32_t)(store_bw * es) : 0u;
+    const uint32_t ring_budget = ((occ == 2) ? 108u * 1024u : 200u * 1024u) - 1024u - stage_out_bytes;
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024;
+    p.store_bw = store_bw;
+    p.store_row_bytes = (uint32_t)(store_bw * es);
+    p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
+    p.ring_bytes = (uint32_t)stages * stage_bytes;          // multiple of 1024: the staging buffers stay aligned
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + stage_out_bytes;
     SY_CHECK(smem_bytes <= (size_t)kMaxDynSmem, SPECYOLO_ERR_INVALID, "smem budget exceeded");
 
     p.bias = a->bias;
@@ -397,7 +426,19 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
     }
 
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const IgemmParams);
+    CUtensorMap map_y = map_b;      // placeholder when the direct-store epilogue is used
+    if (store_bw) {
+        const cuuint64_t pix_b = (cuuint64_t)a->y_pixstride * es;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)gWo, (cuuint64_t)gHo, (cuuint64_t)gB};
+        cuuint64_t strides[3] = {pix_b, pix_b * gWo, pix_b * gWo * gHo};
+        cuuint32_t box[4] = {(cuuint32_t)store_bw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_y, a->y_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->y,
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.store_row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(Y) failed (%d)", (int)r);
+    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams);
     static const KernelFn kernels[8] = {
         conv_igemm_kernel<false, false, false>, conv_igemm_kernel<false, false, true>,
         conv_igemm_kernel<false, true, false>,  conv_igemm_kernel<false, true, true>,
@@ -417,7 +458,7 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     const long resident = (long)sm_count() * occ;
     const unsigned grid = (unsigned)(total_tiles < resident ? total_tiles : resident);
     const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
-    kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+    kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, map_y, p);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

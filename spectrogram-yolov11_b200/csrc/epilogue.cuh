@@ -28,11 +28,21 @@ struct EpiOut {
 // One 16-column chunk of one accumulator row.  `bias16` points at the 16 staged (pre-scaled) bias values of the
 // chunk (16-byte aligned shared memory); `gch` is the first output channel of the chunk inside the output window;
 // `nvalid` (1..16) the number of real channels in it.
-template <bool kSilu, bool kRes, bool kFp32>
-__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const float* bias16, const EpiOut& o, size_t pix,
-                                            int gch, int nvalid, bool vec_ok, const uint4& r0, const uint4& r1,
-                                            bool res_vec) {
-    float f[16];
+// Lanes 2i and 2i+1 hold adjacent accumulator rows.  A 16-byte store per lane at a row stride >= 64 B touches 32
+// different 32-byte sectors and half-fills each one; the partial-sector writes doubled the L1 -> L2 write traffic
+// (ncu: l1tex2xbar write bytes = 2 x the tensor).  `pair` mode: the two lanes swap one 16-byte half so that each
+// store instruction writes one row's full 32-byte sector from the lane pair.
+struct EpiRow {
+    size_t pix;        // own pixel index
+    size_t pix_pair;   // the partner lane's pixel index
+    bool ok, ok_pair;  // row inside the output
+};
+
+// bias + activation + residual of one 16-column chunk -> f[16]
+template <bool kSilu, bool kRes>
+__device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], const float* bias16, const EpiOut& o,
+                                           const EpiRow& row, int gch, int nvalid, const uint4& r0, const uint4& r1,
+                                           bool res_vec, float (&f)[16]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 b = *reinterpret_cast<const float4*>(bias16 + 4 * q);
@@ -59,16 +69,24 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const float
                 f[2 * i] += t.x;
                 f[2 * i + 1] += t.y;
             }
-        } else {
-            const __nv_bfloat16* rp = o.residual + pix * o.r_pixstride + gch;
+        } else if (row.ok) {
+            const __nv_bfloat16* rp = o.residual + row.pix * o.r_pixstride + gch;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (i < nvalid) f[i] += __bfloat162float(rp[i]);
         }
     }
+}
+
+// direct global stores of one chunk (fallback when the output window cannot be described by a TMA tensor map)
+template <bool kFp32>
+__device__ __forceinline__ void epi_store16_direct(const float (&f)[16], const EpiOut& o, const EpiRow& row, int gch,
+                                                   int nvalid, bool vec_ok, int lane) {
+    const size_t pix = row.pix;
     if (kFp32) {
         float* y = reinterpret_cast<float*>(o.y) + pix * o.y_pixstride + gch;
-        if (vec_ok && nvalid == 16) {
+        if (!row.ok) {
+        } else if (vec_ok && nvalid == 16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 reinterpret_cast<float4*>(y)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -78,19 +96,72 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const float
                 if (i < nvalid) y[i] = f[i];
         }
     } else {
-        __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(o.y) + pix * o.y_pixstride + gch;
-        if (vec_ok && nvalid == 16) {
+        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(o.y);
+        if (vec_ok && nvalid == 16) {          // warp-uniform condition: the exchange below is convergent
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
             o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
             o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            reinterpret_cast<uint4*>(y)[0] = o0;
-            reinterpret_cast<uint4*>(y)[1] = o1;
-        } else {
+            const bool odd = lane & 1;
+            // even lane gives its upper half and receives the odd lane's lower half (and vice versa)
+            uint4 give = odd ? o0 : o1, got;
+            got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+            got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+            got.z = __shfl_xor_sync(0xffffffffu, give.z, 1);
+            got.w = __shfl_xor_sync(0xffffffffu, give.w, 1);
+            const size_t pix_e = odd ? row.pix_pair : row.pix, pix_o = odd ? row.pix : row.pix_pair;
+            const bool ok_e = odd ? row.ok_pair : row.ok, ok_o = odd ? row.ok : row.ok_pair;
+            const int half_off = odd ? 8 : 0;
+            // store A: the even row's sector (even lane: own lower half, odd lane: the even lane's upper half)
+            if (ok_e) *reinterpret_cast<uint4*>(yb + pix_e * o.y_pixstride + gch + half_off) = odd ? got : o0;
+            // store B: the odd row's sector
+            if (ok_o) *reinterpret_cast<uint4*>(yb + pix_o * o.y_pixstride + gch + half_off) = odd ? o1 : got;
+        } else if (row.ok) {
+            __nv_bfloat16* y = yb + pix * o.y_pixstride + gch;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (i < nvalid) y[i] = __float2bfloat16_rn(f[i]);
+        }
+    }
+}
+
+// TMA-store staging: the output tile goes to shared memory in the swizzled [row][bw columns] box layout and one
+// thread per half issues cp.async.bulk.tensor stores (full 128-byte lines, clipping at the tensor edges done by
+// the TMA unit).  Per-lane 16-byte global stores at a row stride cost one LSU packet per half-filled sector and,
+// measured, bounded every HBM-bound conv at ~4.4 TB/s of combined traffic.
+struct EpiStage {
+    bool enabled;
+    uint8_t* buf;             // this half's staging buffer: 128 rows x row_bytes, 1024-byte aligned
+    const CUtensorMap* map_y;
+    int bw;                   // columns per store box
+    uint32_t row_bytes;       // bw * element size: 32 / 64 / 128
+    uint32_t swz_mask;        // 1 / 3 / 7: 16-byte unit index ^= (offset >> 7) & mask
+    int bar_id;               // named barrier of this half (4 warps)
+    bool issuer;              // this thread issues the stores of its half
+    int m;                    // this thread's row inside the tile
+    int c0, c1, c2, c3;       // TMA coordinates of the tile's first element; c0 = channel of accumulator column 0
+};
+
+template <bool kFp32>
+__device__ __forceinline__ void epi_store16_stage(const float (&f)[16], const EpiStage& st, int col_in_box) {
+    const uint32_t row_off = (uint32_t)st.m * st.row_bytes;
+    if (kFp32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t off = row_off + (uint32_t)(col_in_box * 4 + u * 16);
+            off ^= ((off >> 7) & st.swz_mask) << 4;
+            *reinterpret_cast<float4*>(st.buf + off) = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uint32_t off = row_off + (uint32_t)(col_in_box * 2 + u * 16);
+            off ^= ((off >> 7) & st.swz_mask) << 4;
+            uint4 o4;
+            o4.x = pack_bf16x2(f[8 * u + 0], f[8 * u + 1]); o4.y = pack_bf16x2(f[8 * u + 2], f[8 * u + 3]);
+            o4.z = pack_bf16x2(f[8 * u + 4], f[8 * u + 5]); o4.w = pack_bf16x2(f[8 * u + 6], f[8 * u + 7]);
+            *reinterpret_cast<uint4*>(st.buf + off) = o4;
         }
     }
 }
@@ -110,7 +181,13 @@ struct EpiCols {
 // quadrant, first column of the buffer).  `half` in {0,1}: which of the two warps sharing the quadrant this is.
 template <bool kSilu, bool kRes, bool kFp32>
 __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, const float* bias_s, const EpiOut& o,
-                                         size_t pix, bool row_ok, int half) {
+                                         size_t pix, bool row_ok, int half, int lane, const EpiStage& st) {
+    EpiRow row;
+    row.pix = pix;
+    row.ok = row_ok;
+    row.pix_pair = ((size_t)__shfl_xor_sync(0xffffffffu, (uint32_t)(pix >> 32), 1) << 32) |
+                   (size_t)__shfl_xor_sync(0xffffffffu, (uint32_t)pix, 1);
+    row.ok_pair = __shfl_xor_sync(0xffffffffu, (int)row_ok, 1) != 0;
     const int nchunks = ec.ncols >> 4;
     const int cut = (nchunks + 1) >> 1;
     const int ch_begin = half ? cut : 0, ch_end = half ? nchunks : cut;
@@ -143,10 +220,45 @@ __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, con
             }
             ptx::tmem_ld_wait();
             if (chunk + 1 < ch_end) ptx::tmem_ld16(t_addr + (uint32_t)(c + 16), vn);   // prefetch the next chunk
-            if (!row_ok || nvalid <= 0) continue;
-            epi_chunk16<kSilu, kRes, kFp32>(v, bias_s + c, o, pix, gch, nvalid, vec_ok, r0, r1, res_vec);
+            float f[16];
+            if (st.enabled) {
+                // box-by-box: wait until the previous store of this half has drained the staging buffer, fill it,
+                // make the writes visible to the async proxy, let one thread issue the store
+                const int cb = c - (ch_begin << 4);              // column inside this half's range
+                const int col_in_box = cb % st.bw;               // bw is a power of two
+                if (col_in_box == 0) {
+                    if (st.issuer) ptx::bulk_wait_read0();
+                    ptx::named_bar_sync(st.bar_id, 128);
+                }
+                epi_math16<kSilu, kRes>(v, bias_s + c, o, row, gch, max(nvalid, 0), r0, r1, res_vec, f);
+                epi_store16_stage<kFp32>(f, st, col_in_box);
+                if (col_in_box + 16 == st.bw) {
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(st.bar_id, 128);
+                    if (st.issuer) {
+                        ptx::tma_store_4d(st.map_y, st.buf, st.c0 + c + 16 - st.bw, st.c1, st.c2, st.c3);
+                        ptx::bulk_commit_group();
+                    }
+                }
+                continue;
+            }
+            if (nvalid <= 0) continue;         // warp-uniform (padding columns of the last group chunk)
+            epi_math16<kSilu, kRes>(v, bias_s + c, o, row, gch, nvalid, r0, r1, res_vec, f);
+            epi_store16_direct<kFp32>(f, o, row, gch, nvalid, vec_ok, lane);
         }
     }
+}
+
+// staging bytes per CTA: two halves x 128 rows x 128 bytes
+static constexpr uint32_t kEpiStageBytes = 2u * 128u * 128u;
+
+// Box width (columns) the two halves of an ncols-wide tile can both be cut into; 0 = TMA store not applicable.
+static inline int epi_stage_box_cols(int ncols, int elem_bytes) {
+    const int nchunks = ncols >> 4;
+    const int h0 = ((nchunks + 1) >> 1) * 16, h1 = (nchunks >> 1) * 16;
+    for (int bw = 128 / elem_bytes; bw >= 16; bw >>= 1)
+        if (h0 % bw == 0 && h1 % bw == 0) return bw;
+    return 0;
 }
 
 }  // namespace specyolo

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace specyolo {
 
@@ -30,6 +31,12 @@ inline EncodeTiledFn get_encode_fn() {
 inline CUtensorMapSwizzle swizzle_for(int row_bytes) {
     return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// debugging / A-B switches read from the environment (evaluated on every call: launch-time only, cheap)
+inline bool env_flag(const char* name) {
+    const char* e = std::getenv(name);
+    return e && e[0] && e[0] != '0';
 }
 
 inline int sm_count() {
