@@ -62,7 +62,7 @@ struct HaloParams {
     int r_pixstride;
     int act;
     // TMA-store epilogue (store_bw == 0: direct stores)
-    int store_bw;
+    int store_bw, pair_stores;
     uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
@@ -229,17 +229,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int half = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
         const int tw = m & (kHaloTW - 1), th = m >> 3;
-        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
-        EpiStage st;
-        st.enabled = p.store_bw != 0;
-        st.buf = a_ring + p.ring_bytes + (uint32_t)half * 128u * p.store_row_bytes;
-        st.map_y = &map_y;
-        st.bw = p.store_bw;
-        st.row_bytes = p.store_row_bytes;
-        st.swz_mask = p.store_swz_mask;
-        st.bar_id = 1 + half;
-        st.issuer = (warp == 2 + 4 * half) && lane == 0;
-        st.m = m;
+        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride, p.pair_stores != 0};
+        EpiStage st = epi_make_stage(a_ring + p.ring_bytes, &map_y, p.ncols, p.store_bw, p.store_row_bytes, p.store_swz_mask,
+                                     warp, half, lane, m);
         EpiCols ec;
         ec.ncols = p.ncols;
         ec.n_pad = p.n_pad;
@@ -354,7 +346,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * es) % 16 ||
             (gcta > 1 && cout_g != p.n_pad) || env_flag("SPECYOLO_NO_TMA_STORE"))
             store_bw = 0;
-        uint32_t stage_out = store_bw ? 2u * 128u * (uint32_t)(store_bw * es) : 0u;
+        uint32_t stage_out = epi_stage_bytes(ncols, store_bw, es);
         if ((long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out < 3L * a_stage) {   // keep a 3-deep ring
             store_bw = 0;
             stage_out = 0;
@@ -392,6 +384,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         plan.occ = occ;
         plan.smem_bytes = 1024 + (size_t)b_region + (size_t)stages * a_stage + stage_out;
         p.store_bw = store_bw;
+        p.pair_stores = (ncols >= 64 && !env_flag("SPECYOLO_NO_PAIR")) ? 1 : 0;
         p.store_row_bytes = (uint32_t)(store_bw * es);
         p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
         p.ring_bytes = (uint32_t)stages * a_stage;

@@ -50,7 +50,7 @@ struct IgemmParams {
     int r_pixstride;
     int act;
     // TMA-store epilogue (store_bw == 0: direct stores)
-    int store_bw;
+    int store_bw, pair_stores;
     uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
@@ -224,17 +224,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         fdivmod((uint32_t)m, p.d_TWTH, tn_u, rem_u);
         fdivmod(rem_u, p.d_TW, th_u, tw_u);
         const int tw = (int)tw_u, th = (int)th_u, tn = (int)tn_u;
-        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride};
-        EpiStage st;
-        st.enabled = p.store_bw != 0;
-        st.buf = ring + p.ring_bytes + (uint32_t)half * 128u * p.store_row_bytes;     // 1024-aligned: ring_bytes is
-        st.map_y = &map_y;
-        st.bw = p.store_bw;
-        st.row_bytes = p.store_row_bytes;
-        st.swz_mask = p.store_swz_mask;
-        st.bar_id = 1 + half;
-        st.issuer = (warp == 2 + 4 * half) && lane == 0;
-        st.m = m;
+        EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride, p.pair_stores != 0};
+        EpiStage st = epi_make_stage(ring + p.ring_bytes, &map_y, p.n_tile, p.store_bw, p.store_row_bytes, p.store_swz_mask,
+                                     warp, half, lane, m);
         EpiCols ec;
         ec.ncols = p.n_tile;
         ec.n_pad = 1 << 20;                   // the tile is a slice of ONE group: column -> (0, within0 + column)
@@ -377,13 +369,17 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * es) % 16 || (groups > 1 && cout_g != a->n_pad) ||
         env_flag("SPECYOLO_NO_TMA_STORE"))
         store_bw = 0;
-    const uint32_t stage_out_bytes = store_bw ? 2u * 128u * (uint32_t)(store_bw * es) : 0u;
+    // long-K layers are tensor-bound: the epilogue is hidden anyway and the staging buffer would cost a ring stage
+    // (measured: 128->128 k3 s2 133 us direct vs 150 us staged)
+    if ((long)a->kh * a->kw * cin_g >= 1024) store_bw = 0;
+    const uint32_t stage_out_bytes = epi_stage_bytes(n_tile, store_bw, es);
     const uint32_t ring_budget = ((occ == 2) ? 108u * 1024u : 200u * 1024u) - 1024u - stage_out_bytes;
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     p.store_bw = store_bw;
+    p.pair_stores = (n_tile >= 64 && !env_flag("SPECYOLO_NO_PAIR")) ? 1 : 0;   // thin tiles: the shuffles cost more than they save
     p.store_row_bytes = (uint32_t)(store_bw * es);
     p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
     p.ring_bytes = (uint32_t)stages * stage_bytes;          // multiple of 1024: the staging buffers stay aligned

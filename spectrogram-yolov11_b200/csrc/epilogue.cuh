@@ -23,6 +23,7 @@ struct EpiOut {
     int y_pixstride;
     const __nv_bfloat16* residual;
     int r_pixstride;
+    bool pair;            // direct bf16 stores: lane pairs exchange halves to write full 32-byte sectors
 };
 
 // One 16-column chunk of one accumulator row.  `bias16` points at the 16 staged (pre-scaled) bias values of the
@@ -97,7 +98,18 @@ __device__ __forceinline__ void epi_store16_direct(const float (&f)[16], const E
         }
     } else {
         __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(o.y);
-        if (vec_ok && nvalid == 16) {          // warp-uniform condition: the exchange below is convergent
+        if (vec_ok && nvalid == 16 && !o.pair) {
+            if (row.ok) {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                uint4* y = reinterpret_cast<uint4*>(yb + pix * o.y_pixstride + gch);
+                y[0] = o0;
+                y[1] = o1;
+            }
+        } else if (vec_ok && nvalid == 16) {          // warp-uniform condition: the exchange below is convergent
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
@@ -137,8 +149,10 @@ struct EpiStage {
     int bw;                   // columns per store box
     uint32_t row_bytes;       // bw * element size: 32 / 64 / 128
     uint32_t swz_mask;        // 1 / 3 / 7: 16-byte unit index ^= (offset >> 7) & mask
-    int bar_id;               // named barrier of this half (4 warps)
-    bool issuer;              // this thread issues the stores of its half
+    bool joint;               // tile rows are <= 128 bytes: ONE box per tile filled by both halves (all 8 warps);
+                              // otherwise every half stores its own 64-column boxes
+    int bar_id, bar_threads;  // named barrier of the warps sharing a box
+    bool issuer;              // this thread issues the stores of its box
     int m;                    // this thread's row inside the tile
     int c0, c1, c2, c3;       // TMA coordinates of the tile's first element; c0 = channel of accumulator column 0
 };
@@ -224,19 +238,21 @@ __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, con
             if (st.enabled) {
                 // box-by-box: wait until the previous store of this half has drained the staging buffer, fill it,
                 // make the writes visible to the async proxy, let one thread issue the store
-                const int cb = c - (ch_begin << 4);              // column inside this half's range
-                const int col_in_box = cb % st.bw;               // bw is a power of two
-                if (col_in_box == 0) {
+                // joint: the box is the whole tile row; per-half: boxes of bw columns inside this half's range
+                const int col_in_box = st.joint ? c : ((c - (ch_begin << 4)) & (st.bw - 1));
+                const bool first = st.joint ? (chunk == ch_begin) : (col_in_box == 0);
+                const bool last = st.joint ? (chunk + 1 == ch_end) : (col_in_box + 16 == st.bw);
+                if (first) {
                     if (st.issuer) ptx::bulk_wait_read0();
-                    ptx::named_bar_sync(st.bar_id, 128);
+                    ptx::named_bar_sync(st.bar_id, st.bar_threads);
                 }
                 epi_math16<kSilu, kRes>(v, bias_s + c, o, row, gch, max(nvalid, 0), r0, r1, res_vec, f);
                 epi_store16_stage<kFp32>(f, st, col_in_box);
-                if (col_in_box + 16 == st.bw) {
+                if (last) {
                     ptx::fence_proxy_async();
-                    ptx::named_bar_sync(st.bar_id, 128);
+                    ptx::named_bar_sync(st.bar_id, st.bar_threads);
                     if (st.issuer) {
-                        ptx::tma_store_4d(st.map_y, st.buf, st.c0 + c + 16 - st.bw, st.c1, st.c2, st.c3);
+                        ptx::tma_store_4d(st.map_y, st.buf, st.joint ? st.c0 : st.c0 + c + 16 - st.bw, st.c1, st.c2, st.c3);
                         ptx::bulk_commit_group();
                     }
                 }
@@ -249,11 +265,39 @@ __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, con
     }
 }
 
-// staging bytes per CTA: two halves x 128 rows x 128 bytes
-static constexpr uint32_t kEpiStageBytes = 2u * 128u * 128u;
+// staging bytes per CTA
+static inline uint32_t epi_stage_bytes(int ncols, int store_bw, int elem_bytes) {
+    if (!store_bw) return 0;
+    return (store_bw == ncols ? 1u : 2u) * 128u * (uint32_t)(store_bw * elem_bytes);
+}
 
-// Box width (columns) the two halves of an ncols-wide tile can both be cut into; 0 = TMA store not applicable.
+// per-thread staging descriptor of an epilogue thread (warp 2..9, `half` = (warp - 2) / 4)
+__device__ __forceinline__ EpiStage epi_make_stage(uint8_t* stage_base, const CUtensorMap* map_y, int ncols, int store_bw,
+                                                   uint32_t row_bytes, uint32_t swz_mask, int warp, int half, int lane,
+                                                   int m) {
+    EpiStage st;
+    st.enabled = store_bw != 0;
+    st.joint = store_bw == ncols;
+    st.buf = stage_base + (st.joint ? 0u : (uint32_t)half * 128u * row_bytes);
+    st.map_y = map_y;
+    st.bw = store_bw;
+    st.row_bytes = row_bytes;
+    st.swz_mask = swz_mask;
+    st.bar_id = st.joint ? 1 : 1 + half;
+    st.bar_threads = (st.joint && ncols > 16) ? 256 : 128;
+    st.issuer = (warp == (st.joint ? 2 : 2 + 4 * half)) && lane == 0;
+    st.m = m;
+    st.c0 = st.c1 = st.c2 = st.c3 = 0;
+    return st;
+}
+
+// Box width (columns): the whole tile row when it is at most 128 bytes (joint mode), else the width the two halves
+// of an ncols-wide tile can both be cut into; 0 = TMA store not applicable.
 static inline int epi_stage_box_cols(int ncols, int elem_bytes) {
+    // thin tiles (<= 32 columns) are dominated by per-tile fixed costs: the two named barriers + store issue of the
+    // staged path cost more than the LSU packets they save (measured: 16->32 k3 95 us direct vs 172 us staged)
+    if (ncols * elem_bytes < 128) return 0;
+    if (ncols * elem_bytes <= 128 && (ncols & (ncols - 1)) == 0) return ncols;    // swizzle spans: 32 / 64 / 128 bytes
     const int nchunks = ncols >> 4;
     const int h0 = ((nchunks + 1) >> 1) * 16, h1 = (nchunks >> 1) * 16;
     for (int bw = 128 / elem_bytes; bw >= 16; bw >>= 1)
