@@ -1,5 +1,6 @@
 // HBM-bound glue kernels of the neck: SPPF pooling and Fusion('ESChannel').
 #include "common.h"
+#include "tma_host.h"
 
 namespace specyolo {
 
@@ -82,107 +83,136 @@ int sppf_pool_launch(void* buf, int B, int H, int W, int c, int pixstride, cudaS
 //   GCT:  e_c = alpha_c * sqrt(sum_hw A_c^2 + eps);  n_c = gamma_c / sqrt(mean_c(e^2) + eps);
 //         gate_c = 1 + tanh(e_c * n_c + beta_c);  G = A * gate
 //   sab (WeightedSpatialAttention, conv.py:1850-1852): x * sigmoid(conv3x3([mean_c x, max_c x]))
-// nn.Upsample(x2, nearest) feeding a Fusion input is folded into the read (upshift).
-// Pass 1 reads every input once: per-(b,channel) partial sums of squares (deterministic partials,
-// no atomics) and per-pixel channel mean / max maps.  Pass 2 re-reads the inputs (L2 resident for
-// the sizes here), rebuilds the k*c gates per CTA and writes the output.
+// nn.Upsample(x2, nearest) feeding a Fusion input is folded into the reads (upshift): its statistics are taken
+// at the SOURCE resolution (sum of squares x 4; mean / max maps stored at source size and read through (h/2, w/2)
+// by the full-resolution 3x3 spatial-attention conv).
+//
+// Two launches.  fusion_stats_kernel: every CTA streams a contiguous run of source pixels of ONE (image, input) —
+// pointer increments only, a lane owns one 8-channel vector — and writes per-channel partial sums of squares plus the
+// per-pixel channel mean / max maps; the last CTA of an image (atomic ticket, partials summed in a fixed order, so the
+// result is deterministic) evaluates the k*c gates.  fusion_apply_kernel: a CTA owns kFusRows rows of one image,
+// builds the k spatial-attention maps of those rows in shared memory and writes out = sum_i x_i * (gate_i + sab_i)
+// with the gates of its channel vector in registers.  v1 of these kernels was issue-bound (runtime div/mod per
+// vector, scalar LDS per FMA, a serial 400-step partial reduction): 291 us for the 80x80 level.
 // ------------------------------------------------------------------------------------------------
-static constexpr int kFusPix = 64;  // pixels per pass-1 CTA
+static constexpr int kFusRows = 4;      // image rows per apply CTA
+static constexpr int kFusMaxParts = 16;
 
 struct FusionParams {
     specyolo_fusion_t a;
-    int nchunks;
-    float* part;  // [B][nchunks][k*c]
-    float* mm;    // [B][k][2][H*W]
-    float* gate;  // [B][k*c]
+    int parts;            // stats CTAs per (image, input)
+    int len[3];           // source pixels per stats CTA of input i (multiple of the pixels processed per step)
+    float* part;          // [B][parts][k*c]
+    float* mm;            // [B][k][2][H*W]   (input i uses the first HWs_i entries of each plane)
+    float* gate;          // [B][k*c]
+    unsigned int* ticket; // [B]
 };
 
-__device__ __forceinline__ const __nv_bfloat16* fus_pix_ptr(const specyolo_fusion_t& a, int i, int b, int h, int w) {
-    const int sh = a.upshift[i];
-    const int Hs = a.H >> sh, Ws = a.W >> sh;
-    return reinterpret_cast<const __nv_bfloat16*>(a.x[i]) +
-           ((size_t)((size_t)b * Hs + (h >> sh)) * Ws + (w >> sh)) * a.pixstride[i];
+__device__ __forceinline__ float redux_max_f32(float v, unsigned mask) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(mask));
+    return r;
 }
 
 __global__ void __launch_bounds__(256)
 fusion_stats_kernel(const __grid_constant__ FusionParams p) {
     const specyolo_fusion_t& a = p.a;
-    const int b = blockIdx.y, chunk = blockIdx.x;
+    // work item -> (image, input, part)
+    int item = blockIdx.x;
+    const int q = item % p.parts;
+    item /= p.parts;
+    const int i = item % a.k;
+    const int b = item / a.k;
+    const int sh = a.upshift[i];
+    const int HWs = (a.H >> sh) * (a.W >> sh);
     const int HW = a.H * a.W;
-    const int vec_per_pix = a.c / 8;           // 16-byte vectors per pixel per input
-    const int pix_par = 256 / vec_per_pix;     // pixels processed in parallel
-    const int v = threadIdx.x % vec_per_pix;
-    const int psub = threadIdx.x / vec_per_pix;
+    const int KC = a.k * a.c;
+    const int vpp = a.c >> 3;                  // 16-byte vectors (= lanes) per pixel: 4, 8, 16 or 32
+    const int pix_par = 256 / vpp;             // pixels per step
+    const int v = threadIdx.x % vpp;
+    const int psub = threadIdx.x / vpp;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = vpp == 32 ? 0xffffffffu : (((1u << vpp) - 1u) << (lane & ~(vpp - 1)));
     __shared__ float red[256 * 8];
-    const int pix_begin = chunk * kFusPix;
-    const int pix_end = min(HW, pix_begin + kFusPix);
+    __shared__ bool is_last;
 
-    for (int i = 0; i < a.k; ++i) {
-        float ssq[8];
+    const int begin = q * p.len[i];
+    const int end = min(HWs, begin + p.len[i]);
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.x[i]) + ((size_t)b * HWs) * a.pixstride[i] + v * 8;
+    float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
+    const float inv_c = 1.0f / (float)a.c;
+
+    float ssq[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ssq[j] = 0.f;
-        for (int pix = pix_begin + psub; pix < pix_begin + kFusPix; pix += pix_par) {
-            const bool ok = pix < pix_end;
+    for (int j = 0; j < 8; ++j) ssq[j] = 0.f;
+    // 4 pixel steps per iteration, all four 16-byte loads issued before any use: one load per thread in flight left
+    // the kernel latency-bound (uniform trip count: the lane reductions below are convergent)
+    for (int pix0 = begin; pix0 < end; pix0 += 4 * pix_par) {
+        uint4 u[4];
+        bool ok[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int pix = pix0 + s4 * pix_par + psub;
+            ok[s4] = pix < end;
+            u[s4] = ok[s4] ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)pix * a.pixstride[i])) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int pix = pix0 + s4 * pix_par + psub;
+            const uint32_t uu[4] = {u[s4].x, u[s4].y, u[s4].z, u[s4].w};
             float s = 0.f, m = -INFINITY;
-            if (ok) {
-                const int h = pix / a.W, w = pix % a.W;
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(fus_pix_ptr(a, i, b, h, w) + v * 8));
-                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16x2(uu[j]);
-                    ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
-                    ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
-                    s += f.x + f.y;
-                    m = fmaxf(m, fmaxf(f.x, f.y));
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(uu[j]);
+                ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
+                ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
+                s += f.x + f.y;
+                m = fmaxf(m, fmaxf(f.x, f.y));
             }
-            // reduce mean / max over the vec_per_pix lanes of this pixel (lanes are contiguous)
-            for (int d = vec_per_pix >> 1; d > 0; d >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, d);
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-            }
-            if (ok && v == 0) {
-                float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
-                mm[pix] = s / (float)a.c;
+            // channel mean / max of the pixel: reduce over its vpp lanes
+            for (int d = vpp >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            m = redux_max_f32(m, gmask);
+            if (ok[s4] && v == 0) {
+                mm[pix] = s * inv_c;
                 mm[HW + pix] = m;
             }
         }
-        // deterministic reduction of ssq over the pix_par sub-groups
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = ssq[j];
-        __syncthreads();
-        if (threadIdx.x < a.c) {
-            const int ch = threadIdx.x;
-            const int vv = ch / 8, jj = ch % 8;
-            float t = 0.f;
-            for (int ps = 0; ps < pix_par; ++ps) t += red[(ps * vec_per_pix + vv) * 8 + jj];
-            p.part[((size_t)b * p.nchunks + chunk) * (a.k * a.c) + i * a.c + ch] = t;
-        }
-        __syncthreads();
     }
-}
-
-// One CTA per image: reduce the per-chunk partial sums (fixed order -> deterministic) and evaluate the k*c gates.
-__global__ void __launch_bounds__(256)
-fusion_gate_kernel(const __grid_constant__ FusionParams p) {
-    const specyolo_fusion_t& a = p.a;
-    const int b = blockIdx.x;
-    const int KC = a.k * a.c;
-    __shared__ float s_red[256];
-    __shared__ float s_e[1024];
+    // deterministic reduction of ssq over the pix_par pixel groups
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = ssq[j];
+    __syncthreads();
+    if ((int)threadIdx.x < a.c) {
+        const int ch = threadIdx.x;
+        const int vv = ch >> 3, jj = ch & 7;
+        float t = 0.f;
+        for (int ps = 0; ps < pix_par; ++ps) t += red[(ps * vpp + vv) * 8 + jj];
+        p.part[((size_t)b * p.parts + q) * KC + i * a.c + ch] = t * (float)(1 << (2 * sh));   // upsampled: each source pixel counts 4x
+    }
+    // ---- last CTA of this image: gates ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(p.ticket + b, 1u);
+        is_last = (t == (unsigned)(a.k * p.parts) - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float* s_e = red;                  // KC <= 1024 floats
+    float* s_red = red + 1024;
     float e2_local = 0.f;
     for (int ch = threadIdx.x; ch < KC; ch += 256) {
-        float ssq = 0.f;
-        for (int q = 0; q < p.nchunks; ++q) ssq += p.part[((size_t)b * p.nchunks + q) * KC + ch];
-        const float e = sqrtf(ssq + a.gct_eps) * a.alpha[ch];
+        float t = 0.f;
+        for (int qq = 0; qq < p.parts; ++qq) t += __ldcg(p.part + ((size_t)b * p.parts + qq) * KC + ch);
+        const float e = sqrtf(t + a.gct_eps) * a.alpha[ch];
         s_e[ch] = e;
         e2_local += e * e;
     }
     s_red[threadIdx.x] = e2_local;
     __syncthreads();
     for (int d = 128; d > 0; d >>= 1) {
-        if (threadIdx.x < d) s_red[threadIdx.x] += s_red[threadIdx.x + d];
+        if ((int)threadIdx.x < d) s_red[threadIdx.x] += s_red[threadIdx.x + d];
         __syncthreads();
     }
     const float inv = 1.0f / sqrtf(s_red[0] / (float)KC + a.gct_eps);
@@ -193,81 +223,131 @@ fusion_gate_kernel(const __grid_constant__ FusionParams p) {
 __global__ void __launch_bounds__(256)
 fusion_apply_kernel(const __grid_constant__ FusionParams p) {
     const specyolo_fusion_t& a = p.a;
-    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int b = blockIdx.y;
+    const int h0 = blockIdx.x * kFusRows;
+    const int rows = min(kFusRows, a.H - h0);
     const int HW = a.H * a.W;
     const int KC = a.k * a.c;
-    extern __shared__ float fs[];  // gate[KC]
-    float* gate = fs;
-    __shared__ float s_sab[3 * kFusPix];
-    for (int ch = threadIdx.x; ch < KC; ch += 256) gate[ch] = p.gate[(size_t)b * KC + ch];
+    const int vpp = a.c >> 3;
+    const int pix_par = 256 / vpp;
+    const int v = threadIdx.x % vpp;
+    const int psub = threadIdx.x / vpp;
+    extern __shared__ float s_sab[];          // [k][rows][W]
 
-    // ---- spatial attention logits for this chunk's pixels ----
-    const int pix_begin = chunk * kFusPix;
-    for (int t = threadIdx.x; t < a.k * kFusPix; t += 256) {
-        const int i = t / kFusPix, pl = t % kFusPix;
-        const int pix = pix_begin + pl;
+    // gates of this thread's channel vector: registers
+    float g[3][8];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[i][j] = (i < a.k) ? __ldg(p.gate + (size_t)b * KC + i * a.c + v * 8 + j) : 0.f;
+
+    // ---- spatial attention of the CTA's rows: sigmoid(conv3x3([mean, max])) at each input's source resolution ----
+    const int npix = rows * a.W;
+    for (int t = threadIdx.x; t < a.k * npix; t += 256) {
+        const int i = t / npix;
+        const int r = t - i * npix;
+        const int hr = r / a.W, w = r - hr * a.W;
+        const int sh = a.upshift[i];
+        const int Ws = a.W >> sh;
+        const int h = h0 + hr;
+        const float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
+        // the 3x3 conv runs on the FULL-resolution (upsampled) maps: neighbours (h+-1, w+-1) -> source (>> sh)
         float acc = 0.f;
-        if (pix < HW) {
-            const int h = pix / a.W, w = pix % a.W;
-            const float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
+        for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int hh = h + ky - 1;
-                    if (hh < 0 || hh >= a.H) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int hh = h + ky - 1;
+                if (hh < 0 || hh >= a.H) continue;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int ww = w + kx - 1;
-                        if (ww < 0 || ww >= a.W) continue;
-                        acc = fmaf(__ldg(a.sab_w + ci * 9 + ky * 3 + kx), mm[(size_t)ci * HW + hh * a.W + ww], acc);
-                    }
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ww = w + kx - 1;
+                    if (ww < 0 || ww >= a.W) continue;
+                    acc = fmaf(__ldg(a.sab_w + ci * 9 + ky * 3 + kx), mm[(size_t)ci * HW + (hh >> sh) * Ws + (ww >> sh)], acc);
                 }
-        }
-        s_sab[t] = 1.0f / (1.0f + expf(-acc));
+            }
+        s_sab[t] = 1.0f / (1.0f + __expf(-acc));
     }
     __syncthreads();
 
     // ---- out = sum_i x_i * (gate_i + sab_i) ----
-    const int vec_per_pix = a.c / 8;
-    for (int t = threadIdx.x; t < kFusPix * vec_per_pix; t += 256) {
-        const int pl = t / vec_per_pix, v = t % vec_per_pix;
-        const int pix = pix_begin + pl;
-        if (pix >= HW) continue;
-        const int h = pix / a.W, w = pix % a.W;
-        float acc[8];
+    const __nv_bfloat16* xb[3];
+    int wshift[3], rowstride[3];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int i = 0; i < a.k; ++i) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(fus_pix_ptr(a, i, b, h, w) + v * 8));
-            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-            const float sab = s_sab[i * kFusPix + pl];
-            const float* g = gate + i * a.c + v * 8;
+    for (int i = 0; i < 3; ++i) {
+        const int ii = i < a.k ? i : 0;
+        const int sh = a.upshift[ii];
+        const int Hs = a.H >> sh, Ws = a.W >> sh;
+        xb[i] = reinterpret_cast<const __nv_bfloat16*>(a.x[ii]) + ((size_t)b * Hs * Ws) * a.pixstride[ii] + v * 8;
+        wshift[i] = sh;
+        rowstride[i] = Ws;
+    }
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)b * HW) * a.y_pixstride + v * 8;
+    for (int hr = 0; hr < rows; ++hr) {
+        const int h = h0 + hr;
+        // two pixels per iteration, their 2k loads issued before any use
+        for (int w0 = psub; w0 < a.W; w0 += 2 * pix_par) {
+            uint4 u[2][3];
+            bool ok[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(uu[j]);
-                acc[2 * j] = fmaf(f.x, g[2 * j] + sab, acc[2 * j]);
-                acc[2 * j + 1] = fmaf(f.y, g[2 * j + 1] + sab, acc[2 * j + 1]);
+            for (int t = 0; t < 2; ++t) {
+                const int w = w0 + t * pix_par;
+                ok[t] = w < a.W;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (i < a.k && ok[t]) {
+                        const size_t spix = (size_t)(h >> wshift[i]) * rowstride[i] + (w >> wshift[i]);
+                        u[t][i] = __ldg(reinterpret_cast<const uint4*>(xb[i] + spix * a.pixstride[i]));
+                    } else {
+                        u[t][i] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (!ok[t]) continue;
+                const int w = w0 + t * pix_par;
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (i >= a.k) break;
+                    const uint32_t uu[4] = {u[t][i].x, u[t][i].y, u[t][i].z, u[t][i].w};
+                    const float sab = s_sab[(i * rows + hr) * a.W + w];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16x2(uu[j]);
+                        acc[2 * j] = fmaf(f.x, g[i][2 * j] + sab, acc[2 * j]);
+                        acc[2 * j + 1] = fmaf(f.y, g[i][2 * j + 1] + sab, acc[2 * j + 1]);
+                    }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(acc[0], acc[1]);
+                o.y = pack_bf16x2(acc[2], acc[3]);
+                o.z = pack_bf16x2(acc[4], acc[5]);
+                o.w = pack_bf16x2(acc[6], acc[7]);
+                *reinterpret_cast<uint4*>(yb + ((size_t)h * a.W + w) * a.y_pixstride) = o;
             }
         }
-        uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]);
-        o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]);
-        o.w = pack_bf16x2(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) +
-                                  ((size_t)b * HW + pix) * a.y_pixstride + v * 8) = o;
     }
 }
 
+static int fusion_parts(int B, int k) {
+    int parts = ceil_div(8 * sm_count(), B * k);
+    if (parts < 1) parts = 1;
+    if (parts > kFusMaxParts) parts = kFusMaxParts;
+    return parts;
+}
+
 size_t fusion_ws_bytes(int k, int B, int H, int W, int c) {
-    const int nchunks = ceil_div(H * W, kFusPix);
-    return ((size_t)B * nchunks * k * c + (size_t)B * k * 2 * H * W + (size_t)B * k * c) * sizeof(float) + 256;
+    return ((size_t)B * kFusMaxParts * k * c + (size_t)B * k * 2 * H * W + (size_t)B * k * c) * sizeof(float) +
+           (size_t)B * sizeof(unsigned int) + 512;
 }
 
 int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     SY_CHECK(a->k == 2 || a->k == 3, SPECYOLO_ERR_INVALID, "fusion: k must be 2 or 3");
-    // c/8 lanes per pixel must be a power of two in [4,32] so that 256/(c/8) pixel groups divide kFusPix
+    // c/8 lanes per pixel must be a power of two in [4,32]
     SY_CHECK(a->c % 8 == 0 && ((a->c / 8) & (a->c / 8 - 1)) == 0 && a->c / 8 >= 4 && a->c / 8 <= 32,
              SPECYOLO_ERR_UNSUPPORTED, "fusion: c must be 32, 64, 128 or 256 (c=%d)", a->c);
     for (int i = 0; i < a->k; ++i) {
@@ -279,22 +359,29 @@ int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     SY_CHECK(a->y_pixstride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, SPECYOLO_ERR_INVALID,
              "fusion: output not 16-byte aligned");
     SY_CHECK(a->ws != nullptr, SPECYOLO_ERR_INVALID, "fusion: workspace missing");
+    SY_CHECK(a->k * a->c <= 1024, SPECYOLO_ERR_UNSUPPORTED, "fusion: k*c must be <= 1024");
+    const size_t sab_smem = (size_t)a->k * kFusRows * a->W * sizeof(float);
+    SY_CHECK(sab_smem <= 48 * 1024, SPECYOLO_ERR_UNSUPPORTED, "fusion: feature map too wide (%d)", a->W);
     FusionParams p{};
     p.a = *a;
-    p.nchunks = ceil_div(a->H * a->W, kFusPix);
+    p.parts = fusion_parts(a->B, a->k);
+    const int pix_par = 256 / (a->c / 8);
+    for (int i = 0; i < a->k; ++i) {
+        const int HWs = (a->H >> a->upshift[i]) * (a->W >> a->upshift[i]);
+        p.len[i] = ceil_div(ceil_div(HWs, p.parts), 4 * pix_par) * 4 * pix_par;
+    }
     float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a->ws) + 255) & ~(uintptr_t)255);
     p.part = ws;
-    p.mm = ws + (size_t)a->B * p.nchunks * a->k * a->c;
+    p.mm = p.part + (size_t)a->B * kFusMaxParts * a->k * a->c;
     p.gate = p.mm + (size_t)a->B * a->k * 2 * a->H * a->W;
-    SY_CHECK(a->k * a->c <= 1024, SPECYOLO_ERR_UNSUPPORTED, "fusion: k*c must be <= 1024");
-    dim3 grid((unsigned)p.nchunks, (unsigned)a->B);
-    fusion_stats_kernel<<<grid, 256, 0, stream>>>(p);
+    p.ticket = reinterpret_cast<unsigned int*>(p.gate + (size_t)a->B * a->k * a->c);
+    SY_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)a->B * sizeof(unsigned int), stream));
+    fusion_stats_kernel<<<(unsigned)(a->B * a->k * p.parts), 256, 0, stream>>>(p);
     SY_LAUNCH_CHECK();
-    fusion_gate_kernel<<<a->B, 256, 0, stream>>>(p);
+    dim3 grid((unsigned)ceil_div(a->H, kFusRows), (unsigned)a->B);
+    fusion_apply_kernel<<<grid, 256, sab_smem, stream>>>(p);
     SY_LAUNCH_CHECK();
-    fusion_apply_kernel<<<grid, 256, (size_t)a->k * a->c * sizeof(float), stream>>>(p);
-    SY_LAUNCH_CHECK();
-    count_launch(3);
+    count_launch(2);
     return SPECYOLO_OK;
 }
 
