@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace specyolo {
 
@@ -80,7 +81,15 @@ int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C,
 int specyolo_conv_merge(int cin, int cout, int groups, int k, int stride, int pad, int dil) {
     if (groups <= 1 || cin <= 0 || cout <= 0 || cin % groups || cout % groups) return 1;
     const int cin_g = cin / groups;
-    if (cin_g == 1 && cout / groups == 1) return 1;    // depthwise: dedicated kernel
+    if (cin_g == 1 && cout / groups == 1) {
+        // depthwise k x k: as a 64-channel block-DIAGONAL implicit GEMM on the halo-tile kernel the layer runs at
+        // ~HBM speed on the otherwise idle tensor pipe (63/64 of the multiplications are by zero, and still 2-3x
+        // faster than the CUDA-core kernel, which is issue-bound at 25 instructions per output element)
+        if (conv_halo_geometry_ok(k, k, stride, pad, dil) && !getenv("SPECYOLO_DW_CUDA_CORES"))
+            for (int m = 64; m >= 16; m >>= 1)
+                if (groups % m == 0) return m;
+        return 1;                                       // dedicated CUDA-core kernel
+    }
     // the halo kernel multiplies every group by its own weight box (UMMA N = cout_g): nothing to merge
     if (cin_g % 16 == 0 && conv_halo_geometry_ok(k, k, stride, pad, dil)) return 1;
     int merge = 1;

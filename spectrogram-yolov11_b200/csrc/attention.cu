@@ -55,6 +55,7 @@ psa_attention_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_co
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
+    ptx::grid_dep_launch();
     const int q0 = blockIdx.x * kAttQ, head = blockIdx.y, b = blockIdx.z;
     const int ch0 = head * (2 * KD + HD);
 
@@ -90,6 +91,7 @@ psa_attention_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    ptx::grid_dep_wait();       // PDL: qkv is read (TMA, pe taps) and `out` written only below
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
     const int nblk = p.nblk;
 
@@ -330,7 +332,7 @@ int psa_attention_launch(const void* qkv, int qkv_pixstride, int B, int H, int W
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     dim3 grid((unsigned)ceil_div(N, kAttQ), (unsigned)heads, (unsigned)B);
-    psa_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(map_qk, map_v, p);
+    SY_CUDA(launch_pdl(psa_attention_kernel, grid, dim3(kAttThreads), (size_t)kAttSmem, stream, map_qk, map_v, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

@@ -97,6 +97,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
+    ptx::grid_dep_launch();     // PDL: the next kernel may be scheduled into SM slots as this grid drains
     const int split = blockIdx.x % p.gsplit;
     const int cta = blockIdx.x / p.gsplit;
     const int ctas = gridDim.x / p.gsplit;
@@ -130,6 +131,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // PDL: the prologue above and the weight loads below (constants) overlap the previous kernel's tail; activations
+    // are read and outputs written only after griddepcontrol.wait
+    if (warp != 0) ptx::grid_dep_wait();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -150,6 +154,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
+            ptx::grid_dep_wait();
             int stage = 0;
             uint32_t ph = 0;
             for (int tile = cta; tile < p.spatial_tiles; tile += ctas) {
@@ -479,7 +484,7 @@ int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
-    kernel<<<plan.grid, kHaloThreads, plan.smem_bytes, stream>>>(map_a, map_b, map_y, p);
+    SY_CUDA(launch_pdl(kernel, dim3(plan.grid), dim3(kHaloThreads), plan.smem_bytes, stream, map_a, map_b, map_y, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

@@ -97,6 +97,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // feed UTMALDG / UTCHMMA (which take uniform registers) without a per-instruction R2UR round trip
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
+    ptx::grid_dep_launch();     // PDL: the next kernel may be scheduled into SM slots as this grid drains
 
     // 1024-byte aligned operand ring (swizzle-128B atoms repeat every 1024 B)
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -125,6 +126,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // PDL: everything above (barriers, TMEM, bias = constants) overlapped the previous kernel's tail; activations
+    // are read and output buffers written only from here on
+    ptx::grid_dep_wait();
 
     const int taps = p.kh * p.kw;
     const int total_chunks = taps * p.cin_chunks;
@@ -454,7 +458,7 @@ int conv_igemm_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     const long resident = (long)sm_count() * occ;
     const unsigned grid = (unsigned)(total_tiles < resident ? total_tiles : resident);
     const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
-    kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, map_y, p);
+    SY_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, map_a, map_b, map_y, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

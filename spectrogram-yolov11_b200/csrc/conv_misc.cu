@@ -3,6 +3,7 @@
 // vector accesses along the contiguous channel axis, grids sized in multiples of the SM count.
 #include "common.h"
 #include "tma_host.h"
+#include "ptx.cuh"
 #include <cstdlib>
 
 namespace specyolo {
@@ -212,6 +213,8 @@ __device__ __forceinline__ float load_raw<uint8_t>(const uint8_t* p, size_t i) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_s2d_kernel(const T* __restrict__ x, int B, int H, int W, __nv_bfloat16* __restrict__ y, int y_pixstride) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int Wo = W >> 1, Ho = H >> 1;
     const size_t total = (size_t)B * Ho * Wo;
     const size_t plane = (size_t)H * W;
@@ -250,11 +253,11 @@ int stem_s2d_launch(const void* x, int x_dtype, int B, int H, int W, void* y, in
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
     if (x_dtype == SPECYOLO_DT_F32)
-        stem_s2d_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, B, H, W, yy, y_pixstride);
+        SY_CUDA(launch_pdl(stem_s2d_kernel<float>, dim3(blocks), dim3(256), 0, stream, (const float*)x, B, H, W, yy, y_pixstride));
     else if (x_dtype == SPECYOLO_DT_BF16)
-        stem_s2d_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, B, H, W, yy, y_pixstride);
+        SY_CUDA(launch_pdl(stem_s2d_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)x, B, H, W, yy, y_pixstride));
     else if (x_dtype == SPECYOLO_DT_U8)
-        stem_s2d_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t*)x, B, H, W, yy, y_pixstride);
+        SY_CUDA(launch_pdl(stem_s2d_kernel<uint8_t>, dim3(blocks), dim3(256), 0, stream, (const uint8_t*)x, B, H, W, yy, y_pixstride));
     else
         SY_CHECK(false, SPECYOLO_ERR_INVALID, "bad x_dtype %d", x_dtype);
     SY_LAUNCH_CHECK();
@@ -277,6 +280,8 @@ dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int B, in
                  const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias, int act,
                  __nv_bfloat16* __restrict__ y, int y_pixstride, FastDiv d_cg, FastDiv d_runs, FastDiv d_h,
                  uint32_t total) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     float wt[9][4], bs[4];
     uint32_t cached = 0xffffffffu;
     // persistent grid: every thread walks many runs and keeps its channels (the grid stride is a multiple of C/4
@@ -380,11 +385,11 @@ int dwconv3x3_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(a->y);
     const FastDiv d_cg = make_fastdiv((uint32_t)cg), d_runs = make_fastdiv((uint32_t)runs_w), d_h = make_fastdiv((uint32_t)a->H);
     if (variant == 1)
-        dwconv3x3_kernel<8, 1><<<blocks, 256, 0, stream>>>(xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
-                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total);
+        SY_CUDA(launch_pdl(dwconv3x3_kernel<8, 1>, dim3(blocks), dim3(256), 0, stream, xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
+                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total));
     else
-        dwconv3x3_kernel<4, 2><<<blocks, 256, 0, stream>>>(xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
-                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total);
+        SY_CUDA(launch_pdl(dwconv3x3_kernel<4, 2>, dim3(blocks), dim3(256), 0, stream, xx, a->x_pixstride, a->B, a->H, a->W, a->Cin, ww, a->bias, a->act, yy,
+                                                           a->y_pixstride, d_cg, d_runs, d_h, (uint32_t)total));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

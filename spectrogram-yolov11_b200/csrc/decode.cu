@@ -9,6 +9,8 @@
 // bins then nc class logits).  HBM-bound: reads no*4 B per anchor, writes (4+nc)*4 B dense output
 // (optional) plus 24 B per surviving candidate.  Everything is fp32.
 #include "common.h"
+#include "ptx.cuh"
+#include "tma_host.h"
 
 namespace specyolo {
 
@@ -21,6 +23,8 @@ struct DecodeParams {
 
 __global__ void __launch_bounds__(SPECYOLO_DECODE_SEG)
 detect_decode_kernel(const __grid_constant__ DecodeParams p) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const specyolo_decode_t& a = p.a;
     const int b = blockIdx.y;
     const int seg = blockIdx.x;
@@ -131,7 +135,7 @@ int detect_decode_launch(const specyolo_decode_t* a, cudaStream_t stream) {
     p.A = off;
     p.nseg = ceil_div(off, SPECYOLO_DECODE_SEG);
     dim3 grid((unsigned)p.nseg, (unsigned)a->B);
-    detect_decode_kernel<<<grid, SPECYOLO_DECODE_SEG, 0, stream>>>(p);
+    SY_CUDA(launch_pdl(detect_decode_kernel, grid, dim3(SPECYOLO_DECODE_SEG), 0, stream, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

@@ -15,6 +15,8 @@
 // round-to-nearest intrinsics (no FMA contraction): boxes are offset by cls*max_wh in fp32
 // (ops.py:305-311), inter/(area_i+area_j-inter) > thr with thr compared as a double.
 #include "common.h"
+#include "ptx.cuh"
+#include "tma_host.h"
 
 namespace specyolo {
 
@@ -117,6 +119,8 @@ __device__ __forceinline__ bool class_allowed(const int* classes, int n_classes,
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_kernel(const __grid_constant__ NmsParams p) {
     extern __shared__ __align__(16) uint8_t nms_smem[];
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(nms_smem);           // kSmemSort
     float4* s_boxes = reinterpret_cast<float4*>(nms_smem + (size_t)kSmemSort * 8);           // kSmemBoxes
     float4* s_kept = s_boxes + kSmemBoxes;                                                    // kMaxKeep
@@ -375,7 +379,7 @@ int nms_launch(const specyolo_nms_t* a, cudaStream_t stream) {
         SY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    nms_kernel<<<a->B, kNmsThreads, smem, stream>>>(p);
+    SY_CUDA(launch_pdl(nms_kernel, dim3(a->B), dim3(kNmsThreads), smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

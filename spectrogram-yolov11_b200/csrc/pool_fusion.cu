@@ -1,6 +1,7 @@
 // HBM-bound glue kernels of the neck: SPPF pooling and Fusion('ESChannel').
 #include "common.h"
 #include "tma_host.h"
+#include "ptx.cuh"
 
 namespace specyolo {
 
@@ -24,6 +25,8 @@ __device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
 __global__ void __launch_bounds__(256)
 sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int H, int W, int c, int pixstride) {
     extern __shared__ __align__(16) uint8_t sp_smem[];
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int HW = H * W;
     uint4* s0 = reinterpret_cast<uint4*>(sp_smem);  // [HW][2] (16 channels = 2 x 16 B)
     uint4* s1 = s0 + HW * 2;
@@ -71,7 +74,7 @@ int sppf_pool_launch(void* buf, int B, int H, int W, int c, int pixstride, cudaS
         attr_smem = smem;
     }
     dim3 grid((unsigned)(c / 16), (unsigned)B);
-    sppf_pool_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), H, W, c, pixstride);
+    SY_CUDA(launch_pdl(sppf_pool_kernel, grid, dim3(256), smem, stream, reinterpret_cast<__nv_bfloat16*>(buf), H, W, c, pixstride));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;
@@ -116,6 +119,8 @@ __device__ __forceinline__ float redux_max_f32(float v, unsigned mask) {
 
 __global__ void __launch_bounds__(256)
 fusion_stats_kernel(const __grid_constant__ FusionParams p) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const specyolo_fusion_t& a = p.a;
     // work item -> (image, input, part)
     int item = blockIdx.x;
@@ -222,6 +227,8 @@ fusion_stats_kernel(const __grid_constant__ FusionParams p) {
 
 __global__ void __launch_bounds__(256)
 fusion_apply_kernel(const __grid_constant__ FusionParams p) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const specyolo_fusion_t& a = p.a;
     const int b = blockIdx.y;
     const int h0 = blockIdx.x * kFusRows;
@@ -376,10 +383,10 @@ int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     p.gate = p.mm + (size_t)a->B * a->k * 2 * a->H * a->W;
     p.ticket = reinterpret_cast<unsigned int*>(p.gate + (size_t)a->B * a->k * a->c);
     SY_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)a->B * sizeof(unsigned int), stream));
-    fusion_stats_kernel<<<(unsigned)(a->B * a->k * p.parts), 256, 0, stream>>>(p);
+    SY_CUDA(launch_pdl(fusion_stats_kernel, dim3((unsigned)(a->B * a->k * p.parts)), dim3(256), 0, stream, p));
     SY_LAUNCH_CHECK();
     dim3 grid((unsigned)ceil_div(a->H, kFusRows), (unsigned)a->B);
-    fusion_apply_kernel<<<grid, 256, sab_smem, stream>>>(p);
+    SY_CUDA(launch_pdl(fusion_apply_kernel, grid, dim3(256), sab_smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch(2);
     return SPECYOLO_OK;

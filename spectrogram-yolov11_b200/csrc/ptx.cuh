@@ -20,6 +20,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// launch_dependents: the next kernel of the stream may start being scheduled (once every CTA of this grid has said so).
+// wait: blocks until all prerequisite grids have completed and their memory is visible.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));

@@ -39,6 +39,27 @@ inline bool env_flag(const char* name) {
     return e && e[0] && e[0] != '0';
 }
 
+// Launch with programmatic dependent launch (PDL) allowed: the grid may be scheduled while the previous kernel of the
+// stream drains (every CTA of it has executed griddepcontrol.launch_dependents or exited); the kernel must execute
+// griddepcontrol.wait (ptx::grid_dep_wait) before it touches memory written or read by its predecessors.  Inside a
+// CUDA-graph capture this becomes a programmatic edge.  ~110 kernels per step, most of them a few microseconds long:
+// without it every launch pays the full drain + ramp-up of its neighbours.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = env_flag("SPECYOLO_NO_PDL") ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

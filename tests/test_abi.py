@@ -46,7 +46,8 @@ def test_pure_host_entry_points(lib):
     assert lib.specyolo_conv_merge(256, 128, 8, 3, 2, 1, 1) == 2   # s2 without matching dilation: per-tap kernel
     assert lib.specyolo_conv_merge(128, 128, 8, 7, 2, 6, 2) == 1   # DDWConv geometry: halo kernel, group by group
     assert lib.specyolo_conv_merge(128, 128, 1, 3, 1, 1, 1) == 1
-    assert lib.specyolo_conv_merge(128, 128, 128, 3, 1, 1, 1) == 1  # depthwise stays on its own kernel
+    assert lib.specyolo_conv_merge(128, 128, 128, 3, 1, 1, 1) == 64  # depthwise 3x3: block-diagonal GEMM on the halo kernel
+    assert lib.specyolo_conv_merge(24, 24, 24, 3, 1, 1, 1) == 1      # odd channel counts: CUDA-core depthwise kernel
     assert lib.specyolo_fusion_ws_bytes(3, 2, 40, 40, 128) > 0
     assert lib.specyolo_nms_ws_bytes(2, 2, 8400, 0) > 0
     lib.specyolo_reset_launch_count()
