@@ -55,6 +55,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -66,15 +73,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        # samples taken inside the timed region (nvidia-smi reports ~50 ms late: allow that much slack at the end)
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.06)]
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 8:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
@@ -148,6 +157,7 @@ def stage_roofline(model, x_dev, peaks):
 
     rec = []
     orig = {}
+    ridge = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)      # flop per byte
 
     def wrap(name, flops_fn=None, bytes_fn=None):
         f = getattr(ops, name)
@@ -158,8 +168,12 @@ def stage_roofline(model, x_dev, peaks):
             e0.record()
             r = f(*a, **k)
             e1.record()
-            nm = "dwconv3x3" if (name == "conv2d" and a[1].n_pad == 1) else name
-            rec.append((nm, e0, e1, flops_fn(*a, **k) if flops_fn else 0.0, bytes_fn(r, *a, **k) if bytes_fn else 0.0))
+            nm = name
+            fl = flops_fn(*a, **k) if flops_fn else 0.0
+            by = bytes_fn(r, *a, **k) if bytes_fn else 0.0
+            if name == "conv2d":     # class by arithmetic intensity against the ridge of the measured peaks
+                nm = "conv2d_tensor_bound" if fl / max(by, 1.0) >= ridge else "conv2d_hbm_bound"
+            rec.append((nm, e0, e1, fl, by))
             return r
         setattr(ops, name, g)
 
@@ -214,10 +228,15 @@ def stage_roofline(model, x_dev, peaks):
         if by:
             s.update(gbs=by / t / 1e9, frac_hbm=by / t / 1e9 / peaks["hbm"])
         stages[name] = s
-    c = agg["conv2d"]
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (all its launches of one step)",
+    c = [sum(agg[n][j] for n in agg if n.startswith("conv2d")) for j in range(4)]
+    traffic = None
+    tf = ROOT / "profiles" / "conv_dram_traffic.json"      # written from an ncu capture by tools/ncu_traffic.py
+    if tf.is_file():
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_halo_kernel: every tcgen05 implicit-GEMM conv launch of one step "
+                                          "(the layers below the ridge are HBM-bound: see stages.conv2d_hbm_bound)",
             "achieved": c[1] / c[0] / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-            "frac": c[1] / c[0] / 1e12 / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " sustained",
+            "frac": c[1] / c[0] / 1e12 / peaks["tf_sust"], "traffic": traffic, "algorithmic_bytes_per_step": c[2], "peak_source": peaks["src"] + " sustained",
             "flops_per_step": c[1], "ms_per_step": 1e3 * c[0], "launches_per_step": c[3],
             "hbm_gbs_same_launches": c[2] / c[0] / 1e9, "frac_hbm_same_launches": c[2] / c[0] / 1e9 / peaks["hbm"]}
     return roof, stages
@@ -249,11 +268,14 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
 
     # ---- resident-input throughput: graph replay, inputs already in HBM ----
     predictor = specyolo.DetectionPredictor(yolo.model, pred_args)
-    for _ in range(max(args.warmup, 3)):
-        out, cnt = predictor.infer(x_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()             # started early: nvidia-smi needs ~0.2 s before its first sample
+    # two batches in flight (DetectionPredictor.infer_pipelined): every step is a full forward + decode + NMS of B
+    # images; consecutive steps overlap on the GPU the way consecutive batches of predict(stream=True) do
+    predictor.infer_pipelined(x_dev, max(args.warmup, 3))
     torch.cuda.synchronize()
     launches_per_step = predictor.last_launches
-    sampler = ClockSampler(local_rank)
 
     def barrier():
         if world > 1:
@@ -261,14 +283,14 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        out, cnt = predictor.infer(x_dev)
+    last = predictor.infer_pipelined(x_dev, args.steps)
+    out, cnt = last[(args.steps - 1) & 1]
     e1.record()
     barrier()
+    sampler.mark_end()
     t_dev = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([t_dev], device=dev, dtype=torch.float64)
@@ -314,6 +336,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
                                    "fwd + fused decode + NMS, 640^2, batch 64 per GPU (BASELINE configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "imgsz": IMGSZ, "conf": CONF, "iou": IOU,
                        "input": "uint8 NCHW, resident in HBM for `value`, pinned host for `e2e`",
+                       "pipelining": "two batches in flight (two CUDA-graph instances on two streams), every step = full fwd+decode+NMS",
                        "l2": "no flush: one step streams ~9 GB of activations, >> 126 MB L2",
                        "sharding": "images split across GPUs, no collective on the data path",
                        "detections_last_step": n_det},

@@ -90,7 +90,8 @@ class _GraphStep:
         self.launches = int(_lib.load().specyolo_launch_count() - n0)
 
     def run(self, x: torch.Tensor):
-        self.static_in.copy_(x, non_blocking=True)
+        if x.data_ptr() != self.static_in.data_ptr():       # callers may fill the static input in place (zero copy)
+            self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.out, self.cnt
 
@@ -110,6 +111,7 @@ class DetectionPredictor:
         self._graphs: Dict[tuple, _GraphStep] = {}
         self._stream_steps: List[Optional[_GraphStep]] = [None, None]   # double-buffered graph instances
         self._stream_host: list = [None, None]                           # their pinned host result buffers
+        self._compute_streams: list = []                                 # one compute stream per instance
         self.last_launches = 0
 
     # -- sources ---------------------------------------------------------------------------------
@@ -165,6 +167,46 @@ class DetectionPredictor:
         self.last_launches = int(_lib.load().specyolo_launch_count() - n0)
         return r
 
+    def _streams(self, dev):
+        if not self._compute_streams:
+            self._compute_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        return self._compute_streams
+
+    def _ensure_stream_step(self, slot: int, im: torch.Tensor, classes):
+        a = self.args
+        steps, host_out = self._stream_steps, self._stream_host
+        if steps[slot] is None or steps[slot].static_in.shape != im.shape or steps[slot].static_in.dtype != im.dtype:
+            example = im.to(next(self.model.parameters()).device) if not im.is_cuda else im
+            steps[slot] = _GraphStep(self.model, example, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"], classes)
+            host_out[slot] = (torch.empty(steps[slot].out.shape, dtype=torch.float32).pin_memory(),
+                              torch.empty(steps[slot].cnt.shape, dtype=torch.int32).pin_memory())
+            self.last_launches = steps[slot].launches
+        return steps[slot]
+
+    @torch.no_grad()
+    def infer_pipelined(self, im: torch.Tensor, steps: int):
+        """`steps` forward + NMS passes over the device-resident batch `im` with TWO batches in flight: two captured
+        graph instances replay alternately on two compute streams, so the low-occupancy phases of one step (the 20x20
+        level, decode, NMS: grids far below 148 SMs) overlap the wide kernels of the other.  Returns the (out, cnt)
+        device tensors of the last step of each instance.  Everything is enqueued behind the caller's current
+        stream and joined back into it."""
+        classes = None
+        if self.args["classes"] is not None:
+            classes = torch.tensor(list(self.args["classes"]), device=im.device, dtype=torch.int32)
+        main = torch.cuda.current_stream(im.device)
+        cs = self._streams(im.device)
+        inst = [self._ensure_stream_step(s, im, classes) for s in (0, 1)]
+        for s in (0, 1):
+            if inst[s].static_in.data_ptr() != im.data_ptr():
+                inst[s].static_in.copy_(im, non_blocking=True)      # once, outside the per-step work
+            cs[s].wait_stream(main)
+        for i in range(steps):
+            with torch.cuda.stream(cs[i & 1]):
+                inst[i & 1].graph.replay()
+        for s in (0, 1):
+            main.wait_stream(cs[s])
+        return [(g.out, g.cnt) for g in inst]
+
     @torch.no_grad()
     def stream(self, batches):
         """`predict(source, stream=True)`: generator over an iterable of batches (engine/predictor.py:169-175 yields per
@@ -175,6 +217,9 @@ class DetectionPredictor:
         dev = next(self.model.parameters()).device
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
+        cs = self._streams(dev)                                          # one compute stream per graph instance
+        for st in cs:
+            st.wait_stream(main)
         steps, host_out = self._stream_steps, self._stream_host          # captured once, reused across calls
         done = [None, None]          # event: results of the batch that used slot s are in pinned host memory
         uploaded = [None, None]
@@ -195,12 +240,7 @@ class DetectionPredictor:
 
         def enqueue_upload(slot, item):
             im, shapes, imgs = prep(item)
-            if steps[slot] is None or steps[slot].static_in.shape != im.shape or steps[slot].static_in.dtype != im.dtype:
-                example = im.to(dev) if not im.is_cuda else im
-                steps[slot] = _GraphStep(self.model, example, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"], classes)
-                host_out[slot] = (torch.empty(steps[slot].out.shape, dtype=torch.float32).pin_memory(),
-                                  torch.empty(steps[slot].cnt.shape, dtype=torch.int32).pin_memory())
-                self.last_launches = steps[slot].launches
+            self._ensure_stream_step(slot, im, classes)
             if done[slot] is not None:
                 copy_stream.wait_event(done[slot])          # the graph that read this input buffer has finished
             with torch.cuda.stream(copy_stream):
@@ -211,12 +251,14 @@ class DetectionPredictor:
             meta[slot] = (shapes, imgs, im.shape[0], tuple(im.shape[2:]))
 
         def launch(slot):
-            main.wait_event(uploaded[slot])
-            steps[slot].graph.replay()
-            host_out[slot][0].copy_(steps[slot].out, non_blocking=True)
-            host_out[slot][1].copy_(steps[slot].cnt, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(main)
+            # the two instances run on their own streams: consecutive batches overlap on the GPU (two in flight)
+            with torch.cuda.stream(cs[slot]):
+                cs[slot].wait_event(uploaded[slot])
+                steps[slot].graph.replay()
+                host_out[slot][0].copy_(steps[slot].out, non_blocking=True)
+                host_out[slot][1].copy_(steps[slot].cnt, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs[slot])
             done[slot] = ev
 
         def collect(slot):
@@ -247,6 +289,8 @@ class DetectionPredictor:
                 break
             i += 1
         yield collect(pending)
+        for st in cs:
+            main.wait_stream(st)
 
     def __call__(self, source) -> List[Results]:
         im, shapes, host_imgs = self.preprocess(source)

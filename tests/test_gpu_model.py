@@ -134,6 +134,12 @@ def test_predict_api_and_fused_path(lib):
     ref1 = yolo.predict(batches[1].cuda(), conf=0.25, iou=0.7)
     for a, c in zip(ref1, outs[1]):
         assert torch.equal(a.boxes.data, c.boxes.data)
+    # two batches in flight on two streams (bench.py's resident-input loop): both instances reproduce the detections
+    out0, cnt0 = yolo.predictor.infer(x)
+    out0, cnt0 = out0.clone(), cnt0.clone()
+    for o, c in yolo.predictor.infer_pipelined(x, 5):
+        torch.cuda.synchronize()
+        assert torch.equal(c, cnt0) and torch.equal(o, out0)
     # uint8 HWC BGR ndarray source (predictor.py:125-136 path)
     img = (synth_images(1, 320, seed=6)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)[..., ::-1]
     r = yolo.predict([np.ascontiguousarray(img)], conf=0.25)

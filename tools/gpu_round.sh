@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest -q -m gpu -p no:cacheprovider tests > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/gpu_tests.log | head -30
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 python - <<'PY'
 import json; d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
 print({k:d[k] for k in ('value','ms_per_step','launches_per_step')}, d['e2e'], d['clocks'], d['cpu_baseline'])
