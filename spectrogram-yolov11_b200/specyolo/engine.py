@@ -223,6 +223,9 @@ class DetectionPredictor:
         steps, host_out = self._stream_steps, self._stream_host          # captured once, reused across calls
         done = [None, None]          # event: results of the batch that used slot s are in pinned host memory
         uploaded = [None, None]
+        consumed = [None, None]      # event: the step has copied its staged input into the graph's static input
+        staging: list = [None, None] # device staging buffers the host uploads into (decoupled from the graph inputs:
+                                     # the upload of batch i+2 may start as soon as step i has STARTED, not finished)
         meta: list = [None, None]
         classes = None
         if a["classes"] is not None:
@@ -241,10 +244,12 @@ class DetectionPredictor:
         def enqueue_upload(slot, item):
             im, shapes, imgs = prep(item)
             self._ensure_stream_step(slot, im, classes)
-            if done[slot] is not None:
-                copy_stream.wait_event(done[slot])          # the graph that read this input buffer has finished
+            if staging[slot] is None or staging[slot].shape != im.shape or staging[slot].dtype != im.dtype:
+                staging[slot] = torch.empty_like(steps[slot].static_in)
+            if consumed[slot] is not None:
+                copy_stream.wait_event(consumed[slot])      # the previous step of this slot has taken its input
             with torch.cuda.stream(copy_stream):
-                steps[slot].static_in.copy_(im, non_blocking=True)
+                staging[slot].copy_(im, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             uploaded[slot] = ev
@@ -254,6 +259,9 @@ class DetectionPredictor:
             # the two instances run on their own streams: consecutive batches overlap on the GPU (two in flight)
             with torch.cuda.stream(cs[slot]):
                 cs[slot].wait_event(uploaded[slot])
+                steps[slot].static_in.copy_(staging[slot], non_blocking=True)
+                consumed[slot] = torch.cuda.Event()
+                consumed[slot].record(cs[slot])
                 steps[slot].graph.replay()
                 host_out[slot][0].copy_(steps[slot].out, non_blocking=True)
                 host_out[slot][1].copy_(steps[slot].cnt, non_blocking=True)
@@ -264,8 +272,9 @@ class DetectionPredictor:
         def collect(slot):
             done[slot].synchronize()
             shapes, imgs, B, img1 = meta[slot]
-            out_h, counts = host_out[slot][0], host_out[slot][1].tolist()
-            return [Results(shapes[b], out_h[b, : counts[b]].clone(), self.model.names, orig_img=imgs[b])
+            counts = host_out[slot][1].tolist()
+            out_h = host_out[slot][0].clone()       # one copy out of the pinned buffer; per-image rows are views of it
+            return [Results(shapes[b], out_h[b, : counts[b]], self.model.names, orig_img=imgs[b])
                     for b in range(B)]
 
         it = iter(batches)
