@@ -273,7 +273,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
         sampler.start()             # started early: nvidia-smi needs ~0.2 s before its first sample
     # two batches in flight (DetectionPredictor.infer_pipelined): every step is a full forward + decode + NMS of B
     # images; consecutive steps overlap on the GPU the way consecutive batches of predict(stream=True) do
-    predictor.infer_pipelined(x_dev, max(args.warmup, 3))
+    predictor.infer_pipelined(x_dev, max(args.warmup, 3), args.inflight)
     torch.cuda.synchronize()
     launches_per_step = predictor.last_launches
 
@@ -286,8 +286,8 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    last = predictor.infer_pipelined(x_dev, args.steps)
-    out, cnt = last[(args.steps - 1) & 1]
+    last = predictor.infer_pipelined(x_dev, args.steps, args.inflight)
+    out, cnt = last[(args.steps - 1) % args.inflight]
     e1.record()
     barrier()
     sampler.mark_end()
@@ -336,7 +336,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
                                    "fwd + fused decode + NMS, 640^2, batch 64 per GPU (BASELINE configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "imgsz": IMGSZ, "conf": CONF, "iou": IOU,
                        "input": "uint8 NCHW, resident in HBM for `value`, pinned host for `e2e`",
-                       "pipelining": "two batches in flight (two CUDA-graph instances on two streams), every step = full fwd+decode+NMS",
+                       "pipelining": f"{args.inflight} batches in flight (one CUDA-graph instance + stream each), every step = full fwd+decode+NMS",
                        "l2": "no flush: one step streams ~9 GB of activations, >> 126 MB L2",
                        "sharding": "images split across GPUs, no collective on the data path",
                        "detections_last_step": n_det},
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight in the resident-input loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -99,6 +99,11 @@ typedef struct {
        ultralytics/nn/modules/block.py:724-726); bf16 NHWC window with Cout channels */
     const void* residual;
     int r_pixstride;
+    /* 1: y is written 2x2-blocked (space-to-depth): pixel (oh, ow), channel c goes to the NHWC tensor
+       [B, Ho/2, Wo/2, 4*Cout] at channel ((oh%2)*2 + ow%2)*Cout + c; y_pixstride is that tensor's pixel stride.
+       A following 3x3 / stride-2 / pad-1 conv then reads it as a 2x2 / stride-1 conv over 4*Cout channels
+       (halo-tile kernel only; Ho, Wo even; bf16 output). */
+    int y_s2d;
 } specyolo_conv_t;
 
 /* y = act(conv(x, W) + b) [+ residual]  — replaces Conv.forward_fuse

@@ -128,13 +128,19 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
     // less padding at the far edge, e.g. the 2x2 space-to-depth form of the stem)
     SY_CHECK(a->Ho >= 1 && a->Wo >= 1 && a->Ho <= ho && a->Wo <= wo, SPECYOLO_ERR_INVALID,
              "conv: Ho/Wo (%d,%d) exceed the geometry (%d,%d)", a->Ho, a->Wo, ho, wo);
-    SY_CHECK(a->x_pixstride >= a->Cin && a->y_pixstride >= a->Cout, SPECYOLO_ERR_INVALID, "conv: pixel stride too small");
+    SY_CHECK(a->x_pixstride >= a->Cin && a->y_pixstride >= (a->y_s2d ? 4 : 1) * a->Cout, SPECYOLO_ERR_INVALID,
+             "conv: pixel stride too small");
+    SY_CHECK(!a->y_s2d || (a->Ho % 2 == 0 && a->Wo % 2 == 0 && !a->y_fp32 && a->groups == 1), SPECYOLO_ERR_INVALID,
+             "conv: blocked (space-to-depth) output needs even Ho/Wo, bf16, groups == 1");
     SY_CHECK(a->act == SPECYOLO_ACT_NONE || a->act == SPECYOLO_ACT_SILU, SPECYOLO_ERR_INVALID, "conv: bad act");
     SY_CHECK(a->x_upshift == 0, SPECYOLO_ERR_UNSUPPORTED, "conv: x_upshift is not implemented");
-    if (a->groups == a->Cin && a->Cin == a->Cout && a->groups > 1)
+    if (a->groups == a->Cin && a->Cin == a->Cout && a->groups > 1) {
+        SY_CHECK(!a->y_s2d, SPECYOLO_ERR_UNSUPPORTED, "conv: blocked output is not available for depthwise convs");
         return dwconv3x3_launch(a, (cudaStream_t)stream);
+    }
     const int r = conv_halo_try_launch(a, (cudaStream_t)stream);   // k x k convs with resident weights
     if (r >= 0) return r;
+    SY_CHECK(!a->y_s2d, SPECYOLO_ERR_UNSUPPORTED, "conv: blocked output is implemented by the halo-tile kernel only");
     return conv_igemm_launch(a, (cudaStream_t)stream);
 }
 

@@ -63,6 +63,7 @@ struct HaloParams {
     int act;
     // TMA-store epilogue (store_bw == 0: direct stores)
     int store_bw, pair_stores;
+    int y_s2d;                   // output written 2x2-blocked (see specyolo_conv_t::y_s2d)
     uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
@@ -183,8 +184,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         {
             const bool leader = ptx::elect_one();
             const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_pad);
-            const uint64_t a_hi = halo_desc(0, (uint32_t)p.halo_w * p.a_row_bytes, p.a_row_bytes);
-            const uint64_t b_hi = halo_desc(0, 8u * p.b_row_bytes, p.b_row_bytes);
+            const uint32_t a_hi = (uint32_t)(halo_desc(0, (uint32_t)p.halo_w * p.a_row_bytes, p.a_row_bytes) >> 32);
+            const uint32_t b_hi = (uint32_t)(halo_desc(0, 8u * p.b_row_bytes, p.b_row_bytes) >> 32);
             const uint32_t a_ring16 = ptx::smem_u32(a_ring) >> 4, b_base16 = ptx::smem_u32(b_s) >> 4;
             const uint32_t b_box16 = p.b_box_bytes >> 4;
             const uint32_t b_tap16 = (uint32_t)p.bchunks * b_box16;       // next tap of the same (group, chunk)
@@ -214,9 +215,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint32_t d_col = d_tmem + gl * (uint32_t)p.n_pad;
                         uint32_t accumulate = cio == 0 ? 0u : 1u;         // first K step of this group
                         for (int tap = 0; tap < p.taps; ++tap) {
-                            if (leader)
-                                ptx::umma_bf16(d_col, a_hi | (uint64_t)(a16k + p.tap_a16[tap]), b_hi | (uint64_t)b16, idesc,
-                                               accumulate);
+                            if (leader) ptx::umma_bf16_lohi(d_col, a16k + p.tap_a16[tap], a_hi, b16, b_hi, idesc, accumulate);
                             accumulate = 1u;
                             b16 += b_tap16;
                         }
@@ -253,7 +252,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t bph = (tl >> 1) & 1u;
             const int ow = (int)tw_i * kHaloTW + tw, oh = (int)th_i * kHaloTH + th;
             const bool row_ok = (ow < p.Wo) && (oh < p.Ho);
-            const size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
+            size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
+            if (p.y_s2d) {      // blocked output: pixel -> (block pixel, channel slab of the 2x2 position)
+                pix = ((size_t)n * (p.Ho >> 1) + (oh >> 1)) * (p.Wo >> 1) + (ow >> 1);
+                ec.gch0 = (((oh & 1) << 1) | (ow & 1)) * p.cout_g;
+            }
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.ncols;
 
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
@@ -349,7 +352,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         const int es = a->y_fp32 ? 4 : 2;
         int store_bw = epi_stage_box_cols(ncols, es);
         if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * es) % 16 ||
-            (gcta > 1 && cout_g != p.n_pad) || env_flag("SPECYOLO_NO_TMA_STORE"))
+            (gcta > 1 && cout_g != p.n_pad) || a->y_s2d || env_flag("SPECYOLO_NO_TMA_STORE"))
             store_bw = 0;
         uint32_t stage_out = epi_stage_bytes(ncols, store_bw, es);
         if ((long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out < 3L * a_stage) {   // keep a 3-deep ring
@@ -415,6 +418,8 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
     p.r_pixstride = a->r_pixstride;
     p.act = a->act;
+    p.y_s2d = a->y_s2d;
+    if (a->y_s2d && (groups != 1 || a->residual)) return false;
     plan.p = p;
     const long resident = (long)sm_count() * plan.occ / p.gsplit;           // CTAs per split
     const long per_split = spatial < resident ? spatial : (resident < 1 ? 1 : resident);

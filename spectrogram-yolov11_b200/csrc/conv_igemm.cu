@@ -181,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_tile);
             const uint32_t row_bytes = p.kc * 2;
             const int kk = p.kc / 16;
-            const uint64_t desc_hi = ptx::umma_smem_desc(0, row_bytes);    // everything but the start address
+            const uint32_t desc_hi = (uint32_t)(ptx::umma_smem_desc(0, row_bytes) >> 32);   // all but the start address
             const uint32_t a_ring_addr = ptx::smem_u32(a_ring), b_ring_addr = ptx::smem_u32(b_ring);
             int stage = 0;
             uint32_t ph = 0, tl = 0;
@@ -203,9 +203,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     uint32_t b16 = (b_ring_addr + (uint32_t)(stage * p.cps) * p.b_chunk_bytes) >> 4;
                     for (int j = 0; j < nch; ++j) {
                         for (int k = 0; k < kk; ++k) {
-                            if (leader)
-                                ptx::umma_bf16(d_tmem, desc_hi | (uint64_t)(a16 + 2u * k), desc_hi | (uint64_t)(b16 + 2u * k),
-                                               idesc, accumulate);
+                            if (leader) ptx::umma_bf16_lohi(d_tmem, a16 + 2u * k, desc_hi, b16 + 2u * k, desc_hi, idesc, accumulate);
                             accumulate = 1;
                         }
                         a16 += p.a_chunk_bytes >> 4;

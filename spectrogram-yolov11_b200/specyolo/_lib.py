@@ -35,7 +35,7 @@ class ConvArgs(C.Structure):
         ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
         ("groups", C.c_int), ("act", C.c_int),
         ("y", C.c_void_p), ("Ho", C.c_int), ("Wo", C.c_int), ("y_pixstride", C.c_int), ("y_fp32", C.c_int),
-        ("residual", C.c_void_p), ("r_pixstride", C.c_int),
+        ("residual", C.c_void_p), ("r_pixstride", C.c_int), ("y_s2d", C.c_int),
     ]
 
 

@@ -167,9 +167,9 @@ class DetectionPredictor:
         self.last_launches = int(_lib.load().specyolo_launch_count() - n0)
         return r
 
-    def _streams(self, dev):
-        if not self._compute_streams:
-            self._compute_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    def _streams(self, dev, n: int = 2):
+        while len(self._compute_streams) < n:
+            self._compute_streams.append(torch.cuda.Stream(device=dev))
         return self._compute_streams
 
     def _ensure_stream_step(self, slot: int, im: torch.Tensor, classes):
@@ -184,7 +184,7 @@ class DetectionPredictor:
         return steps[slot]
 
     @torch.no_grad()
-    def infer_pipelined(self, im: torch.Tensor, steps: int):
+    def infer_pipelined(self, im: torch.Tensor, steps: int, inflight: int = 2):
         """`steps` forward + NMS passes over the device-resident batch `im` with TWO batches in flight: two captured
         graph instances replay alternately on two compute streams, so the low-occupancy phases of one step (the 20x20
         level, decode, NMS: grids far below 148 SMs) overlap the wide kernels of the other.  Returns the (out, cnt)
@@ -194,16 +194,19 @@ class DetectionPredictor:
         if self.args["classes"] is not None:
             classes = torch.tensor(list(self.args["classes"]), device=im.device, dtype=torch.int32)
         main = torch.cuda.current_stream(im.device)
-        cs = self._streams(im.device)
-        inst = [self._ensure_stream_step(s, im, classes) for s in (0, 1)]
-        for s in (0, 1):
+        cs = self._streams(im.device, inflight)
+        while len(self._stream_steps) < inflight:
+            self._stream_steps.append(None)
+            self._stream_host.append(None)
+        inst = [self._ensure_stream_step(s, im, classes) for s in range(inflight)]
+        for s in range(inflight):
             if inst[s].static_in.data_ptr() != im.data_ptr():
                 inst[s].static_in.copy_(im, non_blocking=True)      # once, outside the per-step work
             cs[s].wait_stream(main)
         for i in range(steps):
-            with torch.cuda.stream(cs[i & 1]):
-                inst[i & 1].graph.replay()
-        for s in (0, 1):
+            with torch.cuda.stream(cs[i % inflight]):
+                inst[i % inflight].graph.replay()
+        for s in range(inflight):
             main.wait_stream(cs[s])
         return [(g.out, g.cnt) for g in inst]
 

@@ -65,18 +65,40 @@ class Conv(nn.Module):
                 self.bn.eps, c.stride[0], c.padding[0], c.dilation[0], c.groups, isinstance(self.act, nn.SiLU))
         return self._packed
 
+    def packed_from_blocked(self) -> ops.PackedConv:
+        """This 3x3 / stride-2 conv as a 2x2 conv over a 2x2-blocked input (ops.pack_from_blocked)."""
+        if getattr(self, "_packed_blocked", None) is None:
+            self._packed_blocked = ops.pack_from_blocked(
+                self.conv.weight, None, (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var),
+                self.bn.eps, isinstance(self.act, nn.SiLU))
+        return self._packed_blocked
+
     def invalidate(self):
         self._packed = None
+        self._packed_blocked = None
 
     def _apply(self, fn, *a, **k):
         self._packed = None  # parameters moved / cast: repack lazily
+        self._packed_blocked = None
         return super()._apply(fn, *a, **k)
 
     def _load_from_state_dict(self, *a, **k):
         self._packed = None
+        self._packed_blocked = None
         return super()._load_from_state_dict(*a, **k)
 
     # -- forward -------------------------------------------------------------------------------
+    def is_stem(self) -> bool:
+        c = self.conv
+        return c.in_channels == 3 and c.groups == 1 and c.kernel_size == (3, 3) and c.stride == (2, 2) and \
+            c.padding == (1, 1) and c.dilation == (1, 1)
+
+    def takes_blocked(self) -> bool:
+        """3x3 / s2 / p1 dense conv thin enough to be HBM-bound with K = 16 c: can read a 2x2-blocked input."""
+        c = self.conv
+        return c.groups == 1 and c.kernel_size == (3, 3) and c.stride == (2, 2) and c.padding == (1, 1) and \
+            c.dilation == (1, 1) and c.in_channels % 4 == 0 and c.in_channels <= 32 and c.out_channels <= 256
+
     def forward(self, x, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None):
         if self.conv.in_channels == 3 and self.conv.groups == 1 and x.dim() == 4 and x.stride(1) != 1:
             return ops.stem_conv(x, self.packed(), out)  # NCHW network input straight into the stem

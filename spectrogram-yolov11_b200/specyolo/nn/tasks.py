@@ -200,6 +200,16 @@ class DetectionModel(nn.Module):
         groups = self._parallel_groups()
         layers = list(self.model[:-1])
         i = 0
+        # stem pair: layer 0 writes its output 2x2-blocked and layer 1 (3x3 / s2) reads it as a 2x2 / s1 conv over
+        # 4c channels — one 128-byte-row TMA box per tile instead of nine strided boxes (same arithmetic)
+        if (len(layers) > 1 and isinstance(layers[0], Conv) and type(layers[1]) is Conv and layers[0].is_stem()
+                and layers[1].takes_blocked() and layers[1].f == -1 and 0 not in self.save and x.dim() == 4
+                and x.stride(1) != 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
+                and layers[0].packed().s2d is not None):
+            xb = ops.stem_conv(x, layers[0].packed(), blocked_out=True)
+            x = ops.conv2d(xb, layers[1].packed_from_blocked())
+            y.extend([None, x if 1 in self.save else None])
+            i = 2
         while i < len(layers):
             m = layers[i]
             if i in groups:                     # independent layers: fork / join on side streams

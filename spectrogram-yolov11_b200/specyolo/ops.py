@@ -208,8 +208,11 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
 
 
 def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out_fp32: bool = False) -> torch.Tensor:
-    """y = act(conv(x) + b) [+ residual] on NHWC feature maps (specyolo_conv2d_bias_act)."""
+           residual: Optional[torch.Tensor] = None, out_fp32: bool = False, blocked_out: bool = False) -> torch.Tensor:
+    """y = act(conv(x) + b) [+ residual] on NHWC feature maps (specyolo_conv2d_bias_act).
+
+    blocked_out: the result is written 2x2-blocked (space-to-depth) as a [B, 4*cout, Ho/2, Wo/2] feature map
+    (channel ((oh%2)*2 + ow%2)*cout + c) for a following stride-2 conv packed with `pack_from_blocked`."""
     B, Cin, H, W, xpix = nhwc_meta(x)
     if x.dtype != torch.bfloat16:
         raise TypeError("conv2d expects a bf16 feature map")
@@ -220,11 +223,14 @@ def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
         xp[:, :Cin].copy_(x)
         x, Cin, xpix = xp, pc.cin, pc.cin
     Ho, Wo = pc.out_hw(H, W)
+    oshape = (B, 4 * pc.cout, Ho // 2, Wo // 2) if blocked_out else (B, pc.cout, Ho, Wo)
+    if blocked_out and (Ho % 2 or Wo % 2 or out_fp32 or residual is not None):
+        raise ValueError("conv2d: blocked output needs even Ho/Wo, bf16 output and no residual")
     if out is None:
-        out = new_act(B, pc.cout, Ho, Wo, x.device, torch.float32 if out_fp32 else torch.bfloat16)
+        out = new_act(*oshape, x.device, torch.float32 if out_fp32 else torch.bfloat16)
     oB, oC, oH, oW, ypix = nhwc_meta(out)
-    if (oB, oC, oH, oW) != (B, pc.cout, Ho, Wo):
-        raise ValueError(f"conv2d: out shape {tuple(out.shape)} != {(B, pc.cout, Ho, Wo)}")
+    if (oB, oC, oH, oW) != oshape:
+        raise ValueError(f"conv2d: out shape {tuple(out.shape)} != {oshape}")
     if out.dtype != (torch.float32 if out_fp32 else torch.bfloat16):
         raise TypeError("conv2d: out dtype mismatch")
     a = ConvArgs()
@@ -233,6 +239,7 @@ def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
     a.kh = a.kw = pc.k
     a.stride, a.pad, a.dil, a.groups, a.act = pc.s, pc.p, pc.d, pc.g, pc.act
     a.y, a.Ho, a.Wo, a.y_pixstride, a.y_fp32 = out.data_ptr(), Ho, Wo, ypix, int(out_fp32)
+    a.y_s2d = int(blocked_out)
     if residual is not None:
         rB, rC, rH, rW, rpix = nhwc_meta(residual)
         if (rB, rC, rH, rW) != (B, pc.cout, Ho, Wo) or residual.dtype != torch.bfloat16:
@@ -253,7 +260,31 @@ def stem_space_to_depth(x: torch.Tensor) -> torch.Tensor:
     return blocked
 
 
-def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_from_blocked(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn, eps: float, act: bool) -> PackedConv:
+    """Weights of a 3x3 / stride-2 / pad-1 conv [cout, c, 3, 3] repacked as the equivalent 2x2 / stride-1 conv over the
+    2x2-blocked input (4c channels, taps at block offsets -1, 0): w2[:, (dy*2+dx)*c + ci, ty, tx] = w[:, ci, 2ty+dy-1,
+    2tx+dx-1].  K grows from 9c to 16c (zeros), which is free while the layer is HBM-bound, and the input is then read
+    once through one 128-byte-row TMA box per tile instead of nine strided 64-byte-row boxes."""
+    w = weight.detach().to(torch.float32)
+    cout, c, kh, kw = w.shape
+    if kh != 3 or kw != 3:
+        raise ValueError("pack_from_blocked: 3x3 kernels only")
+    w2 = torch.zeros((cout, 4 * c, 2, 2), device=w.device, dtype=torch.float32)
+    for ty in range(2):
+        for tx in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    ky, kx = 2 * ty + dy - 1, 2 * tx + dx - 1
+                    if 0 <= ky < 3 and 0 <= kx < 3:
+                        c0 = (dy * 2 + dx) * c
+                        w2[:, c0:c0 + c, ty, tx] = w[:, :, ky, kx]
+    q = fold_pack(w2, conv_bias, bn, eps, 1, 1, 1, 1, act)
+    q.trim = 1
+    q.alg_k = 9 * c
+    return q
+
+
+def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, blocked_out: bool = False) -> torch.Tensor:
     """3-channel 3x3/s2 stem reading the NCHW network input (fp32 | bf16 | uint8/255)."""
     _lib.init_device()
     if x.dtype not in _DT:
@@ -264,7 +295,10 @@ def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = Non
     B, Cin, H, W = x.shape
     if pc.s2d is not None and H % 2 == 0 and W % 2 == 0:
         # tensor-core route: space-to-depth (one streaming pass) + a K = 64 implicit GEMM
-        return conv2d(stem_space_to_depth(x), pc.s2d["u8" if x.dtype == torch.uint8 else "f"], out=out)
+        return conv2d(stem_space_to_depth(x), pc.s2d["u8" if x.dtype == torch.uint8 else "f"], out=out,
+                      blocked_out=blocked_out)
+    if blocked_out:
+        raise ValueError("stem_conv: blocked output needs the space-to-depth route (even H, W)")
     Ho, Wo = pc.out_hw(H, W)
     if out is None:
         out = new_act(B, pc.cout, Ho, Wo, x.device)

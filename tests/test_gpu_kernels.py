@@ -168,6 +168,29 @@ def test_stem_conv(lib):
     assert _rel_err(y8, ref8) < 5e-3
 
 
+def test_stem_blocked_pair(lib):
+    """Stem with 2x2-blocked output + 3x3/s2 conv reading it as a 2x2 conv == the two plain convs."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(21)
+    x = torch.rand((2, 3, 64, 96), generator=gen)
+    w0 = torch.randn((32, 3, 3, 3), generator=gen) * 0.3
+    w1 = torch.randn((64, 32, 3, 3), generator=gen) * 0.08
+    b0 = torch.randn(32, generator=gen) * 0.1
+    b1 = torch.randn(64, generator=gen) * 0.1
+    pc0 = ops.fold_pack(w0.to(DEV), b0.to(DEV), None, 0.0, 2, 1, 1, 1, True)
+    xb = ops.stem_conv(x.to(DEV), pc0, blocked_out=True)
+    assert xb.shape == (2, 128, 16, 24)
+    y0 = F.silu(F.conv2d(_bf(x), _bf(w0), b0, 2, 1))                      # [2, 32, 32, 48]
+    got0 = ops.to_nchw_f32(xb).cpu().view(2, 2, 2, 32, 16, 24).permute(0, 3, 4, 1, 5, 2).reshape(2, 32, 32, 48)
+    assert _rel_err(got0, y0) < 6e-3
+    pc1 = ops.pack_from_blocked(w1.to(DEV), b1.to(DEV), None, 0.0, True)
+    y = ops.conv2d(xb, pc1).float().cpu()
+    ref = F.silu(F.conv2d(_bf(got0), _bf(w1), b1, 2, 1))
+    assert y.shape == ref.shape == (2, 64, 16, 24)
+    assert _rel_err(y, ref) < 6e-3
+
+
 def test_depthwise(lib):
     from specyolo import ops
 
