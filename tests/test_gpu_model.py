@@ -150,6 +150,34 @@ def test_predict_api_and_fused_path(lib):
         yolo.predict(x, device="cpu")
 
 
+def test_yolo11s_1280_vs_oracle(lib):
+    """BASELINE config C4: plain yolo11s (nc=80) at 1280x1280 — N = 1600 attention tokens (13 key blocks), 33 600
+    anchors, 144-channel head — against the CPU oracle on the same seeded weights; graph-replayed predict() equals
+    the dense model() + non_max_suppression path."""
+    import specyolo
+    from specyolo.nn.init import synth_images, synth_state_dict
+    from specyolo.utils.ops import non_max_suppression
+
+    yolo = specyolo.YOLO("yolo11s.yaml", nc=80)
+    sd = synth_state_dict(yolo.model, seed=3)
+    yolo.load_state_dict(sd)
+    yolo.to("cuda")
+    x = synth_images(1, 1280, seed=4)
+    y, raw = yolo.model(x.cuda())
+    assert y.shape == (1, 84, 33600)
+    y_ref, _ = _oracle("yolo11.yaml", "s", 80, sd, x)
+    y = y.cpu()
+    err = (y[:, :4] - y_ref[:, :4]).abs().amax(1)
+    A_lvl = [(1280 // s) ** 2 for s in (8, 16, 32)]
+    lim = torch.cat([torch.full((n,), 0.25 * s) for n, s in zip(A_lvl, (8, 16, 32))])
+    assert bool((err <= lim).all()), (err / lim).max().item()
+    assert err.mean().item() < 0.25
+    assert (y[:, 4:] - y_ref[:, 4:]).abs().max().item() < 0.03
+    res = yolo.predict(x.cuda(), conf=0.25, iou=0.7)
+    dense = non_max_suppression(yolo.model(x.cuda())[0], 0.25, 0.7)
+    assert torch.equal(res[0].boxes.data, dense[0].cpu())
+
+
 def test_iq_to_boxes(lib):
     """Raw IQ -> STFT kernel -> detector -> NMS, vs the oracle chain on the kernel's own spectrogram."""
     import specyolo
