@@ -64,6 +64,10 @@ struct HaloParams {
     // TMA-store epilogue (store_bw == 0: direct stores)
     int store_bw, pair_stores;
     int y_s2d;                   // output written 2x2-blocked (see specyolo_conv_t::y_s2d)
+    // residual tile ring (two slots after the staging buffer): the TMA producer loads the tile's residual box(es)
+    // tiles ahead, the epilogue reads them from shared memory (res_box_cols == 0: residual read from global memory)
+    int res_box_cols, res_slots;
+    uint32_t res_row_bytes, res_swz_mask, res_slot_bytes, res_off;
     uint32_t store_row_bytes, store_swz_mask, ring_bytes;
 };
 
@@ -71,6 +75,7 @@ static constexpr int kHaloThreads = kConvThreads;
 static constexpr int kHaloTW = 8, kHaloTH = 16;
 static constexpr int kHaloMaxStages = 8;
 static constexpr int kHaloMaxBias = 1024;
+static constexpr int kHaloMaxResSlots = 6;     // residual tiles in flight (the producer runs this many tiles ahead)
 static constexpr int kHaloMaxDynSmem = 222 * 1024;
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t row_bytes) {
@@ -83,16 +88,21 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes,
     return d;
 }
 
+// (min 2 CTAs/SM: caps the residual variants at 102 registers — at 134 they silently ran one CTA per SM and every
+//  residual layer took 2-2.7x the time of its residual-free twin)
 template <bool kSilu, bool kRes, bool kFp32>
-__global__ void __launch_bounds__(kHaloThreads)
+__global__ void __launch_bounds__(kHaloThreads, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ HaloParams p) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kHaloMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kHaloMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ __align__(8) uint64_t w_bar;
+    __shared__ __align__(8) uint64_t res_full[kHaloMaxResSlots];
+    __shared__ __align__(8) uint64_t res_empty[kHaloMaxResSlots];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[kHaloMaxBias];
 
@@ -121,6 +131,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::mbar_init(&tmem_empty_bar[b], kEpiWarps);
         }
         ptx::mbar_init(&w_bar, 1);
+        for (int b = 0; b < kHaloMaxResSlots; ++b) {
+            ptx::mbar_init(&res_full[b], 1);
+            ptx::mbar_init(&res_empty[b], kEpiWarps);
+        }
+        if (p.res_box_cols) ptx::prefetch_tmap(&map_r);
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -157,13 +172,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             ptx::grid_dep_wait();
             int stage = 0;
-            uint32_t ph = 0;
+            uint32_t ph = 0, rslot = 0, rph = 0;
+            uint8_t* res_ring = a_ring + p.res_off;
             for (int tile = cta; tile < p.spatial_tiles; tile += ctas) {
                 uint32_t n, r, th_i, tw_i;
                 fdivmod((uint32_t)tile, p.d_img, n, r);
                 fdivmod(r, p.d_tw, th_i, tw_i);
                 const int w0 = ((int)tw_i * kHaloTW - p.pad) * p.sub;
                 const int h0 = ((int)th_i * kHaloTH - p.pad) * p.sub;
+                if (kRes && p.res_box_cols) {       // this tile's residual box(es) into the next ring slot
+                    ptx::mbar_wait(&res_empty[rslot], rph ^ 1u);
+                    if (leader) {
+                        ptx::mbar_expect_tx(&res_full[rslot], p.res_slot_bytes);
+                        uint8_t* dst = res_ring + rslot * p.res_slot_bytes;
+                        for (int c = 0; c < p.ncols; c += p.res_box_cols) {
+                            ptx::tma_load_4d(dst, &map_r, &res_full[rslot], split * p.groups_cta * p.cout_g + c,
+                                             (int)tw_i * kHaloTW, (int)th_i * kHaloTH, (int)n);
+                            dst += 128u * p.res_row_bytes;
+                        }
+                    }
+                    if (++rslot == (uint32_t)p.res_slots) { rslot = 0; rph ^= 1u; }
+                }
                 int ch = split * p.cin_cta;
                 for (int box = 0; box < p.boxes; ++box) {
                     ptx::mbar_wait(&empty_bar[stage], ph ^ 1u);
@@ -243,7 +272,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ec.cout_g = p.cout_g;
         ec.within0 = 0;
         ec.gch0 = split * p.groups_cta * p.cout_g;
-        uint32_t tl = 0;
+        uint32_t tl = 0, rslot = 0, rph = 0;
         for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
             uint32_t n, r, th_i, tw_i;
             fdivmod((uint32_t)tile, p.d_img, n, r);
@@ -259,14 +288,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.ncols;
 
+            EpiResSmem rs{nullptr, 1, 0, 0, m};
+            const bool res_ring_on = kRes && p.res_box_cols != 0;
+            if (res_ring_on) {
+                rs.base = a_ring + p.res_off + rslot * p.res_slot_bytes;
+                rs.box_cols = p.res_box_cols;
+                rs.row_bytes = p.res_row_bytes;
+                rs.swz_mask = p.res_swz_mask;
+            }
+            if (kRes && !res_ring_on && tile + ctas < p.spatial_tiles) {    // next tile's residual -> L2
+                uint32_t n2, r2, th2, tw2;
+                fdivmod((uint32_t)(tile + ctas), p.d_img, n2, r2);
+                fdivmod(r2, p.d_tw, th2, tw2);
+                const int ow2 = (int)tw2 * kHaloTW + tw, oh2 = (int)th2 * kHaloTH + th;
+                epi_prefetch_residual_l2<kRes>(ec, eo, ((size_t)n2 * p.Ho + oh2) * p.Wo + ow2, (ow2 < p.Wo) && (oh2 < p.Ho), half);
+            }
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
             ptx::tc_fence_after();
+            if (res_ring_on) ptx::mbar_wait(&res_full[rslot], rph);
             st.c0 = ec.gch0;
             st.c1 = (int)tw_i * kHaloTW; st.c2 = (int)th_i * kHaloTH; st.c3 = (int)n;
-            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st);
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st, rs);
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+            if (lane == 0) {
+                ptx::mbar_arrive(&tmem_empty_bar[buf]);
+                if (res_ring_on) ptx::mbar_arrive(&res_empty[rslot]);
+            }
+            if (res_ring_on && ++rslot == (uint32_t)p.res_slots) { rslot = 0; rph ^= 1u; }
         }
         if (st.enabled && st.issuer) ptx::bulk_wait_read0();   // staging must outlive the last store's read
     }
@@ -359,6 +408,27 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
             store_bw = 0;
             stage_out = 0;
         }
+        // residual ring: slots of [128 rows x ncols] bf16 loaded by the TMA producer (tiles up to 64 columns).  OFF by
+        // default (SPECYOLO_RES_RING=1 enables it): once the residual variants were capped at two CTAs per SM, the
+        // global-memory residual path with its one-tile-ahead L2 prefetch measured the same or better
+        // (32->64 3x3 @80^2: 46 us vs 53 us with the ring) and leaves the shared memory to the operand ring.
+        int res_box = 0, res_slots = 0;
+        uint32_t res_bytes = 0;
+        if (a->residual && ncols <= 64 && (ncols & (ncols - 1)) == 0 && (gcta == 1 || cout_g == p.n_pad) &&
+            !(reinterpret_cast<uintptr_t>(a->residual) & 15) && (a->r_pixstride % 8) == 0 && env_flag("SPECYOLO_RES_RING")) {
+            // as many slots (tiles of run-ahead) as fit beside a 4-deep A ring, 2..kHaloMaxResSlots
+            const uint32_t slot = 128u * (uint32_t)ncols * 2u;
+            const long room = (long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out - 4L * a_stage;
+            res_slots = (int)(room / (long)slot);
+            if (res_slots > kHaloMaxResSlots) res_slots = kHaloMaxResSlots;
+            if (res_slots >= 2) {
+                res_box = ncols;
+                res_bytes = (uint32_t)res_slots * slot;
+            } else {
+                res_slots = 0;
+            }
+        }
+        stage_out += res_bytes;       // same budget line below; split again when the plan is recorded
         const long avail = (long)kHaloMaxDynSmem - 1024 - (long)b_region - (long)stage_out;
         if (avail < 2L * a_stage) continue;
         int stages = (int)(avail / a_stage);
@@ -396,6 +466,12 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         p.store_row_bytes = (uint32_t)(store_bw * es);
         p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
         p.ring_bytes = (uint32_t)stages * a_stage;
+        p.res_box_cols = res_box;
+        p.res_row_bytes = (uint32_t)res_box * 2u;
+        p.res_swz_mask = p.res_row_bytes == 128 ? 7u : (p.res_row_bytes == 64 ? 3u : 1u);
+        p.res_slots = res_slots;
+        p.res_slot_bytes = res_slots ? res_bytes / (uint32_t)res_slots : 0u;
+        p.res_off = p.ring_bytes + (stage_out - res_bytes);
     }
     if (!found) return false;
 
@@ -473,7 +549,19 @@ int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo Y) failed (%d)", (int)r);
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams);
+    CUtensorMap map_r = map_b;      // placeholder when the residual is read from global memory
+    if (p.res_box_cols) {
+        const cuuint64_t pix_b = (cuuint64_t)a->r_pixstride * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)a->Wo, (cuuint64_t)a->Ho, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {pix_b, pix_b * a->Wo, pix_b * a->Wo * a->Ho};
+        cuuint32_t box[4] = {(cuuint32_t)p.res_box_cols, (cuuint32_t)kHaloTW, (cuuint32_t)kHaloTH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->residual), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.res_row_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(halo residual) failed (%d)", (int)r);
+    }
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams);
     static const KernelFn kernels[8] = {
         conv_halo_kernel<false, false, false>, conv_halo_kernel<false, false, true>,
         conv_halo_kernel<false, true, false>,  conv_halo_kernel<false, true, true>,
@@ -489,7 +577,7 @@ int conv_halo_try_launch(const specyolo_conv_t* a, cudaStream_t stream) {
     });
     SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     const KernelFn kernel = kernels[(a->act == SPECYOLO_ACT_SILU ? 4 : 0) + (a->residual ? 2 : 0) + (a->y_fp32 ? 1 : 0)];
-    SY_CUDA(launch_pdl(kernel, dim3(plan.grid), dim3(kHaloThreads), plan.smem_bytes, stream, map_a, map_b, map_y, p));
+    SY_CUDA(launch_pdl(kernel, dim3(plan.grid), dim3(kHaloThreads), plan.smem_bytes, stream, map_a, map_b, map_y, map_r, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

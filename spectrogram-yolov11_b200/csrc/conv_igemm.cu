@@ -82,7 +82,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
 // streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile
 // i overlaps the loads and MMAs of tile i+1.
 template <bool kSilu, bool kRes, bool kFp32>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)     // two CTAs per SM must fit the register file (<= 102 registers)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -246,11 +246,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ec.gch0 = tc.g * p.cout_g;                // group offset inside the output window
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.n_tile;
 
+            if (kRes && tile + (int)gridDim.x < p.total_tiles) {            // next tile's residual -> L2
+                const TileCoord tn2 = decode_tile(p, tile + (int)gridDim.x);
+                const int ow2 = tn2.w0 + tw, oh2 = tn2.h0 + th, on2 = tn2.n0 + tn;
+                EpiCols e2 = ec;
+                e2.within0 = tn2.nt * p.n_tile;
+                e2.gch0 = tn2.g * p.cout_g;
+                epi_prefetch_residual_l2<kRes>(e2, eo, ((size_t)on2 * p.Ho + oh2) * p.Wo + ow2,
+                                               (m < npix) && (ow2 < p.Wo) && (oh2 < p.Ho) && (on2 < p.B), half);
+            }
             ptx::mbar_wait(&tmem_full_bar[buf], bph);
             ptx::tc_fence_after();
             st.c0 = ec.gch0 + ec.within0;
             st.c1 = tc.w0; st.c2 = tc.h0; st.c3 = tc.n0;
-            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s + tc.g * p.n_pad + ec.within0, eo, pix, row_ok, half, lane, st);
+            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s + tc.g * p.n_pad + ec.within0, eo, pix, row_ok, half, lane, st, EpiResSmem{nullptr, 1, 0, 0, 0});
             // all TMEM reads of this accumulator are complete (wait::ld inside): hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();

@@ -191,11 +191,49 @@ struct EpiCols {
     int gch0;         // output-window channel of (group 0 of the tile, index 0)
 };
 
+// L2 prefetch of the residual rows of the NEXT tile of this warp (no registers held): when the epilogue is the slowest
+// stage there is no accumulator wait to hide behind, so the next tile's residual is pulled into L2 one tile ahead
+// and the register loads above then see L2 latency instead of DRAM latency.
+template <bool kRes>
+__device__ __forceinline__ void epi_prefetch_residual_l2(const EpiCols& ec, const EpiOut& o, size_t pix, bool row_ok,
+                                                         int half) {
+    if (!kRes || !row_ok) return;
+    const int nchunks = ec.ncols >> 4;
+    const int cut = (nchunks + 1) >> 1;
+    const int ch_begin = half ? cut : 0, ch_end = half ? nchunks : cut;
+    const __nv_bfloat16* rp = o.residual + pix * o.r_pixstride + ec.gch0 + ec.within0;
+    for (int chunk = ch_begin; chunk < ch_end; ++chunk)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (chunk << 4)));
+}
+
+// Residual tile staged in shared memory by the TMA producer (halo kernel, tiles <= 64 columns): [boxes][128 rows][box
+// row], swizzled like every TMA box.  nullptr = residual read from global memory (paths above).
+struct EpiResSmem {
+    const uint8_t* base;      // this tile's slot, or nullptr
+    int box_cols;             // columns per box (power of two, <= 64)
+    uint32_t row_bytes;       // box_cols * 2
+    uint32_t swz_mask;
+    int m;                    // this thread's row
+};
+__device__ __forceinline__ void epi_res_smem_load(const EpiResSmem& rs, int c, uint4& r0, uint4& r1) {
+    const int box = c / rs.box_cols;           // box_cols is a power of two
+    const int col = c - box * rs.box_cols;
+    const uint32_t box_off = (uint32_t)box * 128u * rs.row_bytes;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        uint32_t off = (uint32_t)rs.m * rs.row_bytes + (uint32_t)(col * 2 + u * 16);
+        off ^= ((off >> 7) & rs.swz_mask) << 4;
+        const uint4 t = *reinterpret_cast<const uint4*>(rs.base + box_off + off);
+        if (u == 0) r0 = t; else r1 = t;
+    }
+}
+
 // All rows/columns of one accumulator buffer handled by this warp.  t_addr = TMEM address of (this warp's lane
 // quadrant, first column of the buffer).  `half` in {0,1}: which of the two warps sharing the quadrant this is.
 template <bool kSilu, bool kRes, bool kFp32>
 __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, const float* bias_s, const EpiOut& o,
-                                         size_t pix, bool row_ok, int half, int lane, const EpiStage& st) {
+                                         size_t pix, bool row_ok, int half, int lane, const EpiStage& st,
+                                         const EpiResSmem& rs) {
     EpiRow row;
     row.pix = pix;
     row.ok = row_ok;
@@ -226,8 +264,10 @@ __device__ __forceinline__ void epi_tile(uint32_t t_addr, const EpiCols& ec, con
             const int align = kFp32 ? 3 : 7;
             const bool vec_ok = y_vec && ((gch & align) == 0);
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-            const bool res_vec = kRes && r_vec && row_ok && nvalid == 16 && ((gch & 7) == 0);
-            if (res_vec) {      // issue the residual loads before waiting on TMEM
+            const bool res_vec = kRes && ((rs.base != nullptr) || (r_vec && row_ok && nvalid == 16 && ((gch & 7) == 0)));
+            if (kRes && rs.base != nullptr) {
+                epi_res_smem_load(rs, c, r0, r1);      // TMA-staged tile: rows / columns outside the tensor are zeros
+            } else if (res_vec) {       // global residual (L2-prefetched one tile ahead): issue before waiting on TMEM
                 const uint4* rp = reinterpret_cast<const uint4*>(o.residual + pix * o.r_pixstride + gch);
                 r0 = __ldg(rp);
                 r1 = __ldg(rp + 1);
