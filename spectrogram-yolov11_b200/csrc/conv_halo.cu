@@ -39,6 +39,7 @@ struct HaloParams {
     int tiles_w, tiles_h;        // 8-wide x 16-high output tiles per image
     int B, Ho, Wo;
     int spatial_tiles;           // B * tiles_h * tiles_w
+    int supert, nsuper;          // output tiles per accumulator stage (thin tiles: amortises the per-stage hand-offs)
     FastDiv d_img, d_tw;         // tile -> (image, tile row, tile column)
     FastDiv d_cin_g, d_npad;     // channel -> (group, channel in group); accumulator column -> (group, column in group)
     int kcb_log2;
@@ -174,7 +175,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0;
             uint32_t ph = 0, rslot = 0, rph = 0;
             uint8_t* res_ring = a_ring + p.res_off;
-            for (int tile = cta; tile < p.spatial_tiles; tile += ctas) {
+            for (int st = cta; st < p.nsuper; st += ctas)
+            for (int sub_t = 0; sub_t < p.supert; ++sub_t) {
+                const int tile = st * p.supert + sub_t;
+                if (tile >= p.spatial_tiles) break;
                 uint32_t n, r, th_i, tw_i;
                 fdivmod((uint32_t)tile, p.d_img, n, r);
                 fdivmod(r, p.d_tw, th_i, tw_i);
@@ -224,12 +228,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::tc_fence_after();
             int stage = 0;
             uint32_t ph = 0, tl = 0;
-            for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            for (int st = cta; st < p.nsuper; st += ctas, ++tl) {
                 const uint32_t buf = tl & 1u;
                 const uint32_t bph = (tl >> 1) & 1u;
                 ptx::mbar_wait(&tmem_empty_bar[buf], bph ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.ncols;
+                for (int sub_t = 0; sub_t < p.supert; ++sub_t) {
+                if (st * p.supert + sub_t >= p.spatial_tiles) break;
+                const uint32_t d_tmem = tmem_base + (buf * (uint32_t)p.supert + (uint32_t)sub_t) * (uint32_t)p.ncols;
                 for (int box = 0; box < p.boxes; ++box) {
                     ptx::mbar_wait(&full_bar[stage], ph);
                     ptx::tc_fence_after();
@@ -252,6 +258,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (leader) ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; ph ^= 1u; }
                 }
+                }
                 if (leader) ptx::umma_commit(&tmem_full_bar[buf]);
             }
         }
@@ -273,49 +280,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ec.within0 = 0;
         ec.gch0 = split * p.groups_cta * p.cout_g;
         uint32_t tl = 0, rslot = 0, rph = 0;
-        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
-            uint32_t n, r, th_i, tw_i;
-            fdivmod((uint32_t)tile, p.d_img, n, r);
-            fdivmod(r, p.d_tw, th_i, tw_i);
+        const bool res_ring_on = kRes && p.res_box_cols != 0;
+        for (int sti = cta; sti < p.nsuper; sti += ctas, ++tl) {
             const uint32_t buf = tl & 1u;
             const uint32_t bph = (tl >> 1) & 1u;
-            const int ow = (int)tw_i * kHaloTW + tw, oh = (int)th_i * kHaloTH + th;
-            const bool row_ok = (ow < p.Wo) && (oh < p.Ho);
-            size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
-            if (p.y_s2d) {      // blocked output: pixel -> (block pixel, channel slab of the 2x2 position)
-                pix = ((size_t)n * (p.Ho >> 1) + (oh >> 1)) * (p.Wo >> 1) + (ow >> 1);
-                ec.gch0 = (((oh & 1) << 1) | (ow & 1)) * p.cout_g;
+            if (kRes && !res_ring_on && sti + ctas < p.nsuper) {            // next stage's residual rows -> L2
+                for (int sub_t = 0; sub_t < p.supert; ++sub_t) {
+                    const int t2 = (sti + ctas) * p.supert + sub_t;
+                    if (t2 >= p.spatial_tiles) break;
+                    uint32_t n2, r2, th2, tw2;
+                    fdivmod((uint32_t)t2, p.d_img, n2, r2);
+                    fdivmod(r2, p.d_tw, th2, tw2);
+                    const int ow2 = (int)tw2 * kHaloTW + tw, oh2 = (int)th2 * kHaloTH + th;
+                    epi_prefetch_residual_l2<kRes>(ec, eo, ((size_t)n2 * p.Ho + oh2) * p.Wo + ow2, (ow2 < p.Wo) && (oh2 < p.Ho), half);
+                }
             }
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.ncols;
-
-            EpiResSmem rs{nullptr, 1, 0, 0, m};
-            const bool res_ring_on = kRes && p.res_box_cols != 0;
-            if (res_ring_on) {
-                rs.base = a_ring + p.res_off + rslot * p.res_slot_bytes;
-                rs.box_cols = p.res_box_cols;
-                rs.row_bytes = p.res_row_bytes;
-                rs.swz_mask = p.res_swz_mask;
-            }
-            if (kRes && !res_ring_on && tile + ctas < p.spatial_tiles) {    // next tile's residual -> L2
-                uint32_t n2, r2, th2, tw2;
-                fdivmod((uint32_t)(tile + ctas), p.d_img, n2, r2);
-                fdivmod(r2, p.d_tw, th2, tw2);
-                const int ow2 = (int)tw2 * kHaloTW + tw, oh2 = (int)th2 * kHaloTH + th;
-                epi_prefetch_residual_l2<kRes>(ec, eo, ((size_t)n2 * p.Ho + oh2) * p.Wo + ow2, (ow2 < p.Wo) && (oh2 < p.Ho), half);
-            }
-            ptx::mbar_wait(&tmem_full_bar[buf], bph);
+            ptx::mbar_wait(&tmem_full_bar[buf], bph);       // all `supert` accumulators of this stage are complete
             ptx::tc_fence_after();
-            if (res_ring_on) ptx::mbar_wait(&res_full[rslot], rph);
-            st.c0 = ec.gch0;
-            st.c1 = (int)tw_i * kHaloTW; st.c2 = (int)th_i * kHaloTH; st.c3 = (int)n;
-            epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st, rs);
+            for (int sub_t = 0; sub_t < p.supert; ++sub_t) {
+                const int tile = sti * p.supert + sub_t;
+                if (tile >= p.spatial_tiles) break;
+                uint32_t n, r, th_i, tw_i;
+                fdivmod((uint32_t)tile, p.d_img, n, r);
+                fdivmod(r, p.d_tw, th_i, tw_i);
+                const int ow = (int)tw_i * kHaloTW + tw, oh = (int)th_i * kHaloTH + th;
+                const bool row_ok = (ow < p.Wo) && (oh < p.Ho);
+                size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
+                if (p.y_s2d) {      // blocked output: pixel -> (block pixel, channel slab of the 2x2 position)
+                    pix = ((size_t)n * (p.Ho >> 1) + (oh >> 1)) * (p.Wo >> 1) + (ow >> 1);
+                    ec.gch0 = (((oh & 1) << 1) | (ow & 1)) * p.cout_g;
+                }
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                        (buf * (uint32_t)p.supert + (uint32_t)sub_t) * (uint32_t)p.ncols;
+                EpiResSmem rs{nullptr, 1, 0, 0, m};
+                if (res_ring_on) {
+                    rs.base = a_ring + p.res_off + rslot * p.res_slot_bytes;
+                    rs.box_cols = p.res_box_cols;
+                    rs.row_bytes = p.res_row_bytes;
+                    rs.swz_mask = p.res_swz_mask;
+                    ptx::mbar_wait(&res_full[rslot], rph);
+                }
+                st.c0 = ec.gch0;
+                st.c1 = (int)tw_i * kHaloTW; st.c2 = (int)th_i * kHaloTH; st.c3 = (int)n;
+                epi_tile<kSilu, kRes, kFp32>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st, rs);
+                if (res_ring_on) {
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
+                    if (++rslot == (uint32_t)p.res_slots) { rslot = 0; rph ^= 1u; }
+                }
+            }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                ptx::mbar_arrive(&tmem_empty_bar[buf]);
-                if (res_ring_on) ptx::mbar_arrive(&res_empty[rslot]);
-            }
-            if (res_ring_on && ++rslot == (uint32_t)p.res_slots) { rslot = 0; rph ^= 1u; }
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
         }
         if (st.enabled && st.issuer) ptx::bulk_wait_read0();   // staging must outlive the last store's read
     }
@@ -433,9 +449,21 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         if (avail < 2L * a_stage) continue;
         int stages = (int)(avail / a_stage);
         // two CTAs per SM when everything fits twice: more epilogue warps per SM for the thin-K layers
+        // thin tiles: several output tiles per accumulator stage (one tmem_full / tmem_empty hand-off per stage) when
+        // every CTA has many tiles to walk; the per-tile hand-off chain, not bandwidth, bounded those layers
+        int supert = 1;
+        {
+            const long spatial_t = (long)a->B * ceil_div(a->Wo, kHaloTW) * ceil_div(a->Ho, kHaloTH);
+            const long per_cta = spatial_t / ((long)sm_count() * 2 / gs + 1);
+            // (measured: pays only for the thinnest tiles — the K = 64 stem conv, 4 MMAs per tile: 188 -> 170 us;
+            //  neutral to slightly negative once a tile carries >= 9 MMAs)
+            const int mmas_per_tile = p.taps * (cin_cta / 16);
+            const int smax = mmas_per_tile > 8 ? 1 : (ncols <= 32 ? 4 : (ncols <= 64 ? 2 : 1));
+            while (supert * 2 <= smax && per_cta >= 4L * supert * 2 && !env_flag("SPECYOLO_NO_SUPERTILE")) supert *= 2;
+        }
         int occ = 1;
         uint32_t cols = 32;
-        while (cols < 2u * (uint32_t)ncols) cols <<= 1;
+        while (cols < 2u * (uint32_t)(ncols * supert)) cols <<= 1;
         // (228 KB per SM, ~5.5 KB of static + reserved shared memory per CTA: two CTAs fit with <= 108 KB dynamic each)
         const long half = 108L * 1024 - 1024 - (long)b_region - (long)stage_out;
         if (cols <= 256 && half >= 2L * a_stage) {
@@ -447,6 +475,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         best_stages = stages;
         found = true;
         p.gsplit = gs;
+        p.supert = supert;
         p.groups_cta = gcta;
         p.cin_cta = cin_cta;
         p.kc_box = kc_box;
@@ -481,6 +510,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
     const long spatial = (long)a->B * p.tiles_w * p.tiles_h;
     if (spatial <= 0 || spatial >= (1L << 30)) return false;
     p.spatial_tiles = (int)spatial;
+    p.nsuper = (int)((spatial + p.supert - 1) / p.supert);
     p.d_img = make_fastdiv((uint32_t)(p.tiles_w * p.tiles_h));
     p.d_tw = make_fastdiv((uint32_t)p.tiles_w);
     p.d_cin_g = make_fastdiv((uint32_t)cin_g);
@@ -498,7 +528,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
     if (a->y_s2d && (groups != 1 || a->residual)) return false;
     plan.p = p;
     const long resident = (long)sm_count() * plan.occ / p.gsplit;           // CTAs per split
-    const long per_split = spatial < resident ? spatial : (resident < 1 ? 1 : resident);
+    const long per_split = p.nsuper < resident ? p.nsuper : (resident < 1 ? 1 : resident);
     plan.grid = (unsigned)(per_split * p.gsplit);
     return true;
 }
