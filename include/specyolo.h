@@ -212,6 +212,16 @@ int specyolo_scale_boxes(float* out, const int* out_count, int B, int max_det,
                          float gain, float pad_w, float pad_h, float img0_w, float img0_h,
                          void* stream);
 
+/* ---- validation: detection <-> ground-truth matching -------------------------------
+ * Replaces box_iou (ultralytics/utils/metrics.py:52-73) + DetectionValidator.match_predictions
+ * (ultralytics/engine/validator.py:224-264, use_scipy=False) per image of a batch.
+ * pred [B, max_det, 6] / pred_count [B]: the NMS output (specyolo_nms); labels [n, 5] = cls, x1, y1, x2, y2 in the
+ * same pixel coordinates, grouped by image with label_off [B+1] (device, prefix offsets); iouv_host: niou IoU
+ * thresholds (HOST pointer, <= 16); correct [B, max_det, niou] uint8 (device), rows >= pred_count[b] are zero. */
+int specyolo_match_predictions(const float* pred, const int* pred_count, int B, int max_det,
+                               const float* labels, const int* label_off, int max_labels_per_image,
+                               const float* iouv_host, int niou, uint8_t* correct, void* stream);
+
 /* ---- IQ -> spectrogram -> letterbox (no reference implementation: README.md:7 only) -------- */
 typedef struct {
     const float* iq;           /* [B, L] complex64 interleaved (re,im)                   */

@@ -10,6 +10,8 @@ the CUDA kernels against them.
   nms_cases.npz     prediction tensors + outputs of the reference's ops.non_max_suppression
                     (torchvision CPU nms) for single-label, agnostic, multi-label, class-filter, max_det cases
   letterbox.npz     LetterBox(auto=False) geometry + cv2 INTER_LINEAR float resize of a float image
+  metrics.npz       validation path: box_iou + DetectionValidator.match_predictions on random detections / labels,
+                    ap_per_class on a pooled synthetic run
 """
 from __future__ import annotations
 
@@ -120,9 +122,55 @@ def gen_letterbox():
     print("letterbox", geo)
 
 
+def gen_metrics():
+    """Validation path: real box_iou / DetectionValidator.match_predictions / ap_per_class on seeded random cases."""
+    from types import SimpleNamespace
+
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+    from ultralytics.utils.metrics import ap_per_class, box_iou
+
+    rng = np.random.default_rng(11)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    out = {"iouv": iouv.numpy()}
+    for k, (nd, nl, nc) in enumerate([(300, 40, 2), (57, 9, 3), (5, 0, 2), (0, 4, 2), (200, 120, 80)]):
+        gxy = rng.uniform(60, 580, (nl, 2)); gwh = rng.uniform(10, 160, (nl, 2))
+        gt = np.concatenate((gxy - gwh / 2, gxy + gwh / 2), 1).astype(np.float32)
+        gcls = rng.integers(0, nc, nl).astype(np.float32)
+        # detections: jittered copies of labels (several per label) + random boxes, sorted by confidence
+        src = rng.integers(0, max(nl, 1), nd)
+        det = (gt[src] + rng.normal(0, 6, (nd, 4)).astype(np.float32)) if nl else rng.uniform(0, 640, (nd, 4)).astype(np.float32)
+        rnd = rng.random(nd) < 0.3
+        det[rnd] = np.sort(rng.uniform(0, 640, (int(rnd.sum()), 4)).astype(np.float32).reshape(-1, 2, 2), 1).reshape(-1, 4)
+        dcls = np.where(rng.random(nd) < 0.8, gcls[src] if nl else 0, rng.integers(0, nc, nd)).astype(np.float32)
+        conf = np.sort(rng.random(nd).astype(np.float32))[::-1].copy()
+        iou = box_iou(torch.from_numpy(gt), torch.from_numpy(det))
+        corr = DetectionValidator.match_predictions(SimpleNamespace(iouv=iouv), torch.from_numpy(dcls), torch.from_numpy(gcls), iou)
+        out.update({f"c{k}_gt": gt, f"c{k}_gcls": gcls, f"c{k}_det": det, f"c{k}_dcls": dcls, f"c{k}_conf": conf,
+                    f"c{k}_iou": iou.numpy(), f"c{k}_correct": corr.numpy()})
+        print("metrics case", k, "correct@.5", int(corr[:, 0].sum()) if nd else 0)
+    # ap_per_class on a pooled synthetic run
+    n, nc = 4000, 5
+    conf = rng.random(n).astype(np.float32)
+    pcls = rng.integers(0, nc, n).astype(np.float32)
+    base = rng.random(n) < (0.2 + 0.7 * conf)
+    tp = np.stack([base & (rng.random(n) < 1.0 - 0.08 * j) for j in range(10)], 1)
+    tcls = rng.integers(0, nc - 1, 1500).astype(np.float32)          # class nc-1 has predictions but no labels
+    r = ap_per_class(tp, conf, pcls, tcls)
+    out.update({"ap_tp": tp, "ap_conf": conf, "ap_pcls": pcls, "ap_tcls": tcls, "ap_tpc": r[0], "ap_fpc": r[1], "ap_p": r[2],
+                "ap_r": r[3], "ap_f1": r[4], "ap_ap": r[5], "ap_classes": r[6]})
+    np.savez_compressed(GOLD / "metrics.npz", **out)
+    print("ap_per_class mAP50", float(r[5][:, 0].mean()), "mAP", float(r[5].mean()))
+
+
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
-    gen_models()
-    gen_nms()
-    gen_letterbox()
+    which = set(sys.argv[1:]) or {"models", "nms", "letterbox", "metrics"}
+    if "models" in which:
+        gen_models()
+    if "nms" in which:
+        gen_nms()
+    if "letterbox" in which:
+        gen_letterbox()
+    if "metrics" in which:
+        gen_metrics()

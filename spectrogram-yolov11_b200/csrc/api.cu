@@ -41,6 +41,8 @@ size_t nms_ws_bytes(int, int, int, int);
 int nms_launch(const specyolo_nms_t*, cudaStream_t);
 int scale_boxes_launch(float*, const int*, int, int, float, float, float, float, float, cudaStream_t);
 int stft_launch(const specyolo_stft_t*, cudaStream_t);
+int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
+                             cudaStream_t);
 int stft_init();
 
 }  // namespace specyolo
@@ -190,6 +192,16 @@ int specyolo_scale_boxes(float* out, const int* out_count, int B, int max_det, f
                          float pad_h, float img0_w, float img0_h, void* stream) {
     SY_CHECK(out && out_count && B > 0 && max_det > 0 && gain > 0.f, SPECYOLO_ERR_INVALID, "scale_boxes: bad arguments");
     return scale_boxes_launch(out, out_count, B, max_det, gain, pad_w, pad_h, img0_w, img0_h, (cudaStream_t)stream);
+}
+
+int specyolo_match_predictions(const float* pred, const int* pred_count, int B, int max_det, const float* labels,
+                               const int* label_off, int max_labels_per_image, const float* iouv_host, int niou,
+                               uint8_t* correct, void* stream) {
+    SY_CHECK(pred && pred_count && label_off && iouv_host && correct && B > 0, SPECYOLO_ERR_INVALID,
+             "match_predictions: bad arguments");
+    SY_CHECK(labels != nullptr || max_labels_per_image == 0, SPECYOLO_ERR_INVALID, "match_predictions: labels missing");
+    return match_predictions_launch(pred, pred_count, B, max_det, labels, label_off, max_labels_per_image, iouv_host, niou,
+                                    correct, (cudaStream_t)stream);
 }
 
 int specyolo_iq_to_letterbox(const specyolo_stft_t* a, void* stream) {

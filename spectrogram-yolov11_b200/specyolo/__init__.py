@@ -5,8 +5,8 @@ surface: `YOLO(cfg).predict()`, `specyolo.nn.modules.{Conv, C3k2, SPPF, C2PSA, D
 `specyolo.utils.ops.non_max_suppression`.  PyTorch is used for tensor plumbing only.
 """
 from . import _lib, ops  # noqa: F401
-from .engine import YOLO, Boxes, DetectionPredictor, Results  # noqa: F401
+from .engine import YOLO, Boxes, DetectionPredictor, DetectionValidator, Results  # noqa: F401
 from .nn.tasks import DetectionModel  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["YOLO", "DetectionModel", "DetectionPredictor", "Results", "Boxes", "ops"]
+__all__ = ["YOLO", "DetectionModel", "DetectionPredictor", "DetectionValidator", "Results", "Boxes", "ops"]

@@ -106,6 +106,8 @@ SIGNATURES = {
     "specyolo_nms_ws_bytes": (C.c_size_t, [C.c_int] * 4),
     "specyolo_nms": (C.c_int, [C.POINTER(NmsArgs), C.c_void_p]),
     "specyolo_scale_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p]),
+    "specyolo_match_predictions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p]),
     "specyolo_iq_to_letterbox": (C.c_int, [C.POINTER(StftArgs), C.c_void_p]),
 }
 

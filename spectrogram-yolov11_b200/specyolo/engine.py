@@ -317,6 +317,75 @@ class DetectionPredictor:
                 for b in range(im.shape[0])]
 
 
+class DetectionValidator:
+    """The validation loop of the reference (models/yolo/detect/val.py:93-193, engine/validator.py:224-264) on the device:
+    dense forward -> `non_max_suppression(conf=0.001, iou=0.7, multi_label=True, max_det=300)` (the batched NMS kernel
+    in its multi-label mode: ~10x the candidates of predict) -> IoU + matching kernel at the ten mAP thresholds ->
+    host-side AP integration (numpy, as in the reference).
+
+    `batches` yields the reference's collated dicts: {"img": [B,3,H,W] uint8 | float in 0..1, "cls": [n] or [n,1],
+    "bboxes": [n,4] normalised xywh, "batch_idx": [n]}.  Images are expected at the network size (ori_shape == imgsz),
+    so the reference's scale_boxes round trip is the identity."""
+
+    def __init__(self, model: DetectionModel, overrides: Optional[dict] = None):
+        self.model = model
+        self.args = dict(conf=0.001, iou=0.7, max_det=300, agnostic_nms=False, single_cls=False)
+        self.args.update(overrides or {})
+        self.iouv = [0.5 + 0.05 * i for i in range(10)]            # val.py:72
+        self.stats = dict(tp=[], conf=[], pred_cls=[], target_cls=[])
+        self.seen = 0
+
+    @torch.no_grad()
+    def update(self, batch: dict):
+        dev = next(self.model.parameters()).device
+        img = batch["img"].to(dev, non_blocking=True)
+        B, _, H, W = img.shape
+        y, _ = self.model(img)
+        a = self.args
+        out, cnt, _, _ = ops.nms(prediction=y.contiguous(), B=B, nc=y.shape[1] - 4, A=y.shape[2], conf_thres=a["conf"],
+                                 iou_thres=a["iou"], agnostic=bool(a["single_cls"] or a["agnostic_nms"]),
+                                 multi_label=True, max_det=a["max_det"])
+        if a["single_cls"]:
+            out[..., 5] = 0
+        # labels -> pixel xyxy grouped by image (val.py:107-118)
+        cls = batch["cls"].reshape(-1).to(torch.float32)
+        bidx = batch["batch_idx"].reshape(-1).to(torch.int64)
+        box = batch["bboxes"].to(torch.float32).reshape(-1, 4)
+        order = torch.argsort(bidx, stable=True)
+        cls, bidx, box = cls[order], bidx[order], box[order]
+        scale = torch.tensor([W, H, W, H], dtype=torch.float32)
+        xyxy = torch.cat((box[:, :2] - box[:, 2:] / 2, box[:, :2] + box[:, 2:] / 2), 1) * scale
+        per_img = torch.bincount(bidx, minlength=B)
+        off = torch.zeros(B + 1, dtype=torch.int32)
+        off[1:] = torch.cumsum(per_img, 0)
+        labels = torch.cat((cls[:, None], xyxy), 1)
+        correct = ops.match_predictions(out, cnt, labels, off, int(per_img.max()) if len(per_img) else 0, self.iouv)
+        counts = cnt.tolist()
+        out_h, corr_h = out.cpu(), correct.cpu()
+        for b in range(B):
+            self.seen += 1
+            n = counts[b]
+            if n == 0 and per_img[b] == 0:
+                continue
+            self.stats["tp"].append(corr_h[b, :n].numpy())
+            self.stats["conf"].append(out_h[b, :n, 4].numpy())
+            self.stats["pred_cls"].append(out_h[b, :n, 5].numpy())
+            self.stats["target_cls"].append(cls[off[b]:off[b + 1]].numpy())
+
+    def results(self) -> dict:
+        from .utils.metrics import results_dict
+
+        if not self.stats["tp"]:
+            return results_dict(np.zeros((0, 10), bool), np.zeros(0), np.zeros(0), np.zeros(0))
+        st = {k: np.concatenate(v, 0) for k, v in self.stats.items()}
+        return results_dict(st["tp"], st["conf"], st["pred_cls"], st["target_cls"])
+
+    def __call__(self, batches) -> dict:
+        for batch in batches:
+            self.update(batch)
+        return self.results()
+
+
 class YOLO:
     """`YOLO(cfg_or_weights).predict(source)` (ultralytics/models/yolo/model.py:11, engine/model.py:82-149, 499-558)."""
 
@@ -383,6 +452,15 @@ class YOLO:
         return self.predictor(source)
 
     __call__ = predict
+
+    def val(self, data=None, validator=None, **kwargs) -> dict:
+        """`model.val(...)` (engine/model.py:601-656) over an iterable of collated batches (see DetectionValidator);
+        returns the reference's `results_dict` (precision, recall, mAP50, mAP50-95, fitness)."""
+        if data is None:
+            raise ValueError("data (an iterable of collated batches) is required: dataset YAMLs / image files are not read")
+        if not next(self.model.parameters()).is_cuda:
+            self.model.to("cuda")
+        return (validator or DetectionValidator)(self.model, kwargs)(data)
 
     def predict_iq(self, iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0,
                    db_max: float = 0.0, **kwargs) -> List[Results]:

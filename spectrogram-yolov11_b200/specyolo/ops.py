@@ -432,6 +432,25 @@ def scale_boxes_(out: torch.Tensor, cnt: torch.Tensor, img1_shape, img0_shape) -
                                            _lib.stream_ptr()))
 
 
+def match_predictions(out: torch.Tensor, cnt: torch.Tensor, labels: torch.Tensor, label_off: torch.Tensor,
+                      max_labels_per_image: int, iouv: Sequence[float]) -> torch.Tensor:
+    """Detections [B,max_det,6] + counts [B] vs ground-truth rows [n,5] (cls, x1,y1,x2,y2) grouped by image
+    (label_off [B+1], int32) -> correct [B, max_det, niou] bool (specyolo_match_predictions)."""
+    _lib.init_device()
+    B, max_det, _ = out.shape
+    niou = len(iouv)
+    if out.dtype != torch.float32 or not out.is_contiguous() or cnt.dtype != torch.int32:
+        raise ValueError("match_predictions: out must be contiguous fp32 [B,max_det,6], cnt int32")
+    labels = labels.to(device=out.device, dtype=torch.float32).contiguous()
+    label_off = label_off.to(device=out.device, dtype=torch.int32).contiguous()
+    correct = torch.empty((B, max_det, niou), device=out.device, dtype=torch.uint8)
+    arr = (C.c_float * niou)(*[float(v) for v in iouv])
+    check(_lib.load().specyolo_match_predictions(out.data_ptr(), cnt.data_ptr(), B, max_det,
+                                                 labels.data_ptr() if labels.numel() else None, label_off.data_ptr(),
+                                                 int(max_labels_per_image), arr, niou, correct.data_ptr(), _lib.stream_ptr()))
+    return correct.bool()
+
+
 # ----------------------------------------------------------------------------------------------
 # front end
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,72 @@
+"""Detection metrics of the validation path: host-side numpy, like the reference, which also computes
+them on the CPU after the device work (ultralytics/utils/metrics.py:547-552 smooth, :605-634 compute_ap, :637-729
+ap_per_class, :840-905 Metric / DetMetrics results).  The device part — IoU + matching — is ops.match_predictions."""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+
+def smooth(y: np.ndarray, f: float = 0.05) -> np.ndarray:
+    """Box filter over a fraction f of the curve, edges padded with the end values (metrics.py:547-552)."""
+    nf = round(len(y) * f * 2) // 2 + 1
+    pad = np.ones(nf // 2)
+    yp = np.concatenate((pad * y[0], y, pad * y[-1]), 0)
+    return np.convolve(yp, np.ones(nf) / nf, mode="valid")
+
+
+def compute_ap(recall: np.ndarray, precision: np.ndarray):
+    """COCO 101-point interpolated AP of one precision/recall curve (metrics.py:605-634)."""
+    mrec = np.concatenate(([0.0], recall, [1.0]))
+    mpre = np.concatenate(([1.0], precision, [0.0]))
+    mpre = np.flip(np.maximum.accumulate(np.flip(mpre)))          # precision envelope
+    x = np.linspace(0, 1, 101)
+    y = np.interp(x, mrec, mpre)
+    ap = float(np.sum((y[1:] + y[:-1]) * 0.5 * np.diff(x)))       # trapezoid rule
+    return ap, mpre, mrec
+
+
+def ap_per_class(tp: np.ndarray, conf: np.ndarray, pred_cls: np.ndarray, target_cls: np.ndarray, eps: float = 1e-16):
+    """Per-class AP at every IoU threshold plus P / R / F1 at the max-F1 confidence (metrics.py:637-729).
+
+    tp [n, niou] bool, conf [n], pred_cls [n], target_cls [m].  Returns (tp_count, fp_count, p, r, f1, ap [nc, niou],
+    unique_classes) — the plotting curves of the reference are not returned.
+    """
+    order = np.argsort(-conf)
+    tp, conf, pred_cls = tp[order], conf[order], pred_cls[order]
+    classes, n_labels = np.unique(target_cls, return_counts=True)
+    nc = classes.shape[0]
+    x = np.linspace(0, 1, 1000)
+    ap = np.zeros((nc, tp.shape[1]))
+    p_curve, r_curve = np.zeros((nc, 1000)), np.zeros((nc, 1000))
+    for ci, c in enumerate(classes):
+        sel = pred_cls == c
+        n_l, n_p = n_labels[ci], int(sel.sum())
+        if n_p == 0 or n_l == 0:
+            continue
+        fpc = (1 - tp[sel]).cumsum(0)
+        tpc = tp[sel].cumsum(0)
+        recall = tpc / (n_l + eps)
+        r_curve[ci] = np.interp(-x, -conf[sel], recall[:, 0], left=0)       # conf decreases: interpolate on -conf
+        precision = tpc / (tpc + fpc)
+        p_curve[ci] = np.interp(-x, -conf[sel], precision[:, 0], left=1)
+        for j in range(tp.shape[1]):
+            ap[ci, j], _, _ = compute_ap(recall[:, j], precision[:, j])
+    f1_curve = 2 * p_curve * r_curve / (p_curve + r_curve + eps)
+    i = smooth(f1_curve.mean(0), 0.1).argmax() if nc else 0
+    p, r, f1 = p_curve[:, i], r_curve[:, i], f1_curve[:, i]
+    tp_count = (r * n_labels).round()
+    fp_count = (tp_count / (p + eps) - tp_count).round()
+    return tp_count, fp_count, p, r, f1, ap, classes.astype(int)
+
+
+def results_dict(tp, conf, pred_cls, target_cls) -> Dict[str, float]:
+    """The reference's `metrics.results_dict` keys for the detect task (metrics.py:860-905, DetMetrics.keys)."""
+    keys = ["metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)"]
+    if len(tp) == 0 or not tp.any():
+        return {k: 0.0 for k in keys} | {"fitness": 0.0}
+    _, _, p, r, _, ap, _ = ap_per_class(tp, conf, pred_cls, target_cls)
+    mp, mr, map50, map_ = float(p.mean()), float(r.mean()), float(ap[:, 0].mean()), float(ap.mean())
+    return {keys[0]: mp, keys[1]: mr, keys[2]: map50, keys[3]: map_,
+            "fitness": float(np.dot([0.0, 0.0, 0.1, 0.9], [mp, mr, map50, map_]))}
