@@ -222,6 +222,16 @@ int specyolo_match_predictions(const float* pred, const int* pred_count, int B, 
                                const float* labels, const int* label_off, int max_labels_per_image,
                                const float* iouv_host, int niou, uint8_t* correct, void* stream);
 
+/* ---- image ingest: LetterBox for uint8 images ----------------------------------------
+ * Replaces LetterBox.__call__ (ultralytics/data/augment.py:1535-1601: cv2.resize INTER_LINEAR + copyMakeBorder) and the
+ * BGR->RGB / HWC->CHW step of BasePredictor.preprocess (ultralytics/engine/predictor.py:125-136), bit-exact with
+ * OpenCV's 8-bit bilinear arithmetic.  src: [B,H,W,3] uint8 (device).  The caller computes the geometry with the
+ * reference's formulas (content new_w x new_h placed at (left, top) inside out_h x out_w, rest = pad_value);
+ * dst: [B,3,out_h,out_w] if chw else [B,out_h,out_w,3]; swap_rb exchanges channels 0 and 2. */
+int specyolo_letterbox_u8(const uint8_t* src_hwc, int B, int H, int W, uint8_t* dst, int out_h, int out_w,
+                          int new_w, int new_h, int left, int top, int pad_value, int swap_rb, int chw,
+                          void* stream);
+
 /* ---- IQ -> spectrogram -> letterbox (no reference implementation: README.md:7 only) -------- */
 typedef struct {
     const float* iq;           /* [B, L] complex64 interleaved (re,im)                   */

@@ -10,6 +10,7 @@ the CUDA kernels against them.
   nms_cases.npz     prediction tensors + outputs of the reference's ops.non_max_suppression
                     (torchvision CPU nms) for single-label, agnostic, multi-label, class-filter, max_det cases
   letterbox.npz     LetterBox(auto=False) geometry + cv2 INTER_LINEAR float resize of a float image
+  letterbox_u8.npz  LetterBox (cv2.resize INTER_LINEAR uint8 + copyMakeBorder) on random images, several geometries
   metrics.npz       validation path: box_iou + DetectionValidator.match_predictions on random detections / labels,
                     ap_per_class on a pooled synthetic run
 """
@@ -122,6 +123,28 @@ def gen_letterbox():
     print("letterbox", geo)
 
 
+LB_CASES = [  # (h, w), new_shape, kwargs
+    ((97, 131), (160, 160), {}), ((333, 517), (192, 256), {}), ((120, 90), (160, 160), dict(auto=True)),
+    ((320, 256), (160, 160), {}), ((64, 96), (160, 160), dict(scaleup=False)), ((50, 300), (128, 160), dict(auto=True, stride=32)),
+    ((160, 160), (160, 160), {}), ((200, 300), (256, 256), dict(center=False)),
+]
+
+
+def gen_letterbox_u8():
+    """Real LetterBox on random uint8 images (cv2.resize INTER_LINEAR + copyMakeBorder)."""
+    from ultralytics.data.augment import LetterBox
+
+    rng = np.random.default_rng(21)
+    out = {}
+    for k, ((h, w), ns, kw) in enumerate(LB_CASES):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        y = LetterBox(ns, **kw)(image=img)
+        out[f"in{k}"] = img
+        out[f"out{k}"] = y
+        print("letterbox_u8", (h, w), ns, kw, "->", y.shape)
+    np.savez_compressed(GOLD / "letterbox_u8.npz", **out)
+
+
 def gen_metrics():
     """Validation path: real box_iou / DetectionValidator.match_predictions / ap_per_class on seeded random cases."""
     from types import SimpleNamespace
@@ -165,7 +188,7 @@ def gen_metrics():
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"models", "nms", "letterbox", "metrics"}
+    which = set(sys.argv[1:]) or {"models", "nms", "letterbox", "metrics", "letterbox_u8"}
     if "models" in which:
         gen_models()
     if "nms" in which:
@@ -174,3 +197,5 @@ if __name__ == "__main__":
         gen_letterbox()
     if "metrics" in which:
         gen_metrics()
+    if "letterbox_u8" in which:
+        gen_letterbox_u8()

@@ -41,6 +41,7 @@ size_t nms_ws_bytes(int, int, int, int);
 int nms_launch(const specyolo_nms_t*, cudaStream_t);
 int scale_boxes_launch(float*, const int*, int, int, float, float, float, float, float, cudaStream_t);
 int stft_launch(const specyolo_stft_t*, cudaStream_t);
+int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
                              cudaStream_t);
 int stft_init();
@@ -202,6 +203,14 @@ int specyolo_match_predictions(const float* pred, const int* pred_count, int B, 
     SY_CHECK(labels != nullptr || max_labels_per_image == 0, SPECYOLO_ERR_INVALID, "match_predictions: labels missing");
     return match_predictions_launch(pred, pred_count, B, max_det, labels, label_off, max_labels_per_image, iouv_host, niou,
                                     correct, (cudaStream_t)stream);
+}
+
+int specyolo_letterbox_u8(const uint8_t* src_hwc, int B, int H, int W, uint8_t* dst, int out_h, int out_w, int new_w,
+                          int new_h, int left, int top, int pad_value, int swap_rb, int chw, void* stream) {
+    SY_CHECK(src_hwc && dst && B > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, SPECYOLO_ERR_INVALID,
+             "letterbox: bad arguments");
+    return letterbox_u8_launch(src_hwc, B, H, W, dst, out_h, out_w, new_w, new_h, left, top, pad_value, swap_rb, chw,
+                               (cudaStream_t)stream);
 }
 
 int specyolo_iq_to_letterbox(const specyolo_stft_t* a, void* stream) {

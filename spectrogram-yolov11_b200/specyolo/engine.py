@@ -132,17 +132,23 @@ class DetectionPredictor:
         if isinstance(source, np.ndarray):
             source = [source]
         if isinstance(source, (list, tuple)) and all(isinstance(s, np.ndarray) for s in source):
-            # HWC BGR uint8 images that already have the network size (the letterbox/resize of arbitrary
-            # image files is SURVEY 8(f3), a "next" row; IQ sources are letterboxed by the STFT kernel)
-            shapes = {s.shape for s in source}
-            if len(shapes) != 1:
-                raise ValueError("ndarray sources must share one shape")
-            h, w, c = source[0].shape
-            if c != 3 or h % 32 or w % 32:
-                raise ValueError("ndarray sources must be HWC uint8 with H, W divisible by 32")
-            im = np.stack(source)[..., ::-1].transpose(0, 3, 1, 2)     # BGR->RGB, BHWC->BCHW (predictor.py:129-131)
-            im = torch.from_numpy(np.ascontiguousarray(im)).to(dev, non_blocking=True)
-            return im, [(h, w)] * len(source), list(source)
+            # HWC BGR uint8 images of any size: pre_transform (predictor.py:147-163) = LetterBox(imgsz, auto=all images
+            # share one shape, stride) per image, then BGR->RGB, HWC->CHW (predictor.py:129-131) — one kernel per shape
+            from .data import LetterBox
+
+            if any(s.ndim != 3 or s.shape[2] != 3 or s.dtype != np.uint8 for s in source):
+                raise ValueError("ndarray sources must be HWC uint8 images with 3 channels")
+            imgsz = self.args.get("imgsz", 640)
+            same = len({s.shape for s in source}) == 1
+            lb = LetterBox(imgsz, auto=same, stride=int(self.model.stride.max()))
+            if same:
+                batch = torch.from_numpy(np.ascontiguousarray(np.stack(source))).to(dev, non_blocking=True)
+                im = lb.to_network_input(batch)
+            else:
+                im = torch.empty((len(source), 3) + tuple(lb.new_shape), device=dev, dtype=torch.uint8)
+                for i, s in enumerate(source):
+                    lb.to_network_input(torch.from_numpy(np.ascontiguousarray(s)).to(dev, non_blocking=True)[None], out=im[i:i + 1])
+            return im, [tuple(s.shape[:2]) for s in source], list(source)
         raise TypeError(f"unsupported source type {type(source)}")   # data/build.py:183
 
     # -- one batch -----------------------------------------------------------------------------
@@ -277,6 +283,10 @@ class DetectionPredictor:
             shapes, imgs, B, img1 = meta[slot]
             counts = host_out[slot][1].tolist()
             out_h = host_out[slot][0].clone()       # one copy out of the pinned buffer; per-image rows are views of it
+            for b in range(B):                      # letterboxed sources: boxes back to original-image coordinates
+                if tuple(shapes[b]) != tuple(img1):
+                    from .utils.ops import scale_boxes
+                    scale_boxes(img1, out_h[b, : counts[b], :4], shapes[b])
             return [Results(shapes[b], out_h[b, : counts[b]], self.model.names, orig_img=imgs[b])
                     for b in range(B)]
 
@@ -309,8 +319,11 @@ class DetectionPredictor:
         out, cnt = self.infer(im)
         # postprocess (detect/predict.py:59-73): boxes back to original-image coordinates
         img1 = tuple(im.shape[2:])
-        if any(s != img1 for s in shapes):
-            raise NotImplementedError("sources must already have the network input size")
+        if any(s != img1 for s in shapes):      # boxes back to original-image coordinates (ops.py:92-127, 335-354)
+            out = out.clone()
+            for b, s in enumerate(shapes):
+                if s != img1:
+                    ops.scale_boxes_(out[b:b + 1], cnt[b:b + 1], img1, s)
         out_h = out.cpu()                       # single D2H of [B, max_det, 6]
         counts = cnt.cpu().tolist()
         return [Results(shapes[b], out_h[b, : counts[b]], self.model.names, orig_img=host_imgs[b])

@@ -432,6 +432,25 @@ def scale_boxes_(out: torch.Tensor, cnt: torch.Tensor, img1_shape, img0_shape) -
                                            _lib.stream_ptr()))
 
 
+def letterbox_u8(imgs: torch.Tensor, geometry, swap_rb: bool = True, chw: bool = True, pad_value: int = 114,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,H,W,3] uint8 (CUDA) -> letterboxed [B,3,oh,ow] (chw) or [B,oh,ow,3]; geometry = (new_w, new_h, left, top, oh, ow)
+    from specyolo.data.LetterBox.geometry (specyolo_letterbox_u8, bit-exact with cv2 INTER_LINEAR)."""
+    _lib.init_device()
+    if imgs.dtype != torch.uint8 or imgs.dim() != 4 or imgs.shape[3] != 3 or not imgs.is_cuda or not imgs.is_contiguous():
+        raise ValueError("letterbox_u8 expects a contiguous CUDA uint8 tensor [B,H,W,3]")
+    B, H, W, _ = imgs.shape
+    new_w, new_h, left, top, oh, ow = (int(v) for v in geometry)
+    shape = (B, 3, oh, ow) if chw else (B, oh, ow, 3)
+    if out is None:
+        out = torch.empty(shape, device=imgs.device, dtype=torch.uint8)
+    elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError(f"letterbox_u8: out must be a contiguous uint8 tensor of shape {shape}")
+    check(_lib.load().specyolo_letterbox_u8(imgs.data_ptr(), B, H, W, out.data_ptr(), oh, ow, new_w, new_h, left, top,
+                                            int(pad_value), int(swap_rb), int(chw), _lib.stream_ptr()))
+    return out
+
+
 def match_predictions(out: torch.Tensor, cnt: torch.Tensor, labels: torch.Tensor, label_off: torch.Tensor,
                       max_labels_per_image: int, iouv: Sequence[float]) -> torch.Tensor:
     """Detections [B,max_det,6] + counts [B] vs ground-truth rows [n,5] (cls, x1,y1,x2,y2) grouped by image
