@@ -27,22 +27,23 @@ static constexpr int NFFT = 1024;
 static constexpr int kCols = 16;      // output columns per CTA
 static constexpr int kFrames = 2 * kCols;
 
-// W32^j = exp(-2 pi i j / 32), j = 0..15
-__device__ __constant__ float kW32c[16] = {
-    1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f,
-    3.826834324e-01f, 1.950903220e-01f, 0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
-    -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
-__device__ __constant__ float kW32s[16] = {
-    -0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f,
-    -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f,
-    -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
-
 __host__ __device__ constexpr int bitrev5(int v) {
     return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
 }
 
 // In-register radix-2 DIF FFT of 32 complex points; X[k] ends up in x[bitrev5(k)].
 __device__ __forceinline__ void fft32(float2 (&x)[32]) {
+    // W32^j = exp(-2 pi i j / 32), j = 0..15: literal constants for the unrolled butterflies (W^0 = 1 and W^8 = -i are
+    // special-cased below: 46 of the 80 butterflies of a 32-point FFT need no multiplication)
+    constexpr float kW32c[16] = {
+    1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f,
+    3.826834324e-01f, 1.950903220e-01f, 0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
+    -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
+    constexpr float kW32s[16] = {
+    -0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f,
+    -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f,
+    -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
+
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         const int half = 16 >> s;
@@ -55,8 +56,14 @@ __device__ __forceinline__ void fft32(float2 (&x)[32]) {
                 x[i0] = make_float2(a.x + b.x, a.y + b.y);
                 const float dr = a.x - b.x, di = a.y - b.y;
                 const int tw = j << s;  // W_{2*half}^j = W32^(j * 32/(2*half)) = W32^(j << s)
-                const float c = kW32c[tw], sn = kW32s[tw];
-                x[i1] = make_float2(dr * c - di * sn, dr * sn + di * c);
+                if (tw == 0) {
+                    x[i1] = make_float2(dr, di);                 // W^0 = 1
+                } else if (tw == 8) {
+                    x[i1] = make_float2(di, -dr);                // W^8 = -i
+                } else {
+                    const float c = kW32c[tw], sn = kW32s[tw];
+                    x[i1] = make_float2(dr * c - di * sn, dr * sn + di * c);
+                }
             }
         }
     }
@@ -155,7 +162,7 @@ stft_letterbox_kernel(const __grid_constant__ StftParams p) {
             const int k = lane + 32 * k2;
             const float pw = fmaxf(x[pp].x * x[pp].x + x[pp].y * x[pp].y, 1e-20f);
             // 10*log10(pw) = 3.0102999566 * log2(pw)
-            float v = fmaf(log2f(pw) * 3.010299956639812f, p.db_scale, p.db_off);
+            float v = fmaf(__log2f(pw) * 3.010299956639812f, p.db_scale, p.db_off);
             v = fminf(fmaxf(v, 0.f), 1.f);
             s_row[(k + NFFT / 2) & (NFFT - 1)] = v;
         }
