@@ -340,8 +340,10 @@ fusion_apply_kernel(const __grid_constant__ FusionParams p) {
     }
 }
 
-static int fusion_parts(int B, int k) {
-    int parts = ceil_div(8 * sm_count(), B * k);
+// stats CTAs per (image, input): a function of the image size ONLY, so that the fp32 summation order of the per-channel
+// sums of squares — and with it every gate, bit for bit — does not depend on the batch an image is part of
+static int fusion_parts(int HW) {
+    int parts = HW / 800;               // 80x80 -> 8, 40x40 -> 2, 20x20 -> 1
     if (parts < 1) parts = 1;
     if (parts > kFusMaxParts) parts = kFusMaxParts;
     return parts;
@@ -371,7 +373,7 @@ int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     SY_CHECK(sab_smem <= 48 * 1024, SPECYOLO_ERR_UNSUPPORTED, "fusion: feature map too wide (%d)", a->W);
     FusionParams p{};
     p.a = *a;
-    p.parts = fusion_parts(a->B, a->k);
+    p.parts = fusion_parts(a->H * a->W);
     const int pix_par = 256 / (a->c / 8);
     for (int i = 0; i < a->k; ++i) {
         const int HWs = (a->H >> a->upshift[i]) * (a->W >> a->upshift[i]);

@@ -150,6 +150,52 @@ def test_predict_api_and_fused_path(lib):
         yolo.predict(x, device="cpu")
 
 
+def test_full_size_properties(lib):
+    """BASELINE config C2 at its full size (batch 64, 640^2, uint8): size-independent properties.
+    (1) batch invariance: an image's detections are bit-identical whether it runs alone or inside the batch of 64
+        (every output pixel has the same K-loop order whatever the tiling);
+    (2) NMS post-conditions per image: scores sorted descending, at most max_det rows, no two kept boxes of one class
+        overlap above the IoU threshold, all scores above conf;
+    (3) NMS idempotence: running NMS again on the kept boxes keeps all of them."""
+    import specyolo
+    from specyolo import ops
+    from specyolo.nn.init import synth_images, synth_state_dict
+
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    x = synth_images(64, 640, seed=0, dtype=torch.uint8).cuda()
+    conf, iou = 0.25, 0.7
+    res = yolo.predict(x, conf=conf, iou=iou)
+    assert len(res) == 64 and sum(len(r) for r in res) > 64
+    for i in (0, 17, 63):
+        alone = yolo.predict(x[i:i + 1], conf=conf, iou=iou)
+        assert torch.equal(alone[0].boxes.data, res[i].boxes.data), f"image {i} differs between B=1 and B=64"
+    for r in res:
+        d = r.boxes.data
+        assert len(d) <= 300 and bool((d[:, 4] > conf).all())
+        assert bool((d[1:, 4] <= d[:-1, 4]).all())
+        if len(d) > 1:
+            b = d[:, :4] + d[:, 5:6] * 7680.0                       # class offset, as in ops.py:305-311
+            lt = torch.max(b[:, None, :2], b[None, :, :2]); rb = torch.min(b[:, None, 2:], b[None, :, 2:])
+            inter = (rb - lt).clamp(min=0).prod(2)
+            area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+            ov = inter / (area[:, None] + area[None, :] - inter)
+            ov.fill_diagonal_(0)
+            assert float(ov.max()) <= iou + 1e-6
+    # idempotence on the image with the most detections: kept boxes as a dense [1, 4+nc, n] prediction
+    r = max(res, key=len)
+    d = r.boxes.data.cuda()
+    n = len(d)
+    pred = torch.zeros((1, 6, n), device="cuda")
+    pred[0, 0] = (d[:, 0] + d[:, 2]) / 2; pred[0, 1] = (d[:, 1] + d[:, 3]) / 2
+    pred[0, 2] = d[:, 2] - d[:, 0]; pred[0, 3] = d[:, 3] - d[:, 1]
+    pred[0, 4 + 0] = torch.where(d[:, 5] == 0, d[:, 4], torch.zeros_like(d[:, 4]))
+    pred[0, 4 + 1] = torch.where(d[:, 5] == 1, d[:, 4], torch.zeros_like(d[:, 4]))
+    out, cnt, _, _ = ops.nms(prediction=pred, B=1, nc=2, A=n, conf_thres=conf, iou_thres=iou + 1e-3)
+    assert int(cnt[0]) == n
+
+
 def test_yolo11s_1280_vs_oracle(lib):
     """BASELINE config C4: plain yolo11s (nc=80) at 1280x1280 — N = 1600 attention tokens (13 key blocks), 33 600
     anchors, 144-channel head — against the CPU oracle on the same seeded weights; graph-replayed predict() equals
