@@ -171,7 +171,7 @@ def stage_roofline(model, x_dev, peaks):
             nm = name
             fl = flops_fn(*a, **k) if flops_fn else 0.0
             by = bytes_fn(r, *a, **k) if bytes_fn else 0.0
-            if name == "conv2d":     # class by arithmetic intensity against the ridge of the measured peaks
+            if name in ("conv2d", "dwconv_pwconv"):     # class by arithmetic intensity against the ridge of the measured peaks
                 nm = "conv2d_tensor_bound" if fl / max(by, 1.0) >= ridge else "conv2d_hbm_bound"
             rec.append((nm, e0, e1, fl, by))
             return r
@@ -187,7 +187,12 @@ def stage_roofline(model, x_dev, peaks):
         B, Cin, H, W = x.shape
         return 2.0 * (B * Cin * H * W + r.numel()) + 2.0 * pc.w.numel()
 
+    def dwpw_flops(x, dw_w, dw_b, pw, *a, **k):
+        B, Cc, H, W = x.shape
+        return 2.0 * B * H * W * Cc * (9 + pw.cout)           # depthwise 3x3 + pointwise 1x1
+
     wrap("conv2d", conv_flops, conv_bytes)
+    wrap("dwconv_pwconv", dwpw_flops, lambda r, x, *a, **k: 2.0 * (x.numel() + r.numel()))
     wrap("stem_space_to_depth", None, lambda r, x, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel())
     wrap("sppf_pool", None, lambda r, buf, c: 2.0 * buf.numel())
     wrap("fusion_eschannel", None, lambda r, xs, *a, **k: 2.0 * (2 * sum(t.numel() for t in xs) + r.numel()))
@@ -233,7 +238,7 @@ def stage_roofline(model, x_dev, peaks):
     tf = ROOT / "profiles" / "conv_dram_traffic.json"      # written from an ncu capture by tools/ncu_traffic.py
     if tf.is_file():
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_halo_kernel: every tcgen05 implicit-GEMM conv launch of one step "
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_halo_kernel + dwpw_kernel: every tcgen05 implicit-GEMM conv launch of one step "
                                           "(the layers below the ridge are HBM-bound: see stages.conv2d_hbm_bound)",
             "achieved": c[1] / c[0] / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
             "frac": c[1] / c[0] / 1e12 / peaks["tf_sust"], "traffic": traffic, "algorithmic_bytes_per_step": c[2], "peak_source": peaks["src"] + " sustained",

@@ -113,6 +113,19 @@ typedef struct {
  * depthwise 3x3 and the 3-channel stem run on dedicated CUDA-core kernels. */
 int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream);
 
+/* Fused DWConv(3x3, s1, p1)+BN+act -> Conv(1x1)+BN+act: the two building blocks of Detect.cv3
+ * (ultralytics/nn/modules/head.py:51-58, Sequential(DWConv(x, x, 3), Conv(x, c3, 1))) in one kernel — the depthwise
+ * result stays in shared memory as the A operand of the pointwise GEMM.  C in {64, 128}; SiLU after both. */
+typedef struct {
+    const void* x; int B, H, W, C, x_pixstride;   /* bf16 NHWC input window                                  */
+    const float* dw_w;                            /* [9][C] BN-folded depthwise weights, tap = ky*3+kx (fp32) */
+    const float* dw_b;                            /* [C]                                                     */
+    const void* pw_packed; const float* pw_bias;  /* from specyolo_fold_pack_conv of the 1x1 conv (groups 1)  */
+    int Cout, n_pad;
+    void* y; int y_pixstride;                     /* bf16 NHWC output window, Cout channels                   */
+} specyolo_dwpw_t;
+int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream);
+
 /* Stem conv reading the NCHW network input directly (first layer, Cin = 3):
  * x is NCHW fp32/bf16/u8 (u8 is scaled by 1/255 like predictor.py:133-135), w is fp32
  * [Cout][3][3][3] *folded* weights (device), output NHWC bf16 with SiLU. */

@@ -41,6 +41,7 @@ size_t nms_ws_bytes(int, int, int, int);
 int nms_launch(const specyolo_nms_t*, cudaStream_t);
 int scale_boxes_launch(float*, const int*, int, int, float, float, float, float, float, cudaStream_t);
 int stft_launch(const specyolo_stft_t*, cudaStream_t);
+int dwpw_launch(const specyolo_dwpw_t*, cudaStream_t);
 int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
                              cudaStream_t);
@@ -145,6 +146,13 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
     if (r >= 0) return r;
     SY_CHECK(!a->y_s2d, SPECYOLO_ERR_UNSUPPORTED, "conv: blocked output is implemented by the halo-tile kernel only");
     return conv_igemm_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->dw_w && a->dw_b && a->pw_packed && a->pw_bias && a->y, SPECYOLO_ERR_INVALID, "dwpw: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->Cout,
+             SPECYOLO_ERR_INVALID, "dwpw: bad sizes");
+    return dwpw_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,

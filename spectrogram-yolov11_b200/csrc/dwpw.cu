@@ -1,0 +1,337 @@
+// Fused DWConv(3x3, s1, p1)+BN+SiLU -> Conv(1x1)+BN+SiLU for sm_100a — the two building blocks of Detect.cv3
+// (ultralytics/nn/modules/head.py:51-58: Sequential(DWConv(x, x, 3), Conv(x, c3, 1))).
+//
+// Run separately, the depthwise layer writes and the pointwise layer re-reads a full [B,H,W,C] tensor, and the
+// depthwise layer itself is either issue-bound on CUDA cores or multiplies 63/64 zeros on the tensor pipe.  Here the
+// depthwise result never leaves the SM:
+//   warp 0      TMA producer: per 16x8-pixel output tile one (18 x 10 pixel) halo box per 64 channels
+//   warps 2-9   depthwise on CUDA cores: a thread owns 4 channels (its 36 folded weights in registers) of two tile
+//               rows, slides the 3x3 window along them reading the halo box from shared memory, applies bias + SiLU and
+//               writes bf16 into the 128 x C tile laid out as the K-major SWIZZLE_128B A operand
+//   warp 1      MMA issuer: A tile (shared memory, double-buffered) x resident 1x1 weights -> fp32 accumulator in TMEM
+//               (tcgen05.mma, M = 128, N = Cout, K = C), double-buffered
+//   warps 10-17 epilogue (epilogue.cuh): bias + SiLU -> bf16 -> staged TMA store
+// HBM traffic: one read of the input (x1.4 halo) + one write of the output; the intermediate is 0 bytes.
+#include "common.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "epilogue.cuh"
+
+namespace specyolo {
+
+static constexpr int kDwpwThreads = 64 + 256 + 256;
+static constexpr int kDwpwTW = 8, kDwpwTH = 16, kDwpwHW = 10, kDwpwHH = 18;
+static constexpr uint32_t kDwpwBoxBytes = kDwpwHW * kDwpwHH * 128;          // 23 040: one 64-channel halo box
+static constexpr uint32_t kDwpwBoxStride = 23552;                            // rounded up to 1024
+static constexpr uint32_t kDwpwAChunk = 128 * 128;                           // 16 KB: 128 pixels x 64 channels
+static constexpr int kDwpwMaxDynSmem = 222 * 1024;
+
+struct DwpwParams {
+    int B, H, W, C, chunks;          // C channels = chunks * 64
+    int tiles_w, tiles_h, spatial_tiles;
+    FastDiv d_img, d_tw;
+    int n_pad, cout;
+    const float* dw_w;               // [9][C] folded depthwise weights (fp32)
+    const float* dw_b;               // [C]
+    const float* pw_b;               // [n_pad]
+    uint32_t x_stage_bytes, w_bytes, a_buf_bytes, x_off, a_off, st_off;
+    uint32_t tmem_cols;
+    void* y;
+    int y_pixstride;
+    int store_bw, pair_stores;
+    uint32_t store_row_bytes, store_swz_mask;
+};
+
+__global__ void __launch_bounds__(kDwpwThreads, 1)
+dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ DwpwParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t x_full[2], x_empty[2], a_full[2], a_empty[2], tmem_full_bar[2], tmem_empty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[256];
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    ptx::grid_dep_launch();
+
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* w_s = base;                       // resident 1x1 weights: `chunks` boxes of [n_pad rows x 128 B]
+    uint8_t* x_ring = base + p.x_off;          // 2 stages x chunks halo boxes
+    uint8_t* a_buf = base + p.a_off;           // 2 A tiles x chunks x 16 KB
+    uint8_t* st_buf = base + p.st_off;         // epilogue staging
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&map_x);
+        ptx::prefetch_tmap(&map_w);
+        if (p.store_bw) ptx::prefetch_tmap(&map_y);
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&x_full[s], 1);
+            ptx::mbar_init(&x_empty[s], 8);
+            ptx::mbar_init(&a_full[s], 8);
+            ptx::mbar_init(&a_empty[s], 1);
+            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
+        }
+        ptx::mbar_init(&w_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_pad; i += kDwpwThreads) bias_s[i] = 0.5f * p.pw_b[i];     // SiLU form (epilogue.cuh)
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    if (warp != 0) ptx::grid_dep_wait();
+    const int cta = blockIdx.x, ctas = gridDim.x;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const bool leader = ptx::elect_one();
+        if (leader) {
+            ptx::mbar_expect_tx(&w_bar, p.w_bytes);
+            for (int c = 0; c < p.chunks; ++c)
+                ptx::tma_load_2d(w_s + (size_t)c * p.n_pad * 128, &map_w, &w_bar, c * 64, 0);
+        }
+        ptx::grid_dep_wait();
+        uint32_t tl = 0;
+        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            uint32_t n, r, th_i, tw_i;
+            fdivmod((uint32_t)tile, p.d_img, n, r);
+            fdivmod(r, p.d_tw, th_i, tw_i);
+            const uint32_t s = tl & 1u;
+            ptx::mbar_wait(&x_empty[s], ((tl >> 1) & 1u) ^ 1u);
+            if (leader) {
+                ptx::mbar_expect_tx(&x_full[s], (uint32_t)p.chunks * kDwpwBoxBytes);
+                for (int c = 0; c < p.chunks; ++c)
+                    ptx::tma_load_4d(x_ring + s * p.x_stage_bytes + (uint32_t)c * kDwpwBoxStride, &map_x, &x_full[s], c * 64,
+                                     (int)tw_i * kDwpwTW - 1, (int)th_i * kDwpwTH - 1, (int)n);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_pad);
+        const uint32_t hi = (uint32_t)(ptx::umma_smem_desc(0, 128) >> 32);
+        const uint32_t a16 = ptx::smem_u32(a_buf) >> 4, w16 = ptx::smem_u32(w_s) >> 4;
+        ptx::mbar_wait(&w_bar, 0);
+        uint32_t tl = 0;
+        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            const uint32_t b = tl & 1u, ph = (tl >> 1) & 1u;
+            ptx::mbar_wait(&tmem_empty_bar[b], ph ^ 1u);
+            ptx::mbar_wait(&a_full[b], ph);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + b * (uint32_t)p.n_pad;
+            uint32_t acc = 0;
+            for (int c = 0; c < p.chunks; ++c) {
+                const uint32_t ac = a16 + ((b * p.a_buf_bytes + (uint32_t)c * kDwpwAChunk) >> 4);
+                const uint32_t wc = w16 + (((uint32_t)c * (uint32_t)p.n_pad * 128u) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (leader) ptx::umma_bf16_lohi(d_tmem, ac + 2u * k, hi, wc + 2u * k, hi, idesc, acc);
+                    acc = 1;
+                }
+            }
+            if (leader) {
+                ptx::umma_commit(&a_empty[b]);
+                ptx::umma_commit(&tmem_full_bar[b]);
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== depthwise 3x3 + bias + SiLU -> A tile (warps 2..9) =====================
+        const int t = threadIdx.x - 64;                 // 0..255
+        const int quads = p.C >> 2;                     // 4-channel groups per pixel: 16 or 32
+        const int cq = t % quads;                       // this thread's channel quad
+        const int rgrp = t / quads;                     // row group: 256/quads of them
+        const int rows_per = (kDwpwTH * quads) >> 8;    // tile rows per thread: 1 (C=64) or 2 (C=128)
+        const int c0 = cq * 4;
+        const int chunk = c0 >> 6;                      // which 64-channel box / A chunk
+        const uint32_t unit = (uint32_t)(c0 & 63) >> 3; // 16-byte unit inside the 128-byte row
+        const uint32_t sub = (uint32_t)(c0 & 7) * 2;    // byte offset inside the unit: 0 or 8
+        float wgt[9][4], bs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bs[j] = p.dw_b[c0 + j];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) wgt[k][j] = p.dw_w[k * p.C + c0 + j];
+        }
+        uint32_t tl = 0;
+        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            const uint32_t s = tl & 1u, ph = (tl >> 1) & 1u;
+            ptx::mbar_wait(&x_full[s], ph);
+            ptx::mbar_wait(&a_empty[s], ph ^ 1u);       // the MMAs that read this A buffer two tiles ago have retired
+            const uint8_t* xs = x_ring + s * p.x_stage_bytes + (uint32_t)chunk * kDwpwBoxStride;
+            uint8_t* as = a_buf + s * p.a_buf_bytes + (uint32_t)chunk * kDwpwAChunk;
+            for (int rr = 0; rr < rows_per; ++rr) {
+                const int th = rgrp * rows_per + rr;    // output row inside the tile
+                // sliding 3x3 window over the 10 halo columns of rows th, th+1, th+2
+                float col[3][3][4];
+                auto load_col = [&](int slot, int hx) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t row = (uint32_t)((th + ky) * kDwpwHW + hx);
+                        const uint2 v = *reinterpret_cast<const uint2*>(xs + row * 128u + ((unit ^ (row & 7u)) << 4) + sub);
+                        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+                        col[slot][ky][0] = f0.x; col[slot][ky][1] = f0.y;
+                        col[slot][ky][2] = f1.x; col[slot][ky][3] = f1.y;
+                    }
+                };
+                load_col(0, 0);
+                load_col(1, 1);
+#pragma unroll
+                for (int tw = 0; tw < kDwpwTW; ++tw) {
+                    load_col((tw + 2) % 3, tw + 2);
+                    float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                acc[j] = fmaf(col[(tw + kx) % 3][ky][j], wgt[ky * 3 + kx][j], acc[j]);
+                    uint2 o;
+                    o.x = pack_bf16x2(silu_tanh(acc[0]), silu_tanh(acc[1]));
+                    o.y = pack_bf16x2(silu_tanh(acc[2]), silu_tanh(acc[3]));
+                    const uint32_t m = (uint32_t)(th * kDwpwTW + tw);      // A row = pixel inside the tile
+                    *reinterpret_cast<uint2*>(as + m * 128u + ((unit ^ (m & 7u)) << 4) + sub) = o;
+                }
+            }
+            ptx::fence_proxy_async();                   // generic-proxy writes of A -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(&a_full[s]);
+                ptx::mbar_arrive(&x_empty[s]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 10..17, see epilogue.cuh) =====================
+        const int quad = warp & 3;
+        const int half = (warp - 10) >> 2;
+        const int m = quad * 32 + lane;
+        const int tw = m & (kDwpwTW - 1), th = m >> 3;
+        EpiOut eo{p.y, p.y_pixstride, nullptr, 0, p.pair_stores != 0};
+        EpiStage st = epi_make_stage(st_buf, &map_y, p.n_pad, p.store_bw, p.store_row_bytes, p.store_swz_mask, warp - 8, half,
+                                     lane, m);
+        EpiCols ec;
+        ec.ncols = p.n_pad;
+        ec.n_pad = 1 << 20;
+        ec.d_npad = FastDiv{1ull << 20, 1u << 20};
+        ec.cout_g = p.cout;
+        ec.within0 = 0;
+        ec.gch0 = 0;
+        uint32_t tl = 0;
+        for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
+            uint32_t n, r, th_i, tw_i;
+            fdivmod((uint32_t)tile, p.d_img, n, r);
+            fdivmod(r, p.d_tw, th_i, tw_i);
+            const uint32_t b = tl & 1u, ph = (tl >> 1) & 1u;
+            const int ow = (int)tw_i * kDwpwTW + tw, oh = (int)th_i * kDwpwTH + th;
+            const bool row_ok = (ow < p.W) && (oh < p.H);
+            const size_t pix = ((size_t)n * p.H + oh) * p.W + ow;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * (uint32_t)p.n_pad;
+            ptx::mbar_wait(&tmem_full_bar[b], ph);
+            ptx::tc_fence_after();
+            st.c0 = 0;
+            st.c1 = (int)tw_i * kDwpwTW; st.c2 = (int)th_i * kDwpwTH; st.c3 = (int)n;
+            epi_tile<true, false, false>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st, EpiResSmem{nullptr, 1, 0, 0, 0});
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[b]);
+        }
+        if (st.enabled && st.issuer) ptx::bulk_wait_read0();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int dwpw_launch(const specyolo_dwpw_t* a, cudaStream_t stream) {
+    SY_CHECK(a->C == 64 || a->C == 128, SPECYOLO_ERR_UNSUPPORTED, "dwpw: C must be 64 or 128 (got %d)", a->C);
+    SY_CHECK(a->n_pad % 16 == 0 && a->n_pad >= a->Cout && a->n_pad <= 256 && a->n_pad >= 64, SPECYOLO_ERR_UNSUPPORTED,
+             "dwpw: n_pad must be a multiple of 16 in [64, 256]");
+    SY_CHECK(a->x_pixstride % 8 == 0 && !(reinterpret_cast<uintptr_t>(a->x) & 15) && !(reinterpret_cast<uintptr_t>(a->pw_packed) & 15),
+             SPECYOLO_ERR_INVALID, "dwpw: x / weights must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    SY_CHECK(encode != nullptr, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    DwpwParams p{};
+    p.B = a->B; p.H = a->H; p.W = a->W; p.C = a->C; p.chunks = a->C / 64;
+    p.tiles_w = ceil_div(a->W, kDwpwTW);
+    p.tiles_h = ceil_div(a->H, kDwpwTH);
+    const long spatial = (long)a->B * p.tiles_w * p.tiles_h;
+    SY_CHECK(spatial > 0 && fastdiv_ok((uint64_t)spatial, (uint32_t)(p.tiles_w * p.tiles_h)), SPECYOLO_ERR_INVALID, "dwpw: bad tile count");
+    p.spatial_tiles = (int)spatial;
+    p.d_img = make_fastdiv((uint32_t)(p.tiles_w * p.tiles_h));
+    p.d_tw = make_fastdiv((uint32_t)p.tiles_w);
+    p.n_pad = a->n_pad; p.cout = a->Cout;
+    p.dw_w = a->dw_w; p.dw_b = a->dw_b; p.pw_b = a->pw_bias;
+    p.y = a->y; p.y_pixstride = a->y_pixstride;
+    p.w_bytes = (uint32_t)p.chunks * (uint32_t)a->n_pad * 128u;
+    p.x_stage_bytes = (uint32_t)p.chunks * kDwpwBoxStride;
+    p.a_buf_bytes = (uint32_t)p.chunks * kDwpwAChunk;
+    p.x_off = (p.w_bytes + 1023u) & ~1023u;
+    p.a_off = p.x_off + 2u * p.x_stage_bytes;
+    p.st_off = p.a_off + 2u * p.a_buf_bytes;
+    int store_bw = epi_stage_box_cols(a->n_pad, 2);
+    if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * 2) % 16) store_bw = 0;
+    uint32_t stage_out = epi_stage_bytes(a->n_pad, store_bw, 2);
+    if (1024 + p.st_off + stage_out > (uint32_t)kDwpwMaxDynSmem) { store_bw = 0; stage_out = 0; }
+    const size_t smem_bytes = 1024 + (size_t)p.st_off + stage_out;
+    SY_CHECK(smem_bytes <= (size_t)kDwpwMaxDynSmem, SPECYOLO_ERR_UNSUPPORTED, "dwpw: shared memory budget exceeded");
+    p.store_bw = store_bw;
+    p.pair_stores = 1;
+    p.store_row_bytes = (uint32_t)(store_bw * 2);
+    p.store_swz_mask = p.store_row_bytes == 128 ? 7u : (p.store_row_bytes == 64 ? 3u : 1u);
+    uint32_t cols = 32;
+    while (cols < 2u * (uint32_t)a->n_pad) cols <<= 1;
+    p.tmem_cols = cols;
+
+    CUtensorMap map_x, map_w, map_y;
+    {
+        const cuuint64_t pix_b = (cuuint64_t)a->x_pixstride * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {pix_b, pix_b * a->W, pix_b * a->W * a->H};
+        cuuint32_t box[4] = {64, kDwpwHW, kDwpwHH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(dwpw X) failed (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a->C, (cuuint64_t)a->n_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)a->C * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)a->n_pad};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->pw_packed), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(dwpw W) failed (%d)", (int)r);
+    }
+    map_y = map_w;
+    if (store_bw) {
+        const cuuint64_t pix_b = (cuuint64_t)a->y_pixstride * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {pix_b, pix_b * a->W, pix_b * a->W * a->H};
+        cuuint32_t box[4] = {(cuuint32_t)store_bw, kDwpwTW, kDwpwTH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->y, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)p.store_row_bytes), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(dwpw Y) failed (%d)", (int)r);
+    }
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(dwpw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwpwMaxDynSmem);
+    });
+    SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    const long resident = sm_count();
+    const unsigned grid = (unsigned)(spatial < resident ? spatial : resident);
+    SY_CUDA(launch_pdl(dwpw_kernel, dim3(grid), dim3(kDwpwThreads), smem_bytes, stream, map_x, map_w, map_y, p));
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
+}  // namespace specyolo

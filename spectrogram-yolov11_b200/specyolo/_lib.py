@@ -39,6 +39,14 @@ class ConvArgs(C.Structure):
     ]
 
 
+class DwpwArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("x_pixstride", C.c_int),
+        ("dw_w", C.c_void_p), ("dw_b", C.c_void_p), ("pw_packed", C.c_void_p), ("pw_bias", C.c_void_p),
+        ("Cout", C.c_int), ("n_pad", C.c_int), ("y", C.c_void_p), ("y_pixstride", C.c_int),
+    ]
+
+
 class FusionArgs(C.Structure):
     _fields_ = [
         ("k", C.c_int), ("x", C.c_void_p * 3), ("pixstride", C.c_int * 3), ("upshift", C.c_int * 3),
@@ -93,6 +101,7 @@ SIGNATURES = {
     "specyolo_conv_merge": (C.c_int, [C.c_int] * 7),
     "specyolo_conv_npad": (C.c_int, [C.c_int, C.c_int]),
     "specyolo_conv2d_bias_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "specyolo_dwconv_pwconv": (C.c_int, [C.POINTER(DwpwArgs), C.c_void_p]),
     "specyolo_stem_conv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_stem_space_to_depth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,

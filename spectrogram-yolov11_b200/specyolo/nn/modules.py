@@ -73,18 +73,37 @@ class Conv(nn.Module):
                 self.bn.eps, isinstance(self.act, nn.SiLU))
         return self._packed_blocked
 
+    def folded_depthwise(self):
+        """(w [9, C] fp32 tap-major, b [C] fp32): BN-folded weights of a depthwise 3x3 conv for ops.dwconv_pwconv
+        (fuse_conv_and_bn, ultralytics/utils/torch_utils.py:238-265, on the device; one-off)."""
+        if getattr(self, "_folded_dw", None) is None:
+            c = self.conv
+            scale = self.bn.weight.detach().float() / torch.sqrt(self.bn.running_var.detach().float() + self.bn.eps)
+            w = (c.weight.detach().float() * scale.view(-1, 1, 1, 1)).view(c.out_channels, 9).t().contiguous()
+            b = (self.bn.bias.detach().float() - self.bn.running_mean.detach().float() * scale).contiguous()
+            self._folded_dw = (w, b)
+        return self._folded_dw
+
+    def is_depthwise3x3(self) -> bool:
+        c = self.conv
+        return c.groups == c.in_channels == c.out_channels and c.kernel_size == (3, 3) and c.stride == (1, 1) and \
+            c.padding == (1, 1) and c.dilation == (1, 1) and isinstance(self.act, nn.SiLU)
+
     def invalidate(self):
         self._packed = None
         self._packed_blocked = None
+        self._folded_dw = None
 
     def _apply(self, fn, *a, **k):
         self._packed = None  # parameters moved / cast: repack lazily
         self._packed_blocked = None
+        self._folded_dw = None
         return super()._apply(fn, *a, **k)
 
     def _load_from_state_dict(self, *a, **k):
         self._packed = None
         self._packed_blocked = None
+        self._folded_dw = None
         return super()._load_from_state_dict(*a, **k)
 
     # -- forward -------------------------------------------------------------------------------
@@ -499,12 +518,19 @@ class Detect(nn.Module):
             t = self.cv2[i][1](self.cv2[i][0](xs[i]))
             ops.conv2d(t, self.cv2[i][2].packed(), out=views[i][:, : 4 * self.reg_max], out_fp32=True)
 
+        def dw_pw(pair, x):
+            """Sequential(DWConv 3x3, Conv 1x1) (head.py:51-58): one fused kernel when the shapes allow it."""
+            dw, pw = pair[0], pair[1]
+            if dw.is_depthwise3x3() and ops.dwconv_pwconv_ok(x.shape[1], pw.packed()):
+                w, b = dw.folded_depthwise()
+                return ops.dwconv_pwconv(x, w, b, pw.packed())
+            return pw(dw(x))
+
         def cls_branch(i):
             if self.legacy:
                 t = self.cv3[i][1](self.cv3[i][0](xs[i]))
             else:
-                t = self.cv3[i][0][1](self.cv3[i][0][0](xs[i]))
-                t = self.cv3[i][1][1](self.cv3[i][1][0](t))
+                t = dw_pw(self.cv3[i][1], dw_pw(self.cv3[i][0], xs[i]))
             ops.conv2d(t, self.cv3[i][2].packed(), out=views[i][:, 4 * self.reg_max: self.no], out_fp32=True)
 
         for i in range(len(xs)):

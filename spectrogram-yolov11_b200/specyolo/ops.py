@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, DecodeArgs, FusionArgs, NmsArgs, StftArgs, check
+from ._lib import ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StftArgs, check
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -248,6 +248,31 @@ def conv2d(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None,
     else:
         a.residual, a.r_pixstride = None, 0
     check(_lib.load().specyolo_conv2d_bias_act(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def dwconv_pwconv_ok(C_in: int, pw: PackedConv) -> bool:
+    """Shapes the fused depthwise + pointwise kernel takes (specyolo_dwconv_pwconv)."""
+    return C_in in (64, 128) and pw.k == 1 and pw.g == 1 and pw.cin == C_in and 64 <= pw.n_pad <= 256 and \
+        pw.act == _lib.ACT_SILU
+
+
+def dwconv_pwconv(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, pw: PackedConv,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SiLU(conv1x1(SiLU(dwconv3x3(x) + b_dw)) + b_pw) in one kernel; dw_w fp32 [9, C] (tap-major), dw_b fp32 [C]."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16 or dw_w.shape != (9, Cc) or dw_w.dtype != torch.float32 or not dw_w.is_contiguous():
+        raise ValueError("dwconv_pwconv: x must be bf16 NHWC, dw_w contiguous fp32 [9, C]")
+    if out is None:
+        out = new_act(B, pw.cout, H, W, x.device)
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, pw.cout, H, W) or out.dtype != torch.bfloat16:
+        raise ValueError("dwconv_pwconv: out shape / dtype mismatch")
+    a = DwpwArgs()
+    a.x, a.B, a.H, a.W, a.C, a.x_pixstride = x.data_ptr(), B, H, W, Cc, xpix
+    a.dw_w, a.dw_b, a.pw_packed, a.pw_bias = dw_w.data_ptr(), dw_b.data_ptr(), pw.w.data_ptr(), pw.bias.data_ptr()
+    a.Cout, a.n_pad, a.y, a.y_pixstride = pw.cout, pw.n_pad, out.data_ptr(), ypix
+    check(_lib.load().specyolo_dwconv_pwconv(C.byref(a), _lib.stream_ptr()))
     return out
 
 

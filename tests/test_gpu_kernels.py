@@ -222,6 +222,27 @@ def test_depthwise_ragged(lib):
     assert _rel_err(y, ref) < 5e-3
 
 
+@pytest.mark.parametrize("C,cout,B,H,W", [(128, 128, 2, 40, 40), (64, 128, 3, 20, 20), (128, 80, 1, 21, 13)])
+def test_dwconv_pwconv_fused(lib, C, cout, B, H, W):
+    """Fused DWConv 3x3 + SiLU -> Conv 1x1 + SiLU (Detect.cv3 pair) vs the two fp32 convs (bf16 intermediate)."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(31 + C + cout)
+    x = torch.randn((B, C, H, W), generator=gen)
+    wd = torch.randn((C, 1, 3, 3), generator=gen) * 0.3
+    bd = torch.randn(C, generator=gen) * 0.1
+    wp = torch.randn((cout, C, 1, 1), generator=gen) * math.sqrt(2.0 / C)
+    bp = torch.randn(cout, generator=gen) * 0.1
+    pw = ops.fold_pack(wp.to(DEV), bp.to(DEV), None, 0.0, 1, 0, 1, 1, True)
+    assert ops.dwconv_pwconv_ok(C, pw)
+    dw_w = wd.view(C, 9).t().contiguous().to(DEV)
+    y = ops.dwconv_pwconv(_fmap(x), dw_w, bd.to(DEV), pw).float().cpu()
+    mid = _bf(F.silu(F.conv2d(_bf(x), wd, bd, 1, 1, 1, C)))
+    ref = F.silu(F.conv2d(mid, _bf(wp), bp))
+    assert y.shape == ref.shape
+    assert _rel_err(y, ref) < 8e-3, _rel_err(y, ref)
+
+
 def test_sppf_pool(lib):
     from specyolo import ops
 

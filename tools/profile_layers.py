@@ -33,9 +33,14 @@ def wrap(name):
             by = 2.0 * (xx.numel() + r.numel() * (2 if r.dtype == torch.float32 else 1)) + 2.0 * pc.w.numel()
             if len(a) > 3 and a[3] is not None or k.get("residual") is not None: by += 2.0 * r.numel()
             desc = f"conv {Cin:4d}->{pc.cout:4d} k{pc.k} s{pc.s} d{pc.d} g{pc.g_orig:3d} {H:3d}x{W:3d} M={Bq*Ho*Wo:8d} K={(pc.cin//pc.g_orig)*pc.k*pc.k:5d}"
+        if name == "dwconv_pwconv":
+            xx, pw = a[0], a[3]
+            Bq, Cc, H, W = xx.shape
+            fl = 2.0 * Bq * H * W * Cc * (9 + pw.cout); by = 2.0 * (xx.numel() + r.numel())
+            desc = f"dw3x3+pw {Cc:4d}->{pw.cout:4d} fused          {H:3d}x{W:3d} M={Bq*H*W:8d} K={Cc+9:5d}"
         rec.append((desc, e0, e1, fl, by)); return r
     setattr(ops, name, g)
-for n in ("conv2d", "stem_space_to_depth", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
+for n in ("conv2d", "dwconv_pwconv", "stem_space_to_depth", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
     wrap(n)
 for _ in range(2):
     yolo.model.detect_fused(x)
