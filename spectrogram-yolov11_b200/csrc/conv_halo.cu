@@ -65,6 +65,7 @@ struct HaloParams {
     // TMA-store epilogue (store_bw == 0: direct stores)
     int store_bw, pair_stores;
     int y_s2d;                   // output written 2x2-blocked (see specyolo_conv_t::y_s2d)
+    int thin;                    // <= 32-column tiles on the paired-task epilogue (see the epilogue branch)
     // residual tile ring (two slots after the staging buffer): the TMA producer loads the tile's residual box(es)
     // tiles ahead, the epilogue reads them from shared memory (res_box_cols == 0: residual read from global memory)
     int res_box_cols, res_slots;
@@ -87,6 +88,71 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes,
     d |= 1ull << 46;
     d |= layout << 61;
     return d;
+}
+
+// Thin tiles (16 / 32 accumulator columns): one epilogue task = one 16-column chunk of one sub-tile of a super-tile
+// stage.  A tile this thin carries ~300 cycles of useful epilogue work behind ~1000 cycles of dependent latency
+// (tile decode -> tcgen05.ld -> bias -> MUFU -> pack -> store; clock64 phase timers), so every warp keeps TWO tasks in
+// flight — both accumulator loads and both residual loads are issued before the single wait — and the bias chunk of
+// the warp lives in registers for the whole kernel.
+struct ThinTask {
+    uint32_t taddr;
+    bool ok;
+    size_t yoff, roff;           // element offsets of this lane's row (first channel of the chunk)
+};
+__device__ __forceinline__ ThinTask thin_setup(const HaloParams& p, int tile, int tw, int th, int gch, uint32_t taddr) {
+    ThinTask t;
+    uint32_t n, r, th_i, tw_i;
+    fdivmod((uint32_t)tile, p.d_img, n, r);
+    fdivmod(r, p.d_tw, th_i, tw_i);
+    const int ow = (int)tw_i * 8 + tw, oh = (int)th_i * 16 + th;
+    t.ok = (ow < p.Wo) && (oh < p.Ho);
+    t.taddr = taddr;
+    const uint32_t pix = ((uint32_t)n * (uint32_t)p.Ho + (uint32_t)oh) * (uint32_t)p.Wo + (uint32_t)ow;
+    if (p.y_s2d) {
+        const uint32_t bpix = ((uint32_t)n * (uint32_t)(p.Ho >> 1) + (uint32_t)(oh >> 1)) * (uint32_t)(p.Wo >> 1) + (uint32_t)(ow >> 1);
+        t.yoff = (size_t)bpix * (uint32_t)p.y_pixstride + (uint32_t)(gch + (((oh & 1) << 1) | (ow & 1)) * p.cout_g);
+    } else {
+        t.yoff = (size_t)pix * (uint32_t)p.y_pixstride + (uint32_t)gch;
+    }
+    t.roff = (size_t)pix * (uint32_t)p.r_pixstride + (uint32_t)gch;
+    return t;
+}
+template <bool kSilu, bool kRes>
+__device__ __forceinline__ void thin_finish(const uint32_t (&v)[16], const float (&bias)[16], const ThinTask& t,
+                                            __nv_bfloat16* y, const uint4& r0, const uint4& r1) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a = __uint_as_float(v[i]);
+        if (kSilu) {
+            const float h = fmaf(a, 0.5f, bias[i]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+            f[i] = fmaf(h, th, h);
+        } else {
+            f[i] = a + bias[i];
+        }
+    }
+    if (kRes) {
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 q = unpack_bf16x2(rr[i]);
+            f[2 * i] += q.x;
+            f[2 * i + 1] += q.y;
+        }
+    }
+    if (t.ok) {
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+        uint4* yp = reinterpret_cast<uint4*>(y + t.yoff);
+        yp[0] = o0;
+        yp[1] = o1;
+    }
 }
 
 // (min 2 CTAs/SM: caps the residual variants at 102 registers — at 134 they silently ran one CTA per SM and every
@@ -224,6 +290,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t b_tap16 = (uint32_t)p.bchunks * b_box16;       // next tap of the same (group, chunk)
             const uint32_t b_grp16 = (uint32_t)p.taps * b_tap16;          // next group
             const int ksteps = p.kc_box / 16;
+            const bool single_group = p.groups_cta == 1;        // (then kc_box == kc_b)
             ptx::mbar_wait(&w_bar, 0);
             ptx::tc_fence_after();
             int stage = 0;
@@ -240,6 +307,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     ptx::mbar_wait(&full_bar[stage], ph);
                     ptx::tc_fence_after();
                     const uint32_t a16 = a_ring16 + (((uint32_t)stage * p.a_stage_bytes) >> 4);
+                    if (single_group) {
+                        // one group per CTA (every dense conv): box == weight chunk, no group / chunk lookup
+                        uint32_t b16k = b_base16 + (uint32_t)box * b_box16;
+                        uint32_t a16k = a16;
+                        for (int k = 0; k < ksteps; ++k) {
+                            uint32_t b16 = b16k;
+                            uint32_t accumulate = (box | k) != 0 ? 1u : 0u;
+                            for (int tap = 0; tap < p.taps; ++tap) {
+                                if (leader) ptx::umma_bf16_lohi(d_tmem, a16k + p.tap_a16[tap], a_hi, b16, b_hi, idesc, accumulate);
+                                accumulate = 1u;
+                                b16 += b_tap16;
+                            }
+                            b16k += 2u;
+                            a16k += 2u;
+                        }
+                    } else
                     for (int k = 0; k < ksteps; ++k) {
                         uint32_t gl, cio;
                         fdivmod((uint32_t)(box * p.kc_box + k * 16), p.d_cin_g, gl, cio);   // channel inside the split
@@ -269,6 +352,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int half = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
         const int tw = m & (kHaloTW - 1), th = m >> 3;
+        if (!kFp32 && p.thin) {
+            // paired-task path (ThinTask above).  32 columns: this half owns chunk `half` of every sub-tile;
+            // 16 columns: the halves take alternate sub-tiles.
+            const bool wide = p.ncols == 32;
+            const int chunk = wide ? half : 0;
+            const int s_first = wide ? 0 : half, s_step = wide ? 1 : 2;
+            const int gch = split * p.cout_g + chunk * 16;
+            float bias_r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bias_r[i] = bias_s[chunk * 16 + i];
+            __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chunk * 16);
+            uint32_t tl = 0;
+            for (int sti = cta; sti < p.nsuper; sti += ctas, ++tl) {
+                const uint32_t buf = tl & 1u;
+                const uint32_t bph = (tl >> 1) & 1u;
+                const int tile0 = sti * p.supert;
+                const int nsub = min(p.supert, p.spatial_tiles - tile0);
+                if (kRes && sti + ctas < p.nsuper) {            // next stage's residual rows of this warp -> L2
+                    const int tile1 = (sti + ctas) * p.supert;
+                    const int nsub1 = min(p.supert, p.spatial_tiles - tile1);
+                    for (int sb = s_first; sb < nsub1; sb += s_step) {
+                        const ThinTask q = thin_setup(p, tile1 + sb, tw, th, gch, 0u);
+                        if (q.ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + q.roff));
+                    }
+                }
+                const uint32_t t_stage = t_lane + buf * (uint32_t)p.supert * (uint32_t)p.ncols;
+                ptx::mbar_wait(&tmem_full_bar[buf], bph);
+                ptx::tc_fence_after();
+                for (int sb = s_first; sb < nsub; sb += 2 * s_step) {
+                    const bool two = sb + s_step < nsub;
+                    uint32_t va[16], vb[16];
+                    const ThinTask ta = thin_setup(p, tile0 + sb, tw, th, gch, t_stage + (uint32_t)sb * (uint32_t)p.ncols);
+                    ptx::tmem_ld16(ta.taddr, va);
+                    ThinTask tb = ta;
+                    if (two) {
+                        tb = thin_setup(p, tile0 + sb + s_step, tw, th, gch, t_stage + (uint32_t)(sb + s_step) * (uint32_t)p.ncols);
+                        ptx::tmem_ld16(tb.taddr, vb);
+                    }
+                    uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+                    if (kRes) {
+                        if (ta.ok) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + ta.roff);
+                            ra0 = __ldg(rp); ra1 = __ldg(rp + 1);
+                        }
+                        if (two && tb.ok) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + tb.roff);
+                            rb0 = __ldg(rp); rb1 = __ldg(rp + 1);
+                        }
+                    }
+                    ptx::tmem_ld_wait();
+                    thin_finish<kSilu, kRes>(va, bias_r, ta, yb, ra0, ra1);
+                    if (two) thin_finish<kSilu, kRes>(vb, bias_r, tb, yb, rb0, rb1);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+            }
+        } else {
         EpiOut eo{p.y, p.y_pixstride, p.residual, p.r_pixstride, p.pair_stores != 0};
         EpiStage st = epi_make_stage(a_ring + p.ring_bytes, &map_y, p.ncols, p.store_bw, p.store_row_bytes, p.store_swz_mask,
                                      warp, half, lane, m);
@@ -334,6 +476,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
         }
         if (st.enabled && st.issuer) ptx::bulk_wait_read0();   // staging must outlive the last store's read
+        }
     }
 
     ptx::tc_fence_before();
@@ -360,6 +503,18 @@ bool conv_halo_geometry_ok(int kh, int kw, int stride, int pad, int dil) {
     if (kh != kw || kh < 2 || kh > 7) return false;
     if (stride < 1 || stride > 2) return false;
     if (dil % stride || pad % stride) return false;
+    return true;
+}
+
+// Paired-task epilogue (ThinTask): one full 16-channel chunk per task, plain 16-byte stores.
+static bool thin_ok(const specyolo_conv_t* a, int ncols, int gcta, int cout_g, int store_bw) {
+    if (env_flag("SPECYOLO_NO_THIN")) return false;
+    if (ncols > 32 || a->y_fp32 || store_bw || gcta != 1 || cout_g != ncols) return false;
+    if ((reinterpret_cast<uintptr_t>(a->y) & 15) || a->y_pixstride % 8) return false;
+    if (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || a->r_pixstride % 8 || a->y_s2d ||
+                        env_flag("SPECYOLO_RES_RING")))
+        return false;
+    if ((long)a->B * a->Ho * a->Wo >= (1L << 31)) return false;
     return true;
 }
 
@@ -452,13 +607,15 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         // thin tiles: several output tiles per accumulator stage (one tmem_full / tmem_empty hand-off per stage) when
         // every CTA has many tiles to walk; the per-tile hand-off chain, not bandwidth, bounded those layers
         int supert = 1;
+        bool thin = false;
         {
             const long spatial_t = (long)a->B * ceil_div(a->Wo, kHaloTW) * ceil_div(a->Ho, kHaloTH);
             const long per_cta = spatial_t / ((long)sm_count() * 2 / gs + 1);
             // (measured: pays only for the thinnest tiles — the K = 64 stem conv, 4 MMAs per tile: 188 -> 170 us;
             //  neutral to slightly negative once a tile carries >= 9 MMAs)
             const int mmas_per_tile = p.taps * (cin_cta / 16);
-            const int smax = mmas_per_tile > 8 ? 1 : (ncols <= 32 ? 4 : (ncols <= 64 ? 2 : 1));
+            thin = thin_ok(a, ncols, gcta, cout_g, store_bw);
+            const int smax = thin ? 4 : (mmas_per_tile > 8 ? 1 : (ncols <= 64 ? 2 : 1));
             while (supert * 2 <= smax && per_cta >= 4L * supert * 2 && !env_flag("SPECYOLO_NO_SUPERTILE")) supert *= 2;
         }
         int occ = 1;
@@ -476,6 +633,7 @@ static bool conv_halo_plan(const specyolo_conv_t* a, HaloPlan& plan) {
         found = true;
         p.gsplit = gs;
         p.supert = supert;
+        p.thin = thin ? 1 : 0;
         p.groups_cta = gcta;
         p.cin_cta = cin_cta;
         p.kc_box = kc_box;
