@@ -1,4 +1,5 @@
 // HBM-bound glue kernels of the neck: SPPF pooling and Fusion('ESChannel').
+#include <cstdlib>
 #include "common.h"
 #include "tma_host.h"
 #include "ptx.cuh"
@@ -91,12 +92,13 @@ int sppf_pool_launch(void* buf, int B, int H, int W, int c, int pixstride, cudaS
 // by the full-resolution 3x3 spatial-attention conv).
 //
 // Two launches.  fusion_stats_kernel: every CTA streams a contiguous run of source pixels of ONE (image, input) —
-// pointer increments only, a lane owns one 8-channel vector — and writes per-channel partial sums of squares plus the
+// pointer increments only, a lane owns four 8-channel vectors of a pixel — and writes per-channel partial sums of squares plus the
 // per-pixel channel mean / max maps; the last CTA of an image (atomic ticket, partials summed in a fixed order, so the
 // result is deterministic) evaluates the k*c gates.  fusion_apply_kernel: a CTA owns kFusRows rows of one image,
 // builds the k spatial-attention maps of those rows in shared memory and writes out = sum_i x_i * (gate_i + sab_i)
 // with the gates of its channel vector in registers.  v1 of these kernels was issue-bound (runtime div/mod per
-// vector, scalar LDS per FMA, a serial 400-step partial reduction): 291 us for the 80x80 level.
+// vector, scalar LDS per FMA, a serial 400-step partial reduction): 291 us for the 80x80 level; v2 (one vector per
+// lane, scalar fp32 math) still spent ~120 warp instructions per 512-byte warp load: 226 us, 2.5 TB/s.
 // ------------------------------------------------------------------------------------------------
 static constexpr int kFusRows = 4;      // image rows per apply CTA
 static constexpr int kFusMaxParts = 16;
@@ -108,7 +110,7 @@ struct FusionParams {
     float* part;          // [B][parts][k*c]
     float* mm;            // [B][k][2][H*W]   (input i uses the first HWs_i entries of each plane)
     float* gate;          // [B][k*c]
-    unsigned int* ticket; // [B]
+    unsigned int* ticket; // [B]   stats CTAs of the image that have finished
 };
 
 __device__ __forceinline__ float redux_max_f32(float v, unsigned mask) {
@@ -116,83 +118,124 @@ __device__ __forceinline__ float redux_max_f32(float v, unsigned mask) {
     asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(mask));
     return r;
 }
+// packed fp32 pairs (FFMA2 / FADD2): both kernels were issue-bound, not bandwidth-bound (ncu: 60 % issue slots busy at
+// 2.5 TB/s, ~120 warp instructions per 512-byte warp load)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};\n\t"
+        "add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// volatile: keeps the loads of one iteration together ahead of the math (the scheduler otherwise interleaves them
+// with the first vectors' arithmetic to save registers, leaving two loads per lane in flight)
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 bf16x2_f2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
 
-__global__ void __launch_bounds__(256)
-fusion_stats_kernel(const __grid_constant__ FusionParams p) {
-    ptx::grid_dep_launch();
-    ptx::grid_dep_wait();
+// LPP = lanes per pixel = c / 32: a lane owns FOUR 16-byte vectors of one pixel (vector j*LPP + l, j = 0..3), so the
+// channel mean / max of a pixel needs log2(LPP) <= 3 shuffle steps per four loads and the max runs packed in bf16.
+template <int LPP>
+__device__ __forceinline__ void fusion_stats_item(const FusionParams& p, int b, int item, float* red, bool* is_last_s) {
     const specyolo_fusion_t& a = p.a;
-    // work item -> (image, input, part)
-    int item = blockIdx.x;
+    constexpr int C = 32 * LPP;
+    constexpr int PPI = 256 / LPP;             // pixels per CTA step
+    // item -> (input, part)
     const int q = item % p.parts;
-    item /= p.parts;
-    const int i = item % a.k;
-    const int b = item / a.k;
+    const int i = item / p.parts;
     const int sh = a.upshift[i];
     const int HWs = (a.H >> sh) * (a.W >> sh);
     const int HW = a.H * a.W;
-    const int KC = a.k * a.c;
-    const int vpp = a.c >> 3;                  // 16-byte vectors (= lanes) per pixel: 4, 8, 16 or 32
-    const int pix_par = 256 / vpp;             // pixels per step
-    const int v = threadIdx.x % vpp;
-    const int psub = threadIdx.x / vpp;
+    const int KC = a.k * C;
+    const int l = threadIdx.x % LPP;
+    const int pg = threadIdx.x / LPP;
     const int lane = threadIdx.x & 31;
-    const unsigned gmask = vpp == 32 ? 0xffffffffu : (((1u << vpp) - 1u) << (lane & ~(vpp - 1)));
-    __shared__ float red[256 * 8];
-    __shared__ bool is_last;
+    const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (lane & ~(LPP - 1)));
+    bool& is_last = *is_last_s;
 
     const int begin = q * p.len[i];
     const int end = min(HWs, begin + p.len[i]);
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.x[i]) + ((size_t)b * HWs) * a.pixstride[i] + v * 8;
+    const size_t pstride = (size_t)a.pixstride[i];
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.x[i]) + ((size_t)b * HWs + begin + pg) * pstride + l * 8;
     float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
-    const float inv_c = 1.0f / (float)a.c;
+    const float inv_c = 1.0f / (float)C;
 
-    float ssq[8];
+    float2 ssq[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ssq[j] = 0.f;
-    // 4 pixel steps per iteration, all four 16-byte loads issued before any use: one load per thread in flight left
-    // the kernel latency-bound (uniform trip count: the lane reductions below are convergent)
-    for (int pix0 = begin; pix0 < end; pix0 += 4 * pix_par) {
-        uint4 u[4];
-        bool ok[4];
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-            const int pix = pix0 + s4 * pix_par + psub;
-            ok[s4] = pix < end;
-            u[s4] = ok[s4] ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)pix * a.pixstride[i])) : make_uint4(0, 0, 0, 0);
+        for (int w = 0; w < 4; ++w) ssq[j][w] = make_float2(0.f, 0.f);
+    // two pixel steps (8 x 16-byte loads per lane) in flight per iteration: with 4 the kernel was latency-bound
+    // (ncu: 0.4 eligible warps per scheduler, 2.9 TB/s).  Uniform trip count: the lane reductions are convergent.
+    for (int pix = begin + pg; pix - pg < end; pix += 2 * PPI, src += (size_t)(2 * PPI) * pstride) {
+        uint4 u[2][4];
+        bool ok[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            ok[t] = pix + t * PPI < end;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                u[t][j] = ok[t] ? ldg_nc_v4(src + (size_t)(t * PPI) * pstride + j * LPP * 8) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-            const int pix = pix0 + s4 * pix_par + psub;
-            const uint32_t uu[4] = {u[s4].x, u[s4].y, u[s4].z, u[s4].w};
-            float s = 0.f, m = -INFINITY;
+        for (int t = 0; t < 2; ++t) {
+            float2 s2 = make_float2(0.f, 0.f);
+            uint32_t mx = 0xff80ff80u;               // (-inf, -inf)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(uu[j]);
-                ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
-                ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
-                s += f.x + f.y;
-                m = fmaxf(m, fmaxf(f.x, f.y));
+                const uint32_t uu[4] = {u[t][j].x, u[t][j].y, u[t][j].z, u[t][j].w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float2 f = bf16x2_f2(uu[w]);
+                    ssq[j][w] = ffma2(f, f, ssq[j][w]);
+                    s2 = fadd2(s2, f);
+                    mx = bf16x2_max(mx, uu[w]);
+                }
             }
-            // channel mean / max of the pixel: reduce over its vpp lanes
-            for (int d = vpp >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            m = redux_max_f32(m, gmask);
-            if (ok[s4] && v == 0) {
-                mm[pix] = s * inv_c;
-                mm[HW + pix] = m;
+            float s = s2.x + s2.y;
+            const float2 mf = bf16x2_f2(mx);
+            float m = fmaxf(mf.x, mf.y);
+#pragma unroll
+            for (int d = LPP >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (LPP > 1) m = redux_max_f32(m, gmask);
+            if (ok[t] && l == 0) {
+                mm[pix + t * PPI] = s * inv_c;
+                mm[HW + pix + t * PPI] = m;
             }
         }
     }
-    // deterministic reduction of ssq over the pix_par pixel groups
+    // deterministic reduction of ssq over the PPI pixel slots
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = ssq[j];
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            red[threadIdx.x * 32 + j * 8 + 2 * w] = ssq[j][w].x;
+            red[threadIdx.x * 32 + j * 8 + 2 * w + 1] = ssq[j][w].y;
+        }
     __syncthreads();
-    if ((int)threadIdx.x < a.c) {
+    if ((int)threadIdx.x < C) {
         const int ch = threadIdx.x;
-        const int vv = ch >> 3, jj = ch & 7;
+        const int vec = ch >> 3, e = ch & 7;
+        const int j = vec / LPP, ll = vec % LPP;
         float t = 0.f;
-        for (int ps = 0; ps < pix_par; ++ps) t += red[(ps * vpp + vv) * 8 + jj];
-        p.part[((size_t)b * p.parts + q) * KC + i * a.c + ch] = t * (float)(1 << (2 * sh));   // upsampled: each source pixel counts 4x
+        for (int g = 0; g < PPI; ++g) t += red[(g * LPP + ll) * 32 + j * 8 + e];
+        p.part[((size_t)b * p.parts + q) * KC + i * C + ch] = t * (float)(1 << (2 * sh));   // upsampled: each source pixel counts 4x
     }
     // ---- last CTA of this image: gates ----
     __threadfence();
@@ -225,39 +268,38 @@ fusion_stats_kernel(const __grid_constant__ FusionParams p) {
         p.gate[(size_t)b * KC + ch] = 1.0f + tanhf(s_e[ch] * (a.gamma[ch] * inv) + a.beta[ch]);
 }
 
-__global__ void __launch_bounds__(256)
-fusion_apply_kernel(const __grid_constant__ FusionParams p) {
-    ptx::grid_dep_launch();
-    ptx::grid_dep_wait();
+// K inputs; a thread owns one 8-channel vector (its K*8 gates packed in registers) and walks the CTA's pixels.
+template <int K>
+__device__ __forceinline__ void fusion_apply_item(const FusionParams& p, int b, int hblk, float* s_sab) {
     const specyolo_fusion_t& a = p.a;
-    const int b = blockIdx.y;
-    const int h0 = blockIdx.x * kFusRows;
+    const int h0 = hblk * kFusRows;
     const int rows = min(kFusRows, a.H - h0);
     const int HW = a.H * a.W;
-    const int KC = a.k * a.c;
+    const int KC = K * a.c;
     const int vpp = a.c >> 3;
     const int pix_par = 256 / vpp;
     const int v = threadIdx.x % vpp;
     const int psub = threadIdx.x / vpp;
-    extern __shared__ float s_sab[];          // [k][rows][W]
-
-    // gates of this thread's channel vector: registers
-    float g[3][8];
+    // s_sab: [K][rows][W]
+    float2 g[K][4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[i][j] = (i < a.k) ? __ldg(p.gate + (size_t)b * KC + i * a.c + v * 8 + j) : 0.f;
+    for (int i = 0; i < K; ++i) {
+        const float4* gp = reinterpret_cast<const float4*>(p.gate + (size_t)b * KC + i * a.c + v * 8);
+        const float4 g0 = __ldcg(gp), g1 = __ldcg(gp + 1);
+        g[i][0] = make_float2(g0.x, g0.y); g[i][1] = make_float2(g0.z, g0.w);
+        g[i][2] = make_float2(g1.x, g1.y); g[i][3] = make_float2(g1.z, g1.w);
+    }
 
     // ---- spatial attention of the CTA's rows: sigmoid(conv3x3([mean, max])) at each input's source resolution ----
     const int npix = rows * a.W;
-    for (int t = threadIdx.x; t < a.k * npix; t += 256) {
+    for (int t = threadIdx.x; t < K * npix; t += 256) {
         const int i = t / npix;
         const int r = t - i * npix;
         const int hr = r / a.W, w = r - hr * a.W;
         const int sh = a.upshift[i];
         const int Ws = a.W >> sh;
         const int h = h0 + hr;
-        const float* mm = p.mm + ((size_t)(b * a.k + i) * 2) * HW;
+        const float* mm = p.mm + ((size_t)(b * K + i) * 2) * HW;
         // the 3x3 conv runs on the FULL-resolution (upsampled) maps: neighbours (h+-1, w+-1) -> source (>> sh)
         float acc = 0.f;
 #pragma unroll
@@ -270,74 +312,99 @@ fusion_apply_kernel(const __grid_constant__ FusionParams p) {
                 for (int kx = 0; kx < 3; ++kx) {
                     const int ww = w + kx - 1;
                     if (ww < 0 || ww >= a.W) continue;
-                    acc = fmaf(__ldg(a.sab_w + ci * 9 + ky * 3 + kx), mm[(size_t)ci * HW + (hh >> sh) * Ws + (ww >> sh)], acc);
+                    acc = fmaf(__ldg(a.sab_w + ci * 9 + ky * 3 + kx), __ldcg(mm + (size_t)ci * HW + (hh >> sh) * Ws + (ww >> sh)), acc);
                 }
             }
         s_sab[t] = 1.0f / (1.0f + __expf(-acc));
     }
     __syncthreads();
 
-    // ---- out = sum_i x_i * (gate_i + sab_i) ----
-    const __nv_bfloat16* xb[3];
-    int wshift[3], rowstride[3];
+    // ---- out = sum_i x_i * (gate_i + sab_i) over the CTA's rows x W pixels (flattened, (hr, w) carried along) ----
+    const __nv_bfloat16* xb[K];
+    int wshift[K], rowstride[K], pstr[K];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int ii = i < a.k ? i : 0;
-        const int sh = a.upshift[ii];
+    for (int i = 0; i < K; ++i) {
+        const int sh = a.upshift[i];
         const int Hs = a.H >> sh, Ws = a.W >> sh;
-        xb[i] = reinterpret_cast<const __nv_bfloat16*>(a.x[ii]) + ((size_t)b * Hs * Ws) * a.pixstride[ii] + v * 8;
+        xb[i] = reinterpret_cast<const __nv_bfloat16*>(a.x[i]) + ((size_t)b * Hs * Ws) * a.pixstride[i] + v * 8;
         wshift[i] = sh;
         rowstride[i] = Ws;
+        pstr[i] = a.pixstride[i];
     }
-    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)b * HW) * a.y_pixstride + v * 8;
-    for (int hr = 0; hr < rows; ++hr) {
-        const int h = h0 + hr;
-        // two pixels per iteration, their 2k loads issued before any use
-        for (int w0 = psub; w0 < a.W; w0 += 2 * pix_par) {
-            uint4 u[2][3];
-            bool ok[2];
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)b * HW + (size_t)h0 * a.W) * a.y_pixstride + v * 8;
+    // two pixels (2K loads) in flight per iteration
+    int hr[2], w[2];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int w = w0 + t * pix_par;
-                ok[t] = w < a.W;
+    for (int t = 0; t < 2; ++t) {
+        hr[t] = 0;
+        w[t] = psub + t * pix_par;
+        while (w[t] >= a.W) { w[t] -= a.W; ++hr[t]; }
+    }
+    for (int q = psub; q < npix; q += 2 * pix_par) {
+        uint4 u[2][K];
+        bool ok[2];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    if (i < a.k && ok[t]) {
-                        const size_t spix = (size_t)(h >> wshift[i]) * rowstride[i] + (w >> wshift[i]);
-                        u[t][i] = __ldg(reinterpret_cast<const uint4*>(xb[i] + spix * a.pixstride[i]));
-                    } else {
-                        u[t][i] = make_uint4(0, 0, 0, 0);
-                    }
-                }
-            }
+        for (int t = 0; t < 2; ++t) {
+            ok[t] = q + t * pix_par < npix;
+            const int h = h0 + hr[t];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (!ok[t]) continue;
-                const int w = w0 + t * pix_par;
-                float acc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    if (i >= a.k) break;
-                    const uint32_t uu[4] = {u[t][i].x, u[t][i].y, u[t][i].z, u[t][i].w};
-                    const float sab = s_sab[(i * rows + hr) * a.W + w];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack_bf16x2(uu[j]);
-                        acc[2 * j] = fmaf(f.x, g[i][2 * j] + sab, acc[2 * j]);
-                        acc[2 * j + 1] = fmaf(f.y, g[i][2 * j + 1] + sab, acc[2 * j + 1]);
-                    }
-                }
-                uint4 o;
-                o.x = pack_bf16x2(acc[0], acc[1]);
-                o.y = pack_bf16x2(acc[2], acc[3]);
-                o.z = pack_bf16x2(acc[4], acc[5]);
-                o.w = pack_bf16x2(acc[6], acc[7]);
-                *reinterpret_cast<uint4*>(yb + ((size_t)h * a.W + w) * a.y_pixstride) = o;
+            for (int i = 0; i < K; ++i) {
+                const int spix = (h >> wshift[i]) * rowstride[i] + (w[t] >> wshift[i]);
+                u[t][i] = ok[t] ? ldg_nc_v4(xb[i] + (size_t)spix * pstr[i]) : make_uint4(0, 0, 0, 0);
             }
         }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!ok[t]) continue;
+            const int qq = q + t * pix_par;
+            float2 acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t uu[4] = {u[t][i].x, u[t][i].y, u[t][i].z, u[t][i].w};
+                const float sab = s_sab[i * npix + qq];
+                const float2 sab2 = make_float2(sab, sab);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = ffma2(bf16x2_f2(uu[j]), fadd2(g[i][j], sab2), acc[j]);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(acc[0].x, acc[0].y);
+            o.y = pack_bf16x2(acc[1].x, acc[1].y);
+            o.z = pack_bf16x2(acc[2].x, acc[2].y);
+            o.w = pack_bf16x2(acc[3].x, acc[3].y);
+            *reinterpret_cast<uint4*>(yb + (size_t)qq * a.y_pixstride) = o;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            w[t] += 2 * pix_par;
+            while (w[t] >= a.W) { w[t] -= a.W; ++hr[t]; }
+        }
     }
+}
+
+// (A single-launch variant — statistics items of image b + D followed by the apply items of image b, handed out in
+//  order by an atomic counter, apply items spinning on a per-image publish flag — was measured: the hoped-for L2 hits
+//  on the second read of the inputs did not materialise; D = 2 .. 24 ran 206 .. 150 us against 160 us for the two
+//  launches below at the 80x80 level, so the simple form stays.)
+template <int LPP>
+__global__ void __launch_bounds__(256)
+fusion_stats_kernel(const __grid_constant__ FusionParams p) {
+    __shared__ float red[256 * 32];
+    __shared__ bool is_last;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    const int S = p.a.k * p.parts;
+    fusion_stats_item<LPP>(p, blockIdx.x / S, blockIdx.x % S, red, &is_last);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 3)
+fusion_apply_kernel(const __grid_constant__ FusionParams p) {
+    extern __shared__ float s_sab[];
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    fusion_apply_item<K>(p, blockIdx.y, blockIdx.x, s_sab);
 }
 
 // stats CTAs per (image, input): a function of the image size ONLY, so that the fp32 summation order of the per-channel
@@ -374,21 +441,28 @@ int fusion_launch(const specyolo_fusion_t* a, cudaStream_t stream) {
     FusionParams p{};
     p.a = *a;
     p.parts = fusion_parts(a->H * a->W);
-    const int pix_par = 256 / (a->c / 8);
+    const int ppi = 256 / (a->c / 32);          // pixels per stats CTA step
     for (int i = 0; i < a->k; ++i) {
         const int HWs = (a->H >> a->upshift[i]) * (a->W >> a->upshift[i]);
-        p.len[i] = ceil_div(ceil_div(HWs, p.parts), 4 * pix_par) * 4 * pix_par;
+        p.len[i] = ceil_div(ceil_div(HWs, p.parts), 2 * ppi) * 2 * ppi;
     }
     float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a->ws) + 255) & ~(uintptr_t)255);
     p.part = ws;
     p.mm = p.part + (size_t)a->B * kFusMaxParts * a->k * a->c;
-    p.gate = p.mm + (size_t)a->B * a->k * 2 * a->H * a->W;
+    p.gate = p.mm + (((size_t)a->B * a->k * 2 * a->H * a->W + 3) & ~(size_t)3);     // float4 reads of the gates
     p.ticket = reinterpret_cast<unsigned int*>(p.gate + (size_t)a->B * a->k * a->c);
     SY_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)a->B * sizeof(unsigned int), stream));
-    SY_CUDA(launch_pdl(fusion_stats_kernel, dim3((unsigned)(a->B * a->k * p.parts)), dim3(256), 0, stream, p));
+    const dim3 sgrid((unsigned)(a->B * a->k * p.parts));
+    switch (a->c) {
+        case 32: SY_CUDA(launch_pdl(fusion_stats_kernel<1>, sgrid, dim3(256), 0, stream, p)); break;
+        case 64: SY_CUDA(launch_pdl(fusion_stats_kernel<2>, sgrid, dim3(256), 0, stream, p)); break;
+        case 128: SY_CUDA(launch_pdl(fusion_stats_kernel<4>, sgrid, dim3(256), 0, stream, p)); break;
+        default: SY_CUDA(launch_pdl(fusion_stats_kernel<8>, sgrid, dim3(256), 0, stream, p)); break;
+    }
     SY_LAUNCH_CHECK();
-    dim3 grid((unsigned)ceil_div(a->H, kFusRows), (unsigned)a->B);
-    SY_CUDA(launch_pdl(fusion_apply_kernel, grid, dim3(256), sab_smem, stream, p));
+    const dim3 grid((unsigned)ceil_div(a->H, kFusRows), (unsigned)a->B);
+    if (a->k == 2) SY_CUDA(launch_pdl(fusion_apply_kernel<2>, grid, dim3(256), sab_smem, stream, p));
+    else SY_CUDA(launch_pdl(fusion_apply_kernel<3>, grid, dim3(256), sab_smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch(2);
     return SPECYOLO_OK;
