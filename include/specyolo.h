@@ -140,6 +140,22 @@ int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W,
 int specyolo_stem_space_to_depth(const void* x, int x_dtype, int B, int H, int W,
                                  void* y, int y_pixstride, void* stream);
 
+/* Fused stem: layers 0 and 1 of the trunk (cfg yolo11*.yaml backbone[0:2], both Conv(k=3, s=2, p=1)+BN+SiLU) in one
+ * kernel for uint8 NCHW input (the /255 of predictor.py:133-135 folded into w0); the layer-0 activations stay in shared
+ * memory.  w0: bf16 [c0][32], column (ky*3+kx)*3 + c holds the folded layer-0 weight / 255, columns 27..31 zero.
+ * w1_packed / b1: specyolo_fold_pack_conv of layer 1 rewritten as a 2x2 / stride-1 conv over the 2x2-blocked layer-0
+ * map (K = 4 taps x 4*c0 channels; blocked channel (dy*2+dx)*c0 + ci, tap (ty,tx) <- w1[ci][2ty+dy-1][2tx+dx-1]).
+ * Output NHWC bf16 [B, H/4, W/4, Cout].  specyolo_stem_pair_ok() tells whether the shape is taken. */
+typedef struct {
+    const void* x; int B, H, W;                   /* uint8 NCHW [B,3,H,W], H % 4 == 0, W % 16 == 0            */
+    const void* w0; const float* b0; int c0;      /* layer 0: 16 or 32 channels                               */
+    const void* w1_packed; const float* b1;
+    int Cout, n_pad;
+    void* y; int y_pixstride;
+} specyolo_stem_pair_t;
+int specyolo_stem_pair_ok(int H, int W, int c0, int Cout, int n_pad);
+int specyolo_stem_pair(const specyolo_stem_pair_t* a, void* stream);
+
 /* ---- SPPF pooling (ultralytics/nn/modules/block.py:194-198) ------------------------------ */
 /* buf is the 4*c-channel concat buffer whose first c channels hold cv1(x); writes the three
  * chained MaxPool2d(5,1,2) results into channels [c,2c), [2c,3c), [3c,4c). */

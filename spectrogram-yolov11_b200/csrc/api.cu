@@ -42,6 +42,8 @@ int nms_launch(const specyolo_nms_t*, cudaStream_t);
 int scale_boxes_launch(float*, const int*, int, int, float, float, float, float, float, cudaStream_t);
 int stft_launch(const specyolo_stft_t*, cudaStream_t);
 int dwpw_launch(const specyolo_dwpw_t*, cudaStream_t);
+bool stem_pair_ok(int, int, int, int, int);
+int stem_pair_launch(const specyolo_stem_pair_t*, cudaStream_t);
 int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
                              cudaStream_t);
@@ -153,6 +155,15 @@ int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream) {
     SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->Cout,
              SPECYOLO_ERR_INVALID, "dwpw: bad sizes");
     return dwpw_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_stem_pair_ok(int H, int W, int c0, int Cout, int n_pad) { return stem_pair_ok(H, W, c0, Cout, n_pad) ? 1 : 0; }
+
+int specyolo_stem_pair(const specyolo_stem_pair_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->w0 && a->b0 && a->w1_packed && a->b1 && a->y, SPECYOLO_ERR_INVALID, "stem_pair: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->y_pixstride >= a->Cout, SPECYOLO_ERR_INVALID,
+             "stem_pair: bad sizes");
+    return stem_pair_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,

@@ -47,6 +47,15 @@ class DwpwArgs(C.Structure):
     ]
 
 
+class StemPairArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("w0", C.c_void_p), ("b0", C.c_void_p), ("c0", C.c_int),
+        ("w1_packed", C.c_void_p), ("b1", C.c_void_p), ("Cout", C.c_int), ("n_pad", C.c_int),
+        ("y", C.c_void_p), ("y_pixstride", C.c_int),
+    ]
+
+
 class FusionArgs(C.Structure):
     _fields_ = [
         ("k", C.c_int), ("x", C.c_void_p * 3), ("pixstride", C.c_int * 3), ("upshift", C.c_int * 3),
@@ -102,6 +111,8 @@ SIGNATURES = {
     "specyolo_conv_npad": (C.c_int, [C.c_int, C.c_int]),
     "specyolo_conv2d_bias_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "specyolo_dwconv_pwconv": (C.c_int, [C.POINTER(DwpwArgs), C.c_void_p]),
+    "specyolo_stem_pair_ok": (C.c_int, [C.c_int] * 5),
+    "specyolo_stem_pair": (C.c_int, [C.POINTER(StemPairArgs), C.c_void_p]),
     "specyolo_stem_conv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_stem_space_to_depth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,

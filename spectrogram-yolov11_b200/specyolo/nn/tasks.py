@@ -206,8 +206,12 @@ class DetectionModel(nn.Module):
                 and layers[1].takes_blocked() and layers[1].f == -1 and 0 not in self.save and x.dim() == 4
                 and x.stride(1) != 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
                 and layers[0].packed().s2d is not None):
-            xb = ops.stem_conv(x, layers[0].packed(), blocked_out=True)
-            x = ops.conv2d(xb, layers[1].packed_from_blocked())
+            if ops.stem_pair_ok(x, layers[0].packed(), layers[1].packed_from_blocked()):
+                # uint8 input: both layers in one kernel, the layer-0 map never leaves shared memory
+                x = ops.stem_pair(x, layers[0].packed(), layers[1].packed_from_blocked())
+            else:
+                xb = ops.stem_conv(x, layers[0].packed(), blocked_out=True)
+                x = ops.conv2d(xb, layers[1].packed_from_blocked())
             y.extend([None, x if 1 in self.save else None])
             i = 2
         while i < len(layers):

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StftArgs, check
+from ._lib import ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StemPairArgs, StftArgs, check
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -142,6 +142,7 @@ class PackedConv:
     w_folded_f32: Optional[torch.Tensor] = None   # stem only: fp32 OIHW folded weights
     alg_k: int = 0           # algorithmic reduction length when it differs from cin/g*k*k (space-to-depth stem: 27)
     trim: int = 0            # far-edge output rows / columns that are not computed (space-to-depth stem: 1)
+    stem_w0: Optional[torch.Tensor] = None   # stem only: bf16 [cout, 32] im2col weights / 255 for ops.stem_pair
     s2d: Optional[dict] = None   # stem only: {"u8": PackedConv, "f": PackedConv} 2x2 convs over the blocked image
 
     def out_hw(self, H: int, W: int):
@@ -198,6 +199,9 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
                             if 0 <= ky < 3 and 0 <= kx < 3:
                                 c0 = (dy * 2 + dx) * 3
                                 w2[:, c0:c0 + 3, ty, tx] = w[:, :, ky, kx]
+            w0p = torch.zeros((cout, 32), device=w.device, dtype=torch.bfloat16)     # column (ky*3 + kx)*3 + c
+            w0p[:, :27] = (pc.w_folded_f32 * (1.0 / 255.0)).permute(0, 2, 3, 1).reshape(cout, 27).to(torch.bfloat16)
+            pc.stem_w0 = w0p
             pc.s2d = {}
             for key, scale in (("u8", 1.0 / 255.0), ("f", 1.0)):
                 q = fold_pack(w2 * scale, conv_bias, bn, eps, 1, 1, 1, 1, act)
@@ -307,6 +311,37 @@ def pack_from_blocked(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], b
     q.trim = 1
     q.alg_k = 9 * c
     return q
+
+
+def stem_pair_ok(x: torch.Tensor, pc0: PackedConv, pc1b: PackedConv) -> bool:
+    """Shapes the fused two-layer stem kernel takes (specyolo_stem_pair_ok): uint8 NCHW input, SiLU on both layers."""
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[1] != 3 or pc0.stem_w0 is None:
+        return False
+    if pc0.act != _lib.ACT_SILU or pc1b.act != _lib.ACT_SILU or pc1b.k != 2 or pc1b.g != 1 or pc1b.cin != 4 * pc0.cout:
+        return False
+    return bool(_lib.load().specyolo_stem_pair_ok(x.shape[2], x.shape[3], pc0.cout, pc1b.cout, pc1b.n_pad))
+
+
+def stem_pair(x: torch.Tensor, pc0: PackedConv, pc1b: PackedConv, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Layers 0 and 1 of the trunk in one kernel (specyolo_stem_pair): uint8 NCHW image -> bf16 NHWC [B, c1, H/4, W/4].
+    pc0 = fold_pack of the 3->c0 stem, pc1b = pack_from_blocked of the c0->c1 3x3/s2 conv."""
+    _lib.init_device()
+    if not stem_pair_ok(x, pc0, pc1b):
+        raise ValueError("stem_pair: unsupported input / weights")
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    if out is None:
+        out = new_act(B, pc1b.cout, H // 4, W // 4, x.device)
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, pc1b.cout, H // 4, W // 4) or out.dtype != torch.bfloat16:
+        raise ValueError("stem_pair: out shape / dtype mismatch")
+    a = StemPairArgs()
+    a.x, a.B, a.H, a.W = x.data_ptr(), B, H, W
+    a.w0, a.b0, a.c0 = pc0.stem_w0.data_ptr(), pc0.bias.data_ptr(), pc0.cout
+    a.w1_packed, a.b1, a.Cout, a.n_pad = pc1b.w.data_ptr(), pc1b.bias.data_ptr(), pc1b.cout, pc1b.n_pad
+    a.y, a.y_pixstride = out.data_ptr(), ypix
+    check(_lib.load().specyolo_stem_pair(C.byref(a), _lib.stream_ptr()))
+    return out
 
 
 def stem_conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, blocked_out: bool = False) -> torch.Tensor:

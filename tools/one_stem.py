@@ -25,3 +25,11 @@ for _ in range(iters):
     torch.cuda.synchronize()
     for i in range(3): ts[i] += e[i].elapsed_time(e[i + 1]) / iters
 print(f"stem B{B} {H}x{W}: s2d {ts[0]*1e3:.1f} us, conv0 (16->32 k2, blocked out) {ts[1]*1e3:.1f} us, conv1 (128->64 k2) {ts[2]*1e3:.1f} us")
+if ops.stem_pair_ok(x, pc0, pc1):
+    for _ in range(3): yf = ops.stem_pair(x, pc0, pc1)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(iters): yf = ops.stem_pair(x, pc0, pc1)
+    b.record(); torch.cuda.synchronize()
+    print(f"   fused stem pair: {a.elapsed_time(b)/iters*1e3:.1f} us   max |fused - layered| = {(yf.float()-y.float()).abs().max().item():.4f}")
