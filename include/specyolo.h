@@ -142,7 +142,9 @@ int specyolo_stem_space_to_depth(const void* x, int x_dtype, int B, int H, int W
 
 /* Fused stem: layers 0 and 1 of the trunk (cfg yolo11*.yaml backbone[0:2], both Conv(k=3, s=2, p=1)+BN+SiLU) in one
  * kernel for uint8 NCHW input (the /255 of predictor.py:133-135 folded into w0); the layer-0 activations stay in shared
- * memory.  w0: bf16 [c0][32], column (ky*3+kx)*3 + c holds the folded layer-0 weight / 255, columns 27..31 zero.
+ * memory.  w0: fp16 [c0][32], column c*9 + ky*3 + kx holds the folded layer-0 weight / 255, columns 27..31 zero; the
+ * kernel feeds the tensor core fp16 values 1024 + pixel, so b0 must be the folded layer-0 bias MINUS
+ * 1024 * sum_k float(w0[n][k]).
  * w1_packed / b1: specyolo_fold_pack_conv of layer 1 rewritten as a 2x2 / stride-1 conv over the 2x2-blocked layer-0
  * map (K = 4 taps x 4*c0 channels; blocked channel (dy*2+dx)*c0 + ci, tap (ty,tx) <- w1[ci][2ty+dy-1][2tx+dx-1]).
  * Output NHWC bf16 [B, H/4, W/4, Cout].  specyolo_stem_pair_ok() tells whether the shape is taken. */

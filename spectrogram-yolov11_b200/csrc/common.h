@@ -99,5 +99,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of arithmetic — the conv epilogues and the
+// Fusion kernels are issue-bound, not bandwidth-bound.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};\n\t"
+        "add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// SiLU of a pair given the accumulator pair a and the HALF-scaled bias pair hb: h = a/2 + hb, silu = h + h*tanh(h)
+__device__ __forceinline__ float2 silu2_half(float2 a, float2 hb) {
+    const float2 h = ffma2(a, make_float2(0.5f, 0.5f), hb);
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+    return ffma2(h, t, h);
+}
+
 }  // namespace specyolo
 #endif

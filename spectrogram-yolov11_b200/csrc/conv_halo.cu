@@ -123,16 +123,12 @@ __device__ __forceinline__ void thin_finish(const uint32_t (&v)[16], const float
                                             __nv_bfloat16* y, const uint4& r0, const uint4& r1) {
     float f[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float a = __uint_as_float(v[i]);
-        if (kSilu) {
-            const float h = fmaf(a, 0.5f, bias[i]);
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-            f[i] = fmaf(h, th, h);
-        } else {
-            f[i] = a + bias[i];
-        }
+    for (int i = 0; i < 8; ++i) {
+        const float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        const float2 b = make_float2(bias[2 * i], bias[2 * i + 1]);
+        const float2 r = kSilu ? silu2_half(a, b) : fadd2(a, b);
+        f[2 * i] = r.x;
+        f[2 * i + 1] = r.y;
     }
     if (kRes) {
         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};

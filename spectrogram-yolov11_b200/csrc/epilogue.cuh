@@ -47,19 +47,17 @@ __device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], const float*
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 b = *reinterpret_cast<const float4*>(bias16 + 4 * q);
-        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float a = __uint_as_float(v[4 * q + i]);
-            if (kSilu) {
-                const float h = fmaf(a, 0.5f, bb[i]);
-                float t;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-                f[4 * q + i] = fmaf(h, t, h);
-            } else {
-                f[4 * q + i] = a + bb[i];
-            }
+        const float2 a0 = make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
+        const float2 a1 = make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        float2 r0, r1;
+        if (kSilu) {        // packed pairs: 2 FFMA2 + 2 MUFU per pair instead of 4 FFMA + 2 MUFU
+            r0 = silu2_half(a0, make_float2(b.x, b.y));
+            r1 = silu2_half(a1, make_float2(b.z, b.w));
+        } else {
+            r0 = fadd2(a0, make_float2(b.x, b.y));
+            r1 = fadd2(a1, make_float2(b.z, b.w));
         }
+        f[4 * q] = r0.x; f[4 * q + 1] = r0.y; f[4 * q + 2] = r1.x; f[4 * q + 3] = r1.y;
     }
     if (kRes) {
         if (res_vec) {

@@ -118,22 +118,8 @@ __device__ __forceinline__ float redux_max_f32(float v, unsigned mask) {
     asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(mask));
     return r;
 }
-// packed fp32 pairs (FFMA2 / FADD2): both kernels were issue-bound, not bandwidth-bound (ncu: 60 % issue slots busy at
-// 2.5 TB/s, ~120 warp instructions per 512-byte warp load)
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};\n\t"
-        "add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
+// (packed fp32 pairs — ffma2 / fadd2 in common.h: both kernels were issue-bound, not bandwidth-bound: ncu 60 % issue
+//  slots busy at 2.5 TB/s, ~120 warp instructions per 512-byte warp load)
 // volatile: keeps the loads of one iteration together ahead of the math (the scheduler otherwise interleaves them
 // with the first vectors' arithmetic to save registers, leaving two loads per lane in flight)
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {

@@ -6,7 +6,7 @@
 // written and re-read) for 0.29 GB of unavoidable traffic (image in, layer-1 map out) — 17 % of the DRAM bytes of the
 // whole forward pass.  Here the layer-0 activations never leave the SM.  Per tile of 16 x 8 layer-1 pixels:
 //   warps 2-9   the (69 x 37 pixel x 3 plane) uint8 image patch of the NEXT tile -> shared memory (cp.async, zero fill
-//               outside the image = the conv padding), then im2col on CUDA cores: 612 layer-0 pixels x 27 taps -> bf16 A0 [640 x 32] (K-major, SWIZZLE_64B)
+//               outside the image = the conv padding), then im2col: 612 layer-0 pixels x 27 taps -> fp16 A0 [640 x 32] (K-major, SWIZZLE_64B)
 //   warp 1      MMA 1 (tcgen05, 5 x M=128, N=c0, K=32) -> TMEM;  MMA 2 below
 //   warps 10-17 epilogue 1: TMEM -> bias + SiLU -> bf16 -> A1 in shared memory, laid out as the 2x2-blocked
 //               (space-to-depth) halo tile [17 x 9 blocked pixels][4*c0 channels] the layer-1 GEMM consumes
@@ -54,7 +54,7 @@ struct StemPairParams {
     const float* b0;
     const float* b1;
     const void* x;                  // uint8 NCHW image
-    const void* w0;                 // bf16 [c0][32]: k = (ky*3 + kx)*3 + c, columns 27..31 zero
+    const void* w0;                 // fp16 [c0][32]: k = c*9 + ky*3 + kx, columns 27..31 zero
     uint32_t w1_bytes, a1_buf_bytes;
     uint32_t off_w0, off_patch, off_a0, off_a1, off_st;
     uint32_t tmem_cols;
@@ -136,7 +136,8 @@ stem_pair_kernel(const __grid_constant__ CUtensorMap map_w,
         // ===================== MMA issuer =====================
         ptx::grid_dep_wait();
         const bool leader = ptx::elect_one();
-        const uint32_t idesc0 = ptx::umma_idesc_bf16(128, (uint32_t)p.c0);
+        // layer 0 runs fp16 x fp16 (A0 = 1024 + pixel, see the im2col warps): format fields 0
+        const uint32_t idesc0 = (1u << 4) | (((uint32_t)p.c0 >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t idesc1 = ptx::umma_idesc_bf16(128, (uint32_t)p.n_pad);
         const uint32_t hi64 = (uint32_t)(ptx::umma_smem_desc(0, 64) >> 32);
         const uint32_t hi128 = (uint32_t)(ptx::umma_smem_desc(0, 128) >> 32);
@@ -174,12 +175,20 @@ stem_pair_kernel(const __grid_constant__ CUtensorMap map_w,
                 const uint32_t ac = a1_16 + ((b * p.a1_buf_bytes + (uint32_t)c * kSpA1Chunk) >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    // the 16 channels of this K step belong to one position (dy, dx) of the 2x2 block; tap (ty, tx) of
+                    // the blocked conv reads it only if 2 ty + dy - 1 and 2 tx + dx - 1 are taps of the 3x3 kernel:
+                    // 18 of the 32 (tap, K step) products are non-zero, the others are skipped (the kernel is bound by
+                    // shared-memory wavefronts, 48 per N = 64 MMA)
+                    const int pos = (c * 64 + k * 16) / p.c0;
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
+                        const bool live = ((tap >> 1) != 0 || (pos >> 1) != 0) && ((tap & 1) != 0 || (pos & 1) != 0);
                         const uint32_t shift = (uint32_t)(((tap >> 1) * kSpHW + (tap & 1)) * 128) >> 4;
                         const uint32_t wb = w1_16 + (uint32_t)(tap * p.chunks1 + c) * wbox16;
-                        if (leader) ptx::umma_bf16_lohi(d, ac + shift + 2u * k, a1_hi, wb + 2u * k, hi128, idesc1, acc);
-                        acc = 1;
+                        if (live) {
+                            if (leader) ptx::umma_bf16_lohi(d, ac + shift + 2u * k, a1_hi, wb + 2u * k, hi128, idesc1, acc);
+                            acc = 1;
+                        }
                     }
                 }
             }
@@ -250,37 +259,34 @@ stem_pair_kernel(const __grid_constant__ CUtensorMap map_w,
                 const int hy = hp / kSpHW, hx = hp - hy * kSpHW;
                 const int ly = 4 * hy + 2 * (pos >> 1);           // patch row of tap ky = 0
                 const int dx = pos & 1;
-                uint32_t b3[3][3];                                // [c][ky]: the three kx bytes of a patch row
+                // A0 holds fp16 values 1024 + pixel: bits 0x6400 | byte, i.e. one byte permute per PAIR of taps and no
+                // int -> float conversion at all (the constant 1024 * sum(w) is folded into the layer-0 bias by the
+                // caller; fp32 accumulation keeps the cancellation exact to ~1e-5).  v1 converted every tap through
+                // fp32 -> bf16: 170 instructions per row, and the kernel as a whole was issue-bound.
+                uint32_t q[9];                                    // [c*3 + ky]: bytes (kx0, kx1, kx2, 0x64)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const uint32_t* row = reinterpret_cast<const uint32_t*>(ps + (c * kSpPatchH + ly + ky) * kSpPatchW + 4 * hx);
                         // taps kx = 0..2 are bytes 3 + 2 dx + kx of the 8 bytes at (patch row, 4 hx)
-                        b3[c][ky] = dx ? (row[1] >> 8) : __funnelshift_r(row[0], row[1], 24);
+                        const uint32_t x3 = dx ? (row[1] >> 8) : __funnelshift_r(row[0], row[1], 24);
+                        q[c * 3 + ky] = (x3 & 0x00ffffffu) | 0x64000000u;
                     }
-                float f[32];
+                uint32_t wds[16];                                 // K slot k = c*9 + ky*3 + kx, two per word
 #pragma unroll
-                for (int k = 0; k < 32; ++k) f[k] = 0.f;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            f[(ky * 3 + kx) * 3 + c] =          // exact uint8 -> fp32 on the FMA pipe (I2F is quarter rate)
-                                __uint_as_float(0x4B000000u | ((b3[c][ky] >> (8 * kx)) & 0xffu)) - 8388608.0f;
+                for (int i = 0; i < 14; ++i) {
+                    const int k0 = 2 * i, k1 = 2 * i + 1;
+                    const uint32_t sel = (uint32_t)(k0 % 3) | (3u << 4) | ((k1 < 27 ? 4u + (uint32_t)(k1 % 3) : 7u) << 8) | (7u << 12);
+                    wds[i] = __byte_perm(q[k0 / 3], q[k1 < 27 ? k1 / 3 : 8], sel);
+                }
+                wds[14] = wds[15] = 0u;
                 const uint32_t swz = ((uint32_t)r >> 1) & 3u;
                 uint8_t* dst = a0_s + (uint32_t)r * 64u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 o;
-                    o.x = pack_bf16x2(f[8 * u + 0], f[8 * u + 1]);
-                    o.y = pack_bf16x2(f[8 * u + 2], f[8 * u + 3]);
-                    o.z = pack_bf16x2(f[8 * u + 4], f[8 * u + 5]);
-                    o.w = pack_bf16x2(f[8 * u + 6], f[8 * u + 7]);
-                    *reinterpret_cast<uint4*>(dst + (((uint32_t)u ^ swz) << 4)) = o;
-                }
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(dst + (((uint32_t)u ^ swz) << 4)) =
+                        make_uint4(wds[4 * u], wds[4 * u + 1], wds[4 * u + 2], wds[4 * u + 3]);
             }
             ptx::fence_proxy_async();                   // generic-proxy writes of A0 -> visible to UMMA
             __syncwarp();
@@ -315,61 +321,78 @@ stem_pair_kernel(const __grid_constant__ CUtensorMap map_w,
             // accumulator loads are in flight per wait (a single load -> wait -> math -> store chain per task left
             // the warps latency-bound: clock64 phase timers, 460 cycles per task)
             const int ntask = kSpMTiles * cchunks;
+            // per-task constants of this thread (at most 5 tasks): A1 byte offset of its two 16-byte units, halo flags
+            constexpr int kMaxT = kSpMTiles;
+            uint32_t t_off[kMaxT], t_col[kMaxT];
+            int t_flags[kMaxT];               // bit 0: halo row 0, bit 1: halo column 0, bit 2: row exists
+            // every task of a warp has the same 16-column chunk (task parity == half): its half-scaled bias lives in
+            // registers (a float4 shared-memory load per 4 columns cost 4 wavefronts each in a kernel that is bound
+            // by shared-memory wavefronts)
+            float2 hb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cc0 = cchunks == 2 ? half : 0;
+                hb[i] = make_float2(bias0_s[cc0 * 16 + 2 * i], bias0_s[cc0 * 16 + 2 * i + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxT; ++k) {
+                const int task = half + 2 * k;
+                const int mt = cchunks == 2 ? (task >> 1) : task;
+                const int cc = cchunks == 2 ? (task & 1) : 0;
+                const int row = mt * 128 + m;
+                const int hp = row >> 2, pos = row & 3;
+                const int hy = hp / kSpHW, hx = hp - hy * kSpHW;
+                const uint32_t off = (uint32_t)(pos * p.c0 * 2 + cc * 32);          // byte offset inside the blocked pixel
+                const uint32_t unit = (off & 127u) >> 4, sw = (uint32_t)hp & 7u;
+                t_off[k] = (off >> 7) * kSpA1Chunk + (uint32_t)hp * 128u + ((unit ^ sw) << 4);
+                t_off[k] |= ((((unit + 1u) ^ sw) << 4) ^ ((unit ^ sw) << 4)) << 24;  // xor distance to the second unit
+                t_col[k] = acc0_col + (uint32_t)(mt * p.c0 + cc * 16);
+                t_flags[k] = (hy == 0 ? 1 : 0) | (hx == 0 ? 2 : 0) | ((task < ntask && row < kSpRows0) ? 4 : 0) | (cc << 3);
+            }
             uint32_t tl = 0;
             for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
                 uint32_t n, r, th_i, tw_i;
                 fdivmod((uint32_t)tile, p.d_img, n, r);
                 fdivmod(r, p.d_tw, th_i, tw_i);
-                const int by0 = (int)th_i * kSpTH - 1, bx0 = (int)tw_i * kSpTW - 1;
+                const int edge = (th_i == 0 ? 1 : 0) | (tw_i == 0 ? 2 : 0);     // halo row / column 0 lies outside the image
                 const uint32_t b = tl & 1u;
                 ptx::mbar_wait(&a1_empty[b], ((tl >> 1) & 1u) ^ 1u);    // MMA 2 of two tiles ago has read this A1 buffer
                 ptx::mbar_wait(&acc0_full, tl & 1u);
                 ptx::tc_fence_after();
                 uint8_t* a1 = a1_s + b * p.a1_buf_bytes;
-                auto finish = [&](const uint32_t (&v)[16], int task) {
-                    const int mt = cchunks == 2 ? (task >> 1) : task;
-                    const int cc = cchunks == 2 ? (task & 1) : 0;
-                    const int row = mt * 128 + m;
-                    const int hp = row >> 2, pos = row & 3;
-                    const int hy = hp / kSpHW, hx = hp - hy * kSpHW;
-                    const bool inside = (by0 + hy >= 0) && (bx0 + hx >= 0);
-                    const uint32_t off = (uint32_t)(pos * p.c0 * 2 + cc * 32);      // byte offset inside the blocked pixel
-                    uint8_t* dst = a1 + (off >> 7) * kSpA1Chunk + (uint32_t)hp * 128u;
-                    const uint32_t unit = (off & 127u) >> 4;
+                auto finish = [&](const uint32_t (&v)[16], int k) {
                     uint32_t o[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float f2[2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const float h = fmaf(__uint_as_float(v[2 * i + j]), 0.5f, bias0_s[cc * 16 + 2 * i + j]);
-                            float tt;
-                            asm("tanh.approx.f32 %0, %1;" : "=f"(tt) : "f"(h));
-                            f2[j] = fmaf(h, tt, h);
+                        const float2 f2 = silu2_half(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), hb[i]);
+                        o[i] = pack_bf16x2(f2.x, f2.y);
+                    }
+                    if (t_flags[k] & 4) {
+                        uint8_t* d0 = a1 + (t_off[k] & 0x00ffffffu);
+                        uint8_t* d1 = a1 + ((t_off[k] & 0x00ffffffu) ^ (t_off[k] >> 24));
+                        if (t_flags[k] & edge) {        // blocked pixel outside the image: layer 1's zero padding
+                            *reinterpret_cast<uint4*>(d0) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(d1) = make_uint4(0, 0, 0, 0);
+                        } else {
+                            *reinterpret_cast<uint4*>(d0) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(d1) = make_uint4(o[4], o[5], o[6], o[7]);
                         }
-                        o[i] = inside ? pack_bf16x2(f2[0], f2[1]) : 0u;
-                    }
-                    if (row < kSpRows0) {
-                        const uint32_t sw = (uint32_t)hp & 7u;
-                        *reinterpret_cast<uint4*>(dst + ((unit ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4*>(dst + (((unit + 1u) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 };
-                auto taddr = [&](int task) {
-                    const int mt = cchunks == 2 ? (task >> 1) : task;
-                    const int cc = cchunks == 2 ? (task & 1) : 0;
-                    return t_quad + acc0_col + (uint32_t)(mt * p.c0 + cc * 16);
-                };
-                for (int task = half; task < ntask; task += 6) {
-                    uint32_t va[16], vb[16], vc[16];
-                    const bool two = task + 2 < ntask, three = task + 4 < ntask;
-                    ptx::tmem_ld16(taddr(task), va);
-                    if (two) ptx::tmem_ld16(taddr(task + 2), vb);
-                    if (three) ptx::tmem_ld16(taddr(task + 4), vc);
-                    ptx::tmem_ld_wait();
-                    finish(va, task);
-                    if (two) finish(vb, task + 2);
-                    if (three) finish(vc, task + 4);
+                {
+                    // tasks of this warp in pairs: two accumulator loads in flight per wait
+                    uint32_t va[16], vb[16];
+#pragma unroll
+                    for (int k = 0; k < kMaxT; k += 2) {
+                        if (half + 2 * k < ntask) {
+                            const bool two = k + 1 < kMaxT && half + 2 * (k + 1) < ntask;
+                            ptx::tmem_ld16(t_quad + t_col[k], va);
+                            if (two) ptx::tmem_ld16(t_quad + t_col[k + 1 < kMaxT ? k + 1 : k], vb);
+                            ptx::tmem_ld_wait();
+                            finish(va, k);
+                            if (two) finish(vb, k + 1 < kMaxT ? k + 1 : k);
+                        }
+                    }
                 }
                 ptx::fence_proxy_async();                   // A1 writes -> visible to UMMA
                 ptx::tc_fence_before();

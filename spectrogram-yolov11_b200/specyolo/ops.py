@@ -142,7 +142,8 @@ class PackedConv:
     w_folded_f32: Optional[torch.Tensor] = None   # stem only: fp32 OIHW folded weights
     alg_k: int = 0           # algorithmic reduction length when it differs from cin/g*k*k (space-to-depth stem: 27)
     trim: int = 0            # far-edge output rows / columns that are not computed (space-to-depth stem: 1)
-    stem_w0: Optional[torch.Tensor] = None   # stem only: bf16 [cout, 32] im2col weights / 255 for ops.stem_pair
+    stem_w0: Optional[torch.Tensor] = None   # stem only: fp16 [cout, 32] im2col weights / 255 for ops.stem_pair
+    stem_b0: Optional[torch.Tensor] = None   # stem only: folded bias - 1024 * sum(stem_w0) (see fold_pack)
     s2d: Optional[dict] = None   # stem only: {"u8": PackedConv, "f": PackedConv} 2x2 convs over the blocked image
 
     def out_hw(self, H: int, W: int):
@@ -199,9 +200,12 @@ def fold_pack(weight: torch.Tensor, conv_bias: Optional[torch.Tensor], bn: Optio
                             if 0 <= ky < 3 and 0 <= kx < 3:
                                 c0 = (dy * 2 + dx) * 3
                                 w2[:, c0:c0 + 3, ty, tx] = w[:, :, ky, kx]
-            w0p = torch.zeros((cout, 32), device=w.device, dtype=torch.bfloat16)     # column (ky*3 + kx)*3 + c
-            w0p[:, :27] = (pc.w_folded_f32 * (1.0 / 255.0)).permute(0, 2, 3, 1).reshape(cout, 27).to(torch.bfloat16)
+            # fused stem kernel (ops.stem_pair): fp16 weights / 255, column c*9 + ky*3 + kx; the kernel's A operand is
+            # 1024 + pixel (fp16 bits 0x6400 | byte), so 1024 * sum(w) comes off the bias
+            w0p = torch.zeros((cout, 32), device=w.device, dtype=torch.float16)
+            w0p[:, :27] = (pc.w_folded_f32 * (1.0 / 255.0)).reshape(cout, 27).to(torch.float16)
             pc.stem_w0 = w0p
+            pc.stem_b0 = (bias[:cout].double() - 1024.0 * w0p.double().sum(dim=1)).float().contiguous()
             pc.s2d = {}
             for key, scale in (("u8", 1.0 / 255.0), ("f", 1.0)):
                 q = fold_pack(w2 * scale, conv_bias, bn, eps, 1, 1, 1, 1, act)
@@ -337,7 +341,7 @@ def stem_pair(x: torch.Tensor, pc0: PackedConv, pc1b: PackedConv, out: Optional[
         raise ValueError("stem_pair: out shape / dtype mismatch")
     a = StemPairArgs()
     a.x, a.B, a.H, a.W = x.data_ptr(), B, H, W
-    a.w0, a.b0, a.c0 = pc0.stem_w0.data_ptr(), pc0.bias.data_ptr(), pc0.cout
+    a.w0, a.b0, a.c0 = pc0.stem_w0.data_ptr(), pc0.stem_b0.data_ptr(), pc0.cout
     a.w1_packed, a.b1, a.Cout, a.n_pad = pc1b.w.data_ptr(), pc1b.bias.data_ptr(), pc1b.cout, pc1b.n_pad
     a.y, a.y_pixstride = out.data_ptr(), ypix
     check(_lib.load().specyolo_stem_pair(C.byref(a), _lib.stream_ptr()))

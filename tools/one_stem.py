@@ -13,7 +13,7 @@ w0 = torch.randn((32, 3, 3, 3), generator=gen) * 0.3; w1 = torch.randn((64, 32, 
 pc0 = ops.fold_pack(w0.cuda(), torch.zeros(32).cuda(), None, 0.0, 2, 1, 1, 1, True)
 pc1 = ops.pack_from_blocked(w1.cuda(), torch.zeros(64).cuda(), None, 0.0, True)
 def ev(): return torch.cuda.Event(enable_timing=True)
-for _ in range(3):
+for _ in range(60):      # long warm-up: the clocks ramp over tens of milliseconds
     xb = ops.stem_conv(x, pc0, blocked_out=True); y = ops.conv2d(xb, pc1)
 torch.cuda.synchronize()
 e = [ev() for _ in range(4)]
@@ -26,7 +26,7 @@ for _ in range(iters):
     for i in range(3): ts[i] += e[i].elapsed_time(e[i + 1]) / iters
 print(f"stem B{B} {H}x{W}: s2d {ts[0]*1e3:.1f} us, conv0 (16->32 k2, blocked out) {ts[1]*1e3:.1f} us, conv1 (128->64 k2) {ts[2]*1e3:.1f} us")
 if ops.stem_pair_ok(x, pc0, pc1):
-    for _ in range(3): yf = ops.stem_pair(x, pc0, pc1)
+    for _ in range(30): yf = ops.stem_pair(x, pc0, pc1)
     torch.cuda.synchronize()
     a, b = ev(), ev()
     a.record()
