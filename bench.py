@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="batches in flight in the resident-input loop")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the resident-input loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

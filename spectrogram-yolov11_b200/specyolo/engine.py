@@ -9,6 +9,7 @@ inside, one small device->host copy of [B, max_det, 6] + counts at the end.
 """
 from __future__ import annotations
 
+import collections
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -106,7 +107,7 @@ class DetectionPredictor:
     def __init__(self, model: DetectionModel, overrides: Optional[dict] = None):
         self.model = model
         self.args = dict(conf=0.25, iou=0.7, max_det=300, agnostic_nms=False, classes=None, imgsz=640, half=False,
-                         use_graph=True)
+                         use_graph=True, stream_slots=3)
         self.args.update(overrides or {})
         self._graphs: Dict[tuple, _GraphStep] = {}
         self._stream_steps: List[Optional[_GraphStep]] = [None, None]   # double-buffered graph instances
@@ -190,9 +191,9 @@ class DetectionPredictor:
         return steps[slot]
 
     @torch.no_grad()
-    def infer_pipelined(self, im: torch.Tensor, steps: int, inflight: int = 2):
-        """`steps` forward + NMS passes over the device-resident batch `im` with TWO batches in flight: two captured
-        graph instances replay alternately on two compute streams, so the low-occupancy phases of one step (the 20x20
+    def infer_pipelined(self, im: torch.Tensor, steps: int, inflight: int = 3):
+        """`steps` forward + NMS passes over the device-resident batch `im` with `inflight` batches in flight: that many
+        captured graph instances replay in turn on their own compute streams, so the low-occupancy phases of one step (the 20x20
         level, decode, NMS: grids far below 148 SMs) overlap the wide kernels of the other.  Returns the (out, cnt)
         device tensors of the last step of each instance.  Everything is enqueued behind the caller's current
         stream and joined back into it."""
@@ -219,23 +220,27 @@ class DetectionPredictor:
     @torch.no_grad()
     def stream(self, batches):
         """`predict(source, stream=True)`: generator over an iterable of batches (engine/predictor.py:169-175 yields per
-        batch too).  Two captured graph instances alternate so that the host->device copy of batch i+1 (copy stream)
-        overlaps the forward + NMS of batch i, and the device->host copy of its [B, max_det, 6] result lands in
-        pinned memory while batch i+1 is already running.  Yields List[Results] per batch, in order."""
+        batch too).  `stream_slots` (default 3) captured graph instances take the batches in turn, each on its own
+        stream: the host->device copy of batch i+1 (copy stream) overlaps the forward + NMS of the batches in
+        flight, and the device->host copy of a [B, max_det, 6] result lands in pinned memory while later batches are
+        already running.  Yields List[Results] per batch, in order."""
         a = self.args
         dev = next(self.model.parameters()).device
+        n = max(2, int(a.get("stream_slots", 3)))                        # graph instances = batches in flight
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        cs = self._streams(dev)                                          # one compute stream per graph instance
-        for st in cs:
+        cs = self._streams(dev, n)                                       # one compute stream per graph instance
+        for st in cs[:n]:
             st.wait_stream(main)
+        while len(self._stream_steps) < n:
+            self._stream_steps.append(None)
+            self._stream_host.append(None)
         steps, host_out = self._stream_steps, self._stream_host          # captured once, reused across calls
-        done = [None, None]          # event: results of the batch that used slot s are in pinned host memory
-        uploaded = [None, None]
-        consumed = [None, None]      # event: the step has copied its staged input into the graph's static input
-        staging: list = [None, None] # device staging buffers the host uploads into (decoupled from the graph inputs:
-                                     # the upload of batch i+2 may start as soon as step i has STARTED, not finished)
-        meta: list = [None, None]
+        uploaded = [None] * n
+        last_done = [None] * n       # event: the slot's most recent launch (graph + result copies) has completed
+        consumed = [None] * n        # event: the step has copied its staged input into the graph's static input
+        staging: list = [None] * n   # device staging buffers the host uploads into (decoupled from the graph inputs:
+                                     # the upload of batch i+n may start as soon as step i has STARTED, not finished)
         classes = None
         if a["classes"] is not None:
             classes = torch.tensor(list(a["classes"]), device=dev, dtype=torch.int32)
@@ -251,21 +256,34 @@ class DetectionPredictor:
             return im, shapes, imgs
 
         def enqueue_upload(slot, item):
+            """Start the host->device copy of `item` into the slot's staging buffer; returns the batch's metadata."""
             im, shapes, imgs = prep(item)
+            st_old = steps[slot]
+            if st_old is not None and last_done[slot] is not None and \
+                    (st_old.static_in.shape != im.shape or st_old.static_in.dtype != im.dtype):
+                last_done[slot].synchronize()       # the slot is about to be re-captured for a new input signature:
+                                                    # its previous batch must have left the old graph's buffers
             self._ensure_stream_step(slot, im, classes)
             if staging[slot] is None or staging[slot].shape != im.shape or staging[slot].dtype != im.dtype:
                 staging[slot] = torch.empty_like(steps[slot].static_in)
+                staging[slot].record_stream(copy_stream)      # written on the copy stream, read on the slot's stream:
+                staging[slot].record_stream(cs[slot])         # the allocator must not recycle it under either
             if consumed[slot] is not None:
                 copy_stream.wait_event(consumed[slot])      # the previous step of this slot has taken its input
+            if im.is_cuda:
+                # device-side preprocess (LetterBox) produced `im` on the current stream; it is read on the copy stream
+                # after this function has dropped its reference
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                im.record_stream(copy_stream)
             with torch.cuda.stream(copy_stream):
                 staging[slot].copy_(im, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             uploaded[slot] = ev
-            meta[slot] = (shapes, imgs, im.shape[0], tuple(im.shape[2:]))
+            return (shapes, imgs, im.shape[0], tuple(im.shape[2:]))
 
-        def launch(slot):
-            # the two instances run on their own streams: consecutive batches overlap on the GPU (two in flight)
+        def launch(slot, meta):
+            # every instance runs on its own stream: consecutive batches overlap on the GPU
             with torch.cuda.stream(cs[slot]):
                 cs[slot].wait_event(uploaded[slot])
                 steps[slot].static_in.copy_(staging[slot], non_blocking=True)
@@ -276,13 +294,16 @@ class DetectionPredictor:
                 host_out[slot][1].copy_(steps[slot].cnt, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs[slot])
-            done[slot] = ev
+            last_done[slot] = ev
+            # the metadata and the pinned result buffers travel with the launch: the slot may be re-armed (even
+            # re-captured with new buffers) before this batch is collected
+            return (host_out[slot], ev, meta)
 
-        def collect(slot):
-            done[slot].synchronize()
-            shapes, imgs, B, img1 = meta[slot]
-            counts = host_out[slot][1].tolist()
-            out_h = host_out[slot][0].clone()       # one copy out of the pinned buffer; per-image rows are views of it
+        def collect(rec):
+            (h_out, h_cnt), ev, (shapes, imgs, B, img1) = rec
+            ev.synchronize()
+            counts = h_cnt.tolist()
+            out_h = h_out.clone()                   # one copy out of the pinned buffer; per-image rows are views of it
             for b in range(B):                      # letterboxed sources: boxes back to original-image coordinates
                 if tuple(shapes[b]) != tuple(img1):
                     from .utils.ops import scale_boxes
@@ -295,23 +316,24 @@ class DetectionPredictor:
             first = next(it)
         except StopIteration:
             return
-        enqueue_upload(0, first)
+        meta_next = enqueue_upload(0, first)
+        inflight = collections.deque()
         i = 0
-        pending = None
         while True:
-            slot = i & 1
-            launch(slot)
+            slot = i % n
+            inflight.append(launch(slot, meta_next))
             nxt = next(it, None)
             if nxt is not None:
-                enqueue_upload(1 - slot, nxt)      # overlaps the graph just launched
-            if pending is not None:
-                yield collect(pending)
-            pending = slot
+                meta_next = enqueue_upload((i + 1) % n, nxt)   # overlaps the graphs already launched
+            # batch i - (n - 1) is collected here, i.e. before launch(i + 1) re-uses its slot's pinned result buffers
+            if len(inflight) > n - 1:
+                yield collect(inflight.popleft())
             if nxt is None:
                 break
             i += 1
-        yield collect(pending)
-        for st in cs:
+        while inflight:
+            yield collect(inflight.popleft())
+        for st in cs[:n]:
             main.wait_stream(st)
 
     def __call__(self, source) -> List[Results]:

@@ -134,7 +134,23 @@ def test_predict_api_and_fused_path(lib):
     ref1 = yolo.predict(batches[1].cuda(), conf=0.25, iou=0.7)
     for a, c in zip(ref1, outs[1]):
         assert torch.equal(a.boxes.data, c.boxes.data)
-    # two batches in flight on two streams (bench.py's resident-input loop): both instances reproduce the detections
+    # streamed ndarray sources whose ORIGINAL sizes differ from batch to batch: every batch's results must carry its
+    # own orig_shape / orig_img and box rescale, with more batches than graph instances (slots are re-armed before the
+    # earlier batch is collected)
+    shapes = [(240, 320), (320, 320), (200, 280), (320, 256), (288, 320)]
+    nd_batches = []
+    for k, (hh, ww) in enumerate(shapes):       # crops of synthetic spectrogram-like images (they produce detections)
+        base = (synth_images(2, 320, seed=40 + k).permute(0, 2, 3, 1).numpy() * 255).round().astype(np.uint8)[..., ::-1]
+        nd_batches.append([np.ascontiguousarray(base[j, :hh, :ww]) for j in range(2)])
+    streamed = list(yolo.predict(nd_batches, stream=True, conf=0.25, iou=0.7, imgsz=320))
+    assert len(streamed) == len(shapes)
+    for k, (hh, ww) in enumerate(shapes):
+        single = yolo.predict(nd_batches[k], conf=0.25, iou=0.7, imgsz=320)
+        for a, c in zip(single, streamed[k]):
+            assert c.orig_shape == (hh, ww) and c.orig_img is not None and c.orig_img.shape[:2] == (hh, ww)
+            assert torch.allclose(a.boxes.data, c.boxes.data, atol=1e-4)
+    assert sum(len(r) for b in streamed for r in b) > 0
+    # several batches in flight (bench.py's resident-input loop): every instance reproduces the detections
     out0, cnt0 = yolo.predictor.infer(x)
     out0, cnt0 = out0.clone(), cnt0.clone()
     for o, c in yolo.predictor.infer_pipelined(x, 5):
