@@ -171,7 +171,7 @@ def stage_roofline(model, x_dev, peaks):
             nm = name
             fl = flops_fn(*a, **k) if flops_fn else 0.0
             by = bytes_fn(r, *a, **k) if bytes_fn else 0.0
-            if name in ("conv2d", "dwconv_pwconv"):     # class by arithmetic intensity against the ridge of the measured peaks
+            if name in ("conv2d", "dwconv_pwconv", "stem_pair"):     # class by arithmetic intensity against the ridge of the measured peaks
                 nm = "conv2d_tensor_bound" if fl / max(by, 1.0) >= ridge else "conv2d_hbm_bound"
             rec.append((nm, e0, e1, fl, by))
             return r
@@ -191,7 +191,12 @@ def stage_roofline(model, x_dev, peaks):
         B, Cc, H, W = x.shape
         return 2.0 * B * H * W * Cc * (9 + pw.cout)           # depthwise 3x3 + pointwise 1x1
 
+    def stem_pair_flops(x, pc0, pc1b, *a, **k):      # layer 0 (K = 27) at H/2 x W/2 + layer 1 (K = 9 c0) at H/4 x W/4
+        B, _, H, W = x.shape
+        return 2.0 * B * ((H // 2) * (W // 2) * pc0.cout * 27 + (H // 4) * (W // 4) * pc1b.cout * 9 * pc0.cout)
+
     wrap("conv2d", conv_flops, conv_bytes)
+    wrap("stem_pair", stem_pair_flops, lambda r, x, pc0, pc1b, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel() + 2.0 * pc1b.w.numel())
     wrap("dwconv_pwconv", dwpw_flops, lambda r, x, *a, **k: 2.0 * (x.numel() + r.numel()))
     wrap("stem_space_to_depth", None, lambda r, x, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel())
     wrap("sppf_pool", None, lambda r, buf, c: 2.0 * buf.numel())
@@ -238,7 +243,7 @@ def stage_roofline(model, x_dev, peaks):
     tf = ROOT / "profiles" / "conv_dram_traffic.json"      # written from an ncu capture by tools/ncu_traffic.py
     if tf.is_file():
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_halo_kernel + dwpw_kernel: every tcgen05 implicit-GEMM conv launch of one step "
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_halo_kernel + dwpw_kernel + stem_pair_kernel: every tcgen05 implicit-GEMM conv launch of one step "
                                           "(the layers below the ridge are HBM-bound: see stages.conv2d_hbm_bound)",
             "achieved": c[1] / c[0] / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
             "frac": c[1] / c[0] / 1e12 / peaks["tf_sust"], "traffic": traffic, "algorithmic_bytes_per_step": c[2], "peak_source": peaks["src"] + " sustained",
@@ -276,7 +281,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()             # started early: nvidia-smi needs ~0.2 s before its first sample
-    # two batches in flight (DetectionPredictor.infer_pipelined): every step is a full forward + decode + NMS of B
+    # several batches in flight (DetectionPredictor.infer_pipelined, --inflight): every step is a full forward + decode + NMS of B
     # images; consecutive steps overlap on the GPU the way consecutive batches of predict(stream=True) do
     predictor.infer_pipelined(x_dev, max(args.warmup, 3), args.inflight)
     torch.cuda.synchronize()

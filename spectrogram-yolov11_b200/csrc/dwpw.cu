@@ -5,12 +5,12 @@
 // depthwise layer itself is either issue-bound on CUDA cores or multiplies 63/64 zeros on the tensor pipe.  Here the
 // depthwise result never leaves the SM:
 //   warp 0      TMA producer: per 16x8-pixel output tile one (18 x 10 pixel) halo box per 64 channels
-//   warps 2-9   depthwise on CUDA cores: a thread owns 4 channels (its 36 folded weights in registers) of two tile
-//               rows, slides the 3x3 window along them reading the halo box from shared memory, applies bias + SiLU and
+//   warps 2-17  depthwise on CUDA cores: a thread owns a channel pair (its 9 folded weight pairs in registers, packed
+//               fp32x2 math) of one or two tile rows, slides the 3x3 window along them reading the halo box from shared memory, applies bias + SiLU and
 //               writes bf16 into the 128 x C tile laid out as the K-major SWIZZLE_128B A operand
 //   warp 1      MMA issuer: A tile (shared memory, double-buffered) x resident 1x1 weights -> fp32 accumulator in TMEM
 //               (tcgen05.mma, M = 128, N = Cout, K = C), double-buffered
-//   warps 10-17 epilogue (epilogue.cuh): bias + SiLU -> bf16 -> staged TMA store
+//   warps 18-25 epilogue (epilogue.cuh): bias + SiLU -> bf16 -> staged TMA store
 // HBM traffic: one read of the input (x1.4 halo) + one write of the output; the intermediate is 0 bytes.
 #include "common.h"
 #include "ptx.cuh"
@@ -19,7 +19,7 @@
 
 namespace specyolo {
 
-static constexpr int kDwpwThreads = 64 + 256 + 256;
+static constexpr int kDwpwThreads = 64 + 512 + 256;     // TMA + MMA warps, 16 depthwise warps, 8 epilogue warps
 static constexpr int kDwpwTW = 8, kDwpwTH = 16, kDwpwHW = 10, kDwpwHH = 18;
 static constexpr uint32_t kDwpwBoxBytes = kDwpwHW * kDwpwHH * 128;          // 23 040: one 64-channel halo box
 static constexpr uint32_t kDwpwBoxStride = 23552;                            // rounded up to 1024
@@ -67,8 +67,8 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
         if (p.store_bw) ptx::prefetch_tmap(&map_y);
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&x_full[s], 1);
-            ptx::mbar_init(&x_empty[s], 8);
-            ptx::mbar_init(&a_full[s], 8);
+            ptx::mbar_init(&x_empty[s], 16);
+            ptx::mbar_init(&a_full[s], 16);
             ptx::mbar_init(&a_empty[s], 1);
             ptx::mbar_init(&tmem_full_bar[s], 1);
             ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
@@ -137,24 +137,25 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 ptx::umma_commit(&tmem_full_bar[b]);
             }
         }
-    } else if (warp < 10) {
-        // ===================== depthwise 3x3 + bias + SiLU -> A tile (warps 2..9) =====================
-        const int t = threadIdx.x - 64;                 // 0..255
-        const int quads = p.C >> 2;                     // 4-channel groups per pixel: 16 or 32
-        const int cq = t % quads;                       // this thread's channel quad
-        const int rgrp = t / quads;                     // row group: 256/quads of them
-        const int rows_per = (kDwpwTH * quads) >> 8;    // tile rows per thread: 1 (C=64) or 2 (C=128)
-        const int c0 = cq * 4;
+    } else if (warp < 18) {
+        // ===================== depthwise 3x3 + bias + SiLU -> A tile (warps 2..17) =====================
+        // a thread owns ONE channel pair (its 9 folded weight pairs in registers) of one or two tile rows: 512 threads,
+        // four warps per scheduler (with 4 channels per thread and 8 warps this role ran at ~6 k cycles per tile and
+        // bounded the kernel)
+        const int t = threadIdx.x - 64;                 // 0..511
+        const int pairs = p.C >> 1;                     // channel pairs per pixel: 32 or 64
+        const int cq = t % pairs;                       // this thread's channel pair
+        const int rgrp = t / pairs;                     // row group: 512/pairs of them
+        const int rows_per = (kDwpwTH * pairs) >> 9;    // tile rows per thread: 1 (C=64) or 2 (C=128)
+        const int c0 = cq * 2;
         const int chunk = c0 >> 6;                      // which 64-channel box / A chunk
         const uint32_t unit = (uint32_t)(c0 & 63) >> 3; // 16-byte unit inside the 128-byte row
-        const uint32_t sub = (uint32_t)(c0 & 7) * 2;    // byte offset inside the unit: 0 or 8
-        float wgt[9][4], bs[4];
+        const uint32_t sub = (uint32_t)(c0 & 7) * 2;    // byte offset inside the unit: 0, 4, 8 or 12
+        // packed fp32 pairs (FFMA2): 9 multiply-adds per pixel, SiLU on the pair
+        float2 wgt[9];
+        const float2 hbs = make_float2(0.5f * p.dw_b[c0], 0.5f * p.dw_b[c0 + 1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            bs[j] = p.dw_b[c0 + j];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) wgt[k][j] = p.dw_w[k * p.C + c0 + j];
-        }
+        for (int k = 0; k < 9; ++k) wgt[k] = make_float2(p.dw_w[k * p.C + c0], p.dw_w[k * p.C + c0 + 1]);
         uint32_t tl = 0;
         for (int tile = cta; tile < p.spatial_tiles; tile += ctas, ++tl) {
             const uint32_t s = tl & 1u, ph = (tl >> 1) & 1u;
@@ -165,15 +166,12 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             for (int rr = 0; rr < rows_per; ++rr) {
                 const int th = rgrp * rows_per + rr;    // output row inside the tile
                 // sliding 3x3 window over the 10 halo columns of rows th, th+1, th+2
-                float col[3][3][4];
+                float2 col[3][3];
                 auto load_col = [&](int slot, int hx) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const uint32_t row = (uint32_t)((th + ky) * kDwpwHW + hx);
-                        const uint2 v = *reinterpret_cast<const uint2*>(xs + row * 128u + ((unit ^ (row & 7u)) << 4) + sub);
-                        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
-                        col[slot][ky][0] = f0.x; col[slot][ky][1] = f0.y;
-                        col[slot][ky][2] = f1.x; col[slot][ky][3] = f1.y;
+                        col[slot][ky] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xs + row * 128u + ((unit ^ (row & 7u)) << 4) + sub));
                     }
                 };
                 load_col(0, 0);
@@ -181,19 +179,18 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
 #pragma unroll
                 for (int tw = 0; tw < kDwpwTW; ++tw) {
                     load_col((tw + 2) % 3, tw + 2);
-                    float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
+                    // two accumulation chains per pixel for instruction-level parallelism
+                    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                acc[j] = fmaf(col[(tw + kx) % 3][ky][j], wgt[ky * 3 + kx][j], acc[j]);
-                    uint2 o;
-                    o.x = pack_bf16x2(silu_tanh(acc[0]), silu_tanh(acc[1]));
-                    o.y = pack_bf16x2(silu_tanh(acc[2]), silu_tanh(acc[3]));
+                        for (int ky = 0; ky < 3; ++ky) {
+                            if ((kx * 3 + ky) & 1) a1 = ffma2(col[(tw + kx) % 3][ky], wgt[ky * 3 + kx], a1);
+                            else a0 = ffma2(col[(tw + kx) % 3][ky], wgt[ky * 3 + kx], a0);
+                        }
+                    const float2 sv = silu2_half(fadd2(a0, a1), hbs);      // SiLU(acc + b) = h + h tanh(h), h = acc/2 + b/2
                     const uint32_t m = (uint32_t)(th * kDwpwTW + tw);      // A row = pixel inside the tile
-                    *reinterpret_cast<uint2*>(as + m * 128u + ((unit ^ (m & 7u)) << 4) + sub) = o;
+                    *reinterpret_cast<uint32_t*>(as + m * 128u + ((unit ^ (m & 7u)) << 4) + sub) = pack_bf16x2(sv.x, sv.y);
                 }
             }
             ptx::fence_proxy_async();                   // generic-proxy writes of A -> visible to UMMA
@@ -204,13 +201,13 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             }
         }
     } else {
-        // ===================== epilogue (warps 10..17, see epilogue.cuh) =====================
+        // ===================== epilogue (warps 18..25, see epilogue.cuh) =====================
         const int quad = warp & 3;
-        const int half = (warp - 10) >> 2;
+        const int half = (warp - 18) >> 2;
         const int m = quad * 32 + lane;
         const int tw = m & (kDwpwTW - 1), th = m >> 3;
         EpiOut eo{p.y, p.y_pixstride, nullptr, 0, p.pair_stores != 0};
-        EpiStage st = epi_make_stage(st_buf, &map_y, p.n_pad, p.store_bw, p.store_row_bytes, p.store_swz_mask, warp - 8, half,
+        EpiStage st = epi_make_stage(st_buf, &map_y, p.n_pad, p.store_bw, p.store_row_bytes, p.store_swz_mask, warp - 16, half,
                                      lane, m);
         EpiCols ec;
         ec.ncols = p.n_pad;

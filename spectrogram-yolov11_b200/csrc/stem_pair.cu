@@ -212,7 +212,9 @@ stem_pair_kernel(const __grid_constant__ CUtensorMap map_w,
         // cp.async chunks (zero-filled outside the image = the conv padding; W % 16 == 0: an aligned chunk is entirely
         // inside or outside).  Every thread's copies signal patch_full through cp.async.mbarrier.arrive.noinc, so
         // nobody waits on memory latency.  (A single loader warp needed 4.3 k cycles per tile to issue the 1242
-        // chunks and bounded the kernel; a TMA box over the uint8 planes never completed its transaction.)
+        // chunks and bounded the kernel; a TMA box over the uint8 planes starting at x = 32 tw - 5 never completed its
+        // transaction — the innermost box offset is not a multiple of 16 bytes there; an aligned 64-byte-wide box is the
+        // obvious next step.)
         const uint8_t* img = reinterpret_cast<const uint8_t*>(p.x);
         const int H = p.H1 * 4, W = p.W1 * 4;
         int c_off[kSpPatchChunks], c_rc[kSpPatchChunks];          // this thread's chunks: offset in the image, (row, col, plane)

@@ -191,34 +191,35 @@ def test_stem_blocked_pair(lib):
     assert _rel_err(y, ref) < 6e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 96), (3, 128, 160), (1, 36, 48)])
+@pytest.mark.parametrize("shape", [(2, 64, 96, 32, 64), (3, 128, 160, 32, 64), (1, 36, 48, 32, 64), (2, 64, 96, 16, 64),
+                                   (1, 96, 64, 16, 96)])
 def test_stem_pair_fused(lib, shape):
     """Layers 0 + 1 in one kernel (uint8 input) == the two plain convs (torch fp32 reference on bf16-rounded operands)
     and == the layer-by-layer route of this library; sizes with partial tiles in both directions."""
     from specyolo import ops
 
-    B, H, W = shape
+    B, H, W, c0, c1 = shape
     gen = torch.Generator().manual_seed(33)
     u8 = (torch.rand((B, 3, H, W), generator=gen) * 255).round().to(torch.uint8)
-    w0 = torch.randn((32, 3, 3, 3), generator=gen) * 0.3
-    w1 = torch.randn((64, 32, 3, 3), generator=gen) * 0.08
-    b0 = torch.randn(32, generator=gen) * 0.1
-    b1 = torch.randn(64, generator=gen) * 0.1
+    w0 = torch.randn((c0, 3, 3, 3), generator=gen) * 0.3
+    w1 = torch.randn((c1, c0, 3, 3), generator=gen) * (0.08 * math.sqrt(32 / c0))
+    b0 = torch.randn(c0, generator=gen) * 0.1
+    b1 = torch.randn(c1, generator=gen) * 0.1
     pc0 = ops.fold_pack(w0.to(DEV), b0.to(DEV), None, 0.0, 2, 1, 1, 1, True)
     pc1 = ops.pack_from_blocked(w1.to(DEV), b1.to(DEV), None, 0.0, True)
     assert ops.stem_pair_ok(u8.to(DEV), pc0, pc1)
     y = ops.stem_pair(u8.to(DEV), pc0, pc1)
-    assert y.shape == (B, 64, H // 4, W // 4)
+    assert y.shape == (B, c1, H // 4, W // 4)
     y0 = _bf(F.silu(F.conv2d(u8.float(), _bf(w0 / 255.0), b0, 2, 1)))
     ref = F.silu(F.conv2d(y0, _bf(w1), b1, 2, 1))
     assert _rel_err(y.float().cpu(), ref) < 6e-3
     two = ops.conv2d(ops.stem_conv(u8.to(DEV), pc0, blocked_out=True), pc1)
     assert _rel_err(y.float().cpu(), two.float().cpu()) < 6e-3
     # the output may be a channel slice of a wider buffer
-    buf = ops.new_act(B, 96, H // 4, W // 4, DEV).zero_()
-    ops.stem_pair(u8.to(DEV), pc0, pc1, out=buf[:, 16:80])
-    assert torch.equal(buf[:, 16:80].float().cpu(), y.float().cpu())
-    assert float(buf[:, :16].float().abs().max()) == 0.0 and float(buf[:, 80:].float().abs().max()) == 0.0
+    buf = ops.new_act(B, c1 + 32, H // 4, W // 4, DEV).zero_()
+    ops.stem_pair(u8.to(DEV), pc0, pc1, out=buf[:, 16:16 + c1])
+    assert torch.equal(buf[:, 16:16 + c1].float().cpu(), y.float().cpu())
+    assert float(buf[:, :16].float().abs().max()) == 0.0 and float(buf[:, 16 + c1:].float().abs().max()) == 0.0
 
 
 def test_depthwise(lib):

@@ -38,9 +38,15 @@ def wrap(name):
             Bq, Cc, H, W = xx.shape
             fl = 2.0 * Bq * H * W * Cc * (9 + pw.cout); by = 2.0 * (xx.numel() + r.numel())
             desc = f"dw3x3+pw {Cc:4d}->{pw.cout:4d} fused          {H:3d}x{W:3d} M={Bq*H*W:8d} K={Cc+9:5d}"
+        if name == "stem_pair":
+            xx, pc0, pc1 = a[0], a[1], a[2]
+            Bq, _, H, W = xx.shape
+            fl = 2.0 * Bq * ((H // 2) * (W // 2) * pc0.cout * 27 + (H // 4) * (W // 4) * pc1.cout * 9 * pc0.cout)
+            by = xx.numel() + 2.0 * r.numel()
+            desc = f"fused stem 3->{pc0.cout}->{pc1.cout} (u8 in)            {H:3d}x{W:3d}"
         rec.append((desc, e0, e1, fl, by)); return r
     setattr(ops, name, g)
-for n in ("conv2d", "dwconv_pwconv", "stem_space_to_depth", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
+for n in ("conv2d", "dwconv_pwconv", "stem_pair", "stem_space_to_depth", "sppf_pool", "fusion_eschannel", "psa_attention", "detect_decode", "nms"):
     wrap(n)
 for _ in range(2):
     yolo.model.detect_fused(x)
