@@ -167,11 +167,14 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 const int th = rgrp * rows_per + rr;    // output row inside the tile
                 // sliding 3x3 window over the 10 halo columns of rows th, th+1, th+2
                 float2 col[3][3];
+                const uint8_t* xrow = xs + (uint32_t)(th * kDwpwHW) * 128u + (uint32_t)((c0 & 63) * 2);
                 auto load_col = [&](int slot, int hx) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t row = (uint32_t)((th + ky) * kDwpwHW + hx);
-                        col[slot][ky] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xs + row * 128u + ((unit ^ (row & 7u)) << 4) + sub));
+                        // halo boxes are loaded UNswizzled: only these warps read them, and a warp reads the 32 consecutive
+                        // channel pairs of one pixel = one 128-byte row, conflict-free as it is; the address is then a
+                        // compile-time offset from the row base instead of ~4 integer ops per load
+                        col[slot][ky] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xrow + (uint32_t)((ky * kDwpwHW + hx) * 128)));
                     }
                 };
                 load_col(0, 0);
@@ -291,7 +294,7 @@ int dwpw_launch(const specyolo_dwpw_t* a, cudaStream_t stream) {
         cuuint32_t box[4] = {64, kDwpwHW, kDwpwHH, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(dwpw X) failed (%d)", (int)r);
     }
