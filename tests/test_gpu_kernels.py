@@ -290,13 +290,15 @@ def test_sppf_pool(lib):
     assert torch.equal(buf.float().cpu(), torch.cat(y, 1))     # max of bf16 values is exact
 
 
-@pytest.mark.parametrize("k,H,W,up", [(3, 16, 16, (1, 0, 0)), (2, 10, 10, (0, 0)), (3, 40, 40, (0, 0, 0))])
-def test_fusion_eschannel(lib, k, H, W, up):
+@pytest.mark.parametrize("k,H,W,up,c", [(3, 16, 16, (1, 0, 0), 128), (2, 10, 10, (0, 0), 128), (3, 40, 40, (0, 0, 0), 128),
+                                        (2, 12, 20, (1, 0), 64), (3, 8, 8, (0, 0, 0), 32), (2, 20, 20, (0, 1), 256),
+                                        (3, 80, 80, (1, 0, 0), 128)])
+def test_fusion_eschannel(lib, k, H, W, up, c):
     from oracle.yolo_ref import Ref
     from specyolo import ops
 
     gen = torch.Generator().manual_seed(10 + k)
-    B, c = 2, 128
+    B = 2           # every channel width the kernels are instantiated for (c / 32 lanes per pixel), ragged and full-size maps
     xs = [torch.randn((B, c, H >> u, W >> u), generator=gen) for u in up]
     sd = {"f.gsc%d.alpha" % k: torch.rand((1, k * c, 1, 1), generator=gen) * 0.5 + 0.75,
           "f.gsc%d.gamma" % k: torch.randn((1, k * c, 1, 1), generator=gen) * 0.3,
