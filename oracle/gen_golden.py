@@ -185,6 +185,54 @@ def gen_metrics():
     print("ap_per_class mAP50", float(r[5][:, 0].mean()), "mAP", float(r[5].mean()))
 
 
+TINY_CFG = {"nc": 2, "scales": {"n": [0.50, 0.25, 1024]}, "scale": "n",
+            "backbone": [[-1, 1, "Conv", [64, 3, 2]], [-1, 1, "Conv", [128, 3, 2]], [-1, 2, "C3k2", [256, False, 0.25]],
+                         [-1, 1, "Conv", [256, 3, 2]], [-1, 1, "DDWConv", [512, 3, 2, 2]], [-1, 1, "SPPF", [512, 5]],
+                         [-1, 1, "C2PSA", [512]]],
+            "head": [[[3, 6], 1, "Detect", ["nc"]]]}
+
+
+def gen_ckpt():
+    """A checkpoint written the way the reference's trainer writes it (engine/trainer.py:512-546: pickled EMA module in
+    fp16 + train_args) for a 0.4 M-parameter detector that uses the fork's own modules, plus the expected tensors."""
+    import io
+    from copy import deepcopy
+    from datetime import datetime
+
+    from ultralytics import __version__ as ref_version
+    from ultralytics.nn.tasks import DetectionModel as RefModel
+
+    torch.manual_seed(11)
+    ref = RefModel(deepcopy(TINY_CFG), nc=2, verbose=False)
+    with torch.no_grad():
+        for m in ref.modules():                      # non-trivial BN statistics, as after training
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.1)
+    ref.names = {0: "wifi", 1: "bluetooth"}
+    ref.args = {"imgsz": 640, "batch": 16}
+    ema = deepcopy(ref).half()
+    ckpt = {"epoch": 7, "best_fitness": 0.5, "model": None, "ema": ema, "updates": 123, "optimizer": None,
+            "train_args": {"task": "detect", "mode": "train", "model": "yolo11s_fusion_sand3_new.yaml",
+                           "data": "Spectrogram.yaml", "imgsz": 640, "batch": 16, "epochs": 300},
+            "train_metrics": {"metrics/mAP50(B)": 0.9, "fitness": 0.5}, "train_results": None,
+            "date": datetime(2024, 1, 1).isoformat(), "version": ref_version, "license": "AGPL-3.0", "docs": ""}
+    buf = io.BytesIO()
+    torch.save(ckpt, buf)
+    (GOLD / "ref_tiny_ckpt.pt").write_bytes(buf.getvalue())
+    sd = ema.float().eval().state_dict()
+    x = torch.rand((1, 3, 64, 96), generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        y, raw = ema.float().eval()(x)
+    out = {"keys": np.asarray(list(sd.keys())), "sums": np.asarray([float(v.double().sum()) for v in sd.values()]),
+           "abs_sums": np.asarray([float(v.double().abs().sum()) for v in sd.values()]),
+           "numel": np.asarray([v.numel() for v in sd.values()], dtype=np.int64), "x": x.numpy(), "y": y.numpy()}
+    np.savez_compressed(GOLD / "ref_tiny_ckpt_expect.npz", **out)
+    print("ckpt bytes", len(buf.getvalue()), "tensors", len(sd), "y", tuple(y.shape))
+
+
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -199,3 +247,5 @@ if __name__ == "__main__":
         gen_metrics()
     if "letterbox_u8" in which:
         gen_letterbox_u8()
+    if "ckpt" in which:
+        gen_ckpt()

@@ -438,13 +438,10 @@ class YOLO:
             if p.suffix in (".yaml", ".yml"):
                 self.model = DetectionModel(str(p), nc=nc, verbose=verbose)
             elif p.suffix == ".pt":
-                ck = torch.load(str(p), map_location="cpu", weights_only=True)   # state-dict checkpoints only
-                cfg = ck.get("cfg") if isinstance(ck, dict) else None
-                if cfg is None or "state_dict" not in ck:
-                    raise NotImplementedError("'.pt' must hold {'cfg': yaml name, 'nc': int, 'state_dict': ...}; pickled "
-                                              "nn.Module checkpoints need the reference package to unpickle")
-                self.model = DetectionModel(cfg, nc=ck.get("nc"), verbose=verbose)
-                self.model.load_state_dict(ck["state_dict"])
+                # the reference's pickled checkpoints (trainer.save_model) or this package's {'cfg','nc','state_dict'}
+                from .nn.checkpoint import attempt_load_one_weight
+                self.model, self.ckpt = attempt_load_one_weight(str(p))
+                self.overrides["imgsz"] = self.model.args.get("imgsz", 640) if isinstance(self.model.args, dict) else 640
             else:
                 raise NotImplementedError(f"unsupported model spec '{model}'")
         self.model.eval()

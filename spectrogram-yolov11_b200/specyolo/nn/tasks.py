@@ -258,3 +258,15 @@ class DetectionModel(nn.Module):
                                  iou_thres=iou_thres, agnostic=agnostic, max_det=max_det, max_nms=max_nms,
                                  max_wh=max_wh, classes=classes)
         return out, cnt
+
+
+def attempt_load_one_weight(weight, device=None, inplace=True, fuse=False):
+    """ultralytics/nn/tasks.py:937-960 (see specyolo.nn.checkpoint)."""
+    from .checkpoint import attempt_load_one_weight as f
+    return f(weight, device=device, inplace=inplace, fuse=fuse)
+
+
+def torch_safe_load(weight):
+    """ultralytics/nn/tasks.py:846-898 (see specyolo.nn.checkpoint)."""
+    from .checkpoint import torch_safe_load as f
+    return f(weight)
