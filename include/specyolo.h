@@ -263,6 +263,13 @@ int specyolo_letterbox_u8(const uint8_t* src_hwc, int B, int H, int W, uint8_t* 
                           int new_w, int new_h, int left, int top, int pad_value, int swap_rb, int chw,
                           void* stream);
 
+/* JPEG file bytes (host) -> uint8 HWC BGR image in device memory, the layout of cv2.imread that specyolo_letterbox_u8
+ * consumes.  Replaces the cv2.imread of LoadImagesAndVideos.__next__ (ultralytics/data/loaders.py:406) for JPEG sources;
+ * nvJPEG (library, dlopen'ed at first use) does Huffman on the host and IDCT / upsampling / colour conversion on the GPU.
+ * specyolo_jpeg_info fills the image size; out must hold H*W*3 bytes.  The decode is asynchronous on `stream`. */
+int specyolo_jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* channels);
+int specyolo_jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, void* stream);
+
 /* ---- IQ -> spectrogram -> letterbox (no reference implementation: README.md:7 only) -------- */
 typedef struct {
     const float* iq;           /* [B, L] complex64 interleaved (re,im)                   */

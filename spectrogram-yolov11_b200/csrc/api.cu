@@ -43,6 +43,8 @@ int scale_boxes_launch(float*, const int*, int, int, float, float, float, float,
 int stft_launch(const specyolo_stft_t*, cudaStream_t);
 int dwpw_launch(const specyolo_dwpw_t*, cudaStream_t);
 bool stem_pair_ok(int, int, int, int, int);
+int jpeg_info(const void*, size_t, int*, int*, int*);
+int jpeg_decode_bgr(const void*, size_t, void*, int, int, cudaStream_t);
 int stem_pair_launch(const specyolo_stem_pair_t*, cudaStream_t);
 int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
@@ -155,6 +157,16 @@ int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream) {
     SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->Cout,
              SPECYOLO_ERR_INVALID, "dwpw: bad sizes");
     return dwpw_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* channels) {
+    SY_CHECK(data && nbytes > 4 && H && W && channels, SPECYOLO_ERR_INVALID, "jpeg_info: bad arguments");
+    return jpeg_info(data, nbytes, H, W, channels);
+}
+
+int specyolo_jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, void* stream) {
+    SY_CHECK(data && nbytes > 4 && out_dev && H > 0 && W > 0, SPECYOLO_ERR_INVALID, "jpeg_decode: bad arguments");
+    return jpeg_decode_bgr(data, nbytes, out_dev, H, W, (cudaStream_t)stream);
 }
 
 int specyolo_stem_pair_ok(int H, int W, int c0, int Cout, int n_pad) { return stem_pair_ok(H, W, c0, Cout, n_pad) ? 1 : 0; }

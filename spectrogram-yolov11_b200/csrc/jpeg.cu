@@ -1,0 +1,78 @@
+// JPEG file bytes -> uint8 HWC BGR image in device memory (image-file ingest).
+// Replaces the cv2.imread of LoadImagesAndVideos.__next__ (ultralytics/data/loaders.py:284-448, imread at :406) for
+// JPEG sources: the Huffman stage runs on the host inside nvJPEG, the IDCT / upsampling / colour conversion on the GPU,
+// and the decoded pixels are born in HBM in the layout specyolo_letterbox_u8 consumes (cv2's HWC BGR) — no host image, no
+// H2D copy of raw pixels.  nvJPEG is a LIBRARY call (like cuBLAS); it is loaded with dlopen at first use so that the
+// rest of libspecyolo never depends on it.
+#include <dlfcn.h>
+#include <mutex>
+
+#include <nvjpeg.h>
+
+#include "common.h"
+
+namespace specyolo {
+
+namespace {
+struct NvJpeg {
+    void* lib = nullptr;
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t state = nullptr;
+    nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*JpegStateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+    nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+    nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t,
+                             nvjpegImage_t*, cudaStream_t) = nullptr;
+    std::mutex mu;          // one decode state: calls are serialised (the decode itself is asynchronous on `stream`)
+    int status = -1;        // -1 not tried, 0 ready, > 0 failed
+};
+NvJpeg g_nj;
+
+int ensure_nvjpeg() {
+    if (g_nj.status >= 0) return g_nj.status;
+    const char* names[] = {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"};
+    for (const char* n : names) {
+        g_nj.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_nj.lib) break;
+    }
+    if (!g_nj.lib) return g_nj.status = 1;
+    g_nj.CreateSimple = reinterpret_cast<decltype(g_nj.CreateSimple)>(dlsym(g_nj.lib, "nvjpegCreateSimple"));
+    g_nj.JpegStateCreate = reinterpret_cast<decltype(g_nj.JpegStateCreate)>(dlsym(g_nj.lib, "nvjpegJpegStateCreate"));
+    g_nj.GetImageInfo = reinterpret_cast<decltype(g_nj.GetImageInfo)>(dlsym(g_nj.lib, "nvjpegGetImageInfo"));
+    g_nj.Decode = reinterpret_cast<decltype(g_nj.Decode)>(dlsym(g_nj.lib, "nvjpegDecode"));
+    if (!g_nj.CreateSimple || !g_nj.JpegStateCreate || !g_nj.GetImageInfo || !g_nj.Decode) return g_nj.status = 2;
+    if (g_nj.CreateSimple(&g_nj.handle) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 3;
+    if (g_nj.JpegStateCreate(g_nj.handle, &g_nj.state) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 4;
+    return g_nj.status = 0;
+}
+}  // namespace
+
+int jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* channels) {
+    std::lock_guard<std::mutex> lk(g_nj.mu);
+    SY_CHECK(ensure_nvjpeg() == 0, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG is not available (dlopen / init step %d)", g_nj.status);
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    const nvjpegStatus_t st = g_nj.GetImageInfo(g_nj.handle, static_cast<const unsigned char*>(data), nbytes, &nc, &ss, ws, hs);
+    SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_INVALID, "not a decodable JPEG stream (nvjpeg status %d)", (int)st);
+    *H = hs[0]; *W = ws[0]; *channels = nc;
+    return SPECYOLO_OK;
+}
+
+int jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_nj.mu);
+    SY_CHECK(ensure_nvjpeg() == 0, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG is not available (dlopen / init step %d)", g_nj.status);
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    nvjpegStatus_t st = g_nj.GetImageInfo(g_nj.handle, static_cast<const unsigned char*>(data), nbytes, &nc, &ss, ws, hs);
+    SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_INVALID, "not a decodable JPEG stream (nvjpeg status %d)", (int)st);
+    SY_CHECK(hs[0] == H && ws[0] == W, SPECYOLO_ERR_INVALID, "jpeg is %dx%d, the output buffer was sized for %dx%d", hs[0], ws[0], H, W);
+    nvjpegImage_t dst{};
+    dst.channel[0] = static_cast<unsigned char*>(out_dev);
+    dst.pitch[0] = (size_t)W * 3;
+    // grayscale files come out replicated to three channels, as cv2.imread(IMREAD_COLOR) returns them
+    st = g_nj.Decode(g_nj.handle, g_nj.state, static_cast<const unsigned char*>(data), nbytes, NVJPEG_OUTPUT_BGRI, &dst, stream);
+    SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_CUDA, "nvjpegDecode failed (status %d)", (int)st);
+    return SPECYOLO_OK;
+}
+
+}  // namespace specyolo

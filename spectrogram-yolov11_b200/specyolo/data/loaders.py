@@ -1,0 +1,117 @@
+"""Image-file ingest: `LoadImagesAndVideos` for image sources, decoded straight into device memory.
+
+Mirrors ultralytics/data/loaders.py:284-448 (constructor arguments, file discovery rules, `(paths, imgs, info)` batches,
+`__len__`), images only: videos and streams are outside the hot path this package rebuilds.  JPEG files are decoded by
+nvJPEG into HBM (`specyolo_jpeg_decode_bgr`: HWC BGR uint8, the layout of `cv2.imread`) — the host only reads the file
+bytes; the pixels never exist in host memory.  Other formats (PNG, BMP, TIFF, WebP ...) have no GPU decoder in this image:
+they are decoded on the host with OpenCV exactly as the reference does (`cv2.imdecode`, loaders.py:406 / patches.py:20)
+and uploaded.  Every image of a batch is then letterboxed by `specyolo_letterbox_u8` (bit-exact with cv2's resize).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import math
+import os
+from pathlib import Path
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp", "pfm"}   # data/utils.py:38 (no HEIC)
+VID_FORMATS = {"asf", "avi", "gif", "m4v", "mkv", "mov", "mp4", "mpeg", "mpg", "ts", "wmv", "webm"}
+
+
+def decode_jpeg(data: bytes, device="cuda") -> torch.Tensor:
+    """JPEG bytes -> [H, W, 3] uint8 BGR CUDA tensor (nvJPEG, asynchronous on the current stream)."""
+    _lib.init_device()
+    lib = _lib.load()
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    h, w, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.specyolo_jpeg_info(C.addressof(buf), len(data), C.byref(h), C.byref(w), C.byref(c)))
+    out = torch.empty((h.value, w.value, 3), dtype=torch.uint8, device=device)
+    _lib.check(lib.specyolo_jpeg_decode_bgr(C.addressof(buf), len(data), out.data_ptr(), h.value, w.value, _lib.stream_ptr()))
+    # nvjpegDecode has consumed the host bytes (Huffman stage) when it returns; `buf` may go away
+    return out
+
+
+def imread_device(path: str, device="cuda") -> torch.Tensor:
+    """An image file -> [H, W, 3] uint8 BGR CUDA tensor; None-like failure raises (the reference warns and skips)."""
+    data = Path(path).read_bytes()
+    if data[:3] == b"\xff\xd8\xff":                       # JPEG magic, whatever the suffix says
+        try:
+            return decode_jpeg(data, device)
+        except RuntimeError:
+            pass                                           # progressive / CMYK / arithmetic-coded streams: host decoder
+    import cv2                                             # the reference's own decoder for everything else
+
+    im = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    if im is None:
+        raise ValueError(f"Image Read Error {path}")
+    return torch.from_numpy(np.ascontiguousarray(im)).to(device, non_blocking=True)
+
+
+class LoadImagesAndVideos:
+    """`for paths, imgs, info in LoadImagesAndVideos(path, batch)`: imgs = list of [H,W,3] uint8 BGR CUDA tensors."""
+
+    def __init__(self, path, batch: int = 1, vid_stride: int = 1, device="cuda"):
+        parent = None
+        if isinstance(path, str) and Path(path).suffix == ".txt":      # *.txt with one source per line
+            parent = Path(path).parent
+            path = Path(path).read_text().splitlines()
+        files: List[str] = []
+        for p in sorted(path) if isinstance(path, (list, tuple)) else [path]:
+            a = str(Path(p).absolute())                                # loaders.py:330-343
+            if "*" in a:
+                files.extend(sorted(glob.glob(a, recursive=True)))
+            elif os.path.isdir(a):
+                files.extend(sorted(glob.glob(os.path.join(a, "*.*"))))
+            elif os.path.isfile(a):
+                files.append(a)
+            elif parent and (parent / p).is_file():
+                files.append(str((parent / p).absolute()))
+            else:
+                raise FileNotFoundError(f"{p} does not exist")
+        images = [f for f in files if f.split(".")[-1].lower() in IMG_FORMATS]
+        videos = [f for f in files if f.split(".")[-1].lower() in VID_FORMATS]
+        if videos:
+            raise NotImplementedError("video sources are outside the path specyolo implements (images only)")
+        self.files = images
+        self.nf = self.ni = len(images)
+        self.video_flag = [False] * self.nf
+        self.mode = "image"
+        self.vid_stride = vid_stride
+        self.bs = batch
+        self.device = device
+        self.count = 0
+        if self.nf == 0:
+            raise FileNotFoundError(f"No images found in {path}. Supported formats are: images: {IMG_FORMATS}")
+
+    def __iter__(self):
+        self.count = 0
+        return self
+
+    def __next__(self) -> Tuple[List[str], List[torch.Tensor], List[str]]:
+        paths, imgs, info = [], [], []
+        while len(imgs) < self.bs:
+            if self.count >= self.nf:
+                if imgs:
+                    return paths, imgs, info
+                raise StopIteration
+            path = self.files[self.count]
+            try:
+                im0 = imread_device(path, self.device)
+            except ValueError:
+                im0 = None                                             # loaders.py:438-439: warn and move on
+            if im0 is not None:
+                paths.append(path)
+                imgs.append(im0)
+                info.append(f"image {self.count + 1}/{self.nf} {path}: ")
+            self.count += 1
+        return paths, imgs, info
+
+    def __len__(self):
+        return math.ceil(self.nf / self.bs)

@@ -150,6 +150,22 @@ class DetectionPredictor:
                 for i, s in enumerate(source):
                     lb.to_network_input(torch.from_numpy(np.ascontiguousarray(s)).to(dev, non_blocking=True)[None], out=im[i:i + 1])
             return im, [tuple(s.shape[:2]) for s in source], list(source)
+        if isinstance(source, (list, tuple)) and source and all(
+                isinstance(s, torch.Tensor) and s.dim() == 3 and s.shape[2] == 3 and s.dtype == torch.uint8 for s in source):
+            # HWC BGR uint8 images already in device memory (specyolo.data.LoadImagesAndVideos: nvJPEG-decoded files)
+            from .data import LetterBox
+
+            imgsz = self.args.get("imgsz", 640)
+            same = len({tuple(s.shape) for s in source}) == 1
+            lb = LetterBox(imgsz, auto=same, stride=int(self.model.stride.max()))
+            src = [s.to(dev, non_blocking=True).contiguous() for s in source]
+            if same:
+                im = lb.to_network_input(torch.stack(src))
+            else:
+                im = torch.empty((len(src), 3) + tuple(lb.new_shape), device=dev, dtype=torch.uint8)
+                for i, s_ in enumerate(src):
+                    lb.to_network_input(s_[None], out=im[i:i + 1])
+            return im, [tuple(s.shape[:2]) for s in source], list(source)
         raise TypeError(f"unsupported source type {type(source)}")   # data/build.py:183
 
     # -- one batch -----------------------------------------------------------------------------
@@ -479,6 +495,32 @@ class YOLO:
             self.model.to("cuda")
         if self.predictor is None or any(self.predictor.args.get(k) != v for k, v in args.items()):
             self.predictor = (predictor or DetectionPredictor)(self.model, args)
+        if isinstance(source, (str, Path)) or (isinstance(source, (list, tuple)) and source and
+                                               all(isinstance(s, (str, Path)) for s in source)):
+            # image files / directory / glob / *.txt list (data/build.py:158-205 -> LoadImagesAndVideos): JPEGs are decoded
+            # by nvJPEG straight into device memory, letterboxed and run batch by batch through the streaming loop
+            from .data import LoadImagesAndVideos
+
+            loader = LoadImagesAndVideos([str(s) for s in source] if isinstance(source, (list, tuple)) else str(source),
+                                         batch=int(args.get("batch", 1)))
+            paths: List[str] = []
+
+            def batches():
+                for pths, imgs, _ in loader:
+                    paths.extend(pths)
+                    yield imgs
+
+            def with_paths():
+                k = 0
+                for res in self.predictor.stream(batches()):
+                    for r in res:
+                        r.path = paths[k]
+                        k += 1
+                    yield res
+
+            if stream:
+                return with_paths()
+            return [r for res in with_paths() for r in res]
         if stream:      # `source` is an iterable of batches; generator of List[Results], copies overlapped with compute
             return self.predictor.stream(source)
         return self.predictor(source)

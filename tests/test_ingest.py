@@ -1,0 +1,120 @@
+"""SURVEY §8 f3 (second half): image-file ingest — LoadImagesAndVideos for image sources with JPEG decode on the GPU."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "spectrogram-yolov11_b200"))
+cv2 = pytest.importorskip("cv2")
+
+
+def _spectrogram_like(h, w, seed):
+    g = np.random.default_rng(seed)
+    img = np.clip(g.normal(64, 12, (h, w)), 0, 255)
+    for _ in range(5):
+        y0, x0 = int(g.integers(0, h - 20)), int(g.integers(0, w - 40))
+        img[y0:y0 + int(g.integers(8, 20)), x0:x0 + int(g.integers(20, 40))] += g.uniform(90, 150)
+    img = cv2.GaussianBlur(np.clip(img, 0, 255).astype(np.uint8), (5, 5), 0)
+    return cv2.applyColorMap(img, cv2.COLORMAP_VIRIDIS)        # HWC BGR, smooth colours like a rendered spectrogram
+
+
+def _write_files(d, synth=False):
+    files = {}
+    for k, (h, w, ext) in enumerate([(240, 320, "jpg"), (240, 320, "png"), (200, 280, "jpeg"), (320, 256, "bmp"), (192, 320, "jpg")]):
+        if synth:       # crops of the images the synthetic weights were calibrated on: they produce detections
+            from specyolo.nn.init import synth_images
+            im = (synth_images(1, 320, seed=60 + k)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)[:h, :w, ::-1]
+            im = np.ascontiguousarray(im)
+        else:
+            im = _spectrogram_like(h, w, 50 + k)
+        p = d / f"img_{k}.{ext}"
+        assert cv2.imwrite(str(p), im)
+        files[str(p)] = im
+    (d / "notes.md").write_text("not an image")
+    return files
+
+
+def test_loader_file_discovery(tmp_path):
+    from specyolo.data import LoadImagesAndVideos
+
+    files = _write_files(tmp_path)
+    ld = LoadImagesAndVideos(str(tmp_path), batch=2)
+    assert ld.nf == 5 and len(ld) == 3 and ld.files == sorted(files)           # the .md file is ignored
+    assert LoadImagesAndVideos(str(tmp_path / "*.jpg"), batch=4).nf == 2
+    (tmp_path / "list.txt").write_text("img_1.png\n" + str(tmp_path / "img_0.jpg") + "\n")
+    assert LoadImagesAndVideos(str(tmp_path / "list.txt")).nf == 2
+    with pytest.raises(FileNotFoundError):
+        LoadImagesAndVideos(str(tmp_path / "missing.jpg"))
+    (tmp_path / "clip.mp4").write_bytes(b"0")
+    with pytest.raises(NotImplementedError):
+        LoadImagesAndVideos(str(tmp_path / "clip.mp4"))
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        LoadImagesAndVideos(str(empty))
+
+
+@pytest.mark.gpu
+def test_gpu_decode_matches_cv2_imread(tmp_path):
+    """PNG / BMP: bit-exact (same decoder as the reference, on the host).  JPEG cannot be bit-exact across decoders:
+    with 4:4:4 sampling nvJPEG and libjpeg-turbo differ only by IDCT / colour-conversion rounding (mean |d| < 0.75, all
+    samples within 4 grey levels); with the default 4:2:0 files the chroma up-sampling filters differ as well (libjpeg's
+    "fancy" triangle filter vs nvJPEG's), so the bound is statistical: mean |d| < 2.5, 99 % of the samples within 12."""
+    from specyolo.data import LoadImagesAndVideos, imread_device
+
+    files = _write_files(tmp_path)
+    for p in sorted(files):
+        ref = cv2.imread(p)
+        got = imread_device(p).cpu().numpy()
+        assert got.shape == ref.shape and got.dtype == np.uint8
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        if p.endswith(("png", "bmp")):
+            assert d.max() == 0
+        else:
+            assert d.mean() < 2.5 and (d <= 12).mean() > 0.99, (p, d.mean(), d.max())
+    p444 = tmp_path / "full_chroma.jpg"
+    cv2.imwrite(str(p444), _spectrogram_like(240, 320, 7), [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                            cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    d = np.abs(imread_device(str(p444)).cpu().numpy().astype(np.int32) - cv2.imread(str(p444)).astype(np.int32))
+    assert d.mean() < 0.75 and d.max() <= 4, (d.mean(), d.max())
+    p444.unlink()
+    seen = []
+    for paths, imgs, info in LoadImagesAndVideos(str(tmp_path), batch=2):
+        assert len(paths) == len(imgs) == len(info) <= 2
+        assert all(i.is_cuda and i.dtype == torch.uint8 and i.shape[2] == 3 for i in imgs)
+        seen += paths
+    assert seen == sorted(files)
+    gray = tmp_path / "gray.jpg"
+    cv2.imwrite(str(gray), _spectrogram_like(64, 96, 1)[:, :, 0])
+    g = imread_device(str(gray)).cpu().numpy()
+    assert g.shape == (64, 96, 3) and np.abs(g.astype(int) - cv2.imread(str(gray)).astype(int)).max() <= 2
+
+
+@pytest.mark.gpu
+def test_predict_from_files(tmp_path):
+    """YOLO.predict(directory) == predict(list of the same decoded pixels as ndarrays), with path / orig_shape attached,
+    batch by batch through the streaming loop; for the lossless files that is predict(cv2.imread(...)) exactly."""
+    import specyolo
+    from specyolo.data import imread_device
+    from specyolo.nn.init import synth_state_dict
+
+    files = _write_files(tmp_path, synth=True)
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    res = yolo.predict(str(tmp_path), conf=0.25, iou=0.7, imgsz=320, batch=2)
+    assert [r.path for r in res] == sorted(files)
+    streamed = [r for b in yolo.predict(str(tmp_path), stream=True, conf=0.25, iou=0.7, imgsz=320, batch=2) for r in b]
+    assert [r.path for r in streamed] == sorted(files)
+    paths = sorted(files)
+    for k in range(0, len(paths), 2):              # the loader's batches: LetterBox(auto) depends on the batch's shapes
+        pix = [cv2.imread(p) if p.endswith(("png", "bmp")) else imread_device(p).cpu().numpy() for p in paths[k:k + 2]]
+        ref = yolo.predict(pix, conf=0.25, iou=0.7, imgsz=320)
+        for p, a, b, c in zip(paths[k:k + 2], ref, res[k:k + 2], streamed[k:k + 2]):
+            assert b.orig_shape == a.orig_shape == cv2.imread(p).shape[:2]
+            assert torch.equal(b.boxes.data, c.boxes.data)
+            assert torch.equal(a.boxes.data, b.boxes.data)
+    assert sum(len(r) for r in res) > 0
