@@ -233,6 +233,60 @@ def gen_ckpt():
     print("ckpt bytes", len(buf.getvalue()), "tensors", len(sd), "y", tuple(y.shape))
 
 
+def gen_dataset():
+    """tests/golden/tiny_dataset (7 PNGs of assorted aspect ratios, YOLO txt labels incl. a missing file, an empty file
+    and a duplicated row) and the batches the REAL reference's validation dataloader makes of it (square and rect)."""
+    import os
+    import shutil
+
+    import cv2
+    from ultralytics.cfg import get_cfg
+    from ultralytics.data.build import build_dataloader, build_yolo_dataset
+
+    root = GOLD / "tiny_dataset"
+    shutil.rmtree(root, ignore_errors=True)
+    (root / "images" / "val").mkdir(parents=True)
+    (root / "labels" / "val").mkdir(parents=True)
+    g = np.random.default_rng(5)
+    for k, (h, w) in enumerate([(60, 100), (100, 60), (80, 80), (50, 120), (120, 48), (64, 96), (90, 70)]):
+        img = cv2.GaussianBlur(g.integers(0, 255, (h, w, 3), dtype=np.uint8), (5, 5), 0)
+        cv2.imwrite(str(root / "images" / "val" / f"im{k}.png"), img)
+        n = int(g.integers(0, 4))
+        if k == 3:
+            continue                                   # no label file: background image
+        rows = []
+        for _ in range(n):
+            cx, cy = g.uniform(0.2, 0.8, 2)
+            bw, bh = g.uniform(0.05, 0.3, 2)
+            rows.append(f"{int(g.integers(0, 2))} {cx:.6f} {cy:.6f} {bw:.6f} {bh:.6f}")
+        if k == 5 and rows:
+            rows.append(rows[0])                       # duplicate row
+        (root / "labels" / "val" / f"im{k}.txt").write_text("\n".join(rows) + ("\n" if rows else ""))
+    (root / "data.yaml").write_text("path: .\ntrain: images/val\nval: images/val\nnames:\n  0: wifi\n  1: bluetooth\n")
+    data = {"path": str(root), "val": str(root / "images" / "val"), "train": str(root / "images" / "val"),
+            "names": {0: "wifi", 1: "bluetooth"}, "nc": 2}      # what check_det_dataset returns (it also wants fonts)
+    out = {}
+    for rect in (False, True):
+        cfg = get_cfg(overrides=dict(imgsz=96, task="detect", rect=rect, workers=0))
+        ds = build_yolo_dataset(cfg, data["val"], 3, data, mode="val", stride=32)
+        bi = -1
+        for bi, b in enumerate(build_dataloader(ds, 3, 0, shuffle=False, rank=-1)):
+            p = f"r{int(rect)}_b{bi}_"
+            out[p + "img"] = b["img"].numpy()
+            out[p + "cls"] = b["cls"].numpy()
+            out[p + "bboxes"] = b["bboxes"].numpy()
+            out[p + "batch_idx"] = b["batch_idx"].numpy()
+            out[p + "files"] = np.asarray([os.path.basename(f) for f in b["im_file"]])
+            out[p + "ori_shape"] = np.asarray(b["ori_shape"])
+            out[p + "ratio"] = np.asarray([rp[0] for rp in b["ratio_pad"]], dtype=np.float64)
+            out[p + "pad"] = np.asarray([rp[1] for rp in b["ratio_pad"]])
+        out[f"r{int(rect)}_nb"] = np.int64(bi + 1)
+    for c in (root / "labels").glob("*.cache"):
+        c.unlink()                                     # the reference caches the label scan next to the labels
+    np.savez_compressed(GOLD / "tiny_dataset_batches.npz", **out)
+    print("dataset batches", len(out))
+
+
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -249,3 +303,5 @@ if __name__ == "__main__":
         gen_letterbox_u8()
     if "ckpt" in which:
         gen_ckpt()
+    if "dataset" in which:
+        gen_dataset()

@@ -375,8 +375,9 @@ class DetectionValidator:
     host-side AP integration (numpy, as in the reference).
 
     `batches` yields the reference's collated dicts: {"img": [B,3,H,W] uint8 | float in 0..1, "cls": [n] or [n,1],
-    "bboxes": [n,4] normalised xywh, "batch_idx": [n]}.  Images are expected at the network size (ori_shape == imgsz),
-    so the reference's scale_boxes round trip is the identity."""
+    "bboxes": [n,4] normalised xywh, "batch_idx": [n]} and, from the dataset loader (specyolo.data.YOLODataset), "ori_shape"
+    + "ratio_pad" per image: predictions and labels are then compared in original-image coordinates like the reference
+    does; without them the images are taken to be at the network size (the scale_boxes round trip is the identity)."""
 
     def __init__(self, model: DetectionModel, overrides: Optional[dict] = None):
         self.model = model
@@ -406,6 +407,23 @@ class DetectionValidator:
         cls, bidx, box = cls[order], bidx[order], box[order]
         scale = torch.tensor([W, H, W, H], dtype=torch.float32)
         xyxy = torch.cat((box[:, :2] - box[:, 2:] / 2, box[:, :2] + box[:, 2:] / 2), 1) * scale
+        rp, osh = batch.get("ratio_pad"), batch.get("ori_shape")
+        if rp is not None and osh is not None:
+            # batches of the dataset loader: predictions and labels go back to original-image coordinates and are clipped
+            # there (val.py:107-128: scale_boxes with the recorded ratio_pad on both)
+            for b in range(B):
+                ops.scale_boxes_(out[b:b + 1], cnt[b:b + 1], (H, W), osh[b], ratio_pad=rp[b])
+            for b in range(B):
+                m = bidx == b
+                if bool(m.any()):
+                    (gain, _), (pw, ph) = rp[b]
+                    bb = xyxy[m]
+                    bb[:, [0, 2]] -= pw
+                    bb[:, [1, 3]] -= ph
+                    bb /= gain
+                    bb[:, [0, 2]] = bb[:, [0, 2]].clamp(0, osh[b][1])
+                    bb[:, [1, 3]] = bb[:, [1, 3]].clamp(0, osh[b][0])
+                    xyxy[m] = bb
         per_img = torch.bincount(bidx, minlength=B)
         off = torch.zeros(B + 1, dtype=torch.int32)
         off[1:] = torch.cumsum(per_img, 0)
@@ -531,9 +549,20 @@ class YOLO:
         """`model.val(...)` (engine/model.py:601-656) over an iterable of collated batches (see DetectionValidator);
         returns the reference's `results_dict` (precision, recall, mAP50, mAP50-95, fitness)."""
         if data is None:
-            raise ValueError("data (an iterable of collated batches) is required: dataset YAMLs / image files are not read")
+            raise ValueError("data is required: a dataset YAML or an iterable of collated batches")
         if not next(self.model.parameters()).is_cuda:
             self.model.to("cuda")
+        if isinstance(data, (str, Path)):
+            # dataset YAML -> rectangular validation batches (engine/model.py:639 custom = {"rect": True};
+            # validator.get_dataloader -> build_yolo_dataset(mode="val")), decoded and letterboxed on the device
+            from .data import build_yolo_dataset, check_det_dataset
+
+            d = check_det_dataset(data)
+            split = kwargs.pop("split", "val")
+            cfg = {"imgsz": kwargs.pop("imgsz", 640), "rect": kwargs.pop("rect", True),
+                   "single_cls": kwargs.get("single_cls", False), "classes": kwargs.pop("classes", None)}
+            data = build_yolo_dataset(cfg, d[split], int(kwargs.pop("batch", 16)), d, mode="val",
+                                      stride=max(int(self.model.stride.max()), 32))
         return (validator or DetectionValidator)(self.model, kwargs)(data)
 
     def predict_iq(self, iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0,

@@ -485,11 +485,16 @@ def nms(prediction: Optional[torch.Tensor] = None, cand: Optional[torch.Tensor] 
     return out, cnt, keep, ncand
 
 
-def scale_boxes_(out: torch.Tensor, cnt: torch.Tensor, img1_shape, img0_shape) -> None:
-    """In-place scale_boxes + clip_boxes on the NMS output (ops.py:92-127 geometry)."""
-    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
-    pad_w = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
-    pad_h = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+def scale_boxes_(out: torch.Tensor, cnt: torch.Tensor, img1_shape, img0_shape, ratio_pad=None) -> None:
+    """In-place scale_boxes + clip_boxes on the NMS output (ops.py:92-127 geometry; `ratio_pad` = ((rh, rw), (left, top))
+    as the validation dataloader records it: gain = rh, pads as given)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad_w = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+        pad_h = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    else:
+        gain = ratio_pad[0][0]
+        pad_w, pad_h = ratio_pad[1]
     B, max_det, _ = out.shape
     check(_lib.load().specyolo_scale_boxes(out.data_ptr(), cnt.data_ptr(), B, max_det, float(gain), float(pad_w),
                                            float(pad_h), float(img0_shape[1]), float(img0_shape[0]),
