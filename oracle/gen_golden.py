@@ -281,6 +281,46 @@ def gen_dataset():
             out[p + "ratio"] = np.asarray([rp[0] for rp in b["ratio_pad"]], dtype=np.float64)
             out[p + "pad"] = np.asarray([rp[1] for rp in b["ratio_pad"]])
         out[f"r{int(rect)}_nb"] = np.int64(bi + 1)
+    # crafted detections per image (jittered labels, some flipped classes, boxes reaching into the padding / beyond the
+    # image) through the REAL validator's _prepare_batch / _prepare_pred / _process_batch -> the expected tp matrices
+    import functools
+    import types
+
+    from ultralytics.engine.validator import BaseValidator
+    from ultralytics.models.yolo.detect.val import DetectionValidator as RefVal
+
+    ns = types.SimpleNamespace(device="cpu", iouv=torch.linspace(0.5, 0.95, 10), niou=10)
+    ns.match_predictions = functools.partial(BaseValidator.match_predictions, ns)
+    rng = np.random.default_rng(17)
+    cfg = get_cfg(overrides=dict(imgsz=96, task="detect", rect=True, workers=0))
+    ds = build_yolo_dataset(cfg, data["val"], 3, data, mode="val", stride=32)
+    for bi, b in enumerate(build_dataloader(ds, 3, 0, shuffle=False, rank=-1)):
+        B, _, H, W = b["img"].shape
+        max_n = 12
+        preds = np.zeros((B, max_n, 6), np.float32)
+        cnts = np.zeros(B, np.int32)
+        for si in range(B):
+            m = (b["batch_idx"] == si).numpy()
+            bb = b["bboxes"].numpy()[m] * np.array([W, H, W, H], np.float32)
+            cl = b["cls"].numpy().reshape(-1)[m]
+            rows = []
+            for (cx, cy, w, h), c in zip(bb, cl):
+                j = rng.normal(0, 1.5, 4)
+                rows.append([cx - w / 2 + j[0], cy - h / 2 + j[1], cx + w / 2 + j[2], cy + h / 2 + j[3], rng.uniform(0.3, 0.9),
+                             c if rng.uniform() > 0.25 else 1 - c])
+            for _ in range(3):                          # boxes that stick out of the content area / the tensor
+                x1, y1 = rng.uniform(-10, W - 20), rng.uniform(-10, H - 20)
+                rows.append([x1, y1, x1 + rng.uniform(10, 60), y1 + rng.uniform(10, 60), rng.uniform(0.05, 0.5), int(rng.integers(0, 2))])
+            rows.sort(key=lambda r: -r[4])              # NMS output order: confidence descending
+            preds[si, :len(rows)] = np.asarray(rows, np.float32)
+            cnts[si] = len(rows)
+            pb = RefVal._prepare_batch(ns, si, b)
+            predn = RefVal._prepare_pred(ns, torch.from_numpy(preds[si, :len(rows)]), pb)
+            tp = RefVal._process_batch(ns, predn, pb["bbox"], pb["cls"]) if len(pb["cls"]) else torch.zeros((len(rows), 10), dtype=torch.bool)
+            out[f"match_b{bi}_tp{si}"] = tp.numpy()
+            out[f"match_b{bi}_predn{si}"] = predn.numpy()
+        out[f"match_b{bi}_preds"] = preds
+        out[f"match_b{bi}_cnt"] = cnts
     for c in (root / "labels").glob("*.cache"):
         c.unlink()                                     # the reference caches the label scan next to the labels
     np.savez_compressed(GOLD / "tiny_dataset_batches.npz", **out)

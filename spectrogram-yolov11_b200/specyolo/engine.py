@@ -399,6 +399,12 @@ class DetectionValidator:
                                  multi_label=True, max_det=a["max_det"])
         if a["single_cls"]:
             out[..., 5] = 0
+        self.match(out, cnt, batch, H, W)
+
+    @torch.no_grad()
+    def match(self, out: torch.Tensor, cnt: torch.Tensor, batch: dict, H: int, W: int):
+        """NMS output [B, max_det, 6] (letterboxed pixels) + counts vs the batch's labels -> stats (val.py:107-193)."""
+        B = out.shape[0]
         # labels -> pixel xyxy grouped by image (val.py:107-118)
         cls = batch["cls"].reshape(-1).to(torch.float32)
         bidx = batch["batch_idx"].reshape(-1).to(torch.int64)

@@ -91,3 +91,32 @@ def test_val_from_dataset_yaml():
     assert r1 == r2
     r3 = yolo.val(data=str(DS / "data.yaml"), imgsz=96, batch=3, rect=False)
     assert set(r3) == set(r1)
+
+
+@pytest.mark.gpu
+def test_validator_matching_in_original_coordinates():
+    """Crafted detections (jittered labels, flipped classes, boxes reaching into the padding) for the rect batches: the
+    validator's scale-back + clip + matching reproduces the REAL reference's _prepare_batch / _prepare_pred /
+    _process_batch results — the scaled boxes to 1e-4 px and the tp matrices exactly."""
+    import specyolo
+    from specyolo import ops
+    from specyolo.engine import DetectionValidator
+
+    exp = np.load(EXP)
+    model = specyolo.DetectionModel("yolo11n.yaml", nc=2).to("cuda")          # only its device is used here
+    for bi, batch in enumerate(_dataset(True)):
+        v = DetectionValidator(model)
+        preds = torch.from_numpy(exp[f"match_b{bi}_preds"]).cuda()
+        cnt = torch.from_numpy(exp[f"match_b{bi}_cnt"]).cuda()
+        B, _, H, W = batch["img"].shape
+        out = preds.clone()
+        v.match(out, cnt, batch, H, W)
+        k = 0
+        for si in range(B):
+            n = int(cnt[si])
+            want_tp, want_box = exp[f"match_b{bi}_tp{si}"], exp[f"match_b{bi}_predn{si}"]
+            assert np.allclose(out[si, :n].cpu().numpy(), want_box, rtol=0, atol=1e-4)
+            got_tp = v.stats["tp"][k]
+            k += 1
+            assert got_tp.shape == want_tp.shape and np.array_equal(got_tp, want_tp), (bi, si)
+    assert any(exp[f"match_b{b}_tp{s}"].any() for b in range(3) for s in range(int(exp[f"match_b{b}_cnt"].shape[0])))
