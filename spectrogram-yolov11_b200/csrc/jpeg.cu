@@ -5,6 +5,7 @@
 // H2D copy of raw pixels.  nvJPEG is a LIBRARY call (like cuBLAS); it is loaded with dlopen at first use so that the
 // rest of libspecyolo never depends on it.
 #include <dlfcn.h>
+#include <atomic>
 #include <mutex>
 
 #include <nvjpeg.h>
@@ -17,13 +18,16 @@ namespace {
 struct NvJpeg {
     void* lib = nullptr;
     nvjpegHandle_t handle = nullptr;
-    nvjpegJpegState_t state = nullptr;
+    static constexpr int kStates = 16;      // decode states: one per concurrently decoding host thread
+    nvjpegJpegState_t state[kStates] = {};
+    std::mutex state_mu[kStates];
     nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
     nvjpegStatus_t (*JpegStateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
     nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
     nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t,
                              nvjpegImage_t*, cudaStream_t) = nullptr;
-    std::mutex mu;          // one decode state: calls are serialised (the decode itself is asynchronous on `stream`)
+    std::mutex mu;          // guards initialisation; decodes take one of the per-state mutexes (the Huffman stage of
+                            // nvjpegDecode runs on the calling host thread: a loader thread pool scales it with the cores)
     int status = -1;        // -1 not tried, 0 ready, > 0 failed
 };
 NvJpeg g_nj;
@@ -42,7 +46,8 @@ int ensure_nvjpeg() {
     g_nj.Decode = reinterpret_cast<decltype(g_nj.Decode)>(dlsym(g_nj.lib, "nvjpegDecode"));
     if (!g_nj.CreateSimple || !g_nj.JpegStateCreate || !g_nj.GetImageInfo || !g_nj.Decode) return g_nj.status = 2;
     if (g_nj.CreateSimple(&g_nj.handle) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 3;
-    if (g_nj.JpegStateCreate(g_nj.handle, &g_nj.state) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 4;
+    for (int i = 0; i < NvJpeg::kStates; ++i)
+        if (g_nj.JpegStateCreate(g_nj.handle, &g_nj.state[i]) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 4;
     return g_nj.status = 0;
 }
 }  // namespace
@@ -59,8 +64,10 @@ int jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* channels) {
 }
 
 int jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, cudaStream_t stream) {
-    std::lock_guard<std::mutex> lk(g_nj.mu);
-    SY_CHECK(ensure_nvjpeg() == 0, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG is not available (dlopen / init step %d)", g_nj.status);
+    {
+        std::lock_guard<std::mutex> lk(g_nj.mu);
+        SY_CHECK(ensure_nvjpeg() == 0, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG is not available (dlopen / init step %d)", g_nj.status);
+    }
     int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
     nvjpegChromaSubsampling_t ss;
     nvjpegStatus_t st = g_nj.GetImageInfo(g_nj.handle, static_cast<const unsigned char*>(data), nbytes, &nc, &ss, ws, hs);
@@ -69,8 +76,22 @@ int jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W
     nvjpegImage_t dst{};
     dst.channel[0] = static_cast<unsigned char*>(out_dev);
     dst.pitch[0] = (size_t)W * 3;
+    // a free decode state: first one whose mutex can be taken, else wait for a slot picked by the thread's identity
+    static std::atomic<unsigned> next{0};
+    int slot = -1;
+    for (int i = 0; i < NvJpeg::kStates && slot < 0; ++i) {
+        const int c = (int)((next.load(std::memory_order_relaxed) + (unsigned)i) % NvJpeg::kStates);
+        if (g_nj.state_mu[c].try_lock()) slot = c;
+    }
+    if (slot < 0) {
+        slot = (int)(next.fetch_add(1, std::memory_order_relaxed) % NvJpeg::kStates);
+        g_nj.state_mu[slot].lock();
+    } else {
+        next.store((unsigned)slot + 1u, std::memory_order_relaxed);
+    }
     // grayscale files come out replicated to three channels, as cv2.imread(IMREAD_COLOR) returns them
-    st = g_nj.Decode(g_nj.handle, g_nj.state, static_cast<const unsigned char*>(data), nbytes, NVJPEG_OUTPUT_BGRI, &dst, stream);
+    st = g_nj.Decode(g_nj.handle, g_nj.state[slot], static_cast<const unsigned char*>(data), nbytes, NVJPEG_OUTPUT_BGRI, &dst, stream);
+    g_nj.state_mu[slot].unlock();
     SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_CUDA, "nvjpegDecode failed (status %d)", (int)st);
     return SPECYOLO_OK;
 }

@@ -25,6 +25,19 @@ IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp",
 VID_FORMATS = {"asf", "avi", "gif", "m4v", "mkv", "mov", "mp4", "mpeg", "mpg", "ts", "wmv", "webm"}
 
 
+_POOL = None
+
+
+def _pool():
+    """Host threads of the decode stage (file read + entropy decoding), shared by every loader."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 4))), thread_name_prefix="specyolo-ingest")
+    return _POOL
+
+
 def decode_jpeg(data: bytes, device="cuda") -> torch.Tensor:
     """JPEG bytes -> [H, W, 3] uint8 BGR CUDA tensor (nvJPEG, asynchronous on the current stream)."""
     _lib.init_device()
@@ -95,22 +108,31 @@ class LoadImagesAndVideos:
         return self
 
     def __next__(self) -> Tuple[List[str], List[torch.Tensor], List[str]]:
+        if self.count >= self.nf:
+            raise StopIteration
         paths, imgs, info = [], [], []
-        while len(imgs) < self.bs:
-            if self.count >= self.nf:
-                if imgs:
-                    return paths, imgs, info
-                raise StopIteration
-            path = self.files[self.count]
-            try:
-                im0 = imread_device(path, self.device)
-            except ValueError:
-                im0 = None                                             # loaders.py:438-439: warn and move on
-            if im0 is not None:
-                paths.append(path)
-                imgs.append(im0)
-                info.append(f"image {self.count + 1}/{self.nf} {path}: ")
-            self.count += 1
+        while len(imgs) < self.bs and self.count < self.nf:
+            # the next files of the batch, decoded concurrently: the host part of a JPEG decode (file read + Huffman) runs
+            # on the calling thread and releases the GIL, the library keeps one nvJPEG state per in-flight decode
+            chunk = self.files[self.count:self.count + (self.bs - len(imgs))]
+            stream = torch.cuda.current_stream()
+
+            def load(path):
+                with torch.cuda.stream(stream):
+                    try:
+                        return imread_device(path, self.device)
+                    except ValueError:
+                        return None                                    # loaders.py:438-439: warn and move on
+
+            decoded = list(_pool().map(load, chunk)) if len(chunk) > 1 else [load(chunk[0])]
+            for k, (path, im0) in enumerate(zip(chunk, decoded)):
+                if im0 is not None:
+                    paths.append(path)
+                    imgs.append(im0)
+                    info.append(f"image {self.count + k + 1}/{self.nf} {path}: ")
+            self.count += len(chunk)
+        if not imgs:
+            raise StopIteration
         return paths, imgs, info
 
     def __len__(self):
