@@ -6,6 +6,7 @@
 // rest of libspecyolo never depends on it.
 #include <dlfcn.h>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include <nvjpeg.h>
@@ -22,6 +23,7 @@ struct NvJpeg {
     nvjpegJpegState_t state[kStates] = {};
     std::mutex state_mu[kStates];
     nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*CreateEx)(nvjpegBackend_t, nvjpegDevAllocator_t*, nvjpegPinnedAllocator_t*, unsigned int, nvjpegHandle_t*) = nullptr;
     nvjpegStatus_t (*JpegStateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
     nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
     nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t,
@@ -45,7 +47,15 @@ int ensure_nvjpeg() {
     g_nj.GetImageInfo = reinterpret_cast<decltype(g_nj.GetImageInfo)>(dlsym(g_nj.lib, "nvjpegGetImageInfo"));
     g_nj.Decode = reinterpret_cast<decltype(g_nj.Decode)>(dlsym(g_nj.lib, "nvjpegDecode"));
     if (!g_nj.CreateSimple || !g_nj.JpegStateCreate || !g_nj.GetImageInfo || !g_nj.Decode) return g_nj.status = 2;
-    if (g_nj.CreateSimple(&g_nj.handle) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 3;
+    g_nj.CreateEx = reinterpret_cast<decltype(g_nj.CreateEx)>(dlsym(g_nj.lib, "nvjpegCreateEx"));
+    // SPECYOLO_NVJPEG_BACKEND = 1 (hybrid: CPU Huffman) | 2 (GPU-assisted Huffman) | 3 (hardware engine); default: the library's
+    const char* be = std::getenv("SPECYOLO_NVJPEG_BACKEND");
+    if (be && be[0] >= '1' && be[0] <= '3' && g_nj.CreateEx) {
+        if (g_nj.CreateEx(static_cast<nvjpegBackend_t>(be[0] - '0'), nullptr, nullptr, 0, &g_nj.handle) != NVJPEG_STATUS_SUCCESS)
+            return g_nj.status = 3;
+    } else if (g_nj.CreateSimple(&g_nj.handle) != NVJPEG_STATUS_SUCCESS) {
+        return g_nj.status = 3;
+    }
     for (int i = 0; i < NvJpeg::kStates; ++i)
         if (g_nj.JpegStateCreate(g_nj.handle, &g_nj.state[i]) != NVJPEG_STATUS_SUCCESS) return g_nj.status = 4;
     return g_nj.status = 0;
