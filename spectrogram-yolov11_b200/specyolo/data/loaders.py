@@ -70,7 +70,7 @@ def imread_device(path: str, device="cuda") -> torch.Tensor:
 class LoadImagesAndVideos:
     """`for paths, imgs, info in LoadImagesAndVideos(path, batch)`: imgs = list of [H,W,3] uint8 BGR CUDA tensors."""
 
-    def __init__(self, path, batch: int = 1, vid_stride: int = 1, device="cuda"):
+    def __init__(self, path, batch: int = 1, vid_stride: int = 1, device="cuda", rank: int = 0, world: int = 1):
         parent = None
         if isinstance(path, str) and Path(path).suffix == ".txt":      # *.txt with one source per line
             parent = Path(path).parent
@@ -92,6 +92,11 @@ class LoadImagesAndVideos:
         videos = [f for f in files if f.split(".")[-1].lower() in VID_FORMATS]
         if videos:
             raise NotImplementedError("video sources are outside the path specyolo implements (images only)")
+        if world > 1:       # multi-GPU: files are independent, every rank takes a contiguous share, no collective
+            from ..dist import shard_range
+
+            b, e = shard_range(len(images), rank, world)
+            images = images[b:e]
         self.files = images
         self.nf = self.ni = len(images)
         self.video_flag = [False] * self.nf
@@ -100,7 +105,7 @@ class LoadImagesAndVideos:
         self.bs = batch
         self.device = device
         self.count = 0
-        if self.nf == 0:
+        if self.nf == 0 and world == 1:
             raise FileNotFoundError(f"No images found in {path}. Supported formats are: images: {IMG_FORMATS}")
 
     def __iter__(self):

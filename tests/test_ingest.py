@@ -44,6 +44,8 @@ def test_loader_file_discovery(tmp_path):
     ld = LoadImagesAndVideos(str(tmp_path), batch=2)
     assert ld.nf == 5 and len(ld) == 3 and ld.files == sorted(files)           # the .md file is ignored
     assert LoadImagesAndVideos(str(tmp_path / "*.jpg"), batch=4).nf == 2
+    shards = [LoadImagesAndVideos(str(tmp_path), batch=2, rank=r, world=3).files for r in range(3)]       # multi-GPU split
+    assert sum(shards, []) == sorted(files) and [len(x) for x in shards] == [2, 2, 1]
     (tmp_path / "list.txt").write_text("img_1.png\n" + str(tmp_path / "img_0.jpg") + "\n")
     assert LoadImagesAndVideos(str(tmp_path / "list.txt")).nf == 2
     with pytest.raises(FileNotFoundError):
