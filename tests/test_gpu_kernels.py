@@ -69,6 +69,10 @@ CONV_CASES = [
     (32, 48, 5, 1, 1, 1, 1, 19, 21, True, False),       # 5x5, Cout not a multiple of 16... of 32
     (64, 64, 7, 2, 2, 4, 2, 36, 28, True, False),       # grouped, sub-lattice stride 2
     (128, 128, 3, 1, 1, 1, 2, 20, 20, True, True),      # weights too large to stay resident: per-tap kernel
+    # thin tiles (<= 32 columns): paired-task epilogue over super-tiles of 4
+    (16, 32, 3, 1, 1, 1, 3, 19, 21, True, True),        # ragged edges, tile count not a multiple of the super-tile
+    (32, 16, 3, 1, 1, 1, 5, 17, 40, True, False),       # 16 columns: the two warps of a quadrant alternate sub-tiles
+    (32, 32, 3, 1, 1, 1, 7, 40, 24, False, True),       # no activation + shortcut
 ]
 
 
@@ -189,6 +193,27 @@ def test_stem_blocked_pair(lib):
     ref = F.silu(F.conv2d(_bf(got0), _bf(w1), b1, 2, 1))
     assert y.shape == ref.shape == (2, 64, 16, 24)
     assert _rel_err(y, ref) < 6e-3
+
+
+def test_conv_thin_concat_slices(lib):
+    """Thin-tile path with input, output and residual all being channel windows of wider buffers."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(15)
+    B, H, W = 3, 26, 22
+    big_in = torch.randn((B, 96, H, W), generator=gen)
+    big_res = torch.randn((B, 80, H, W), generator=gen)
+    w = torch.randn((32, 32, 3, 3), generator=gen) * 0.08
+    b = torch.randn(32, generator=gen) * 0.1
+    pc = ops.fold_pack(w.to(DEV), b.to(DEV), None, 0.0, 1, 1, 1, 1, True)
+    fin, fres = _fmap(big_in), _fmap(big_res)
+    out_big = ops.new_act(B, 64, H, W, DEV)
+    out_big.zero_()
+    ops.conv2d(fin[:, 32:64], pc, out=out_big[:, 16:48], residual=fres[:, 48:80])
+    ref = F.silu(F.conv2d(_bf(big_in[:, 32:64]), _bf(w), b, 1, 1)) + _bf(big_res[:, 48:80])
+    got = out_big.float().cpu()
+    assert float(got[:, :16].abs().max()) == 0.0 and float(got[:, 48:].abs().max()) == 0.0
+    assert _rel_err(got[:, 16:48], ref) < 6e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 96, 32, 64), (3, 128, 160, 32, 64), (1, 36, 48, 32, 64), (2, 64, 96, 16, 64),
