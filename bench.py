@@ -206,7 +206,7 @@ def stage_roofline(model, x_dev, peaks):
     wrap("nms", None, None)
     # modules bind `ops.<fn>` at call time through the module attribute, so patching ops is enough
     ops.CONCURRENT = False          # time every kernel alone (the graph runs independent branches concurrently)
-    reps = 3
+    reps = 5
     try:
         for _ in range(2):          # warm the eager path (caching allocator: a cudaMalloc would serialise the host)
             model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
@@ -221,14 +221,15 @@ def stage_roofline(model, x_dev, peaks):
         for n, f in orig.items():
             setattr(ops, n, f)
     agg = {}
-    for name, e0, e1, fl, by in rec:                 # per-step averages over `reps` eager passes
+    per = len(rec) // reps                           # every pass issues the same launch sequence
+    for i in range(per):                             # per launch: MEDIAN over the passes (an eager pass now and then
+        name, _, _, fl, by = rec[i]                  # catches one launch behind a host hiccup; the mean let a single
+        ts = sorted(rec[i + r * per][1].elapsed_time(rec[i + r * per][2]) for r in range(reps))   # outlier move the group)
         a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-        a[0] += e0.elapsed_time(e1) * 1e-3 / reps
-        a[1] += fl / reps
-        a[2] += by / reps
+        a[0] += ts[reps // 2] * 1e-3
+        a[1] += fl
+        a[2] += by
         a[3] += 1
-    for a in agg.values():
-        a[3] //= reps
     total = sum(a[0] for a in agg.values())
     stages = {}
     for name, (t, fl, by, n) in agg.items():
