@@ -269,6 +269,11 @@ int specyolo_letterbox_u8(const uint8_t* src_hwc, int B, int H, int W, uint8_t* 
  * specyolo_jpeg_info fills the image size; out must hold H*W*3 bytes.  The decode is asynchronous on `stream`. */
 int specyolo_jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* channels);
 int specyolo_jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, void* stream);
+/* n streams in one nvjpegDecodeBatched call; backend 2 = GPU-assisted Huffman, 3 = hardware engine; out_dev[i] holds
+ * H_i * W[i] * 3 bytes.  Returns SPECYOLO_ERR_UNSUPPORTED when the back end / a stream is not supported (fall back to
+ * specyolo_jpeg_decode_bgr). */
+int specyolo_jpeg_decode_batch_bgr(const void* const* data, const size_t* nbytes, void* const* out_dev, const int* W, int n,
+                                   int backend, void* stream);
 
 /* ---- IQ -> spectrogram -> letterbox (no reference implementation: README.md:7 only) -------- */
 typedef struct {

@@ -45,6 +45,7 @@ int dwpw_launch(const specyolo_dwpw_t*, cudaStream_t);
 bool stem_pair_ok(int, int, int, int, int);
 int jpeg_info(const void*, size_t, int*, int*, int*);
 int jpeg_decode_bgr(const void*, size_t, void*, int, int, cudaStream_t);
+int jpeg_decode_batch_bgr(const void* const*, const size_t*, void* const*, const int*, int, int, cudaStream_t);
 int stem_pair_launch(const specyolo_stem_pair_t*, cudaStream_t);
 int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
@@ -167,6 +168,12 @@ int specyolo_jpeg_info(const void* data, size_t nbytes, int* H, int* W, int* cha
 int specyolo_jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W, void* stream) {
     SY_CHECK(data && nbytes > 4 && out_dev && H > 0 && W > 0, SPECYOLO_ERR_INVALID, "jpeg_decode: bad arguments");
     return jpeg_decode_bgr(data, nbytes, out_dev, H, W, (cudaStream_t)stream);
+}
+
+int specyolo_jpeg_decode_batch_bgr(const void* const* data, const size_t* nbytes, void* const* out_dev, const int* W, int n,
+                                   int backend, void* stream) {
+    SY_CHECK(data && nbytes && out_dev && W && n > 0, SPECYOLO_ERR_INVALID, "jpeg_decode_batch: bad arguments");
+    return jpeg_decode_batch_bgr(data, nbytes, out_dev, W, n, backend, (cudaStream_t)stream);
 }
 
 int specyolo_stem_pair_ok(int H, int W, int c0, int Cout, int n_pad) { return stem_pair_ok(H, W, c0, Cout, n_pad) ? 1 : 0; }

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include <nvjpeg.h>
 
@@ -28,6 +29,14 @@ struct NvJpeg {
     nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
     nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t,
                              nvjpegImage_t*, cudaStream_t) = nullptr;
+    nvjpegStatus_t (*BatchedInit)(nvjpegHandle_t, nvjpegJpegState_t, int, int, nvjpegOutputFormat_t) = nullptr;
+    nvjpegStatus_t (*DecodeBatched)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char* const*, const size_t*, nvjpegImage_t*,
+                                    cudaStream_t) = nullptr;
+    // batched decode (GPU-assisted Huffman or the hardware engine): one handle + state per back end, created on demand
+    nvjpegHandle_t b_handle[4] = {};
+    nvjpegJpegState_t b_state[4] = {};
+    int b_size[4] = {0, 0, 0, 0};
+    std::mutex b_mu;
     std::mutex mu;          // guards initialisation; decodes take one of the per-state mutexes (the Huffman stage of
                             // nvjpegDecode runs on the calling host thread: a loader thread pool scales it with the cores)
     int status = -1;        // -1 not tried, 0 ready, > 0 failed
@@ -48,6 +57,8 @@ int ensure_nvjpeg() {
     g_nj.Decode = reinterpret_cast<decltype(g_nj.Decode)>(dlsym(g_nj.lib, "nvjpegDecode"));
     if (!g_nj.CreateSimple || !g_nj.JpegStateCreate || !g_nj.GetImageInfo || !g_nj.Decode) return g_nj.status = 2;
     g_nj.CreateEx = reinterpret_cast<decltype(g_nj.CreateEx)>(dlsym(g_nj.lib, "nvjpegCreateEx"));
+    g_nj.BatchedInit = reinterpret_cast<decltype(g_nj.BatchedInit)>(dlsym(g_nj.lib, "nvjpegDecodeBatchedInitialize"));
+    g_nj.DecodeBatched = reinterpret_cast<decltype(g_nj.DecodeBatched)>(dlsym(g_nj.lib, "nvjpegDecodeBatched"));
     // SPECYOLO_NVJPEG_BACKEND = 1 (hybrid: CPU Huffman) | 2 (GPU-assisted Huffman) | 3 (hardware engine); default: the library's
     const char* be = std::getenv("SPECYOLO_NVJPEG_BACKEND");
     if (be && be[0] >= '1' && be[0] <= '3' && g_nj.CreateEx) {
@@ -103,6 +114,43 @@ int jpeg_decode_bgr(const void* data, size_t nbytes, void* out_dev, int H, int W
     st = g_nj.Decode(g_nj.handle, g_nj.state[slot], static_cast<const unsigned char*>(data), nbytes, NVJPEG_OUTPUT_BGRI, &dst, stream);
     g_nj.state_mu[slot].unlock();
     SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_CUDA, "nvjpegDecode failed (status %d)", (int)st);
+    return SPECYOLO_OK;
+}
+
+// n JPEG streams in one nvjpegDecodeBatched call on back end 2 (GPU-assisted Huffman) or 3 (hardware engine).
+int jpeg_decode_batch_bgr(const void* const* data, const size_t* nbytes, void* const* out_dev, const int* W, int n, int backend,
+                          cudaStream_t stream) {
+    {
+        std::lock_guard<std::mutex> lk(g_nj.mu);
+        SY_CHECK(ensure_nvjpeg() == 0, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG is not available (dlopen / init step %d)", g_nj.status);
+    }
+    SY_CHECK(backend == 2 || backend == 3, SPECYOLO_ERR_INVALID, "jpeg batch decode: backend must be 2 or 3");
+    SY_CHECK(g_nj.CreateEx && g_nj.BatchedInit && g_nj.DecodeBatched, SPECYOLO_ERR_UNSUPPORTED, "nvJPEG batched API not found");
+    std::lock_guard<std::mutex> lk(g_nj.b_mu);
+    if (!g_nj.b_handle[backend]) {
+        nvjpegHandle_t h = nullptr;
+        nvjpegStatus_t st = g_nj.CreateEx(static_cast<nvjpegBackend_t>(backend), nullptr, nullptr, 0, &h);
+        SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_UNSUPPORTED, "nvjpegCreateEx(backend %d) failed (status %d)", backend, (int)st);
+        nvjpegJpegState_t s2 = nullptr;
+        st = g_nj.JpegStateCreate(h, &s2);
+        SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_CUDA, "nvjpegJpegStateCreate failed (status %d)", (int)st);
+        g_nj.b_handle[backend] = h;
+        g_nj.b_state[backend] = s2;
+    }
+    if (g_nj.b_size[backend] != n) {
+        const nvjpegStatus_t st = g_nj.BatchedInit(g_nj.b_handle[backend], g_nj.b_state[backend], n, 1, NVJPEG_OUTPUT_BGRI);
+        SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_UNSUPPORTED, "nvjpegDecodeBatchedInitialize failed (status %d)", (int)st);
+        g_nj.b_size[backend] = n;
+    }
+    std::vector<nvjpegImage_t> dst((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        dst[i] = nvjpegImage_t{};
+        dst[i].channel[0] = static_cast<unsigned char*>(out_dev[i]);
+        dst[i].pitch[0] = (size_t)W[i] * 3;
+    }
+    const nvjpegStatus_t st = g_nj.DecodeBatched(g_nj.b_handle[backend], g_nj.b_state[backend],
+                                                 reinterpret_cast<const unsigned char* const*>(data), nbytes, dst.data(), stream);
+    SY_CHECK(st == NVJPEG_STATUS_SUCCESS, SPECYOLO_ERR_UNSUPPORTED, "nvjpegDecodeBatched failed (status %d)", (int)st);
     return SPECYOLO_OK;
 }
 

@@ -130,6 +130,8 @@ SIGNATURES = {
                                              C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p]),
     "specyolo_jpeg_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "specyolo_jpeg_decode_bgr": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "specyolo_jpeg_decode_batch_bgr": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
     "specyolo_letterbox_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "specyolo_iq_to_letterbox": (C.c_int, [C.POINTER(StftArgs), C.c_void_p]),
 }

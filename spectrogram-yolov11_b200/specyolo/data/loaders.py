@@ -51,6 +51,28 @@ def decode_jpeg(data: bytes, device="cuda") -> torch.Tensor:
     return out
 
 
+def decode_jpeg_batch(blobs: List[bytes], backend: int = 2, device="cuda") -> List[torch.Tensor]:
+    """n JPEG byte strings -> n [H, W, 3] uint8 BGR CUDA tensors in ONE nvjpegDecodeBatched call (backend 2: GPU-assisted
+    Huffman, 3: hardware engine).  Raises RuntimeError when the back end rejects the batch (callers fall back to decode_jpeg)."""
+    _lib.init_device()
+    lib = _lib.load()
+    n = len(blobs)
+    bufs = [(C.c_char * len(b)).from_buffer_copy(b) for b in blobs]
+    outs, widths = [], []
+    for buf, b in zip(bufs, blobs):
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.specyolo_jpeg_info(C.addressof(buf), len(b), C.byref(h), C.byref(w), C.byref(c)))
+        outs.append(torch.empty((h.value, w.value, 3), dtype=torch.uint8, device=device))
+        widths.append(w.value)
+    data = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+    sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+    dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    ws = (C.c_int * n)(*widths)
+    _lib.check(lib.specyolo_jpeg_decode_batch_bgr(data, sizes, dst, ws, n, int(backend), _lib.stream_ptr()))
+    torch.cuda.current_stream().synchronize()          # the bitstreams (`bufs`) must outlive the decode
+    return outs
+
+
 def imread_device(path: str, device="cuda") -> torch.Tensor:
     """An image file -> [H, W, 3] uint8 BGR CUDA tensor; None-like failure raises (the reference warns and skips)."""
     data = Path(path).read_bytes()
