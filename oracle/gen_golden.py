@@ -327,6 +327,35 @@ def gen_dataset():
     print("dataset batches", len(out))
 
 
+def gen_results():
+    """Egress formats of the REAL reference's Results (verbose / summary / to_json / save_txt) for a fixed detection set."""
+    import json
+    import tempfile
+
+    from ultralytics.engine.results import Results as RefResults
+
+    rng = np.random.default_rng(23)
+    n = 7
+    xy = rng.uniform(5, 300, (n, 2))
+    wh = rng.uniform(8, 120, (n, 2))
+    boxes = np.concatenate([xy, xy + wh, rng.uniform(0.26, 0.97, (n, 1)), rng.integers(0, 2, (n, 1))], 1).astype(np.float32)
+    boxes = boxes[np.argsort(-boxes[:, 4])]
+    names = {0: "wifi", 1: "bluetooth"}
+    cases = {}
+    for tag, b in (("some", boxes), ("none", boxes[:0])):
+        r = RefResults(np.zeros((360, 480, 3), np.uint8), path="x.jpg", names=names, boxes=torch.from_numpy(b))
+        with tempfile.TemporaryDirectory() as td:
+            r.save_txt(f"{td}/a.txt", save_conf=True)
+            r.save_txt(f"{td}/b.txt", save_conf=False)
+            ta = open(f"{td}/a.txt").read() if len(b) else ""
+            tb = open(f"{td}/b.txt").read() if len(b) else ""
+        cases[tag] = {"boxes": b.tolist(), "orig_shape": [360, 480], "verbose": r.verbose(), "summary": r.summary(),
+                      "summary_norm": r.summary(normalize=True, decimals=3), "to_json": r.to_json(), "txt_conf": ta, "txt": tb,
+                      "xywhn": r.boxes.xywhn.tolist(), "xyxyn": r.boxes.xyxyn.tolist()}
+    (GOLD / "results_egress.json").write_text(json.dumps(cases, indent=1))
+    print("results egress", {k: len(v["boxes"]) for k, v in cases.items()})
+
+
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -345,3 +374,5 @@ if __name__ == "__main__":
         gen_ckpt()
     if "dataset" in which:
         gen_dataset()
+    if "results" in which:
+        gen_results()

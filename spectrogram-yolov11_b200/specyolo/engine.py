@@ -44,6 +44,23 @@ class Boxes:
         b = self.xyxy
         return torch.cat(((b[:, :2] + b[:, 2:]) / 2, b[:, 2:] - b[:, :2]), 1)
 
+    @property
+    def xyxyn(self):
+        """Boxes normalised by the original image size (engine/results.py:1185-1206)."""
+        xyxy = self.xyxy.clone() if isinstance(self.xyxy, torch.Tensor) else np.copy(self.xyxy)
+        xyxy[..., [0, 2]] /= self.orig_shape[1]
+        xyxy[..., [1, 3]] /= self.orig_shape[0]
+        return xyxy
+
+    @property
+    def xywhn(self):
+        """(cx, cy, w, h) normalised by the original image size (engine/results.py:1209-1229)."""
+        xywh = self.xywh
+        xywh = xywh.clone() if isinstance(xywh, torch.Tensor) else np.copy(xywh)
+        xywh[..., [0, 2]] /= self.orig_shape[1]
+        xywh[..., [1, 3]] /= self.orig_shape[0]
+        return xywh
+
     def __len__(self):
         return self.data.shape[0]
 
@@ -69,6 +86,56 @@ class Results:
 
     def __len__(self):
         return len(self.boxes)
+
+    # ---- egress formats of the reference (engine/results.py) ------------------------------------
+    def verbose(self) -> str:
+        """'2 wifis, 1 bluetooth, ' (engine/results.py:630-666)."""
+        if len(self) == 0:
+            return "(no detections), "
+        cls = self.boxes.data[:, 5]
+        s = ""
+        for c in torch.unique(cls.cpu()) if isinstance(cls, torch.Tensor) else np.unique(cls):
+            n = int((cls == c).sum())
+            s += f"{n} {self.names[int(c)]}{'s' * (n > 1)}, "
+        return s
+
+    def summary(self, normalize: bool = False, decimals: int = 5) -> list:
+        """[{name, class, confidence, box{x1,y1,x2,y2}}] (engine/results.py:759-824)."""
+        d = self.boxes.data
+        d = d.cpu() if isinstance(d, torch.Tensor) else torch.from_numpy(np.asarray(d))
+        h, w = self.orig_shape if normalize else (1, 1)
+        out = []
+        for row in d:
+            class_id, conf = int(row[5]), round(row[4].item(), decimals)
+            box = row[:4].reshape(-1, 2).tolist()
+            xy = {}
+            for j, b in enumerate(box):
+                xy[f"x{j + 1}"] = round(b[0] / w, decimals)
+                xy[f"y{j + 1}"] = round(b[1] / h, decimals)
+            out.append({"name": self.names[class_id], "class": class_id, "confidence": conf, "box": xy})
+        return out
+
+    def to_json(self, normalize: bool = False, decimals: int = 5) -> str:
+        """engine/results.py:907-944."""
+        import json
+
+        return json.dumps(self.summary(normalize=normalize, decimals=decimals), indent=2)
+
+    tojson = to_json
+
+    def save_txt(self, txt_file, save_conf: bool = False):
+        """YOLO label lines `cls cx cy w h [conf]`, normalised, appended to txt_file (engine/results.py:669-722)."""
+        d = self.boxes.data
+        d = d.cpu() if isinstance(d, torch.Tensor) else torch.from_numpy(np.asarray(d))
+        nb = Boxes(d, self.orig_shape)
+        texts = []
+        for row, xywhn in zip(d, nb.xywhn):
+            line = (int(row[5]), *xywhn.view(-1)) + ((float(row[4]),) if save_conf else ())
+            texts.append(("%g " * len(line)).rstrip() % line)
+        if texts:
+            Path(txt_file).parent.mkdir(parents=True, exist_ok=True)
+            with open(txt_file, "a") as f:
+                f.writelines(t + "\n" for t in texts)
 
 
 class _GraphStep:
