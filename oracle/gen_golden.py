@@ -350,7 +350,8 @@ def gen_results():
             ta = open(f"{td}/a.txt").read() if len(b) else ""
             tb = open(f"{td}/b.txt").read() if len(b) else ""
         cases[tag] = {"boxes": b.tolist(), "orig_shape": [360, 480], "verbose": r.verbose(), "summary": r.summary(),
-                      "summary_norm": r.summary(normalize=True, decimals=3), "to_json": r.to_json(), "txt_conf": ta, "txt": tb,
+                      "summary_norm": r.summary(normalize=True, decimals=3), "to_json": r.to_json(), "to_csv": r.to_csv(),
+                      "txt_conf": ta, "txt": tb,
                       "xywhn": r.boxes.xywhn.tolist(), "xyxyn": r.boxes.xyxyn.tolist()}
     (GOLD / "results_egress.json").write_text(json.dumps(cases, indent=1))
     print("results egress", {k: len(v["boxes"]) for k, v in cases.items()})

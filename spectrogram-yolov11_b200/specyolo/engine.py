@@ -123,6 +123,16 @@ class Results:
 
     tojson = to_json
 
+    def to_df(self, normalize: bool = False, decimals: int = 5):
+        """engine/results.py:826-849."""
+        import pandas as pd
+
+        return pd.DataFrame(self.summary(normalize=normalize, decimals=decimals))
+
+    def to_csv(self, normalize: bool = False, decimals: int = 5, *args, **kwargs):
+        """engine/results.py:851-877."""
+        return self.to_df(normalize=normalize, decimals=decimals).to_csv(*args, **kwargs)
+
     def save_txt(self, txt_file, save_conf: bool = False):
         """YOLO label lines `cls cx cy w h [conf]`, normalised, appended to txt_file (engine/results.py:669-722)."""
         d = self.boxes.data

@@ -24,6 +24,7 @@ def test_egress_formats_match_reference(tag, tmp_path):
     assert r.summary() == c["summary"]
     assert r.summary(normalize=True, decimals=3) == c["summary_norm"]
     assert r.to_json() == c["to_json"] and r.tojson() == c["to_json"]
+    assert r.to_csv() == c["to_csv"]
     r.save_txt(tmp_path / "sub" / "a.txt", save_conf=True)
     r.save_txt(tmp_path / "sub" / "b.txt", save_conf=False)
     if len(boxes):
