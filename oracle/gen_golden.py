@@ -291,6 +291,9 @@ def gen_dataset():
 
     ns = types.SimpleNamespace(device="cpu", iouv=torch.linspace(0.5, 0.95, 10), niou=10)
     ns.match_predictions = functools.partial(BaseValidator.match_predictions, ns)
+    from ultralytics.utils.metrics import ConfusionMatrix as RefCM
+
+    cm = RefCM(nc=2, conf=0.001, iou_thres=0.45)         # conf 0.001 -> 0.25 inside, as the validator constructs it
     rng = np.random.default_rng(17)
     cfg = get_cfg(overrides=dict(imgsz=96, task="detect", rect=True, workers=0))
     ds = build_yolo_dataset(cfg, data["val"], 3, data, mode="val", stride=32)
@@ -319,8 +322,12 @@ def gen_dataset():
             tp = RefVal._process_batch(ns, predn, pb["bbox"], pb["cls"]) if len(pb["cls"]) else torch.zeros((len(rows), 10), dtype=torch.bool)
             out[f"match_b{bi}_tp{si}"] = tp.numpy()
             out[f"match_b{bi}_predn{si}"] = predn.numpy()
+            out[f"match_b{bi}_gt{si}"] = torch.cat((pb["cls"].reshape(-1, 1).float(), pb["bbox"].reshape(-1, 4).float()), 1).numpy()
+            cm.process_batch(predn, pb["bbox"], pb["cls"])
         out[f"match_b{bi}_preds"] = preds
         out[f"match_b{bi}_cnt"] = cnts
+    out["confusion_matrix"] = cm.matrix
+    out["confusion_tp"], out["confusion_fp"] = cm.tp_fp()
     for c in (root / "labels").glob("*.cache"):
         c.unlink()                                     # the reference caches the label scan next to the labels
     np.savez_compressed(GOLD / "tiny_dataset_batches.npz", **out)

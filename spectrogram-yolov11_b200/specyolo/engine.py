@@ -463,6 +463,11 @@ class DetectionValidator:
         self.iouv = [0.5 + 0.05 * i for i in range(10)]            # val.py:72
         self.stats = dict(tp=[], conf=[], pred_cls=[], target_cls=[])
         self.seen = 0
+        self.confusion_matrix = None                               # val.py:77 / :166: filled when plots=True
+        if self.args.get("plots"):
+            from .utils.metrics import ConfusionMatrix
+
+            self.confusion_matrix = ConfusionMatrix(nc=len(model.names), conf=self.args["conf"])
 
     @torch.no_grad()
     def update(self, batch: dict):
@@ -523,6 +528,9 @@ class DetectionValidator:
             self.stats["conf"].append(out_h[b, :n, 4].numpy())
             self.stats["pred_cls"].append(out_h[b, :n, 5].numpy())
             self.stats["target_cls"].append(cls[off[b]:off[b + 1]].numpy())
+            if self.confusion_matrix is not None:
+                lb = labels[off[b]:off[b + 1]].numpy()
+                self.confusion_matrix.process_batch(out_h[b, :n].numpy() if n else None, lb[:, 1:], lb[:, 0])
 
     def results(self) -> dict:
         from .utils.metrics import results_dict
@@ -646,7 +654,8 @@ class YOLO:
                    "single_cls": kwargs.get("single_cls", False), "classes": kwargs.pop("classes", None)}
             data = build_yolo_dataset(cfg, d[split], int(kwargs.pop("batch", 16)), d, mode="val",
                                       stride=max(int(self.model.stride.max()), 32))
-        return (validator or DetectionValidator)(self.model, kwargs)(data)
+        self.validator = (validator or DetectionValidator)(self.model, kwargs)     # kept: .confusion_matrix, .stats
+        return self.validator(data)
 
     def predict_iq(self, iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0,
                    db_max: float = 0.0, **kwargs) -> List[Results]:

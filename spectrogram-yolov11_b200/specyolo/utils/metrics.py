@@ -70,3 +70,71 @@ def results_dict(tp, conf, pred_cls, target_cls) -> Dict[str, float]:
     mp, mr, map50, map_ = float(p.mean()), float(r.mean()), float(ap[:, 0].mean()), float(ap.mean())
     return {keys[0]: mp, keys[1]: mr, keys[2]: map50, keys[3]: map_,
             "fitness": float(np.dot([0.0, 0.0, 0.1, 0.9], [mp, mr, map50, map_]))}
+
+
+def box_iou(box1: np.ndarray, box2: np.ndarray, eps: float = 1e-7) -> np.ndarray:
+    """[N,4] x [M,4] xyxy -> [N,M] IoU in float32, the operation order of ultralytics/utils/metrics.py:52-71."""
+    b1, b2 = np.asarray(box1, np.float32), np.asarray(box2, np.float32)
+    a1, a2 = b1[:, None, :2], b1[:, None, 2:]
+    c1, c2 = b2[None, :, :2], b2[None, :, 2:]
+    inter = np.clip(np.minimum(a2, c2) - np.maximum(a1, c1), 0, None).prod(2)
+    return inter / ((a2 - a1).prod(2) + (c2 - c1).prod(2) - inter + np.float32(eps))
+
+
+class ConfusionMatrix:
+    """Detection confusion matrix (ultralytics/utils/metrics.py:394-493, without the plot): rows = predicted class, columns =
+    true class, index nc = background.  Host-side numpy like the reference (a few hundred boxes per image)."""
+
+    def __init__(self, nc: int, conf: float = 0.25, iou_thres: float = 0.45, task: str = "detect"):
+        if task != "detect":
+            raise NotImplementedError("specyolo implements the detect task only")
+        self.task = task
+        self.matrix = np.zeros((nc + 1, nc + 1))
+        self.nc = nc
+        self.conf = 0.25 if conf in {None, 0.001} else conf          # default val conf -> 0.25 (metrics.py:411)
+        self.iou_thres = iou_thres
+
+    def process_batch(self, detections, gt_bboxes, gt_cls):
+        """detections [N,6] (x1,y1,x2,y2,conf,cls) | None, gt_bboxes [M,4] xyxy, gt_cls [M] (metrics.py:426-482)."""
+        gt_cls = np.asarray(gt_cls).reshape(-1)
+        if gt_cls.shape[0] == 0:
+            if detections is not None:
+                detections = np.asarray(detections, np.float32)
+                for dc in detections[detections[:, 4] > self.conf][:, 5].astype(int):
+                    self.matrix[dc, self.nc] += 1            # false positives
+            return
+        if detections is None:
+            for gc in gt_cls.astype(int):
+                self.matrix[self.nc, gc] += 1                # background FN
+            return
+        detections = np.asarray(detections, np.float32)
+        detections = detections[detections[:, 4] > self.conf]
+        gt_classes = gt_cls.astype(int)
+        detection_classes = detections[:, 5].astype(int)
+        iou = box_iou(np.asarray(gt_bboxes, np.float32).reshape(-1, 4), detections[:, :4])
+        x = np.nonzero(iou > self.iou_thres)
+        if x[0].shape[0]:
+            matches = np.concatenate((np.stack(x, 1).astype(np.float32), iou[x[0], x[1]][:, None]), 1)
+            if x[0].shape[0] > 1:
+                matches = matches[matches[:, 2].argsort()[::-1]]
+                matches = matches[np.unique(matches[:, 1], return_index=True)[1]]
+                matches = matches[matches[:, 2].argsort()[::-1]]
+                matches = matches[np.unique(matches[:, 0], return_index=True)[1]]
+        else:
+            matches = np.zeros((0, 3))
+        n = matches.shape[0] > 0
+        m0, m1, _ = matches.transpose().astype(int)
+        for i, gc in enumerate(gt_classes):
+            j = m0 == i
+            if n and j.sum() == 1:
+                self.matrix[detection_classes[m1[j]], gc] += 1   # correct
+            else:
+                self.matrix[self.nc, gc] += 1                    # true background
+        for i, dc in enumerate(detection_classes):
+            if not (m1 == i).any():
+                self.matrix[dc, self.nc] += 1                    # predicted background
+
+    def tp_fp(self):
+        tp = self.matrix.diagonal()
+        fp = self.matrix.sum(1) - tp
+        return tp[:-1], fp[:-1]

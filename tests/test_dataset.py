@@ -104,14 +104,14 @@ def test_validator_matching_in_original_coordinates():
 
     exp = np.load(EXP)
     model = specyolo.DetectionModel("yolo11n.yaml", nc=2).to("cuda")          # only its device is used here
+    v = DetectionValidator(model, {"plots": True})          # plots=True: the confusion matrix is accumulated as well
+    k = 0
     for bi, batch in enumerate(_dataset(True)):
-        v = DetectionValidator(model)
         preds = torch.from_numpy(exp[f"match_b{bi}_preds"]).cuda()
         cnt = torch.from_numpy(exp[f"match_b{bi}_cnt"]).cuda()
         B, _, H, W = batch["img"].shape
         out = preds.clone()
         v.match(out, cnt, batch, H, W)
-        k = 0
         for si in range(B):
             n = int(cnt[si])
             want_tp, want_box = exp[f"match_b{bi}_tp{si}"], exp[f"match_b{bi}_predn{si}"]
@@ -120,3 +120,4 @@ def test_validator_matching_in_original_coordinates():
             k += 1
             assert got_tp.shape == want_tp.shape and np.array_equal(got_tp, want_tp), (bi, si)
     assert any(exp[f"match_b{b}_tp{s}"].any() for b in range(3) for s in range(int(exp[f"match_b{b}_cnt"].shape[0])))
+    assert np.array_equal(v.confusion_matrix.matrix, exp["confusion_matrix"])

@@ -122,3 +122,33 @@ def test_val_end_to_end(lib):
     bad = dict(batch, bboxes=batch["bboxes"].flip(0).clone() * 0.37)
     m2 = yolo.val(data=[bad])
     assert m2["metrics/mAP50-95(B)"] < 0.3 * m["metrics/mAP50-95(B)"] + 0.05, (m, m2)
+
+
+def test_confusion_matrix_matches_reference():
+    """ConfusionMatrix.process_batch / tp_fp on the crafted detections of the tiny dataset == the REAL reference's matrix
+    (tests/golden/tiny_dataset_batches.npz: inputs and result written by oracle/gen_golden.py dataset)."""
+    import sys
+    from pathlib import Path
+
+    import numpy as np
+
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "spectrogram-yolov11_b200"))
+    from specyolo.utils.metrics import ConfusionMatrix, box_iou
+
+    exp = np.load(root / "tests" / "golden" / "tiny_dataset_batches.npz")
+    cm = ConfusionMatrix(nc=2, conf=0.001, iou_thres=0.45)
+    assert cm.conf == 0.25
+    for bi in range(3):
+        for si in range(int(exp[f"match_b{bi}_cnt"].shape[0])):
+            gt = exp[f"match_b{bi}_gt{si}"]
+            cm.process_batch(exp[f"match_b{bi}_predn{si}"], gt[:, 1:], gt[:, 0])
+    assert np.array_equal(cm.matrix, exp["confusion_matrix"])
+    tp, fp = cm.tp_fp()
+    assert np.array_equal(tp, exp["confusion_tp"]) and np.array_equal(fp, exp["confusion_fp"])
+    # degenerate inputs (metrics.py:437-448)
+    cm2 = ConfusionMatrix(nc=2)
+    cm2.process_batch(None, np.zeros((2, 4), np.float32), np.array([0.0, 1.0]))
+    cm2.process_batch(np.array([[0, 0, 5, 5, 0.9, 1], [0, 0, 5, 5, 0.1, 0]], np.float32), np.zeros((0, 4), np.float32), np.zeros(0))
+    assert cm2.matrix.tolist() == [[0, 0, 0], [0, 0, 1], [1, 1, 0]]
+    assert abs(float(box_iou(np.array([[0, 0, 2, 2]]), np.array([[1, 1, 3, 3]]))[0, 0]) - 1 / 7) < 1e-6
