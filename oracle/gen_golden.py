@@ -181,6 +181,14 @@ def gen_metrics():
     r = ap_per_class(tp, conf, pcls, tcls)
     out.update({"ap_tp": tp, "ap_conf": conf, "ap_pcls": pcls, "ap_tcls": tcls, "ap_tpc": r[0], "ap_fpc": r[1], "ap_p": r[2],
                 "ap_r": r[3], "ap_f1": r[4], "ap_ap": r[5], "ap_classes": r[6]})
+    # DetMetrics on the same pooled run: what validator.metrics reports (names for all 5 classes)
+    from ultralytics.utils.metrics import DetMetrics
+
+    dm = DetMetrics(names={i: f"c{i}" for i in range(nc)})
+    dm.process(tp, conf, pcls, tcls)
+    out.update({"dm_mean": np.asarray(dm.mean_results()), "dm_maps": dm.maps, "dm_fitness": np.float64(dm.fitness),
+                "dm_class2": np.asarray(dm.class_result(2)), "dm_index": np.asarray(dm.ap_class_index),
+                "dm_map75": np.float64(dm.box.map75), "dm_results": np.asarray(list(dm.results_dict.values()))})
     np.savez_compressed(GOLD / "metrics.npz", **out)
     print("ap_per_class mAP50", float(r[5][:, 0].mean()), "mAP", float(r[5].mean()))
 

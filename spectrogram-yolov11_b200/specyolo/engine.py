@@ -533,12 +533,16 @@ class DetectionValidator:
                 self.confusion_matrix.process_batch(out_h[b, :n].numpy() if n else None, lb[:, 1:], lb[:, 0])
 
     def results(self) -> dict:
-        from .utils.metrics import results_dict
+        """`metrics.results_dict` of the reference; the full `DetMetrics` mirror stays on `self.metrics`
+        (`.box.maps`, `.class_result(i)`, `.ap_class_index`, ... : val.py:195-211, utils/metrics.py:898-965)."""
+        from .utils.metrics import DetMetrics
 
-        if not self.stats["tp"]:
-            return results_dict(np.zeros((0, 10), bool), np.zeros(0), np.zeros(0), np.zeros(0))
-        st = {k: np.concatenate(v, 0) for k, v in self.stats.items()}
-        return results_dict(st["tp"], st["conf"], st["pred_cls"], st["target_cls"])
+        self.metrics = DetMetrics(names=self.model.names)
+        if self.stats["tp"]:
+            st = {k: np.concatenate(v, 0) for k, v in self.stats.items()}
+            if len(st["tp"]) and st["tp"].any():
+                self.metrics.process(st["tp"], st["conf"], st["pred_cls"], st["target_cls"])
+        return {k: float(v) for k, v in self.metrics.results_dict.items()}
 
     def __call__(self, batches) -> dict:
         for batch in batches:

@@ -138,3 +138,100 @@ class ConfusionMatrix:
         tp = self.matrix.diagonal()
         fp = self.matrix.sum(1) - tp
         return tp[:-1], fp[:-1]
+
+
+class Metric:
+    """Per-class and mean detection metrics (ultralytics/utils/metrics.py:726-873), plots / curves left out."""
+
+    def __init__(self):
+        self.p, self.r, self.f1, self.all_ap, self.ap_class_index = [], [], [], [], []
+        self.nc = 0
+
+    @property
+    def ap50(self):
+        return self.all_ap[:, 0] if len(self.all_ap) else []
+
+    @property
+    def ap(self):
+        return self.all_ap.mean(1) if len(self.all_ap) else []
+
+    @property
+    def mp(self):
+        return self.p.mean() if len(self.p) else 0.0
+
+    @property
+    def mr(self):
+        return self.r.mean() if len(self.r) else 0.0
+
+    @property
+    def map50(self):
+        return self.all_ap[:, 0].mean() if len(self.all_ap) else 0.0
+
+    @property
+    def map75(self):
+        return self.all_ap[:, 5].mean() if len(self.all_ap) else 0.0
+
+    @property
+    def map(self):
+        return self.all_ap.mean() if len(self.all_ap) else 0.0
+
+    def mean_results(self):
+        return [self.mp, self.mr, self.map50, self.map]
+
+    def class_result(self, i):
+        return self.p[i], self.r[i], self.ap50[i], self.ap[i]
+
+    @property
+    def maps(self):
+        maps = np.zeros(self.nc) + self.map
+        for i, c in enumerate(self.ap_class_index):
+            maps[c] = self.ap[i]
+        return maps
+
+    def fitness(self):
+        w = [0.0, 0.0, 0.1, 0.9]
+        return (np.array(self.mean_results()) * w).sum()
+
+    def update(self, results):
+        self.p, self.r, self.f1, self.all_ap, self.ap_class_index = results
+
+
+class DetMetrics:
+    """`validator.metrics` of the reference (ultralytics/utils/metrics.py:898-965) without the plots."""
+
+    def __init__(self, names=None):
+        self.names = names or {}
+        self.box = Metric()
+        self.speed = {"preprocess": 0.0, "inference": 0.0, "loss": 0.0, "postprocess": 0.0}
+        self.task = "detect"
+
+    def process(self, tp, conf, pred_cls, target_cls):
+        _, _, p, r, f1, ap, classes = ap_per_class(tp, conf, pred_cls, target_cls)
+        self.box.nc = len(self.names)
+        self.box.update((p, r, f1, ap, classes))
+
+    @property
+    def keys(self):
+        return ["metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)"]
+
+    def mean_results(self):
+        return self.box.mean_results()
+
+    def class_result(self, i):
+        return self.box.class_result(i)
+
+    @property
+    def maps(self):
+        return self.box.maps
+
+    @property
+    def fitness(self):
+        return self.box.fitness()
+
+    @property
+    def ap_class_index(self):
+        return self.box.ap_class_index
+
+    @property
+    def results_dict(self):
+        return dict(zip(self.keys + ["fitness"], self.mean_results() + [self.fitness]))

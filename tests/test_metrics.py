@@ -152,3 +152,27 @@ def test_confusion_matrix_matches_reference():
     cm2.process_batch(np.array([[0, 0, 5, 5, 0.9, 1], [0, 0, 5, 5, 0.1, 0]], np.float32), np.zeros((0, 4), np.float32), np.zeros(0))
     assert cm2.matrix.tolist() == [[0, 0, 0], [0, 0, 1], [1, 1, 0]]
     assert abs(float(box_iou(np.array([[0, 0, 2, 2]]), np.array([[1, 1, 3, 3]]))[0, 0]) - 1 / 7) < 1e-6
+
+
+def test_detmetrics_matches_reference():
+    """DetMetrics / Metric (mean_results, maps, class_result, fitness, map75, results_dict) vs the real reference's."""
+    import sys
+    from pathlib import Path
+
+    import numpy as np
+
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "spectrogram-yolov11_b200"))
+    from specyolo.utils.metrics import DetMetrics
+
+    g = np.load(root / "tests" / "golden" / "metrics.npz")
+    dm = DetMetrics(names={i: f"c{i}" for i in range(5)})
+    assert dm.mean_results() == [0.0, 0.0, 0.0, 0.0] and dm.results_dict["fitness"] == 0.0      # before any data
+    dm.process(g["ap_tp"], g["ap_conf"], g["ap_pcls"], g["ap_tcls"])
+    assert np.allclose(np.asarray(dm.mean_results()), g["dm_mean"], rtol=0, atol=1e-9)
+    assert np.allclose(dm.maps, g["dm_maps"], rtol=0, atol=1e-9) and dm.maps.shape == (5,)
+    assert np.allclose(np.asarray(dm.class_result(2)), g["dm_class2"], rtol=0, atol=1e-9)
+    assert np.array_equal(np.asarray(dm.ap_class_index), g["dm_index"])
+    assert abs(float(dm.fitness) - float(g["dm_fitness"])) < 1e-9 and abs(float(dm.box.map75) - float(g["dm_map75"])) < 1e-9
+    assert list(dm.results_dict) == ["metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)", "fitness"]
+    assert np.allclose(np.asarray(list(dm.results_dict.values())), g["dm_results"], rtol=0, atol=1e-9)
