@@ -93,29 +93,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's predict path
+# CPU arm: the reference's own predict path on the host cores (oracle/_ref = the unmodified reference installed by
+# oracle/Makefile), or — where that directory did not travel — the oracle port with BN folded as the reference's
+# predict path does (nn/autobackend.py:152)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_images_per_s(batch: int, repeats: int, warmup: int, seed: int = 0):
-    import numpy as np
+def _reference_yolo(sd):
+    """The REAL reference `YOLO` object carrying the synthetic weights, or None when oracle/_ref is absent."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        return None
+    ultralytics = ref_loader.import_reference()
+    from ultralytics.nn.tasks import DetectionModel as RefModel
+
+    cfg = Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG
+    m = RefModel(str(cfg), nc=NC, verbose=False)
+    m.load_state_dict(sd, strict=True)
+    y = ultralytics.YOLO(str(cfg), task="detect")
+    y.model = m.eval()
+    return y
+
+
+def cpu_reference_images_per_s(batch: int, repeats: int, warmup: int, seed: int = 0):
+    """(images/s, threads, per-step times, kind): `YOLO(cfg).predict(x, device='cpu')` of the real reference when
+    oracle/_ref is present (kind "reference"), else the oracle port (kind "port")."""
     import torch
     import yaml
 
     import specyolo
-    from oracle import nms_ref, yolo_ref
     from specyolo.nn.init import synth_images, synth_state_dict
 
     threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     m = specyolo.DetectionModel(CFG, nc=NC)           # parameter shapes only (CPU tensors, never run)
     sd = synth_state_dict(m, seed=seed)
-    graph = yolo_ref.parse_graph(yaml.safe_load((PKG / "specyolo" / "cfg" / CFG_FILE).read_text()), "s", NC)
     x = synth_images(batch, IMGSZ, seed=seed, dtype=torch.uint8)
+    ref = _reference_yolo(sd)
+    if ref is not None:
+        kind = "reference"
+        xf = x.float() / 255                          # what LoadTensor hands to preprocess for a tensor source
 
-    def step():
-        with torch.no_grad():
-            im = x.float() / 255                      # predictor.py:133-135
-            y, _ = yolo_ref.forward(graph, sd, im)
-        return nms_ref.non_max_suppression(y.numpy(), CONF, IOU, max_det=MAX_DET)
+        def step():
+            return ref.predict(xf, device="cpu", conf=CONF, iou=IOU, max_det=MAX_DET, verbose=False)
+
+        step()                                        # builds the predictor (select_device caps torch threads at min(8, n-1))
+        torch.set_num_threads(threads)                # ... lift that cap: the arm gets every host thread
+    else:
+        kind = "port"
+        from oracle import nms_ref, yolo_ref
+
+        torch.set_num_threads(threads)
+        graph = yolo_ref.parse_graph(yaml.safe_load((PKG / "specyolo" / "cfg" / CFG_FILE).read_text()), "s", NC)
+        R = yolo_ref.Ref(sd, fuse=True)               # BN folded once, as AutoBackend does before predict
+
+        def step():
+            with torch.no_grad():
+                y, _ = yolo_ref.forward(graph, R, x.float() / 255)
+            return nms_ref.non_max_suppression(y.numpy(), CONF, IOU, max_det=MAX_DET)
 
     for _ in range(warmup):
         step()
@@ -124,21 +157,24 @@ def cpu_port_images_per_s(batch: int, repeats: int, warmup: int, seed: int = 0):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), threads, times
+    return batch * len(times) / sum(times), threads, times, kind
 
 
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
-    ips, threads, times = cpu_port_images_per_s(args.cpu_batch, args.steps, args.warmup)
+    ips, threads, times, kind = cpu_reference_images_per_s(args.cpu_batch, args.steps, args.warmup)
     sample = f"{args.cpu_batch} synthetic 640^2 uint8 images per step, {args.steps} timed steps"
+    path = ("the unmodified reference (oracle/_ref): ultralytics.YOLO(cfg).predict(x, device='cpu'), fp32, BN fused, "
+            "torchvision NMS, all host threads" if kind == "reference" else
+            "oracle port of the reference CPU predict path (PyTorch CPU fp32, BN folded, numpy NMS)")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "spectrogram-yolov11-s nc=2 640^2 predict (fwd + NMS)", "cpu_batch": args.cpu_batch,
-                   "path": "oracle port of the reference CPU predict path (PyTorch CPU fp32 + numpy NMS)"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+                   "path": path},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -148,114 +184,47 @@ def run_reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
-def stage_roofline(model, x_dev, peaks):
-    """One eager (un-graphed) step with CUDA events around every libspecyolo call; a device-side sleep is
-    queued first so the host runs ahead and the events see kernel time only."""
-    import torch
+def graph_roofline(fn, peaks, kernel_desc: str):
+    """`roofline` + `stages` of one captured step from IN-GRAPH kernel durations (specyolo/utils/kprof.py: the step's
+    graph on one stream without PDL, CUPTI activity records over 5 replays, per-launch median).  `serial_ms` is the step
+    time of that same execution, so the group's kernel time is <= it by construction."""
+    from specyolo.utils import kprof
 
-    from specyolo import ops
-
-    rec = []
-    orig = {}
-    ridge = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)      # flop per byte
-
-    def wrap(name, flops_fn=None, bytes_fn=None):
-        f = getattr(ops, name)
-        orig[name] = f
-
-        def g(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = f(*a, **k)
-            e1.record()
-            nm = name
-            fl = flops_fn(*a, **k) if flops_fn else 0.0
-            by = bytes_fn(r, *a, **k) if bytes_fn else 0.0
-            if name in ("conv2d", "dwconv_pwconv", "stem_pair"):     # class by arithmetic intensity against the ridge of the measured peaks
-                nm = "conv2d_tensor_bound" if fl / max(by, 1.0) >= ridge else "conv2d_hbm_bound"
-            rec.append((nm, e0, e1, fl, by))
-            return r
-        setattr(ops, name, g)
-
-    def conv_flops(x, pc, *a, **k):
-        B, _, H, W = x.shape
-        Ho, Wo = pc.out_hw(H, W)
-        kk = pc.alg_k or (pc.cin // pc.g_orig) * pc.k * pc.k                       # algorithmic (source groups, no padding)
-        return 2.0 * B * Ho * Wo * pc.cout * kk
-
-    def conv_bytes(r, x, pc, *a, **k):
-        B, Cin, H, W = x.shape
-        return 2.0 * (B * Cin * H * W + r.numel()) + 2.0 * pc.w.numel()
-
-    def dwpw_flops(x, dw_w, dw_b, pw, *a, **k):
-        B, Cc, H, W = x.shape
-        return 2.0 * B * H * W * Cc * (9 + pw.cout)           # depthwise 3x3 + pointwise 1x1
-
-    def stem_pair_flops(x, pc0, pc1b, *a, **k):      # layer 0 (K = 27) at H/2 x W/2 + layer 1 (K = 9 c0) at H/4 x W/4
-        B, _, H, W = x.shape
-        return 2.0 * B * ((H // 2) * (W // 2) * pc0.cout * 27 + (H // 4) * (W // 4) * pc1b.cout * 9 * pc0.cout)
-
-    wrap("conv2d", conv_flops, conv_bytes)
-    wrap("stem_pair", stem_pair_flops, lambda r, x, pc0, pc1b, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel() + 2.0 * pc1b.w.numel())
-    wrap("dwconv_pwconv", dwpw_flops, lambda r, x, *a, **k: 2.0 * (x.numel() + r.numel()))
-    wrap("stem_space_to_depth", None, lambda r, x, *a, **k: x.numel() * x.element_size() + 2.0 * r.numel())
-    wrap("sppf_pool", None, lambda r, buf, c: 2.0 * buf.numel())
-    wrap("fusion_eschannel", None, lambda r, xs, *a, **k: 2.0 * (2 * sum(t.numel() for t in xs) + r.numel()))
-    wrap("psa_attention", None, lambda r, qkv, *a, **k: 2.0 * (qkv.numel() + r.numel()))
-    wrap("detect_decode", None, lambda r, logits, *a, **k: 4.0 * sum(t.numel() for t in logits))
-    wrap("nms", None, None)
-    # modules bind `ops.<fn>` at call time through the module attribute, so patching ops is enough
-    ops.CONCURRENT = False          # time every kernel alone (the graph runs independent branches concurrently)
-    reps = 5
-    try:
-        for _ in range(2):          # warm the eager path (caching allocator: a cudaMalloc would serialise the host)
-            model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
-        rec.clear()
-        for _ in range(reps):
-            torch.cuda.synchronize()
-            torch.cuda._sleep(int(4e8))
-            model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
-        torch.cuda.synchronize()
-    finally:
-        ops.CONCURRENT = True
-        for n, f in orig.items():
-            setattr(ops, n, f)
-    agg = {}
-    per = len(rec) // reps                           # every pass issues the same launch sequence
-    for i in range(per):                             # per launch: MEDIAN over the passes (an eager pass now and then
-        name, _, _, fl, by = rec[i]                  # catches one launch behind a host hiccup; the mean let a single
-        ts = sorted(rec[i + r * per][1].elapsed_time(rec[i + r * per][2]) for r in range(reps))   # outlier move the group)
-        a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-        a[0] += ts[reps // 2] * 1e-3
-        a[1] += fl
-        a[2] += by
-        a[3] += 1
-    total = sum(a[0] for a in agg.values())
-    stages = {}
-    for name, (t, fl, by, n) in agg.items():
-        s = {"launches": n, "ms": 1e3 * t, "share": t / total if total else None}
-        if fl:
-            s.update(tflops=fl / t / 1e12, frac_tensor=fl / t / 1e12 / peaks["tf_sust"])
-        if by:
-            s.update(gbs=by / t / 1e9, frac_hbm=by / t / 1e9 / peaks["hbm"])
-        stages[name] = s
-    c = [sum(agg[n][j] for n in agg if n.startswith("conv2d")) for j in range(4)]
+    prof = kprof.profile_graph(fn)
+    c, stages, total = kprof.summarise(prof, peaks)
     traffic = None
     tf = ROOT / "profiles" / "conv_dram_traffic.json"      # written from an ncu capture by tools/ncu_traffic.py
     if tf.is_file():
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
-    # 61 of the 86 conv launches (54 % of the conv time) sit below the ridge point of the measured peaks, i.e. are
-    # HBM-bound at bf16: the headline roofline of the group is therefore the bandwidth one; the tensor-pipe view of the
-    # same launches is reported beside it, and `stages` splits the launches at the ridge.
     gbs = c[2] / c[0] / 1e9
     tfs = c[1] / c[0] / 1e12
-    roof = {"bound": "hbm", "kernel": "conv_igemm_kernel + conv_halo_kernel + dwpw_kernel + stem_pair_kernel: every tcgen05 implicit-GEMM conv launch of one step "
-                                       "(most layers are below the ridge point, i.e. HBM-bound; stages.conv2d_tensor_bound / conv2d_hbm_bound split them)",
+    # most conv launches (and most of their time) sit below the ridge point of the measured peaks, i.e. are HBM-bound at
+    # bf16: the headline roofline of the group is the bandwidth one, the tensor-pipe view of the same launches is
+    # reported beside it, and `stages` splits the launches at the ridge.
+    roof = {"bound": "hbm", "kernel": kernel_desc,
             "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-            "traffic": traffic, "algorithmic_bytes_per_step": c[2], "peak_source": peaks["src"] + " (HBM copy bandwidth; bf16 sustained for the tensor view)",
-            "flops_per_step": c[1], "ms_per_step": 1e3 * c[0], "launches_per_step": c[3],
-            "tflops_same_launches": tfs, "frac_tensor_same_launches": tfs / peaks["tf_sust"], "tensor_peak": peaks["tf_sust"]}
-    return roof, stages
+            "traffic": traffic, "algorithmic_bytes_per_step": c[2],
+            "peak_source": peaks["src"] + " (HBM copy bandwidth; bf16 sustained for the tensor view)",
+            "flops_per_step": c[1], "group_ms_per_step": 1e3 * c[0], "launches_per_step": c[3],
+            "tflops_same_launches": tfs, "frac_tensor_same_launches": tfs / peaks["tf_sust"], "tensor_peak": peaks["tf_sust"],
+            "timing": {"source": prof["source"], "note": prof["note"],
+                       "serial_graph_ms_per_step": prof["serial_ms"], "all_kernels_ms_per_step": 1e3 * total,
+                       "what": "kernel durations inside a single-stream, PDL-off capture of the step; the headline "
+                               "ms_per_step is the same kernels with PDL, parallel branches and several batches in flight"}}
+    return roof, stages, prof
+
+
+def time_pipelined(predictor, x_dev, steps, inflight, barrier):
+    """steps full passes with `inflight` graph instances; returns (device seconds, last (out, cnt))."""
+    import torch
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = predictor.infer_pipelined(x_dev, steps, inflight)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) * 1e-3, last[(steps - 1) % inflight]
 
 
 def run_product_arm(args, rank: int, world: int, local_rank: int):
@@ -263,7 +232,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
 
     import specyolo
-    from specyolo.nn.init import synth_images, synth_state_dict
+    from specyolo.nn.init import synth_images, synth_iq, synth_state_dict
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
@@ -274,8 +243,20 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     peaks = measured_peaks()
     B = args.batch
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     yolo = specyolo.YOLO(CFG, nc=NC)
-    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    sd = synth_state_dict(yolo.model, seed=0)
+    yolo.load_state_dict(sd)
     yolo.to(dev)
     yolo.fuse()
     x_host = synth_images(B, IMGSZ, seed=rank, dtype=torch.uint8).pin_memory()   # what predict() uploads (uint8)
@@ -292,27 +273,11 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     predictor.infer_pipelined(x_dev, max(args.warmup, 3), args.inflight)
     torch.cuda.synchronize()
     launches_per_step = predictor.last_launches
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    barrier()
     sampler.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    last = predictor.infer_pipelined(x_dev, args.steps, args.inflight)
-    out, cnt = last[(args.steps - 1) % args.inflight]
-    e1.record()
-    barrier()
+    t_dev, (out, cnt) = time_pipelined(predictor, x_dev, args.steps, args.inflight, barrier)
     sampler.mark_end()
-    t_dev = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([t_dev], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_max = float(t.item())
+    t_max = max_over_ranks(t_dev)
     n_det = int(cnt.sum().item())
 
     # ---- end to end through the public API: pinned host uint8 -> predict() -> Results on the host ----
@@ -329,21 +294,101 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     t_e2e = time.perf_counter() - t0
     assert n_e2e == B * args.steps
     barrier()
-    te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e_max = float(te.item())
+    t_e2e_max = max_over_ranks(t_e2e)
     h2d = x_host.numel() * x_host.element_size()
     d2h = B * MAX_DET * 6 * 4 + B * 4
 
+    roof = stages = None
     if rank == 0:
-        roof, stages = stage_roofline(yolo.model, x_dev, peaks)
-        cpu = None
+        roof, stages, _ = graph_roofline(
+            lambda: yolo.model.detect_fused(x_dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET), peaks,
+            "conv_igemm_kernel + conv_halo_kernel + dwpw_kernel + stem_pair_kernel: every tcgen05 implicit-GEMM conv launch "
+            "of one step (most layers are below the ridge point, i.e. HBM-bound; stages.conv2d_tensor_bound / "
+            "conv2d_hbm_bound split them)")
+    # free the C2 graphs before the larger configurations are captured
+    yolo.predictor = None
+    del predictor
+    torch.cuda.empty_cache()
+
+    # ---- c3: raw IQ -> boxes (BASELINE configs[2]: 256 bursts of 2^20 samples over 8 GPUs = 32 per GPU), the STFT
+    # kernel inside the captured step; IQ resident in HBM for `value` (8.4 MB per burst: a host feed would be PCIe-bound)
+    c3 = None
+    if not args.no_extra:
+        nb = args.iq_bursts
+        iq = torch.view_as_real(synth_iq(nb, 1 << 20, seed=100 + rank)).contiguous().to(dev)
+        front = specyolo.engine.IQFrontEnd(out_hw=(IMGSZ, IMGSZ))
+        p3 = specyolo.DetectionPredictor(yolo.model, pred_args, front=front)
+        p3.infer_pipelined(iq, 3, args.inflight)
+        torch.cuda.synchronize()
+        l3 = p3.last_launches
+        steps3 = max(10, args.steps // 2)
+        t3, (_, cnt3) = time_pipelined(p3, iq, steps3, args.inflight, barrier)
+        t3 = max_over_ranks(t3)
+        c3 = {"workload": f"raw IQ -> STFT 1024/256 -> letterbox 640^2 -> spectrogram-yolov11-s -> NMS, {nb} bursts of 2^20 "
+                          f"complex64 samples per GPU (BASELINE configs[2]), STFT kernel inside the captured graph, IQ resident in HBM",
+              "value": world * nb * steps3 / t3, "unit": "bursts/s", "ms_per_step": 1e3 * t3 / steps3, "steps": steps3,
+              "bursts_per_gpu": nb, "launches_per_step": l3, "detections_last_step": int(cnt3.sum().item()),
+              "parity": "STFT stage unpinned (the reference has no IQ code); detector + NMS pinned"}
+        if rank == 0:
+            from specyolo.utils import kprof
+
+            prof3 = kprof.profile_graph(lambda: yolo.model.detect_fused(front(iq), conf_thres=CONF, iou_thres=IOU,
+                                                                        max_det=MAX_DET))
+            st = [c for c in prof3["calls"] if c["stage"] == "stft_letterbox"]
+            if st:
+                us = sum(c["us"] for c in st)
+                by = sum(c["bytes"] for c in st)
+                c3["roofline"] = {"bound": "hbm", "kernel": "stft_letterbox_kernel", "achieved": by / us / 1e3,
+                                  "peak": peaks["hbm"], "unit": "GB/s", "frac": by / us / 1e3 / peaks["hbm"],
+                                  "algorithmic_bytes_per_launch": by, "us_per_launch": us, "traffic": None,
+                                  "timing": prof3["source"], "serial_graph_ms_per_step": prof3["serial_ms"]}
+        del p3, iq
+        torch.cuda.empty_cache()
+
+    # ---- c4: stock yolo11s (nc=80) at 1280^2, batch 128 per GPU (BASELINE configs[3]) ----
+    c4 = None
+    if not args.no_extra:
+        B4 = args.c4_batch
+        y4 = specyolo.YOLO("yolo11s.yaml", nc=80)
+        y4.load_state_dict(synth_state_dict(y4.model, seed=3))
+        y4.to(dev)
+        y4.fuse()
+        x4 = synth_images(B4, 1280, seed=200 + rank, dtype=torch.uint8).to(dev)
+        p4 = specyolo.DetectionPredictor(y4.model, pred_args)
+        p4.infer_pipelined(x4, 3, 2)
+        torch.cuda.synchronize()
+        l4 = p4.last_launches
+        steps4 = max(6, args.steps // 10)
+        t4, (_, cnt4) = time_pipelined(p4, x4, steps4, 2, barrier)
+        t4 = max_over_ranks(t4)
+        c4 = {"workload": f"yolo11s (nc=80) predict at 1280^2, batch {B4} per GPU, bf16 (BASELINE configs[3]), uint8 input resident in HBM, "
+                          f"2 batches in flight",
+              "value": world * B4 * steps4 / t4, "unit": "images/s", "ms_per_step": 1e3 * t4 / steps4, "steps": steps4,
+              "batch_per_gpu": B4, "launches_per_step": l4, "detections_last_step": int(cnt4.sum().item()),
+              "tflops": world * B4 * steps4 / t4 * 87.8e9 / 1e12,
+              "frac_tensor": B4 * steps4 / t4 * 87.8e9 / 1e12 / peaks["tf_sust"]}
+        del p4
+        torch.cuda.empty_cache()
+        if rank == 0:
+            r4, s4, _ = graph_roofline(lambda: y4.model.detect_fused(x4, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET),
+                                       peaks, "every tcgen05 implicit-GEMM conv launch of one yolo11s 1280^2 step")
+            r4["traffic"] = None
+            c4["roofline"] = r4
+            c4["stages"] = {k: {kk: v[kk] for kk in ("launches", "ms", "frac_tensor", "frac_hbm") if kk in v} for k, v in s4.items()}
+        del y4, x4
+        torch.cuda.empty_cache()
+
+    if rank == 0:
+        cpu = lib_bar = None
         if world == 1 and not args.no_cpu_baseline:
-            ips, threads, times = cpu_port_images_per_s(args.cpu_batch, 2, 1)
-            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_batch} of the same synthetic 640^2 images per step, 2 timed steps, oracle port "
-                             f"(PyTorch CPU fp32 forward + numpy NMS)"}
+            ips, threads, times, kind = cpu_reference_images_per_s(args.cpu_batch, 2, 1)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                   "sample": f"{args.cpu_batch} of the same synthetic 640^2 images per step, 2 timed steps, " +
+                             ("the unmodified reference's YOLO.predict(device='cpu') from oracle/_ref (fp32, BN fused, "
+                              "torchvision NMS)" if kind == "reference" else
+                              "oracle port (PyTorch CPU fp32 forward with BN folded + numpy NMS)")}
+        if world == 1 and not args.no_extra:
+            lib_bar = library_bar(sd, x_dev, dev)
         line = {
             "metric": METRIC, "value": world * B * args.steps / t_max, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps,
@@ -357,14 +402,76 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
                        "sharding": "images split across GPUs, no collective on the data path",
                        "detections_last_step": n_det},
             "e2e": {"value": world * B * args.steps / t_e2e_max, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "specyolo.YOLO.predict(iterable of pinned uint8 batches, stream=True)"},
+                    "d2h_bytes_per_step": d2h, "h2d_gbs_per_gpu": h2d * args.steps / t_e2e_max / 1e9,
+                    "api": "specyolo.YOLO.predict(iterable of pinned uint8 batches, stream=True)"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "roofline": roof, "stages": stages, "clocks": clocks, "cpu_baseline": cpu,
+            "c3": c3, "c4": c4, "library_bar": lib_bar,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def library_bar(sd, x_dev, dev):
+    """BASELINE.md 3.7 / SURVEY 2.1: the same network through the LIBRARY path on the same GPU — the reference's own
+    `YOLO.predict(x, device=0, half=True)` (cuDNN / cuBLAS fp16 + torchvision CUDA nms) when oracle/_ref is present, and
+    the oracle port's functional forward in bf16 channels-last + torchvision nms otherwise.  Images/s on the bench's
+    batch; this is the bar every hand-written kernel has to beat, not the CPU."""
+    import torch
+    import torchvision
+    import yaml
+
+    out = {"unit": "images/s", "batch": int(x_dev.shape[0])}
+    xf = (x_dev.float() / 255).contiguous()
+
+    def timeit(step, reps=5):
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        torch.cuda.synchronize()
+        return xf.shape[0] * reps / (time.perf_counter() - t0)
+
+    try:
+        ref = _reference_yolo(sd)
+        if ref is not None:
+            idx = dev.index or 0
+            for half in (True, False):
+                ref.predictor = None
+                step = lambda: ref.predict(xf, device=idx, half=half, conf=CONF, iou=IOU, max_det=MAX_DET, verbose=False)  # noqa: E731
+                out["reference_predict_fp16" if half else "reference_predict_fp32"] = timeit(step)
+            out["what"] = ("the unmodified reference's YOLO.predict(tensor, device=0) on this GPU: PyTorch eager cuDNN/cuBLAS "
+                           "(half=True: fp16) + its Python NMS loop over torchvision.ops.nms (CUDA)")
+    except Exception as ex:      # the library bar must never take the bench line down
+        out["reference_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    try:
+        from oracle import yolo_ref
+
+        graph = yolo_ref.parse_graph(yaml.safe_load((PKG / "specyolo" / "cfg" / CFG_FILE).read_text()), "s", NC)
+        R = yolo_ref.Ref(sd, fuse=True, device=dev, dtype=torch.bfloat16)
+        xb = xf.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+        def step_port():
+            with torch.no_grad():
+                y, _ = yolo_ref.forward(graph, R, xb)
+                y = y.float()
+                for b in range(y.shape[0]):          # the reference's per-image loop, on the device (ops.py:262-327)
+                    p = y[b].t()
+                    sc, j = p[:, 4:].max(1)
+                    m = sc > CONF
+                    p, sc, j = p[m], sc[m], j[m]
+                    bx = torch.cat((p[:, :2] - p[:, 2:4] / 2, p[:, :2] + p[:, 2:4] / 2), 1)
+                    torchvision.ops.nms(bx + j[:, None].float() * 7680, sc, IOU)[:MAX_DET]
+        out["torch_bf16_channels_last"] = timeit(step_port)
+        out["what_port"] = ("the oracle port's functional forward on this GPU in bf16 channels-last (cuDNN/cuBLAS, BN folded) + "
+                            "threshold + torchvision.ops.nms (CUDA) per image")
+    except Exception as ex:
+        out["port_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    return out
 
 
 def main():
@@ -377,6 +484,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the resident-input loop")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / library_bar keys")
+    ap.add_argument("--iq-bursts", type=int, default=32, help="IQ bursts per GPU per step of the c3 workload")
+    ap.add_argument("--c4-batch", type=int, default=128, help="images per GPU per step of the c4 workload (yolo11s 1280^2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

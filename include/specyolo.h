@@ -232,6 +232,10 @@ typedef struct {
                                   (the `i` of ops.py:312-313); may be NULL               */
     int*   n_cand;             /* [B] number of candidates that entered NMS; may be NULL */
     void*  ws;                 /* workspace, specyolo_nms_ws_bytes() bytes               */
+    /* > 0: the kept boxes are clamped to [0, clip_w] x [0, clip_h] as they are written — the clip_boxes that
+       ends every scale_boxes of construct_result (ultralytics/utils/ops.py:124-127, 335-354), which the
+       reference also runs when the source already has the network shape (gain 1, pad 0).  0: boxes as NMS saw them. */
+    float  clip_w, clip_h;
 } specyolo_nms_t;
 size_t specyolo_nms_ws_bytes(int B, int nc, int A, int multi_label);
 int    specyolo_nms(const specyolo_nms_t* a, void* stream);

@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE — imports the upstream reference (read-only, /root/reference) on CPU.
+"""TEST INFRASTRUCTURE — imports the upstream reference package.
 
-Only usable in the build container: the GPU box has no /root/reference, so nothing under `-m gpu`,
-smoke() or bench.py may call this.  It exists to (a) validate the restatements in oracle/*.py against
-the real reference and (b) generate the committed fixtures in tests/golden/ (oracle/gen_golden.py).
+Two locations, in this order: `oracle/_ref/` (the unmodified reference installed by `make -C oracle`, git-ignored but
+shipped to the GPU box with the snapshot) and `/root/reference` (build container only; nothing on the GPU box reads it).
+It exists to (a) validate the restatements in oracle/*.py against the real reference, (b) generate the committed
+fixtures in tests/golden/ (oracle/gen_golden.py), (c) time the reference as itself in bench.py's CPU / library-bar
+legs and (d) host the drop-in test of specyolo.ultralytics_shim.
 
 The reference imports three packages that are absent from this image and cannot be installed
 (no network): matplotlib, thop, timm.  None of them is executed on the hot path, so they are
@@ -16,7 +18,9 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("SPECYOLO_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("SPECYOLO_REFERENCE_ROOT") or (
+    _VENDORED if os.path.isfile(os.path.join(_VENDORED, "ultralytics", "__init__.py")) else "/root/reference")
 
 
 def reference_available() -> bool:

@@ -3,9 +3,9 @@
 This is the oracle for the floating-point part of the hot path: every function cites the reference
 file:line it restates (paths relative to the upstream repo, a fork of Ultralytics 8.3.70).  It is
 pure function of (model yaml dict, state_dict, input) — it owns no weights and imports nothing from
-the product package.  Pinned against the real reference by tests/test_oracle_vs_reference.py (run in
-the build container where /root/reference exists) and by the fixtures in tests/golden/ that
-oracle/gen_golden.py produced from the real reference.
+the product package.  Pinned against the real reference by the fixtures in tests/golden/ that oracle/gen_golden.py produced from
+the real reference (checked by tests/test_oracle_golden.py), and — where the vendored copy oracle/_ref exists —
+directly by tests/test_reference_live.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module; the product path never does.
@@ -101,12 +101,30 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
 class Ref:
     """Functional forward over a state_dict."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor]):
-        self.sd = {k: v.detach().to(torch.float32) for k, v in sd.items() if v.is_floating_point()}
+    def __init__(self, sd: Dict[str, torch.Tensor], fuse: bool = False, device=None, dtype=torch.float32):
+        self.sd = {k: v.detach().to(device=device, dtype=dtype) for k, v in sd.items() if v.is_floating_point()}
+        self.fuse = fuse
+        self._folded: Dict[str, tuple] = {}
 
-    # Conv = Conv2d(bias=False) + BatchNorm2d(eval) + SiLU  (conv.py:65-79)
+    def folded(self, p):
+        """fuse_conv_and_bn (ultralytics/utils/torch_utils.py:238-265): what the predict path runs after
+        AutoBackend's model.fuse() (nn/autobackend.py:152) — W' = diag(gamma / sqrt(var + eps)) W, b' = beta - mean * scale."""
+        t = self._folded.get(p)
+        if t is None:
+            sd = self.sd
+            scale = sd[p + ".bn.weight"].float() / torch.sqrt(sd[p + ".bn.running_var"].float() + BN_EPS)
+            w = (sd[p + ".conv.weight"].float() * scale.view(-1, 1, 1, 1)).to(sd[p + ".conv.weight"].dtype)
+            b = (sd[p + ".bn.bias"].float() - sd[p + ".bn.running_mean"].float() * scale).to(w.dtype)
+            t = self._folded[p] = (w, b)
+        return t
+
+    # Conv = Conv2d(bias=False) + BatchNorm2d(eval) + SiLU  (conv.py:65-79); forward_fuse (conv.py:81-83) when fused
     def conv(self, x, p, k=1, s=1, g=1, d=1, act=True):
         sd = self.sd
+        if self.fuse:
+            w, b = self.folded(p)
+            y = F.conv2d(x, w, b, s, autopad(k, None, d), d, g)
+            return F.silu(y) if act else y
         w = sd[p + ".conv.weight"]
         y = F.conv2d(x, w, None, s, autopad(k, None, d), d, g)
         y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],
@@ -148,10 +166,10 @@ class Ref:
         key_dim = int(head_dim * 0.5)
         scale = key_dim ** -0.5
         qkv = self.conv(x, p + ".qkv", act=False)
-        q, k, v = qkv.view(B, num_heads, key_dim * 2 + head_dim, N).split([key_dim, key_dim, head_dim], dim=2)
+        q, k, v = qkv.reshape(B, num_heads, key_dim * 2 + head_dim, N).split([key_dim, key_dim, head_dim], dim=2)
         attn = (q.transpose(-2, -1) @ k) * scale
         attn = attn.softmax(dim=-1)
-        y = (v @ attn.transpose(-2, -1)).view(B, C, H, W) + self.conv(v.reshape(B, C, H, W), p + ".pe", 3, 1, g=C, act=False)
+        y = (v @ attn.transpose(-2, -1)).reshape(B, C, H, W) + self.conv(v.reshape(B, C, H, W), p + ".pe", 3, 1, g=C, act=False)
         return self.conv(y, p + ".proj", act=False)
 
     # PSABlock (block.py:1995-2007), C2PSA (block.py:2125-2139)
@@ -207,14 +225,14 @@ class Ref:
 
 
 # make_anchors (utils/tal.py:334-346)
-def make_anchors(hw: Sequence[tuple], strides: Sequence[float], offset=0.5):
+def make_anchors(hw: Sequence[tuple], strides: Sequence[float], offset=0.5, device=None):
     pts, st = [], []
     for (h, w), s in zip(hw, strides):
-        sx = torch.arange(w, dtype=torch.float32) + offset
-        sy = torch.arange(h, dtype=torch.float32) + offset
+        sx = torch.arange(w, dtype=torch.float32, device=device) + offset
+        sy = torch.arange(h, dtype=torch.float32, device=device) + offset
         sy, sx = torch.meshgrid(sy, sx, indexing="ij")
         pts.append(torch.stack((sx, sy), -1).view(-1, 2))
-        st.append(torch.full((h * w, 1), float(s), dtype=torch.float32))
+        st.append(torch.full((h * w, 1), float(s), dtype=torch.float32, device=device))
     return torch.cat(pts), torch.cat(st)
 
 
@@ -222,12 +240,12 @@ def make_anchors(hw: Sequence[tuple], strides: Sequence[float], offset=0.5):
 def detect_decode(raw: Sequence[torch.Tensor], strides: Sequence[float], nc: int, reg_max: int = 16):
     B = raw[0].shape[0]
     no = nc + 4 * reg_max
-    x_cat = torch.cat([xi.reshape(B, no, -1) for xi in raw], 2)
-    anchors, st = make_anchors([tuple(xi.shape[2:]) for xi in raw], strides)
+    x_cat = torch.cat([xi.reshape(B, no, -1) for xi in raw], 2).float()
+    anchors, st = make_anchors([tuple(xi.shape[2:]) for xi in raw], strides, device=x_cat.device)
     anchors, st = anchors.transpose(0, 1), st.transpose(0, 1)
     box, cls = x_cat.split((reg_max * 4, nc), 1)
     b, _, a = box.shape
-    proj = torch.arange(reg_max, dtype=torch.float32).view(1, reg_max, 1, 1)
+    proj = torch.arange(reg_max, dtype=torch.float32, device=x_cat.device).view(1, reg_max, 1, 1)
     dist = (box.view(b, 4, reg_max, a).transpose(2, 1).softmax(1) * proj).sum(1)  # DFL conv with weights 0..15
     lt, rb = dist.chunk(2, 1)
     x1y1 = anchors.unsqueeze(0) - lt
@@ -239,11 +257,13 @@ def detect_decode(raw: Sequence[torch.Tensor], strides: Sequence[float], nc: int
 # ------------------------------------------------------------------------------------------------
 # whole model: BaseModel._predict_once (tasks.py:161-188)
 # ------------------------------------------------------------------------------------------------
-def forward(graph: List[dict], sd: Dict[str, torch.Tensor], x: torch.Tensor, strides=(8.0, 16.0, 32.0),
-            return_layers: bool = False):
-    """Returns (y [B,4+nc,A], raw list) like Detect in eval mode; optionally every layer output."""
-    R = Ref(sd)
-    x = x.to(torch.float32)
+def forward(graph: List[dict], sd, x: torch.Tensor, strides=(8.0, 16.0, 32.0),
+            return_layers: bool = False, fuse: bool = False):
+    """Returns (y [B,4+nc,A], raw list) like Detect in eval mode; optionally every layer output.
+    `sd` is a state_dict or a prepared `Ref` (device / dtype / folded weights kept across calls); `fuse=True` runs
+    Conv.forward_fuse on BN-folded weights as the reference's predict path does (autobackend.py:152)."""
+    R = sd if isinstance(sd, Ref) else Ref(sd, fuse=fuse)
+    x = x.to(next(iter(R.sd.values())).dtype)
     ys: List[torch.Tensor] = []
     legacy = not any(L["type"] == "C3k2" for L in graph)  # tasks.py:1097 sets legacy False for YOLO11
     for L in graph:

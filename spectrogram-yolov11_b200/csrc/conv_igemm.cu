@@ -11,11 +11,11 @@
 //   * B operand: TMA 2-D box {kc, n_tile} of the packed weights [groups*n_pad][taps*Cin_g].
 //   * D: fp32 accumulator in TMEM (n_tile columns x 128 lanes), issued by one thread with
 //     tcgen05.mma.cta_group::1.kind::f16, M=128, N=n_tile, K=16 per instruction.
-//   * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer, warps2-5 = epilogue
-//     (tcgen05.ld -> +bias -> SiLU -> +residual -> bf16/fp32 NHWC store at a channel offset, so
-//     concat buffers are written in place and no torch.cat copy exists).
-//   * Non-persistent: one output tile per CTA; 2+ CTAs/SM overlap one tile's epilogue with the
-//     next tile's main loop.
+//   * Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM owner + MMA issuer, warps2-9 = epilogue
+//     (two warps per TMEM lane quadrant; tcgen05.ld -> +bias -> SiLU -> +residual -> bf16/fp32 NHWC store at a
+//     channel offset, so concat buffers are written in place and no torch.cat copy exists).
+//   * Persistent: a CTA walks tiles blockIdx.x + i*gridDim.x; the accumulator is double-buffered in TMEM so the
+//     epilogue of tile i overlaps the loads / MMAs of tile i+1.
 //
 // Replaces Conv.forward_fuse (ultralytics/nn/modules/conv.py:81-83) = cuDNN conv + bias + SiLU.
 #include "common.h"

@@ -338,7 +338,11 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     for (int k = tid; k < kept; k += kNmsThreads) {
         const int r = s_kept_rank[k];
         const int idx = (int)(keys[r] & 0xffffffffu);
-        const float4 bx = cbox[idx];
+        float4 bx = cbox[idx];
+        if (a.clip_w > 0.f) {       // clip_boxes (ops.py:335-354)
+            bx.x = fminf(fmaxf(bx.x, 0.f), a.clip_w); bx.z = fminf(fmaxf(bx.z, 0.f), a.clip_w);
+            bx.y = fminf(fmaxf(bx.y, 0.f), a.clip_h); bx.w = fminf(fmaxf(bx.w, 0.f), a.clip_h);
+        }
         float* o = a.out + ((size_t)b * a.max_det + k) * 6;
         o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
         o[4] = cconf[idx]; o[5] = (float)ccls[idx];
@@ -374,11 +378,8 @@ int nms_launch(const specyolo_nms_t* a, cudaStream_t stream) {
     p.nseg = ceil_div(a->A, SPECYOLO_DECODE_SEG);
     SY_CHECK(p.nseg <= kSmemSort * 2, SPECYOLO_ERR_UNSUPPORTED, "too many anchors");
     const size_t smem = (size_t)kSmemSort * 8 + (size_t)(kSmemBoxes + kMaxKeep) * 16 + (size_t)kMaxKeep * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    // the attribute is per device: set it on every launch (a host-side table lookup, no device work)
+    SY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SY_CUDA(launch_pdl(nms_kernel, dim3(a->B), dim3(kNmsThreads), smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch();

@@ -82,7 +82,7 @@ class NmsArgs(C.Structure):
         ("agnostic", C.c_int), ("multi_label", C.c_int), ("max_det", C.c_int), ("max_nms", C.c_int),
         ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int),
         ("out", C.c_void_p), ("out_count", C.c_void_p), ("keep_idx", C.c_void_p), ("n_cand", C.c_void_p),
-        ("ws", C.c_void_p),
+        ("ws", C.c_void_p), ("clip_w", C.c_float), ("clip_h", C.c_float),
     ]
 
 

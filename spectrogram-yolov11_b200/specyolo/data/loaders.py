@@ -73,10 +73,51 @@ def decode_jpeg_batch(blobs: List[bytes], backend: int = 2, device="cuda") -> Li
     return outs
 
 
+def jpeg_exif_orientation(data: bytes) -> int:
+    """EXIF orientation tag (0x0112) of a JPEG byte string, 1 when absent / unreadable.  Walks the marker segments up to
+    the first scan; reads the TIFF header of the APP1 "Exif" segment (either byte order) and IFD0 only, like OpenCV's
+    ExifReader does for `cv2.imread` (which rotates / flips the decoded pixels unless IMREAD_IGNORE_ORIENTATION)."""
+    import struct
+
+    n = len(data)
+    i = 2
+    while i + 4 <= n and data[i] == 0xFF:
+        marker = data[i + 1]
+        if marker in (0xD8, 0x01) or 0xD0 <= marker <= 0xD7:          # standalone markers
+            i += 2
+            continue
+        if marker == 0xDA or marker == 0xD9:                            # start of scan / end of image: no EXIF ahead
+            break
+        seglen = struct.unpack(">H", data[i + 2:i + 4])[0]
+        if marker == 0xE1 and data[i + 4:i + 10] == b"Exif\x00\x00":
+            t = i + 10                                                  # TIFF header
+            bo = {b"II": "<", b"MM": ">"}.get(data[t:t + 2])
+            if bo is None or t + 8 > n:
+                return 1
+            ifd = t + struct.unpack(bo + "I", data[t + 4:t + 8])[0]
+            if ifd + 2 > n:
+                return 1
+            for k in range(struct.unpack(bo + "H", data[ifd:ifd + 2])[0]):
+                e = ifd + 2 + 12 * k
+                if e + 12 > n:
+                    break
+                tag, typ = struct.unpack(bo + "HH", data[e:e + 4])
+                if tag == 0x0112:
+                    v = struct.unpack(bo + "H", data[e + 8:e + 10])[0] if typ == 3 else \
+                        struct.unpack(bo + "I", data[e + 8:e + 12])[0]
+                    return int(v) if 1 <= v <= 8 else 1
+            return 1
+        i += 2 + seglen
+    return 1
+
+
 def imread_device(path: str, device="cuda") -> torch.Tensor:
     """An image file -> [H, W, 3] uint8 BGR CUDA tensor; None-like failure raises (the reference warns and skips)."""
     data = Path(path).read_bytes()
-    if data[:3] == b"\xff\xd8\xff":                       # JPEG magic, whatever the suffix says
+    # nvJPEG ignores EXIF; cv2.imread (the reference, loaders.py:406) applies the orientation tag.  Files that carry a
+    # non-trivial orientation go through the reference's own decoder so pixels, `exif_size` (dataset._image_hw) and
+    # labels stay in one frame.
+    if data[:3] == b"\xff\xd8\xff" and jpeg_exif_orientation(data) == 1:   # JPEG magic, whatever the suffix says
         try:
             return decode_jpeg(data, device)
         except RuntimeError:

@@ -73,3 +73,48 @@ def gather_counts(counts: torch.Tensor) -> List[torch.Tensor]:
     outs = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad)
     return [o[: int(s)] for o, s in zip(outs, sizes)]
+
+
+def gather_detections(dets: List[torch.Tensor], device: torch.device | str = "cpu") -> List[torch.Tensor]:
+    """Per-image [n_i, 6] detection tensors of this rank's shard -> the detections of the WHOLE global batch in input
+    order on every rank.  Two collectives on results only (counts, then rows padded to the largest per-rank total); the
+    data path itself has none."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(dets)
+    world = dist.get_world_size()
+    counts = torch.tensor([int(d.shape[0]) for d in dets], dtype=torch.int64, device=device)
+    per_rank = gather_counts(counts)
+    rows = torch.cat([d.to(device=device, dtype=torch.float32).reshape(-1, 6) for d in dets]) if dets else \
+        torch.zeros((0, 6), dtype=torch.float32, device=device)
+    mx = max(int(c.sum()) for c in per_rank)
+    pad = torch.zeros((max(mx, 1), 6), dtype=torch.float32, device=device)
+    pad[: rows.shape[0]] = rows
+    outs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    result: List[torch.Tensor] = []
+    for o, c in zip(outs, per_rank):
+        off = 0
+        for n in c.tolist():
+            result.append(o[off: off + n].cpu())
+            off += n
+    return result
+
+
+def predict_sharded(predict_fn, batch: torch.Tensor, device: torch.device | str | None = None) -> List[torch.Tensor]:
+    """One GLOBAL batch (images [B,3,H,W] or IQ bursts [B,L], the same tensor on every rank, e.g. pinned host memory) ->
+    per-image detections [n_i, 6] of all B units in input order, on every rank (contiguous shards, one
+    replica per GPU, results concatenated on the host in input order).
+
+    `predict_fn(shard) -> List[Results | Tensor[n,6]]` is the per-rank replica: `yolo.predict` for images,
+    `yolo.predict_iq` for bursts.  Ranks whose shard is empty (B < world) run nothing."""
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    lo, hi = shard_range(int(batch.shape[0]), rank, world)
+    dets: List[torch.Tensor] = []
+    if hi > lo:
+        for r in predict_fn(batch[lo:hi]):
+            d = r.boxes.data if hasattr(r, "boxes") else r
+            dets.append(torch.as_tensor(d).reshape(-1, 6))
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if (
+            dist.is_initialized() and dist.get_backend() == "nccl") else "cpu"
+    return gather_detections(dets, device)

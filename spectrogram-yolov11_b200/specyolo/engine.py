@@ -151,20 +151,25 @@ class Results:
 class _GraphStep:
     """A captured forward for one static input signature."""
 
-    def __init__(self, model: DetectionModel, example: torch.Tensor, conf, iou, agnostic, max_det, classes):
+    def __init__(self, model: DetectionModel, example: torch.Tensor, conf, iou, agnostic, max_det, classes, front=None):
         self.static_in = example.clone()
-        args = dict(conf_thres=conf, iou_thres=iou, agnostic=agnostic, max_det=max_det, classes=classes)
+        self.front = front          # optional device-side front end captured with the detector (IQ -> spectrogram image)
+        # the class-filter tensor's address is baked into the captured NMS launch: the graph owns its own copy
+        self.classes = None if classes is None else classes.detach().clone()
+        args = dict(conf_thres=conf, iou_thres=iou, agnostic=agnostic, max_det=max_det, classes=self.classes)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        fwd = (lambda x: model.detect_fused(x, **args)) if front is None else \
+            (lambda x: model.detect_fused(front(x), **args))
         with torch.cuda.stream(side):      # warm-up: lazy weight packing, attribute setup, allocator
             for _ in range(2):
-                model.detect_fused(self.static_in, **args)
+                fwd(self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = _lib.load().specyolo_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out, self.cnt = model.detect_fused(self.static_in, **args)
+            self.out, self.cnt = fwd(self.static_in)
         self.launches = int(_lib.load().specyolo_launch_count() - n0)
 
     def run(self, x: torch.Tensor):
@@ -175,17 +180,60 @@ class _GraphStep:
 
     def clone(self, model: DetectionModel, conf, iou, agnostic, max_det, classes) -> "_GraphStep":
         """A second, independent instance (own static input / outputs) for double-buffered streaming."""
-        return _GraphStep(model, self.static_in, conf, iou, agnostic, max_det, classes)
+        return _GraphStep(model, self.static_in, conf, iou, agnostic, max_det, classes, front=self.front)
+
+
+class IQFrontEnd:
+    """IQ bursts -> letterboxed spectrogram images on the device (absent in the reference): the callable a
+    `_GraphStep` captures in front of the detector, so one graph replay = STFT kernel + ~95 detector launches.
+    Input: float32 [B, L, 2] (complex64 viewed as real), output bf16 NCHW [B, 3, H, W] in [0, 1]."""
+
+    def __init__(self, nfft=1024, hop=256, db_min=-100.0, db_max=0.0, out_hw=(640, 640)):
+        self.nfft, self.hop, self.db_min, self.db_max, self.out_hw = nfft, hop, db_min, db_max, tuple(out_hw)
+
+    def key(self):
+        return ("iq", self.nfft, self.hop, self.db_min, self.db_max, self.out_hw)
+
+    @staticmethod
+    def as_real(iq: torch.Tensor) -> torch.Tensor:
+        if iq.dim() == 1 or (iq.dim() == 2 and not iq.is_complex() and iq.shape[-1] == 2):
+            iq = iq.unsqueeze(0)
+        if iq.is_complex():
+            if iq.dtype != torch.complex64:
+                raise TypeError("IQ bursts must be complex64")
+            iq = torch.view_as_real(iq)
+        if iq.dtype != torch.float32 or iq.dim() != 3 or iq.shape[-1] != 2:
+            raise ValueError(f"IQ bursts must be complex64 [B, L] (or float32 [B, L, 2]); got {tuple(iq.shape)} {iq.dtype}")
+        return iq.contiguous()
+
+    def __call__(self, iq_real: torch.Tensor) -> torch.Tensor:
+        return ops.iq_to_letterbox(iq_real, self.nfft, self.hop, self.db_min, self.db_max, self.out_hw)
+
+
+def _classes_tensor(classes, device) -> Optional[torch.Tensor]:
+    """`classes=` of predict (int, or list of ints; ops.py:294-295) as an int32 device tensor."""
+    if classes is None:
+        return None
+    if isinstance(classes, (int, np.integer)):
+        classes = [int(classes)]
+    return torch.tensor([int(c) for c in classes], device=device, dtype=torch.int32)
+
+
+def _classes_key(classes):
+    if classes is None:
+        return None
+    return (int(classes),) if isinstance(classes, (int, np.integer)) else tuple(int(c) for c in classes)
 
 
 class DetectionPredictor:
     """preprocess -> inference -> postprocess (engine/predictor.py:221-306), all on the device."""
 
-    def __init__(self, model: DetectionModel, overrides: Optional[dict] = None):
+    def __init__(self, model: DetectionModel, overrides: Optional[dict] = None, front: Optional[IQFrontEnd] = None):
         self.model = model
         self.args = dict(conf=0.25, iou=0.7, max_det=300, agnostic_nms=False, classes=None, imgsz=640, half=False,
                          use_graph=True, stream_slots=3)
         self.args.update(overrides or {})
+        self.front = front            # device-side front end (IQ -> image) run inside the captured step
         self._graphs: Dict[tuple, _GraphStep] = {}
         self._stream_steps: List[Optional[_GraphStep]] = [None, None]   # double-buffered graph instances
         self._stream_host: list = [None, None]                           # their pinned host result buffers
@@ -196,6 +244,11 @@ class DetectionPredictor:
     def preprocess(self, source) -> (torch.Tensor, list, list):
         """Returns (device tensor [B,3,H,W] (fp32/bf16 in 0..1 or uint8), original shapes, host images)."""
         dev = next(self.model.parameters()).device
+        if self.front is not None:
+            if not isinstance(source, torch.Tensor):
+                raise TypeError("the IQ front end takes complex64 tensors [B, L]")
+            iq = IQFrontEnd.as_real(source).to(dev, non_blocking=True)
+            return iq, [self.front.out_hw] * iq.shape[0], [None] * iq.shape[0]
         if isinstance(source, torch.Tensor):
             # LoadTensor._single_check (data/loaders.py:548-566): BCHW, stride-32 sizes
             im = source if source.dim() == 4 else source.unsqueeze(0)
@@ -249,23 +302,27 @@ class DetectionPredictor:
     @torch.no_grad()
     def infer(self, im: torch.Tensor):
         a = self.args
-        classes = None
-        if a["classes"] is not None:
-            classes = torch.tensor(list(a["classes"]), device=im.device, dtype=torch.int32)
+        classes = _classes_tensor(a["classes"], im.device)
         if a["use_graph"]:
             key = (tuple(im.shape), im.dtype, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"],
-                   None if a["classes"] is None else tuple(a["classes"]))
+                   _classes_key(a["classes"]), None if self.front is None else self.front.key())
             step = self._graphs.get(key)
             if step is None:
                 step = self._graphs[key] = _GraphStep(self.model, im, a["conf"], a["iou"], a["agnostic_nms"],
-                                                      a["max_det"], classes)
+                                                      a["max_det"], classes, front=self.front)
             self.last_launches = step.launches
             return step.run(im)
         n0 = _lib.load().specyolo_launch_count()
+        if self.front is not None:
+            im = self.front(im)
         r = self.model.detect_fused(im, conf_thres=a["conf"], iou_thres=a["iou"], agnostic=a["agnostic_nms"],
                                     max_det=a["max_det"], classes=classes)
         self.last_launches = int(_lib.load().specyolo_launch_count() - n0)
         return r
+
+    def _net_hw(self, im: torch.Tensor):
+        """(H, W) of the detector's input for the batch `im` (the front end's output size when there is one)."""
+        return tuple(im.shape[2:]) if self.front is None else self.front.out_hw
 
     def _streams(self, dev, n: int = 2):
         while len(self._compute_streams) < n:
@@ -277,7 +334,8 @@ class DetectionPredictor:
         steps, host_out = self._stream_steps, self._stream_host
         if steps[slot] is None or steps[slot].static_in.shape != im.shape or steps[slot].static_in.dtype != im.dtype:
             example = im.to(next(self.model.parameters()).device) if not im.is_cuda else im
-            steps[slot] = _GraphStep(self.model, example, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"], classes)
+            steps[slot] = _GraphStep(self.model, example, a["conf"], a["iou"], a["agnostic_nms"], a["max_det"], classes,
+                                     front=self.front)
             host_out[slot] = (torch.empty(steps[slot].out.shape, dtype=torch.float32).pin_memory(),
                               torch.empty(steps[slot].cnt.shape, dtype=torch.int32).pin_memory())
             self.last_launches = steps[slot].launches
@@ -290,9 +348,7 @@ class DetectionPredictor:
         level, decode, NMS: grids far below 148 SMs) overlap the wide kernels of the other.  Returns the (out, cnt)
         device tensors of the last step of each instance.  Everything is enqueued behind the caller's current
         stream and joined back into it."""
-        classes = None
-        if self.args["classes"] is not None:
-            classes = torch.tensor(list(self.args["classes"]), device=im.device, dtype=torch.int32)
+        classes = _classes_tensor(self.args["classes"], im.device)
         main = torch.cuda.current_stream(im.device)
         cs = self._streams(im.device, inflight)
         while len(self._stream_steps) < inflight:
@@ -334,11 +390,12 @@ class DetectionPredictor:
         consumed = [None] * n        # event: the step has copied its staged input into the graph's static input
         staging: list = [None] * n   # device staging buffers the host uploads into (decoupled from the graph inputs:
                                      # the upload of batch i+n may start as soon as step i has STARTED, not finished)
-        classes = None
-        if a["classes"] is not None:
-            classes = torch.tensor(list(a["classes"]), device=dev, dtype=torch.int32)
+        classes = _classes_tensor(a["classes"], dev)
 
         def prep(item):
+            if self.front is not None:      # IQ bursts: stay where they are (pinned host): the copy stream uploads them
+                iq = IQFrontEnd.as_real(item)
+                return iq, [self.front.out_hw] * iq.shape[0], [None] * iq.shape[0]
             if isinstance(item, torch.Tensor):
                 im = item if item.dim() == 4 else item.unsqueeze(0)
                 if im.dim() != 4 or im.shape[1] != 3 or im.shape[2] % 32 or im.shape[3] % 32:
@@ -373,7 +430,7 @@ class DetectionPredictor:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             uploaded[slot] = ev
-            return (shapes, imgs, im.shape[0], tuple(im.shape[2:]))
+            return (shapes, imgs, im.shape[0], self._net_hw(im))
 
         def launch(slot, meta):
             # every instance runs on its own stream: consecutive batches overlap on the GPU
@@ -433,7 +490,7 @@ class DetectionPredictor:
         im, shapes, host_imgs = self.preprocess(source)
         out, cnt = self.infer(im)
         # postprocess (detect/predict.py:59-73): boxes back to original-image coordinates
-        img1 = tuple(im.shape[2:])
+        img1 = self._net_hw(im)
         if any(s != img1 for s in shapes):      # boxes back to original-image coordinates (ops.py:92-127, 335-354)
             out = out.clone()
             for b, s in enumerate(shapes):
@@ -512,6 +569,9 @@ class DetectionValidator:
                     bb[:, [0, 2]] = bb[:, [0, 2]].clamp(0, osh[b][1])
                     bb[:, [1, 3]] = bb[:, [1, 3]].clamp(0, osh[b][0])
                     xyxy[m] = bb
+        else:
+            # images at the network size: _prepare_pred still ends in clip_boxes (val.py:121-128 -> ops.py:124-127)
+            ops.scale_boxes_(out, cnt, (H, W), (H, W))
         per_img = torch.bincount(bidx, minlength=B)
         off = torch.zeros(B + 1, dtype=torch.int32)
         off[1:] = torch.cumsum(per_img, 0)
@@ -581,12 +641,12 @@ class YOLO:
 
     def to(self, device):
         self.model.to(device)
-        self.predictor = None
+        self.predictor = self._iq_predictor = None
         return self
 
     def load_state_dict(self, sd, strict=True):
         r = self.model.load_state_dict(sd, strict=strict)
-        self.predictor = None
+        self.predictor = self._iq_predictor = None
         return r
 
     def fuse(self):
@@ -661,12 +721,21 @@ class YOLO:
         self.validator = (validator or DetectionValidator)(self.model, kwargs)     # kept: .confusion_matrix, .stats
         return self.validator(data)
 
-    def predict_iq(self, iq: torch.Tensor, nfft: int = 1024, hop: int = 256, db_min: float = -100.0,
-                   db_max: float = 0.0, **kwargs) -> List[Results]:
-        """Raw IQ bursts [B, L] complex64 -> boxes: STFT/letterbox kernel -> detector, all on the device."""
+    def predict_iq(self, iq, nfft: int = 1024, hop: int = 256, db_min: float = -100.0, db_max: float = 0.0,
+                   stream: bool = False, **kwargs):
+        """Raw IQ bursts -> boxes (BASELINE configs[2]).  `iq`: complex64 [B, L] (or float32 [B, L, 2]) — or, with
+        `stream=True`, an iterable of such batches (pinned host tensors are uploaded on the copy stream while earlier
+        batches compute).  The STFT / log / letterbox kernel runs INSIDE the captured step: one CUDA-graph replay per batch
+        covers IQ samples -> spectrogram image -> detector -> decode -> NMS, all on the device."""
         if not next(self.model.parameters()).is_cuda:
             self.model.to("cuda")
-        dev = next(self.model.parameters()).device
         imgsz = kwargs.pop("imgsz", 640)
-        im = ops.iq_to_letterbox(iq.to(dev, non_blocking=True), nfft, hop, db_min, db_max, (imgsz, imgsz))
-        return self.predict(im, **kwargs)
+        front = IQFrontEnd(nfft, hop, db_min, db_max, (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz))
+        args = {**self.overrides, "conf": 0.25, **kwargs}
+        args.pop("device", None), args.pop("verbose", None)
+        p = getattr(self, "_iq_predictor", None)
+        if p is None or p.front.key() != front.key() or any(p.args.get(k) != v for k, v in args.items()):
+            p = self._iq_predictor = DetectionPredictor(self.model, args, front=front)
+        if stream:
+            return p.stream(iq)
+        return p(iq)

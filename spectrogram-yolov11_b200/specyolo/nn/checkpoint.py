@@ -6,7 +6,13 @@
 names resolve to inert stand-ins (an `nn.Module` subclass per name, created on demand) that exist only long enough to
 hand over what the checkpoint holds — the model YAML dict, the `state_dict`, `names`, `args` — and the detector is
 rebuilt from the YAML with this package's own modules (same sub-module names and `state_dict` keys as the reference,
-so the load is strict) and repacked for the B200 kernels on first use.  Nothing of the pickled code is executed.
+so the load is strict) and repacked for the B200 kernels on first use.
+
+Trust model: the unpickler resolves globals through an ALLOWLIST only — `ultralytics.*` (inert stand-ins), `torch.nn`
+module classes, torch's tensor / storage rebuild helpers, `collections.OrderedDict`, numpy array / scalar
+reconstructors, a few value types (`pathlib` paths, `datetime`) and data-only builtins.  Any other global
+(`os.system`, `builtins.eval`, `subprocess.*`, ...) raises `pickle.UnpicklingError`, so a crafted `.pt` cannot name
+a callable outside that list (tests/test_checkpoint.py::test_malicious_pickle_is_refused).
 """
 from __future__ import annotations
 
@@ -33,11 +39,42 @@ def _stand_in(module: str, name: str) -> type:
     return cls
 
 
+_SAFE_BUILTINS = {"set", "frozenset", "slice", "range", "complex", "dict", "list", "tuple", "int", "float", "bool",
+                  "str", "bytes", "bytearray", "object"}
+_SAFE_GLOBALS = {
+    "collections": {"OrderedDict", "defaultdict", "deque"},
+    "copyreg": {"_reconstructor"},
+    "torch._utils": {"_rebuild_tensor", "_rebuild_tensor_v2", "_rebuild_parameter", "_rebuild_parameter_with_state",
+                     "_rebuild_qtensor"},
+    "torch.serialization": {"_get_layout"},
+    "torch._tensor": {"_rebuild_from_type_v2"},
+    "numpy.core.multiarray": {"scalar", "_reconstruct"},
+    "numpy._core.multiarray": {"scalar", "_reconstruct"},
+    "numpy": {"dtype", "ndarray", "float32", "float64", "int32", "int64", "bool_"},
+    "pathlib": {"Path", "PosixPath", "PurePosixPath", "WindowsPath", "PureWindowsPath", "PurePath"},
+    "datetime": {"datetime", "date", "timedelta"},
+    "argparse": {"Namespace"},
+    "types": {"SimpleNamespace"},
+}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "ultralytics" or module.startswith("ultralytics."):
             return _stand_in(module, name)
-        return super().find_class(module, name)
+        if module in ("builtins", "__builtin__") and name in _SAFE_BUILTINS:
+            return super().find_class("builtins", name)
+        if name in _SAFE_GLOBALS.get(module, ()):
+            return super().find_class(module, name)
+        if module == "torch" and (name.endswith("Storage") or name in ("Size", "device", "dtype", "Tensor", "FloatTensor",
+                                                                        "HalfTensor", "BFloat16Tensor", "LongTensor")):
+            return super().find_class(module, name)
+        if module.startswith("torch.nn.modules.") or module == "torch.nn.parameter":
+            obj = super().find_class(module, name)
+            if isinstance(obj, type) and (issubclass(obj, nn.Module) or module == "torch.nn.parameter"):
+                return obj
+        raise pickle.UnpicklingError(f"global '{module}.{name}' is not on the checkpoint allowlist "
+                                     "(specyolo.nn.checkpoint refuses to resolve arbitrary callables)")
 
 
 _pickle_module = types.ModuleType("specyolo_checkpoint_pickle")

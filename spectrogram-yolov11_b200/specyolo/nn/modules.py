@@ -475,6 +475,7 @@ class Detect(nn.Module):
         super().__init__()
         self.nc = nc
         self.nl = len(ch)
+        self.legacy = bool(type(self).legacy)   # frozen per instance: a later model with another flag must not change this one
         self.reg_max = 16
         self.no = nc + self.reg_max * 4
         self.stride = torch.zeros(self.nl)

@@ -113,7 +113,7 @@ def parse_model(d: dict, ch: int, verbose: bool = False):
             args = [[chans[x] for x in f], "ESChannel"]   # tasks.py:1132-1135
         elif mod is Detect:
             args.append([chans[x] for x in f])
-            Detect.legacy = legacy
+            Detect.legacy = legacy      # read by Detect.__init__ only, which copies it onto the instance (head.py:43-58)
         m_ = nn.Sequential(*(mod(*args) for _ in range(n))) if n > 1 else mod(*args)
         m_.np = sum(x.numel() for x in m_.parameters())
         m_.i, m_.f, m_.type = i, f, m
@@ -245,9 +245,11 @@ class DetectionModel(nn.Module):
 
     @torch.no_grad()
     def detect_fused(self, x, conf_thres=0.25, iou_thres=0.7, agnostic=False, max_det=300, max_nms=30000,
-                     max_wh=7680.0, classes: Optional[torch.Tensor] = None):
+                     max_wh=7680.0, classes: Optional[torch.Tensor] = None, clip: bool = True):
         """Trunk -> head logits -> fused decode+threshold -> batched NMS, never materialising the dense
-        [B, 4+nc, A] prediction.  Returns device tensors (out [B,max_det,6], count [B])."""
+        [B, 4+nc, A] prediction.  Returns device tensors (out [B,max_det,6], count [B]).  `clip`: kept boxes are
+        clamped to the network input's (H, W) as they are written — the clip_boxes every construct_result ends with
+        (detect/predict.py:59-73 -> ops.scale_boxes :124-127), also when gain is 1 and the padding 0."""
         det: Detect = self.model[-1]
         feats = self._run_trunk(x)
         bufs, hw = det.head_logits(feats)
@@ -256,7 +258,8 @@ class DetectionModel(nn.Module):
         A = sum(h * w for h, w in hw)
         out, cnt, _, _ = ops.nms(cand=cand, seg_count=seg, B=bufs[0].shape[0], nc=det.nc, A=A, conf_thres=conf_thres,
                                  iou_thres=iou_thres, agnostic=agnostic, max_det=max_det, max_nms=max_nms,
-                                 max_wh=max_wh, classes=classes)
+                                 max_wh=max_wh, classes=classes,
+                                 clip_hw=tuple(x.shape[2:]) if clip else None)
         return out, cnt
 
 

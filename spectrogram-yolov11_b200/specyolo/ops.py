@@ -463,8 +463,9 @@ def detect_decode(logits: Sequence[torch.Tensor], hw: Sequence[tuple], strides: 
 def nms(prediction: Optional[torch.Tensor] = None, cand: Optional[torch.Tensor] = None,
         seg_count: Optional[torch.Tensor] = None, *, B: int, nc: int, A: int, conf_thres: float, iou_thres: float,
         agnostic: bool = False, multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
-        max_wh: float = 7680.0, classes: Optional[torch.Tensor] = None):
-    """Batched NMS; returns (out [B,max_det,6], count [B], keep_idx [B,max_det], n_cand [B]) on device."""
+        max_wh: float = 7680.0, classes: Optional[torch.Tensor] = None, clip_hw: Optional[tuple] = None):
+    """Batched NMS; returns (out [B,max_det,6], count [B], keep_idx [B,max_det], n_cand [B]) on device.
+    clip_hw = (H, W): kept boxes are clamped to the image as they are written (clip_boxes, ops.py:335-354)."""
     _lib.init_device()
     lib = _lib.load()
     dev = (prediction if prediction is not None else cand).device
@@ -481,6 +482,7 @@ def nms(prediction: Optional[torch.Tensor] = None, cand: Optional[torch.Tensor] 
     a.agnostic, a.multi_label, a.max_det, a.max_nms, a.max_wh = int(agnostic), int(ml), max_det, max_nms, float(max_wh)
     a.classes, a.n_classes = _p(classes), 0 if classes is None else classes.numel()
     a.out, a.out_count, a.keep_idx, a.n_cand, a.ws = out.data_ptr(), cnt.data_ptr(), keep.data_ptr(), ncand.data_ptr(), ws.data_ptr()
+    a.clip_h, a.clip_w = (0.0, 0.0) if clip_hw is None else (float(clip_hw[0]), float(clip_hw[1]))
     check(lib.specyolo_nms(C.byref(a), _lib.stream_ptr()))
     return out, cnt, keep, ncand
 

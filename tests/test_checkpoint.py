@@ -92,3 +92,29 @@ def test_checkpoint_model_forward_matches_reference_output():
     # boxes in pixels (64 x 96 input), scores in [0, 1]: bf16 operands against the fp32 reference
     assert float((got[:, :4] - ref[:, :4]).abs().max()) < 1.0
     assert float((got[:, 4:] - ref[:, 4:]).abs().max()) < 0.03
+
+
+def test_malicious_pickle_is_refused(tmp_path):
+    """a crafted .pt must not be able to name arbitrary callables (os.system, eval, ...)."""
+    import pickle
+
+    sys.path.insert(0, str(ROOT / "spectrogram-yolov11_b200"))
+    from specyolo.nn.checkpoint import torch_safe_load
+
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, (f"touch {marker}",))
+
+    class Evil2:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getcwd()",))
+
+    for i, payload in enumerate((Evil(), Evil2())):
+        f = tmp_path / f"evil{i}.pt"
+        torch.save({"model": payload, "train_args": {}}, f)
+        with pytest.raises(pickle.UnpicklingError):
+            torch_safe_load(f)
+    assert not marker.exists()

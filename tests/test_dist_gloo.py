@@ -35,9 +35,15 @@ def _worker(rank, world, port, q):
     t = sdist.max_over_ranks(0.1 * (rank + 1))
     total = sdist.sum_over_ranks(float(hi - lo))
     allc = sdist.gather_counts(counts)
+    # the product's sharded predict API: one global batch in, all detections back in input order on every rank
+    fn = lambda shard: [torch.from_numpy(o) for o in nms_ref.non_max_suppression(shard.numpy(), 0.5, 0.5)]
+    full = sdist.predict_sharded(fn, pred)
+    tiny = sdist.predict_sharded(fn, pred[:1])              # fewer units than ranks: rank 1's shard is empty
     sdist.barrier()
+    ref = nms_ref.non_max_suppression(pred.numpy(), 0.5, 0.5)
+    assert len(full) == n_global and all(torch.equal(a, torch.from_numpy(b)) for a, b in zip(full, ref))
+    assert len(tiny) == 1 and torch.equal(tiny[0], torch.from_numpy(ref[0]))
     if rank == 0:
-        ref = nms_ref.non_max_suppression(pred.numpy(), 0.5, 0.5)
         q.put((t, total, torch.cat(allc).tolist(), [len(o) for o in ref]))
     dist.destroy_process_group()
 

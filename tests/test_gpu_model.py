@@ -16,6 +16,14 @@ import yaml
 
 pytestmark = pytest.mark.gpu
 
+
+def _clip(d: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """clip_boxes (utils/ops.py:335-354): what construct_result applies to the NMS output, also at gain 1 / pad 0."""
+    d = d.clone()
+    d[:, [0, 2]] = d[:, [0, 2]].clamp(0, w)
+    d[:, [1, 3]] = d[:, [1, 3]].clamp(0, h)
+    return d
+
 ROOT = Path(__file__).resolve().parent.parent
 CFG = ROOT / "spectrogram-yolov11_b200" / "specyolo" / "cfg"
 GOLD = ROOT / "tests" / "golden"
@@ -121,7 +129,7 @@ def test_predict_api_and_fused_path(lib):
     for a, b, c, d in zip(res_graph, res_graph2, res_eager, dense):
         assert torch.equal(a.boxes.data, b.boxes.data)
         assert torch.equal(a.boxes.data, c.boxes.data)
-        assert torch.equal(a.boxes.data, d.cpu())
+        assert torch.equal(a.boxes.data, _clip(d.cpu(), 320, 320))
         assert a.boxes.data.shape[1] == 6 and a.orig_shape == (320, 320)
     # stream=True: double-buffered copies, same detections batch by batch
     batches = [x.cpu().pin_memory(), synth_images(4, 320, seed=7).pin_memory(), x.cpu().pin_memory()]
@@ -164,6 +172,58 @@ def test_predict_api_and_fused_path(lib):
         yolo.predict(torch.zeros(1, 3, 100, 100))                # not stride-32 (loaders.py:554-562)
     with pytest.raises(RuntimeError):
         yolo.predict(x, device="cpu")
+
+
+def test_predict_classes_filter_survives_graph_replay(lib):
+    """the class-filter tensor baked into the captured NMS launch must outlive the call that built it.
+    predict(classes=[1]) twice with unrelated small CUDA allocations in between (they would recycle a freed block), for
+    the one-shot and the streaming graphs; an int is accepted like a list."""
+    import specyolo
+    from specyolo.nn.init import synth_images, synth_state_dict
+
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    x = synth_images(4, 320, seed=5).cuda()
+    full = yolo.predict(x, conf=0.25, iou=0.7)
+    want = [r.boxes.data[r.boxes.data[:, 5] == 1] for r in full]
+    assert sum(len(w) for w in want) > 0 and sum(len(r) for r in full) > sum(len(w) for w in want)
+    for classes in ([1], 1):
+        first = yolo.predict(x, conf=0.25, iou=0.7, classes=classes)
+        junk = [torch.full((k,), 7, device="cuda", dtype=torch.int32) for k in (1, 2, 3, 4, 8, 16, 64, 128)]
+        torch.cuda.synchronize()
+        again = yolo.predict(x, conf=0.25, iou=0.7, classes=classes)
+        eager = yolo.predict(x, conf=0.25, iou=0.7, classes=classes, use_graph=False)
+        for a, b, c, w in zip(first, again, eager, want):
+            assert torch.equal(a.boxes.data, w) and torch.equal(b.boxes.data, w) and torch.equal(c.boxes.data, w)
+        del junk
+    s1 = list(yolo.predict([x.cpu().pin_memory()] * 2, stream=True, conf=0.25, iou=0.7, classes=[1]))
+    junk = [torch.full((k,), 9, device="cuda", dtype=torch.int32) for k in (1, 2, 4, 8, 32)]
+    s2 = list(yolo.predict([x.cpu().pin_memory()] * 4, stream=True, conf=0.25, iou=0.7, classes=[1]))
+    for batch in s1 + s2:
+        for a, w in zip(batch, want):
+            assert torch.equal(a.boxes.data, w.cpu())
+
+
+def test_boxes_are_clipped_to_the_image(lib):
+    """construct_result always ends in clip_boxes (detect/predict.py:59-73 -> ops.py:124-127), also
+    for tensor sources whose shape equals the network shape.  Low conf so that boxes reaching over the border exist."""
+    import specyolo
+    from specyolo.nn.init import synth_images, synth_state_dict
+    from specyolo.utils.ops import non_max_suppression
+
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    x = synth_images(4, 320, seed=5).cuda()
+    dense = non_max_suppression(yolo.model(x)[0], 0.02, 0.7)
+    assert any(bool(((d[:, :4] < 0) | (d[:, :4] > 320)).any()) for d in dense), "no box crosses the border: test is vacuous"
+    for res in (yolo.predict(x, conf=0.02, iou=0.7), yolo.predict(x, conf=0.02, iou=0.7, use_graph=False),
+                list(yolo.predict([x.cpu().pin_memory()], stream=True, conf=0.02, iou=0.7))[0]):
+        for r, d in zip(res, dense):
+            assert torch.equal(r.boxes.data.cpu(), _clip(d.cpu(), 320, 320))
+            n = r.boxes.xyxyn
+            assert float(n.min()) >= 0.0 and float(n.max()) <= 1.0
 
 
 def test_full_size_properties(lib):
@@ -237,7 +297,7 @@ def test_yolo11s_1280_vs_oracle(lib):
     assert (y[:, 4:] - y_ref[:, 4:]).abs().max().item() < 0.03
     res = yolo.predict(x.cuda(), conf=0.25, iou=0.7)
     dense = non_max_suppression(yolo.model(x.cuda())[0], 0.25, 0.7)
-    assert torch.equal(res[0].boxes.data, dense[0].cpu())
+    assert torch.equal(res[0].boxes.data, _clip(dense[0].cpu(), 1280, 1280))
 
 
 def test_iq_to_boxes(lib):
@@ -256,6 +316,6 @@ def test_iq_to_boxes(lib):
     y, _ = yolo.model(img)
     ref = nms_ref.non_max_suppression(y.cpu().numpy(), 0.25, 0.7)
     for r, e in zip(res, ref):
-        assert np.array_equal(r.boxes.data.numpy(), e)
+        assert np.array_equal(r.boxes.data.numpy(), _clip(torch.from_numpy(e), 640, 640).numpy())
     y_ref, _ = _oracle("yolo11_fusion_sand3_new.yaml", "s", 2, sd, img.float().cpu())
     assert (y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max().item() < 0.05

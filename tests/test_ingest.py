@@ -120,3 +120,50 @@ def test_predict_from_files(tmp_path):
             assert torch.equal(b.boxes.data, c.boxes.data)
             assert torch.equal(a.boxes.data, b.boxes.data)
     assert sum(len(r) for r in res) > 0
+
+
+def _jpeg_with_orientation(path, im_bgr, orientation):
+    from PIL import Image
+
+    pil = Image.fromarray(np.ascontiguousarray(im_bgr[:, :, ::-1]))
+    ex = Image.Exif()
+    if orientation:
+        ex[274] = orientation
+    pil.save(str(path), quality=95, subsampling=0, exif=ex.tobytes() if orientation else b"")
+
+
+def test_exif_orientation_parser(tmp_path):
+    """the host-side EXIF walk finds the orientation tag cv2.imread honours (both byte orders via PIL/handmade)."""
+    from specyolo.data.loaders import jpeg_exif_orientation
+
+    im = _spectrogram_like(48, 80, 3)
+    for o in (None, 1, 2, 3, 6, 8):
+        p = tmp_path / f"o{o}.jpg"
+        _jpeg_with_orientation(p, im, o)
+        data = p.read_bytes()
+        assert jpeg_exif_orientation(data) == (o or 1)
+        ref = cv2.imread(str(p))
+        assert ref.shape[:2] == ((80, 48) if o in (6, 8) else (48, 80))
+    # big-endian TIFF header, hand-made APP1 segment
+    import struct
+    tiff = b"MM\x00\x2a" + struct.pack(">I", 8) + struct.pack(">H", 1) + struct.pack(">HHI", 0x0112, 3, 1) + \
+        struct.pack(">H", 6) + b"\x00\x00" + struct.pack(">I", 0)
+    app1 = b"Exif\x00\x00" + tiff
+    base = (tmp_path / "oNone.jpg").read_bytes()
+    data = base[:2] + b"\xff\xe1" + struct.pack(">H", len(app1) + 2) + app1 + base[2:]
+    assert jpeg_exif_orientation(data) == 6
+    assert jpeg_exif_orientation(b"\xff\xd8\xff\xd9") == 1 and jpeg_exif_orientation(b"") == 1
+
+
+@pytest.mark.gpu
+def test_exif_rotated_jpeg_matches_cv2(tmp_path):
+    """A JPEG tagged orientation=6 must come back in cv2.imread's (rotated) frame, bit for bit (host decoder route)."""
+    from specyolo.data.loaders import imread_device
+
+    im = _spectrogram_like(96, 160, 9)
+    for o in (3, 6, 8):
+        p = tmp_path / f"rot{o}.jpg"
+        _jpeg_with_orientation(p, im, o)
+        ref = cv2.imread(str(p))
+        got = imread_device(str(p)).cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), o
