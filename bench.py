@@ -232,12 +232,16 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
 
     import specyolo
-    from specyolo.nn.init import synth_images, synth_iq, synth_state_dict
+    from specyolo.nn.init import (EMISSION_DB_RANGE, IQ_CLS_BIAS, YOLO11S_1280_CLS_BIAS, synth_images,
+                                  synth_iq_emissions, synth_state_dict)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from specyolo.dist import bind_to_gpu_numa
+
+    numa = bind_to_gpu_numa(local_rank)     # before any pinned allocation: first touch puts the staging buffers on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = measured_peaks()
@@ -315,8 +319,11 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     c3 = None
     if not args.no_extra:
         nb = args.iq_bursts
-        iq = torch.view_as_real(synth_iq(nb, 1 << 20, seed=100 + rank)).contiguous().to(dev)
-        front = specyolo.engine.IQFrontEnd(out_hw=(IMGSZ, IMGSZ))
+        iq = torch.view_as_real(synth_iq_emissions(nb, 1 << 20, seed=100 + rank)).contiguous().to(dev)
+        front = specyolo.engine.IQFrontEnd(db_min=EMISSION_DB_RANGE[0], db_max=EMISSION_DB_RANGE[1], out_hw=(IMGSZ, IMGSZ))
+        # same architecture and seed, class-logit bias raised for letterboxed spectrograms (specyolo/nn/init.py)
+        yolo.load_state_dict(synth_state_dict(yolo.model, seed=0, cls_bias=IQ_CLS_BIAS))
+        yolo.fuse()
         p3 = specyolo.DetectionPredictor(yolo.model, pred_args, front=front)
         p3.infer_pipelined(iq, 3, args.inflight)
         torch.cuda.synchronize()
@@ -350,7 +357,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
     if not args.no_extra:
         B4 = args.c4_batch
         y4 = specyolo.YOLO("yolo11s.yaml", nc=80)
-        y4.load_state_dict(synth_state_dict(y4.model, seed=3))
+        y4.load_state_dict(synth_state_dict(y4.model, seed=3, cls_bias=YOLO11S_1280_CLS_BIAS))
         y4.to(dev)
         y4.fuse()
         x4 = synth_images(B4, 1280, seed=200 + rank, dtype=torch.uint8).to(dev)
@@ -402,7 +409,7 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
                        "sharding": "images split across GPUs, no collective on the data path",
                        "detections_last_step": n_det},
             "e2e": {"value": world * B * args.steps / t_e2e_max, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "h2d_gbs_per_gpu": h2d * args.steps / t_e2e_max / 1e9,
+                    "d2h_bytes_per_step": d2h, "h2d_gbs_per_gpu": h2d * args.steps / t_e2e_max / 1e9, "numa": numa,
                     "api": "specyolo.YOLO.predict(iterable of pinned uint8 batches, stream=True)"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,

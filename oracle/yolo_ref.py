@@ -101,9 +101,15 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
 class Ref:
     """Functional forward over a state_dict."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], fuse: bool = False, device=None, dtype=torch.float32):
+    def __init__(self, sd: Dict[str, torch.Tensor], fuse: bool = False, device=None, dtype=torch.float32,
+                 bf16_storage: bool = False):
+        """bf16_storage: emulate a bf16 pipeline with fp32 accumulation on the CPU — BN-folded weights rounded to bf16,
+        every Conv output rounded to bf16 (what any bf16 implementation stores between layers), all arithmetic fp32.
+        Used by the parity tests to measure the error FLOOR of bf16 storage against the fp32 reference, i.e. how far a
+        numerically ideal bf16 implementation sits from fp32 on the same weights."""
         self.sd = {k: v.detach().to(device=device, dtype=dtype) for k, v in sd.items() if v.is_floating_point()}
-        self.fuse = fuse
+        self.fuse = fuse or bf16_storage
+        self.bf16_storage = bf16_storage
         self._folded: Dict[str, tuple] = {}
 
     def folded(self, p):
@@ -115,6 +121,8 @@ class Ref:
             scale = sd[p + ".bn.weight"].float() / torch.sqrt(sd[p + ".bn.running_var"].float() + BN_EPS)
             w = (sd[p + ".conv.weight"].float() * scale.view(-1, 1, 1, 1)).to(sd[p + ".conv.weight"].dtype)
             b = (sd[p + ".bn.bias"].float() - sd[p + ".bn.running_mean"].float() * scale).to(w.dtype)
+            if self.bf16_storage:
+                w = w.to(torch.bfloat16).to(w.dtype)
             t = self._folded[p] = (w, b)
         return t
 
@@ -123,8 +131,11 @@ class Ref:
         sd = self.sd
         if self.fuse:
             w, b = self.folded(p)
+            if self.bf16_storage:
+                x = x.to(torch.bfloat16).to(x.dtype)
             y = F.conv2d(x, w, b, s, autopad(k, None, d), d, g)
-            return F.silu(y) if act else y
+            y = F.silu(y) if act else y
+            return y.to(torch.bfloat16).to(y.dtype) if self.bf16_storage else y
         w = sd[p + ".conv.weight"]
         y = F.conv2d(x, w, None, s, autopad(k, None, d), d, g)
         y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],

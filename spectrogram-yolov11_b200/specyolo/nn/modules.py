@@ -36,6 +36,8 @@ def _as_fmap(x: torch.Tensor) -> torch.Tensor:
     """Accept what reference callers pass (NCHW fp32/bf16/uint8) and bring it to NHWC bf16."""
     if x.dtype == torch.bfloat16 and x.dim() == 4 and (x.stride(1) == 1 or x.shape[1] == 1):
         return x
+    if x.dtype == torch.float16:        # the reference's half=True path hands fp16 tensors to the first block
+        x = x.float()
     return ops.to_nhwc_bf16(x)
 
 
@@ -57,20 +59,27 @@ class Conv(nn.Module):
         self._packed: Optional[ops.PackedConv] = None
 
     # -- weight prep ---------------------------------------------------------------------------
+    def _bn_terms(self):
+        """(conv bias or None, (gamma, beta, mean, var) or None, eps): `bn` is gone once the reference's BaseModel.fuse()
+        (nn/tasks.py:223-251) has folded it into `conv` — the instance may be a reference Conv behind the shim."""
+        bn = getattr(self, "bn", None)
+        if bn is None:
+            return self.conv.bias, None, 0.0
+        return self.conv.bias, (bn.weight, bn.bias, bn.running_mean, bn.running_var), bn.eps
+
     def packed(self) -> ops.PackedConv:
-        if self._packed is None:
+        if getattr(self, "_packed", None) is None:
             c = self.conv
-            self._packed = ops.fold_pack(
-                c.weight, None, (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var),
-                self.bn.eps, c.stride[0], c.padding[0], c.dilation[0], c.groups, isinstance(self.act, nn.SiLU))
+            cb, bn, eps = self._bn_terms()
+            self._packed = ops.fold_pack(c.weight, cb, bn, eps, c.stride[0], c.padding[0], c.dilation[0], c.groups,
+                                         isinstance(self.act, nn.SiLU))
         return self._packed
 
     def packed_from_blocked(self) -> ops.PackedConv:
         """This 3x3 / stride-2 conv as a 2x2 conv over a 2x2-blocked input (ops.pack_from_blocked)."""
         if getattr(self, "_packed_blocked", None) is None:
-            self._packed_blocked = ops.pack_from_blocked(
-                self.conv.weight, None, (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var),
-                self.bn.eps, isinstance(self.act, nn.SiLU))
+            cb, bn, eps = self._bn_terms()
+            self._packed_blocked = ops.pack_from_blocked(self.conv.weight, cb, bn, eps, isinstance(self.act, nn.SiLU))
         return self._packed_blocked
 
     def folded_depthwise(self):
@@ -78,10 +87,14 @@ class Conv(nn.Module):
         (fuse_conv_and_bn, ultralytics/utils/torch_utils.py:238-265, on the device; one-off)."""
         if getattr(self, "_folded_dw", None) is None:
             c = self.conv
-            scale = self.bn.weight.detach().float() / torch.sqrt(self.bn.running_var.detach().float() + self.bn.eps)
-            w = (c.weight.detach().float() * scale.view(-1, 1, 1, 1)).view(c.out_channels, 9).t().contiguous()
-            b = (self.bn.bias.detach().float() - self.bn.running_mean.detach().float() * scale).contiguous()
-            self._folded_dw = (w, b)
+            cb, bn, eps = self._bn_terms()
+            w = c.weight.detach().float()
+            b = torch.zeros(c.out_channels, device=w.device) if cb is None else cb.detach().float()
+            if bn is not None:
+                scale = bn[0].detach().float() / torch.sqrt(bn[3].detach().float() + eps)
+                w = w * scale.view(-1, 1, 1, 1)
+                b = bn[1].detach().float() + (b - bn[2].detach().float()) * scale
+            self._folded_dw = (w.view(c.out_channels, 9).t().contiguous(), b.contiguous())
         return self._folded_dw
 
     def is_depthwise3x3(self) -> bool:
@@ -175,14 +188,15 @@ class C3(nn.Module):
     def forward(self, x, out=None):
         x = _as_fmap(x)
         B, _, H, W = x.shape
-        cat = ops.new_act(B, 2 * self.c_, H, W, x.device)
+        c_ = self.cv1.conv.out_channels
+        cat = ops.new_act(B, 2 * c_, H, W, x.device)
         t = self.cv1(x)
         last = len(self.m) - 1
         for j, m in enumerate(self.m):
-            t = m(t, out=cat[:, : self.c_] if j == last else None)
+            t = m(t, out=cat[:, : c_] if j == last else None)
         if last < 0:
-            cat[:, : self.c_].copy_(t)
-        self.cv2(x, out=cat[:, self.c_:])
+            cat[:, : c_].copy_(t)
+        self.cv2(x, out=cat[:, c_:])
         return self.cv3(cat, out=out)
 
 
@@ -241,9 +255,10 @@ class SPPF(nn.Module):
     def forward(self, x, out=None):
         x = _as_fmap(x)
         B, _, H, W = x.shape
-        cat = ops.new_act(B, 4 * self.c_, H, W, x.device)
-        self.cv1(x, out=cat[:, : self.c_])
-        ops.sppf_pool(cat, self.c_)
+        c_ = self.cv1.conv.out_channels
+        cat = ops.new_act(B, 4 * c_, H, W, x.device)
+        self.cv1(x, out=cat[:, : c_])
+        ops.sppf_pool(cat, c_)
         return self.cv2(cat, out=out)
 
 
@@ -264,12 +279,11 @@ class Attention(nn.Module):
         self._pe_f32 = None
 
     def _pe_weights(self):
-        if self._pe_f32 is None or self._pe_f32[0].device != self.pe.conv.weight.device:
-            bn = self.pe.bn
-            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
-            w = (self.pe.conv.weight.detach().float().view(-1, 9) * s[:, None]).contiguous()
-            b = (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
-            self._pe_f32 = (w, b)
+        cur = getattr(self, "_pe_f32", None)
+        if cur is None or cur[0].device != self.pe.conv.weight.device:
+            w9, b = self.pe.folded_depthwise()               # [9, C] tap-major, BN folded (or already fused)
+            self._pe_f32 = (w9.t().contiguous(), b)
+            self.pe._folded_dw = None
         return self._pe_f32
 
     def _apply(self, fn, *a, **k):
@@ -453,6 +467,13 @@ class _HeadConv(nn.Conv2d):
         return super()._load_from_state_dict(*a, **k)
 
 
+def head_packed(conv: nn.Conv2d) -> ops.PackedConv:
+    """Packed weights of the plain nn.Conv2d(c, n, 1) (with bias) that ends a Detect branch; cached on the module."""
+    if getattr(conv, "_packed", None) is None:
+        conv._packed = ops.fold_pack(conv.weight, conv.bias, None, 0.0, 1, 0, 1, 1, act=False)
+    return conv._packed
+
+
 class Detect(nn.Module):
     """YOLO Detect head (ultralytics/nn/modules/head.py:21-172).
 
@@ -508,16 +529,17 @@ class Detect(nn.Module):
         The 2 x nl branches are independent chains of small convs: they run as parallel streams."""
         bufs, hw, views, fns = [], [], [], []
         xs = [_as_fmap(x) for x in xs]
+        no_stride = (self.no + 3) // 4 * 4
         for x in xs:
             B, _, H, W = x.shape
-            buf = torch.empty((B, H * W, self.no_stride), device=x.device, dtype=torch.float32)
-            views.append(buf.view(B, H, W, self.no_stride).permute(0, 3, 1, 2))   # [B, no_stride, H, W], NHWC memory
+            buf = torch.empty((B, H * W, no_stride), device=x.device, dtype=torch.float32)
+            views.append(buf.view(B, H, W, no_stride).permute(0, 3, 1, 2))   # [B, no_stride, H, W], NHWC memory
             bufs.append(buf)
             hw.append((H, W))
 
         def box_branch(i):
             t = self.cv2[i][1](self.cv2[i][0](xs[i]))
-            ops.conv2d(t, self.cv2[i][2].packed(), out=views[i][:, : 4 * self.reg_max], out_fp32=True)
+            ops.conv2d(t, head_packed(self.cv2[i][2]), out=views[i][:, : 4 * self.reg_max], out_fp32=True)
 
         def dw_pw(pair, x):
             """Sequential(DWConv 3x3, Conv 1x1) (head.py:51-58): one fused kernel when the shapes allow it."""
@@ -532,7 +554,7 @@ class Detect(nn.Module):
                 t = self.cv3[i][1](self.cv3[i][0](xs[i]))
             else:
                 t = dw_pw(self.cv3[i][1], dw_pw(self.cv3[i][0], xs[i]))
-            ops.conv2d(t, self.cv3[i][2].packed(), out=views[i][:, 4 * self.reg_max: self.no], out_fp32=True)
+            ops.conv2d(t, head_packed(self.cv3[i][2]), out=views[i][:, 4 * self.reg_max: self.no], out_fp32=True)
 
         for i in range(len(xs)):
             fns.append(lambda i=i: box_branch(i))
@@ -543,5 +565,5 @@ class Detect(nn.Module):
     def forward(self, xs: List[torch.Tensor]):
         bufs, hw = self.head_logits(xs)
         y, _, _ = ops.detect_decode(bufs, hw, [float(s) for s in self.stride], self.nc, want_dense=True)
-        raw = [b.view(b.shape[0], h, w, self.no_stride)[..., : self.no].permute(0, 3, 1, 2) for b, (h, w) in zip(bufs, hw)]
+        raw = [b.view(b.shape[0], h, w, b.shape[2])[..., : self.no].permute(0, 3, 1, 2) for b, (h, w) in zip(bufs, hw)]
         return y if self.export else (y, raw)

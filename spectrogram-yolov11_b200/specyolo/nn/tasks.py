@@ -197,12 +197,13 @@ class DetectionModel(nn.Module):
     def _run_trunk(self, x):
         """All layers except Detect; returns the list of Detect inputs."""
         y = []
-        groups = self._parallel_groups()
+        groups = DetectionModel._parallel_groups(self)      # (self may be the reference's model behind the shim)
         layers = list(self.model[:-1])
         i = 0
         # stem pair: layer 0 writes its output 2x2-blocked and layer 1 (3x3 / s2) reads it as a 2x2 / s1 conv over
         # 4c channels — one 128-byte-row TMA box per tile instead of nine strided boxes (same arithmetic)
-        if (len(layers) > 1 and isinstance(layers[0], Conv) and type(layers[1]) is Conv and layers[0].is_stem()
+        if (len(layers) > 1 and hasattr(layers[0], "is_stem") and hasattr(layers[1], "takes_blocked")
+                and type(layers[1]).__name__ == "Conv" and layers[0].is_stem()
                 and layers[1].takes_blocked() and layers[1].f == -1 and 0 not in self.save and x.dim() == 4
                 and x.stride(1) != 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
                 and layers[0].packed().s2d is not None):
@@ -226,9 +227,9 @@ class DetectionModel(nn.Module):
                 continue
             if m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
-            if isinstance(x, UpsampledView) and not isinstance(m, Fusion):
+            if isinstance(x, UpsampledView) and type(m).__name__ != "Fusion":
                 x = x.materialise()
-            if isinstance(m, Concat):
+            if type(m).__name__ == "Concat":
                 x = [t.materialise() if isinstance(t, UpsampledView) else t for t in x]
             x = m(x)
             y.append(x if m.i in self.save else None)

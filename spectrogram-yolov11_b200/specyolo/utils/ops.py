@@ -8,6 +8,21 @@ import torch
 from .. import ops as _ops
 
 
+# torchvision.ops.nms (the call at ultralytics/utils/ops.py:312) has two kernels that disagree on pairs whose IoU sits
+# within one ulp of the threshold: the CPU kernel compares the fp32 IoU with the threshold as a DOUBLE, the CUDA kernel
+# takes the threshold as a FLOAT (measured on the B200: profiles/parity_nms_vs_torchvision_cuda.json — boxes at exactly
+# IoU 1/3 or 3/5 are suppressed by the CPU kernel and kept by the CUDA kernel).  "cpu" (default) is the semantics the
+# golden vectors of the real reference pin (tests/golden/nms_cases.npz); "cuda" reproduces what the reference returns
+# when it runs on a GPU.  Everything else (stable descending sort, fp32 IoU arithmetic, strict >) is common.
+TORCHVISION_NMS_SEMANTICS = "cpu"
+
+
+def _iou_threshold(iou_thres: float) -> float:
+    if TORCHVISION_NMS_SEMANTICS == "cuda":
+        return float(torch.tensor(iou_thres, dtype=torch.float32).item())   # (double)(float)thr: compare as floats
+    return float(iou_thres)
+
+
 def xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
     """ultralytics/utils/ops.py:432-449 (plumbing; the kernels do this conversion themselves)."""
     assert x.shape[-1] == 4, f"input shape last dimension expected 4 but input shape is {x.shape}"
@@ -54,7 +69,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     cls_t: Optional[torch.Tensor] = None
     if classes is not None:
         cls_t = torch.tensor(list(classes), device=pred.device, dtype=torch.int32)
-    out, cnt, keep, _ = _ops.nms(prediction=pred, B=bs, nc=nc, A=A, conf_thres=conf_thres, iou_thres=iou_thres,
+    out, cnt, keep, _ = _ops.nms(prediction=pred, B=bs, nc=nc, A=A, conf_thres=conf_thres, iou_thres=_iou_threshold(iou_thres),
                                  agnostic=agnostic, multi_label=multi_label, max_det=max_det, max_nms=max_nms,
                                  max_wh=float(max_wh), classes=cls_t)
     counts = cnt.tolist()  # the one device->host sync of the whole batch

@@ -185,21 +185,31 @@ def test_predict_classes_filter_survives_graph_replay(lib):
     yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
     yolo.to("cuda")
     x = synth_images(4, 320, seed=5).cuda()
-    full = yolo.predict(x, conf=0.25, iou=0.7)
-    want = [r.boxes.data[r.boxes.data[:, 5] == 1] for r in full]
-    assert sum(len(w) for w in want) > 0 and sum(len(r) for r in full) > sum(len(w) for w in want)
-    for classes in ([1], 1):
-        first = yolo.predict(x, conf=0.25, iou=0.7, classes=classes)
-        junk = [torch.full((k,), 7, device="cuda", dtype=torch.int32) for k in (1, 2, 3, 4, 8, 16, 64, 128)]
-        torch.cuda.synchronize()
-        again = yolo.predict(x, conf=0.25, iou=0.7, classes=classes)
-        eager = yolo.predict(x, conf=0.25, iou=0.7, classes=classes, use_graph=False)
-        for a, b, c, w in zip(first, again, eager, want):
-            assert torch.equal(a.boxes.data, w) and torch.equal(b.boxes.data, w) and torch.equal(c.boxes.data, w)
-        del junk
-    s1 = list(yolo.predict([x.cpu().pin_memory()] * 2, stream=True, conf=0.25, iou=0.7, classes=[1]))
+    for conf in (0.05, 0.1, 0.15, 0.2, 0.25):                   # lowest threshold at which max_det does not truncate
+        full = yolo.predict(x, conf=conf, iou=0.7)
+        if max(len(r) for r in full) < 300:
+            break
+    ncls = [sum(int((r.boxes.data[:, 5] == c).sum()) for r in full) for c in (0, 1)]
+    assert sum(ncls) > 0
+    keep_c = 0 if ncls[0] >= ncls[1] else 1                     # the class that certainly has detections
+    # per-class NMS (class offsets, ops.py:305-311) + max_det far away: filtering before NMS == filtering its output
+    assert max(len(r) for r in full) < 300
+    for cls_id in (keep_c, 1 - keep_c):
+        want = [r.boxes.data[r.boxes.data[:, 5] == cls_id] for r in full]
+        for classes in ([cls_id], cls_id):
+            first = yolo.predict(x, conf=conf, iou=0.7, classes=classes)
+            junk = [torch.full((k,), 7, device="cuda", dtype=torch.int32) for k in (1, 2, 3, 4, 8, 16, 64, 128)]
+            torch.cuda.synchronize()
+            again = yolo.predict(x, conf=conf, iou=0.7, classes=classes)
+            eager = yolo.predict(x, conf=conf, iou=0.7, classes=classes, use_graph=False)
+            for a, b, c, w in zip(first, again, eager, want):
+                assert torch.equal(a.boxes.data, w) and torch.equal(b.boxes.data, w) and torch.equal(c.boxes.data, w)
+            del junk
+    want = [r.boxes.data[r.boxes.data[:, 5] == keep_c] for r in full]
+    assert sum(len(w) for w in want) > 0
+    s1 = list(yolo.predict([x.cpu().pin_memory()] * 2, stream=True, conf=conf, iou=0.7, classes=[keep_c]))
     junk = [torch.full((k,), 9, device="cuda", dtype=torch.int32) for k in (1, 2, 4, 8, 32)]
-    s2 = list(yolo.predict([x.cpu().pin_memory()] * 4, stream=True, conf=0.25, iou=0.7, classes=[1]))
+    s2 = list(yolo.predict([x.cpu().pin_memory()] * 4, stream=True, conf=conf, iou=0.7, classes=[keep_c]))
     for batch in s1 + s2:
         for a, w in zip(batch, want):
             assert torch.equal(a.boxes.data, w.cpu())
@@ -251,6 +261,11 @@ def test_full_size_properties(lib):
         d = r.boxes.data
         assert len(d) <= 300 and bool((d[:, 4] > conf).all())
         assert bool((d[1:, 4] <= d[:-1, 4]).all())
+        if len(d) == 0:
+            continue
+        assert float(d[:, :4].min()) >= 0.0 and float(d[:, :4].max()) <= 640.0      # clip_boxes (ops.py:335-354)
+        # suppression was decided on the UNCLIPPED boxes: check the overlap post-condition on boxes the clip left alone
+        d = d[(d[:, 0] > 0) & (d[:, 1] > 0) & (d[:, 2] < 640) & (d[:, 3] < 640)]
         if len(d) > 1:
             b = d[:, :4] + d[:, 5:6] * 7680.0                       # class offset, as in ops.py:305-311
             lt = torch.max(b[:, None, :2], b[None, :, :2]); rb = torch.min(b[:, None, 2:], b[None, :, 2:])
@@ -262,6 +277,7 @@ def test_full_size_properties(lib):
     # idempotence on the image with the most detections: kept boxes as a dense [1, 4+nc, n] prediction
     r = max(res, key=len)
     d = r.boxes.data.cuda()
+    d = d[(d[:, 0] > 0) & (d[:, 1] > 0) & (d[:, 2] < 640) & (d[:, 3] < 640)]      # boxes the final clip left alone
     n = len(d)
     pred = torch.zeros((1, 6, n), device="cuda")
     pred[0, 0] = (d[:, 0] + d[:, 2]) / 2; pred[0, 1] = (d[:, 1] + d[:, 3]) / 2

@@ -1,0 +1,117 @@
+"""Executable drop-in: specyolo.ultralytics_shim binds the B200 kernels into the REFERENCE package
+(oracle/_ref, installed by oracle/Makefile) and the reference's own `YOLO(cfg).predict()` runs them.
+
+CPU: the shim classes are subclasses of the reference's, build through the reference's parse_model (including its CPU
+stride probe), keep its state_dict keys, and leave CPU inference untouched (bit-identical fall-through).
+GPU: `ultralytics.YOLO(cfg).predict(x, device=0)` with the shim vs without it, at detection level."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from _parity import compare_detections, record
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+CFG = "yolo11s_fusion_sand3_new.yaml"
+
+
+def _reference():
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference package not available (oracle/_ref absent)")
+    return ref_loader.import_reference()
+
+
+def _ref_yolo(ultralytics, sd):
+    from ultralytics.nn.tasks import DetectionModel as RefModel
+
+    cfg = Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG
+    m = RefModel(str(cfg), nc=2, verbose=False)
+    m.load_state_dict(sd, strict=True)
+    y = ultralytics.YOLO(str(cfg), task="detect")
+    y.model = m.eval()
+    return y
+
+
+def _sd():
+    import specyolo
+    from specyolo.nn.init import synth_state_dict
+
+    return synth_state_dict(specyolo.DetectionModel(CFG, nc=2), seed=0)
+
+
+def test_shim_builds_through_the_reference_and_falls_through_on_cpu(lib):
+    ultralytics = _reference()
+    import ultralytics.nn.modules.block as rblock
+    import ultralytics.nn.modules.conv as rconv
+    import ultralytics.nn.tasks as rtasks
+    import ultralytics.utils.ops as rops
+    from specyolo import ultralytics_shim as shim
+    from specyolo.nn.init import synth_images
+
+    sd = _sd()
+    x = synth_images(2, 160, seed=3)
+    plain = _ref_yolo(ultralytics, sd)
+    keys_plain = list(plain.model.state_dict().keys())
+    res_plain = plain.predict(x, device="cpu", conf=0.25, verbose=False)
+    orig = (rtasks.Conv, rtasks.C3k2, rtasks.Detect, rops.non_max_suppression, rtasks.BaseModel._predict_once)
+    shims = shim.install()
+    try:
+        assert rtasks.Conv is shims["Conv"] and rblock.Bottleneck is shims["Bottleneck"] and rconv.Conv is shims["Conv"]
+        for name, cls in shims.items():
+            base = [b for b in cls.__mro__[1:] if b.__module__.startswith("ultralytics.")]
+            assert base and base[0].__name__ == name, name                  # a subclass of the reference's own class
+        y = _ref_yolo(ultralytics, sd)                                      # parse_model + CPU stride probe with the shims bound
+        assert type(y.model.model[0]) is shims["Conv"] and type(y.model.model[-1]) is shims["Detect"]
+        assert type(y.model.model[2].m[0]) is shims["Bottleneck"] and type(y.model.model[10].m[0].attn) is shims["Attention"]
+        assert list(y.model.state_dict().keys()) == keys_plain
+        assert [float(s) for s in y.model.stride] == [8.0, 16.0, 32.0]
+        res = y.predict(x, device="cpu", conf=0.25, verbose=False)          # CPU: the reference's own code, untouched
+        for a, b in zip(res, res_plain):
+            assert torch.equal(a.boxes.data, b.boxes.data)
+        assert sum(len(r.boxes) for r in res) > 0
+    finally:
+        shim.uninstall()
+    assert (rtasks.Conv, rtasks.C3k2, rtasks.Detect, rops.non_max_suppression, rtasks.BaseModel._predict_once) == orig
+
+
+@pytest.mark.gpu
+def test_reference_predict_with_shim_vs_without(lib):
+    """The reference's public API on the GPU, shim bound vs stock (PyTorch eager cuDNN fp32 + torchvision CUDA nms)."""
+    ultralytics = _reference()
+    from specyolo import _lib
+    from specyolo import ultralytics_shim as shim
+    from specyolo.nn.init import synth_images
+
+    sd = _sd()
+    x = (synth_images(64, 640, seed=0, dtype=torch.uint8)[:16].float() / 255)
+    stock = _ref_yolo(ultralytics, sd)
+    ref = [r.boxes.data.cpu().numpy() for r in stock.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+    shim.install()
+    try:
+        y = _ref_yolo(ultralytics, sd)
+        n0 = _lib.load().specyolo_launch_count()
+        got_res = y.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)
+        launches = int(_lib.load().specyolo_launch_count() - n0)
+        got = [r.boxes.data.cpu().numpy() for r in got_res]
+        again = [r.boxes.data.cpu().numpy() for r in y.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+        half = [r.boxes.data.cpu().numpy() for r in y.predict(x, device=0, half=True, conf=0.25, iou=0.7, verbose=False)]
+    finally:
+        shim.uninstall()
+    assert launches > 80, f"the B200 kernels did not run behind the reference API ({launches} launches)"
+    for a, b in zip(got, again):
+        assert np.array_equal(a, b)
+    stats = compare_detections(ref, got)
+    stats["launches"] = launches
+    record("shim_reference_api_b16_640", stats)
+    # stock arm = PyTorch eager fp32 on the GPU (cuDNN, TF32 allowed by default); shim arm = bf16 tcgen05 kernels: the
+    # difference is the bf16 storage floor measured in tests/test_parity_baseline.py, plus NMS-winner flips among
+    # near-identical overlapping candidates.  Asserted: the reference's confident detections are found.
+    assert stats["matched_rate"] >= 0.97, stats
+    s2 = compare_detections(ref, half)                                       # half=True: fp16 input, weights repacked from fp16
+    record("shim_reference_api_b16_640_half", s2)
+    assert s2["matched_rate"] >= 0.96, s2
