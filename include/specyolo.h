@@ -126,6 +126,21 @@ typedef struct {
 } specyolo_dwpw_t;
 int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream);
 
+/* Fused Bottleneck: y = [x +] cv2(cv1(x)) with cv1 = Conv(C, Cmid, 3) and cv2 = Conv(Cmid, Cout, 3), both 3x3 / stride 1 /
+ * pad 1 + BN + SiLU (ultralytics/nn/modules/block.py:713-726, the inner block of C3k2 :1659-1671) in ONE kernel: the Cmid-
+ * channel intermediate stays in shared memory (14 x 14-pixel output tiles, 1-pixel halo recomputed), the shortcut is
+ * added in the second epilogue.  w*_packed / b* come from specyolo_fold_pack_conv of the two convs (groups 1).
+ * Shapes taken: C = Cout in {32, 64}, Cmid in {16, 32} (specyolo_bottleneck_ok); others run as two conv launches. */
+typedef struct {
+    const void* x; int B, H, W, C, x_pixstride;                 /* bf16 NHWC input window (also the shortcut)            */
+    const void* w1_packed; const float* b1; int Cmid, n_pad1;
+    const void* w2_packed; const float* b2; int Cout, n_pad2;
+    int add;                                                    /* 1: shortcut (Bottleneck.add: shortcut and c1 == c2)    */
+    void* y; int y_pixstride;                                   /* bf16 NHWC output window, Cout channels                */
+} specyolo_bneck_t;
+int specyolo_bottleneck_ok(int C, int Cmid, int Cout, int n_pad1, int n_pad2);
+int specyolo_bottleneck(const specyolo_bneck_t* a, void* stream);
+
 /* Stem conv reading the NCHW network input directly (first layer, Cin = 3):
  * x is NCHW fp32/bf16/u8 (u8 is scaled by 1/255 like predictor.py:133-135), w is fp32
  * [Cout][3][3][3] *folded* weights (device), output NHWC bf16 with SiLU. */

@@ -51,6 +51,8 @@ int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, 
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
                              cudaStream_t);
 int stft_init();
+bool bneck_pair_ok(int, int, int, int, int);
+int bneck_pair_launch(const specyolo_bneck_t*, cudaStream_t);
 
 }  // namespace specyolo
 
@@ -183,6 +185,17 @@ int specyolo_stem_pair(const specyolo_stem_pair_t* a, void* stream) {
     SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->y_pixstride >= a->Cout, SPECYOLO_ERR_INVALID,
              "stem_pair: bad sizes");
     return stem_pair_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_bottleneck_ok(int C, int Cmid, int Cout, int n_pad1, int n_pad2) {
+    return bneck_pair_ok(C, Cmid, Cout, n_pad1, n_pad2) ? 1 : 0;
+}
+
+int specyolo_bottleneck(const specyolo_bneck_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->w1_packed && a->b1 && a->w2_packed && a->b2 && a->y, SPECYOLO_ERR_INVALID, "bottleneck: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->Cout,
+             SPECYOLO_ERR_INVALID, "bottleneck: bad sizes");
+    return bneck_pair_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_stem_conv3x3s2(const void* x, int x_dtype, int B, int H, int W, const float* w, const float* bias,

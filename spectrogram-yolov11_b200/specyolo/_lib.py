@@ -56,6 +56,15 @@ class StemPairArgs(C.Structure):
     ]
 
 
+class BneckArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("x_pixstride", C.c_int),
+        ("w1_packed", C.c_void_p), ("b1", C.c_void_p), ("Cmid", C.c_int), ("n_pad1", C.c_int),
+        ("w2_packed", C.c_void_p), ("b2", C.c_void_p), ("Cout", C.c_int), ("n_pad2", C.c_int),
+        ("add", C.c_int), ("y", C.c_void_p), ("y_pixstride", C.c_int),
+    ]
+
+
 class FusionArgs(C.Structure):
     _fields_ = [
         ("k", C.c_int), ("x", C.c_void_p * 3), ("pixstride", C.c_int * 3), ("upshift", C.c_int * 3),
@@ -113,6 +122,8 @@ SIGNATURES = {
     "specyolo_dwconv_pwconv": (C.c_int, [C.POINTER(DwpwArgs), C.c_void_p]),
     "specyolo_stem_pair_ok": (C.c_int, [C.c_int] * 5),
     "specyolo_stem_pair": (C.c_int, [C.POINTER(StemPairArgs), C.c_void_p]),
+    "specyolo_bottleneck_ok": (C.c_int, [C.c_int] * 5),
+    "specyolo_bottleneck": (C.c_int, [C.POINTER(BneckArgs), C.c_void_p]),
     "specyolo_stem_conv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_stem_space_to_depth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,

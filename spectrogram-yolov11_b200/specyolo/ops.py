@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StemPairArgs, StftArgs, check
+from ._lib import BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StemPairArgs, StftArgs, check
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -281,6 +281,37 @@ def dwconv_pwconv(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, pw: P
     a.dw_w, a.dw_b, a.pw_packed, a.pw_bias = dw_w.data_ptr(), dw_b.data_ptr(), pw.w.data_ptr(), pw.bias.data_ptr()
     a.Cout, a.n_pad, a.y, a.y_pixstride = pw.cout, pw.n_pad, out.data_ptr(), ypix
     check(_lib.load().specyolo_dwconv_pwconv(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def bottleneck_ok(x: torch.Tensor, pc1: PackedConv, pc2: PackedConv) -> bool:
+    """Shapes the fused Bottleneck kernel takes (specyolo_bottleneck_ok): two dense 3x3 / s1 / p1 SiLU convs, C -> Cmid -> C."""
+    for pc in (pc1, pc2):
+        if pc.k != 3 or pc.s != 1 or pc.p != 1 or pc.d != 1 or pc.g != 1 or pc.g_orig != 1 or pc.act != _lib.ACT_SILU:
+            return False
+    if x.dtype != torch.bfloat16 or x.shape[1] != pc1.cin or pc1.cout != pc2.cin or pc1.cin != pc1.cin_true or \
+            pc2.cin != pc2.cin_true:
+        return False
+    return bool(_lib.load().specyolo_bottleneck_ok(pc1.cin, pc1.cout, pc2.cout, pc1.n_pad, pc2.n_pad))
+
+
+def bottleneck(x: torch.Tensor, pc1: PackedConv, pc2: PackedConv, add: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = [x +] conv3x3(conv3x3(x)) (Conv + BN + SiLU each) in one kernel (specyolo_bottleneck): the intermediate stays
+    in shared memory, the shortcut is added in the second epilogue."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if not bottleneck_ok(x, pc1, pc2) or (add and pc2.cout != Cc):
+        raise ValueError("bottleneck: unsupported shapes / weights")
+    if out is None:
+        out = new_act(B, pc2.cout, H, W, x.device)
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, pc2.cout, H, W) or out.dtype != torch.bfloat16:
+        raise ValueError("bottleneck: out shape / dtype mismatch")
+    a = BneckArgs()
+    a.x, a.B, a.H, a.W, a.C, a.x_pixstride = x.data_ptr(), B, H, W, Cc, xpix
+    a.w1_packed, a.b1, a.Cmid, a.n_pad1 = pc1.w.data_ptr(), pc1.bias.data_ptr(), pc1.cout, pc1.n_pad
+    a.w2_packed, a.b2, a.Cout, a.n_pad2 = pc2.w.data_ptr(), pc2.bias.data_ptr(), pc2.cout, pc2.n_pad
+    a.add, a.y, a.y_pixstride = int(bool(add)), out.data_ptr(), ypix
+    check(_lib.load().specyolo_bottleneck(C.byref(a), _lib.stream_ptr()))
     return out
 
 

@@ -56,8 +56,16 @@ def _stem_pair_work(r, x, pc0, pc1b, out=None):
             f"fused stem 3->{pc0.cout}->{pc1b.cout} (u8 in) {H:4d}x{W:4d}")
 
 
+def _bneck_work(r, x, pc1, pc2, add, out=None):
+    B, C, H, W = x.shape
+    fl = 2.0 * B * H * W * 9 * (C * pc1.cout + pc1.cout * pc2.cout)
+    return ("conv2d", fl, 2.0 * (x.numel() + r.numel()) + 2.0 * (pc1.w.numel() + pc2.w.numel()),
+            f"bottleneck {C:4d}->{pc1.cout:3d}->{pc2.cout:4d} 3x3+3x3 fused {H:4d}x{W:4d} M={B * H * W:8d}" + (" +res" if add else ""))
+
+
 _WORK = {
     "conv2d": _conv_work,
+    "bottleneck": _bneck_work,
     "dwconv_pwconv": _dwpw_work,
     "stem_pair": _stem_pair_work,
     "stem_space_to_depth": lambda r, x: ("stem_space_to_depth", 0.0, x.numel() * x.element_size() + 2.0 * r.numel(),

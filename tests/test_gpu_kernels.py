@@ -247,6 +247,45 @@ def test_stem_pair_fused(lib, shape):
     assert float(buf[:, :16].float().abs().max()) == 0.0 and float(buf[:, 16 + c1:].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 16, 56, 56, True), (3, 64, 32, 40, 40, True), (1, 64, 32, 29, 47, True),
+                                   (2, 32, 32, 20, 20, True), (1, 32, 16, 160, 160, True), (2, 64, 32, 33, 15, False),
+                                   (5, 64, 16, 14, 14, True), (1, 32, 16, 13, 31, False)])
+def test_bottleneck_fused(lib, shape):
+    """Bottleneck (3x3 -> 3x3 + shortcut, block.py:713-726) in one kernel == the two plain convs: torch fp32 reference on
+    bf16-rounded operands with the intermediate rounded to bf16 (what the two-launch route stores), and == the
+    two-launch route of this library.  Sizes with partial 14 x 14 tiles in both directions, tiles that are entirely
+    border, and the output written into a channel slice of a wider buffer (as C3k2 does)."""
+    from specyolo import ops
+
+    B, C, Cm, H, W, add = shape
+    gen = torch.Generator().manual_seed(57 + C + Cm + H)
+    x = torch.randn((B, C, H, W), generator=gen)
+    w1 = torch.randn((Cm, C, 3, 3), generator=gen) * math.sqrt(2.0 / (9 * C))
+    w2 = torch.randn((C, Cm, 3, 3), generator=gen) * math.sqrt(2.0 / (9 * Cm))
+    b1 = torch.randn(Cm, generator=gen) * 0.2
+    b2 = torch.randn(C, generator=gen) * 0.2
+    pc1 = ops.fold_pack(w1.to(DEV), b1.to(DEV), None, 0.0, 1, 1, 1, 1, True)
+    pc2 = ops.fold_pack(w2.to(DEV), b2.to(DEV), None, 0.0, 1, 1, 1, 1, True)
+    xf = _fmap(x)
+    assert ops.bottleneck_ok(xf, pc1, pc2)
+    y = ops.bottleneck(xf, pc1, pc2, add)
+    assert y.shape == (B, C, H, W)
+    mid = _bf(F.silu(F.conv2d(_bf(x), _bf(w1), b1, 1, 1)))
+    ref = F.silu(F.conv2d(mid, _bf(w2), b2, 1, 1)) + (_bf(x) if add else 0)
+    got = y.float().cpu()
+    assert _rel_err(got, ref) < 6e-3, _rel_err(got, ref)
+    assert float((got - ref).abs().max()) < 0.06 * float(ref.abs().max())
+    two = ops.conv2d(ops.conv2d(xf, pc1), pc2, residual=xf if add else None)
+    assert _rel_err(got, two.float().cpu()) < 6e-3
+    # x read from, and y written into, channel slices of wider buffers
+    src = ops.new_act(B, C + 32, H, W, DEV).zero_()
+    src[:, 16:16 + C].copy_(xf)
+    buf = ops.new_act(B, C + 48, H, W, DEV).zero_()
+    ops.bottleneck(src[:, 16:16 + C], pc1, pc2, add, out=buf[:, 32:32 + C])
+    assert torch.equal(buf[:, 32:32 + C].float().cpu(), got)
+    assert float(buf[:, :32].float().abs().max()) == 0.0 and float(buf[:, 32 + C:].float().abs().max()) == 0.0
+
+
 def test_depthwise(lib):
     from specyolo import ops
 
