@@ -338,11 +338,14 @@ def test_dwconv_pwconv_fused(lib, C, cout, B, H, W):
     assert _rel_err(y, ref) < 8e-3, _rel_err(y, ref)
 
 
-def test_sppf_pool(lib):
+@pytest.mark.parametrize("c,B,H,W", [(32, 2, 20, 20), (256, 3, 20, 20), (128, 2, 40, 40), (64, 2, 13, 27), (256, 1, 5, 3),
+                                     (128, 1, 33, 17)])
+def test_sppf_pool(lib, c, B, H, W):
+    """three chained MaxPool2d(5, 1, 2) (block.py:194-198): both CTA shapes (64 / 16 channels), ragged and tiny maps,
+    maps smaller than the window, the 40 x 40 map of a 1280^2 input."""
     from specyolo import ops
 
     gen = torch.Generator().manual_seed(9)
-    c, B, H, W = 32, 2, 20, 20
     y0 = torch.randn((B, c, H, W), generator=gen)
     buf = ops.new_act(B, 4 * c, H, W, DEV)
     buf.zero_()
