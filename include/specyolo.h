@@ -122,7 +122,13 @@ typedef struct {
     const float* dw_b;                            /* [C]                                                     */
     const void* pw_packed; const float* pw_bias;  /* from specyolo_fold_pack_conv of the 1x1 conv (groups 1)  */
     int Cout, n_pad;
-    void* y; int y_pixstride;                     /* bf16 NHWC output window, Cout channels                   */
+    void* y; int y_pixstride;                     /* bf16 NHWC output window, Cout channels (may be NULL with a head) */
+    /* optional fused head: the closing nn.Conv2d(c3, nc, 1) of a Detect.cv3 branch (head.py:56) for nc <= 4 classes,
+     * evaluated in the epilogue on the fp32 activations — head_y[pix * head_pixstride + j] = head_b[j] +
+     * sum_c act[c] * head_w[j * Cout + c].  With a head the Cout-channel tensor is NOT stored (y is ignored). */
+    const float* head_w;                          /* fp32 [nc][Cout] (device) or NULL                         */
+    const float* head_b;                          /* fp32 [nc]                                                */
+    float* head_y; int head_nc, head_pixstride;   /* fp32 rows of head_pixstride floats per pixel             */
 } specyolo_dwpw_t;
 int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream);
 

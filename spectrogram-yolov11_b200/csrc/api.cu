@@ -156,8 +156,9 @@ int specyolo_conv2d_bias_act(const specyolo_conv_t* a, void* stream) {
 }
 
 int specyolo_dwconv_pwconv(const specyolo_dwpw_t* a, void* stream) {
-    SY_CHECK(a && a->x && a->dw_w && a->dw_b && a->pw_packed && a->pw_bias && a->y, SPECYOLO_ERR_INVALID, "dwpw: null pointer");
-    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->Cout,
+    SY_CHECK(a && a->x && a->dw_w && a->dw_b && a->pw_packed && a->pw_bias && (a->y || a->head_w), SPECYOLO_ERR_INVALID,
+             "dwpw: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->x_pixstride >= a->C && (a->head_w || a->y_pixstride >= a->Cout),
              SPECYOLO_ERR_INVALID, "dwpw: bad sizes");
     return dwpw_launch(a, (cudaStream_t)stream);
 }

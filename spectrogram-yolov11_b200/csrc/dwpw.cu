@@ -40,8 +40,17 @@ struct DwpwParams {
     int y_pixstride;
     int store_bw, pair_stores;
     uint32_t store_row_bytes, store_swz_mask;
+    // fused head (kHead): logits[pix][j] = head_b[j] + sum_c SiLU(pw(x))[c] * head_w[j][c], j < head_nc <= kDwpwMaxNc
+    const float* head_w;
+    const float* head_b;
+    float* head_y;
+    int head_nc, head_pixstride;
 };
+static constexpr int kDwpwMaxNc = 4;
 
+// kHead: the pointwise result is not stored; it feeds the Detect branch's closing Conv2d(c3, nc, 1) (head.py:56) inside
+// the epilogue — nc <= 4 dot products per pixel on the fp32 SiLU outputs — and only the nc class logits go to memory.
+template <bool kHead>
 __global__ void __launch_bounds__(kDwpwThreads, 1)
 dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
             const __grid_constant__ CUtensorMap map_y, const __grid_constant__ DwpwParams p) {
@@ -49,6 +58,8 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     __shared__ __align__(8) uint64_t x_full[2], x_empty[2], a_full[2], a_empty[2], tmem_full_bar[2], tmem_empty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[256];
+    __shared__ __align__(16) float head_ws[kHead ? kDwpwMaxNc * 256 : 4];     // [nc][n_pad] fp32 (zero beyond cout)
+    __shared__ __align__(16) float head_part[kHead ? 2 * 128 * kDwpwMaxNc : 4]; // [tile parity][row][nc]: partial sums of the second column half
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -78,6 +89,11 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     }
     if (warp == 1) ptx::tmem_alloc(&tmem_base_smem, p.tmem_cols);
     for (int i = threadIdx.x; i < p.n_pad; i += kDwpwThreads) bias_s[i] = 0.5f * p.pw_b[i];     // SiLU form (epilogue.cuh)
+    if (kHead)
+        for (int i = threadIdx.x; i < p.head_nc * p.n_pad; i += kDwpwThreads) {
+            const int j = i / p.n_pad, c = i - j * p.n_pad;
+            head_ws[j * p.n_pad + c] = c < p.cout ? p.head_w[j * p.cout + c] : 0.f;
+        }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -231,6 +247,65 @@ dwpw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * (uint32_t)p.n_pad;
             ptx::mbar_wait(&tmem_full_bar[b], ph);
             ptx::tc_fence_after();
+            if (kHead) {
+                // this warp's half of the 16-column chunks -> SiLU -> nc running dot products; the two halves of a row meet in
+                // shared memory (double-buffered by tile parity: one named barrier per tile orders both directions)
+                const int nchunks = p.n_pad >> 4, cut = (nchunks + 1) >> 1;
+                const int ch_begin = half ? cut : 0, ch_end = half ? nchunks : cut;
+                // packed fp32 pairs, two independent chains per output: the kernel is issue-bound (16 depthwise warps share the
+                // schedulers), a scalar 64-deep FMA chain per output made this epilogue the slowest role
+                float2 acc2[kDwpwMaxNc][2];
+#pragma unroll
+                for (int j = 0; j < kDwpwMaxNc; ++j) acc2[j][0] = acc2[j][1] = make_float2(0.f, 0.f);
+                uint32_t va[16], vb[16];
+                ptx::tmem_ld16(t_addr + (uint32_t)(ch_begin << 4), va);
+#pragma unroll 1
+                for (int ch = ch_begin; ch < ch_end; ch += 2) {
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int chunk = ch + hlf;
+                        if (chunk >= ch_end) break;
+                        uint32_t(&v)[16] = hlf ? vb : va;
+                        uint32_t(&vn)[16] = hlf ? va : vb;
+                        ptx::tmem_ld_wait();
+                        if (chunk + 1 < ch_end) ptx::tmem_ld16(t_addr + (uint32_t)((chunk + 1) << 4), vn);
+                        float2 f2[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 hb = *reinterpret_cast<const float4*>(bias_s + (chunk << 4) + 4 * q);
+                            f2[2 * q] = silu2_half(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), make_float2(hb.x, hb.y));
+                            f2[2 * q + 1] = silu2_half(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), make_float2(hb.z, hb.w));
+                        }
+#pragma unroll
+                        for (int j = 0; j < kDwpwMaxNc; ++j)
+                            if (j < p.head_nc) {
+                                const float4* wv = reinterpret_cast<const float4*>(head_ws + j * p.n_pad + (chunk << 4));
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 w4 = wv[q];
+                                    acc2[j][0] = ffma2(f2[2 * q], make_float2(w4.x, w4.y), acc2[j][0]);
+                                    acc2[j][1] = ffma2(f2[2 * q + 1], make_float2(w4.z, w4.w), acc2[j][1]);
+                                }
+                            }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[b]);
+                float acc[kDwpwMaxNc];
+#pragma unroll
+                for (int j = 0; j < kDwpwMaxNc; ++j) acc[j] = (acc2[j][0].x + acc2[j][0].y) + (acc2[j][1].x + acc2[j][1].y);
+                float* part = head_part + (b * 128 + m) * kDwpwMaxNc;
+                if (half) *reinterpret_cast<float4*>(part) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                ptx::named_bar_sync(3, 256);
+                if (!half && row_ok) {
+                    float* yo = p.head_y + pix * p.head_pixstride;
+#pragma unroll
+                    for (int j = 0; j < kDwpwMaxNc; ++j)
+                        if (j < p.head_nc) yo[j] = acc[j] + part[j] + p.head_b[j];
+                }
+                continue;
+            }
             st.c0 = 0;
             st.c1 = (int)tw_i * kDwpwTW; st.c2 = (int)th_i * kDwpwTH; st.c3 = (int)n;
             epi_tile<true, false, false>(t_addr, ec, bias_s, eo, pix, row_ok, half, lane, st, EpiResSmem{nullptr, 1, 0, 0, 0});
@@ -266,6 +341,14 @@ int dwpw_launch(const specyolo_dwpw_t* a, cudaStream_t stream) {
     p.n_pad = a->n_pad; p.cout = a->Cout;
     p.dw_w = a->dw_w; p.dw_b = a->dw_b; p.pw_b = a->pw_bias;
     p.y = a->y; p.y_pixstride = a->y_pixstride;
+    const bool head = a->head_w != nullptr;
+    if (head) {
+        SY_CHECK(a->head_nc >= 1 && a->head_nc <= kDwpwMaxNc && a->head_b && a->head_y && a->head_pixstride >= a->head_nc,
+                 SPECYOLO_ERR_UNSUPPORTED, "dwpw: fused head takes 1..%d outputs", kDwpwMaxNc);
+        p.head_w = a->head_w; p.head_b = a->head_b; p.head_y = a->head_y; p.head_nc = a->head_nc; p.head_pixstride = a->head_pixstride;
+    } else {
+        SY_CHECK(a->y != nullptr, SPECYOLO_ERR_INVALID, "dwpw: null output");
+    }
     p.w_bytes = (uint32_t)p.chunks * (uint32_t)a->n_pad * 128u;
     p.x_stage_bytes = (uint32_t)p.chunks * kDwpwBoxStride;
     p.a_buf_bytes = (uint32_t)p.chunks * kDwpwAChunk;
@@ -273,11 +356,12 @@ int dwpw_launch(const specyolo_dwpw_t* a, cudaStream_t stream) {
     p.a_off = p.x_off + 2u * p.x_stage_bytes;
     p.st_off = p.a_off + 2u * p.a_buf_bytes;
     int store_bw = epi_stage_box_cols(a->n_pad, 2);
-    if ((reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * 2) % 16) store_bw = 0;
+    if (head || (reinterpret_cast<uintptr_t>(a->y) & 15) || ((size_t)a->y_pixstride * 2) % 16) store_bw = 0;
     uint32_t stage_out = epi_stage_bytes(a->n_pad, store_bw, 2);
     if (1024 + p.st_off + stage_out > (uint32_t)kDwpwMaxDynSmem) { store_bw = 0; stage_out = 0; }
     const size_t smem_bytes = 1024 + (size_t)p.st_off + stage_out;
-    SY_CHECK(smem_bytes <= (size_t)kDwpwMaxDynSmem, SPECYOLO_ERR_UNSUPPORTED, "dwpw: shared memory budget exceeded");
+    SY_CHECK(smem_bytes <= (size_t)kDwpwMaxDynSmem - (head ? 10 * 1024 : 0), SPECYOLO_ERR_UNSUPPORTED,
+             "dwpw: shared memory budget exceeded");
     p.store_bw = store_bw;
     p.pair_stores = 1;
     p.store_row_bytes = (uint32_t)(store_bw * 2);
@@ -320,15 +404,15 @@ int dwpw_launch(const specyolo_dwpw_t* a, cudaStream_t stream) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SY_CHECK(r == CUDA_SUCCESS, SPECYOLO_ERR_CUDA, "cuTensorMapEncodeTiled(dwpw Y) failed (%d)", (int)r);
     }
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(dwpw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwpwMaxDynSmem);
-    });
-    SY_CHECK(attr_err == cudaSuccess, SPECYOLO_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    // per-device attribute: set on every launch (host-side table lookup)
+    SY_CUDA(cudaFuncSetAttribute(dwpw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwpwMaxDynSmem));
+    SY_CUDA(cudaFuncSetAttribute(dwpw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwpwMaxDynSmem - 10 * 1024));   // 8 KB more static
     const long resident = sm_count();
     const unsigned grid = (unsigned)(spatial < resident ? spatial : resident);
-    SY_CUDA(launch_pdl(dwpw_kernel, dim3(grid), dim3(kDwpwThreads), smem_bytes, stream, map_x, map_w, map_y, p));
+    if (head)
+        SY_CUDA(launch_pdl(dwpw_kernel<true>, dim3(grid), dim3(kDwpwThreads), smem_bytes, stream, map_x, map_w, map_y, p));
+    else
+        SY_CUDA(launch_pdl(dwpw_kernel<false>, dim3(grid), dim3(kDwpwThreads), smem_bytes, stream, map_x, map_w, map_y, p));
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

@@ -44,6 +44,8 @@ class DwpwArgs(C.Structure):
         ("x", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("x_pixstride", C.c_int),
         ("dw_w", C.c_void_p), ("dw_b", C.c_void_p), ("pw_packed", C.c_void_p), ("pw_bias", C.c_void_p),
         ("Cout", C.c_int), ("n_pad", C.c_int), ("y", C.c_void_p), ("y_pixstride", C.c_int),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_y", C.c_void_p), ("head_nc", C.c_int),
+        ("head_pixstride", C.c_int),
     ]
 
 

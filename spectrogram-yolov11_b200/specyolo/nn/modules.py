@@ -463,11 +463,11 @@ class _HeadConv(nn.Conv2d):
         return self._packed
 
     def _apply(self, fn, *a, **k):
-        self._packed = None
+        self._packed = self._f32 = None
         return super()._apply(fn, *a, **k)
 
     def _load_from_state_dict(self, *a, **k):
-        self._packed = None
+        self._packed = self._f32 = None
         return super()._load_from_state_dict(*a, **k)
 
 
@@ -476,6 +476,14 @@ def head_packed(conv: nn.Conv2d) -> ops.PackedConv:
     if getattr(conv, "_packed", None) is None:
         conv._packed = ops.fold_pack(conv.weight, conv.bias, None, 0.0, 1, 0, 1, 1, act=False)
     return conv._packed
+
+
+def head_f32(conv: nn.Conv2d):
+    """(w [n, c] fp32, b [n] fp32) of a plain 1x1 nn.Conv2d for the fused class head of ops.dwconv_pwconv; cached."""
+    if getattr(conv, "_f32", None) is None or conv._f32[0].device != conv.weight.device:
+        conv._f32 = (conv.weight.detach().float().reshape(conv.out_channels, conv.in_channels).contiguous(),
+                     conv.bias.detach().float().contiguous())
+    return conv._f32
 
 
 class Detect(nn.Module):
@@ -554,11 +562,20 @@ class Detect(nn.Module):
             return pw(dw(x))
 
         def cls_branch(i):
+            cls_view = views[i][:, 4 * self.reg_max: self.no]
             if self.legacy:
                 t = self.cv3[i][1](self.cv3[i][0](xs[i]))
             else:
-                t = dw_pw(self.cv3[i][1], dw_pw(self.cv3[i][0], xs[i]))
-            ops.conv2d(t, head_packed(self.cv3[i][2]), out=views[i][:, 4 * self.reg_max: self.no], out_fp32=True)
+                t = dw_pw(self.cv3[i][0], xs[i])
+                dw, pw, last = self.cv3[i][1][0], self.cv3[i][1][1], self.cv3[i][2]
+                if self.nc <= ops.DWPW_HEAD_MAX_NC and dw.is_depthwise3x3() and ops.dwconv_pwconv_ok(t.shape[1], pw.packed()):
+                    # few classes (the 5G / LTE detector has 2): the closing Conv2d(c3, nc, 1) rides in the epilogue of the
+                    # second DWConv + Conv pair; its c3-channel output is never written
+                    w, b = dw.folded_depthwise()
+                    ops.dwconv_pwconv(t, w, b, pw.packed(), head=head_f32(last) + (cls_view,))
+                    return
+                t = dw_pw(self.cv3[i][1], t)
+            ops.conv2d(t, head_packed(self.cv3[i][2]), out=cls_view, out_fp32=True)
 
         for i in range(len(xs)):
             fns.append(lambda i=i: box_branch(i))

@@ -265,21 +265,43 @@ def dwconv_pwconv_ok(C_in: int, pw: PackedConv) -> bool:
         pw.act == _lib.ACT_SILU
 
 
+DWPW_HEAD_MAX_NC = 4
+
+
 def dwconv_pwconv(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, pw: PackedConv,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """SiLU(conv1x1(SiLU(dwconv3x3(x) + b_dw)) + b_pw) in one kernel; dw_w fp32 [9, C] (tap-major), dw_b fp32 [C]."""
+                  out: Optional[torch.Tensor] = None, head: Optional[tuple] = None) -> Optional[torch.Tensor]:
+    """SiLU(conv1x1(SiLU(dwconv3x3(x) + b_dw)) + b_pw) in one kernel; dw_w fp32 [9, C] (tap-major), dw_b fp32 [C].
+
+    head = (w [nc, Cout] fp32, b [nc] fp32, y fp32 view [B, nc, H, W] with NHWC memory): the closing Conv2d(Cout, nc, 1)
+    of a Detect.cv3 branch (nc <= DWPW_HEAD_MAX_NC) evaluated in the epilogue; the Cout-channel tensor is then never
+    written and the function returns None."""
     B, Cc, H, W, xpix = nhwc_meta(x)
     if x.dtype != torch.bfloat16 or dw_w.shape != (9, Cc) or dw_w.dtype != torch.float32 or not dw_w.is_contiguous():
         raise ValueError("dwconv_pwconv: x must be bf16 NHWC, dw_w contiguous fp32 [9, C]")
+    a = DwpwArgs()
+    a.x, a.B, a.H, a.W, a.C, a.x_pixstride = x.data_ptr(), B, H, W, Cc, xpix
+    a.dw_w, a.dw_b, a.pw_packed, a.pw_bias = dw_w.data_ptr(), dw_b.data_ptr(), pw.w.data_ptr(), pw.bias.data_ptr()
+    a.Cout, a.n_pad = pw.cout, pw.n_pad
+    if head is not None:
+        hw, hb, hy = head
+        nc = hw.shape[0]
+        hB, hC, hH, hW_, hpix = nhwc_meta(hy)
+        if hw.shape != (nc, pw.cout) or hw.dtype != torch.float32 or not hw.is_contiguous() or hb.shape != (nc,) or \
+                hb.dtype != torch.float32 or hy.dtype != torch.float32 or (hB, hC, hH, hW_) != (B, nc, H, W) or \
+                nc > DWPW_HEAD_MAX_NC:
+            raise ValueError("dwconv_pwconv: bad fused-head tensors")
+        a.y, a.y_pixstride = None, pw.cout
+        a.head_w, a.head_b, a.head_y, a.head_nc, a.head_pixstride = hw.data_ptr(), hb.data_ptr(), hy.data_ptr(), nc, hpix
+        check(_lib.load().specyolo_dwconv_pwconv(C.byref(a), _lib.stream_ptr()))
+        return None
     if out is None:
         out = new_act(B, pw.cout, H, W, x.device)
     oB, oC, oH, oW, ypix = nhwc_meta(out)
     if (oB, oC, oH, oW) != (B, pw.cout, H, W) or out.dtype != torch.bfloat16:
         raise ValueError("dwconv_pwconv: out shape / dtype mismatch")
-    a = DwpwArgs()
-    a.x, a.B, a.H, a.W, a.C, a.x_pixstride = x.data_ptr(), B, H, W, Cc, xpix
-    a.dw_w, a.dw_b, a.pw_packed, a.pw_bias = dw_w.data_ptr(), dw_b.data_ptr(), pw.w.data_ptr(), pw.bias.data_ptr()
-    a.Cout, a.n_pad, a.y, a.y_pixstride = pw.cout, pw.n_pad, out.data_ptr(), ypix
+    a.y, a.y_pixstride = out.data_ptr(), ypix
+    a.head_w = a.head_b = a.head_y = None
+    a.head_nc = a.head_pixstride = 0
     check(_lib.load().specyolo_dwconv_pwconv(C.byref(a), _lib.stream_ptr()))
     return out
 

@@ -124,7 +124,7 @@ def _make_detect(ref_cls):
         def forward(self, x):
             if _is_cuda(x) and not self.training and not self.end2end and not self.export:
                 for br in list(self.cv2) + list(self.cv3):     # plain nn.Conv2d tails: drop packs of moved / cast weights
-                    _fresh(br[-1], ("_packed",))
+                    _fresh(br[-1], ("_packed", "_f32"))
                 return mine.forward(self, x)
             return ref_cls.forward(self, x)
 

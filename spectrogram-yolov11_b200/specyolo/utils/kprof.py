@@ -43,8 +43,12 @@ def _conv_work(r, x, pc, out=None, residual=None, out_fp32=False, blocked_out=Fa
     return "conv2d", fl, by, label
 
 
-def _dwpw_work(r, x, dw_w, dw_b, pw, out=None):
+def _dwpw_work(r, x, dw_w, dw_b, pw, out=None, head=None):
     B, C, H, W = x.shape
+    if head is not None:        # + the closing Conv2d(cout, nc, 1); only nc fp32 logits per pixel are written
+        nc = head[0].shape[0]
+        return ("conv2d", 2.0 * B * H * W * (C * (9 + pw.cout) + pw.cout * nc), 2.0 * x.numel() + 4.0 * B * H * W * nc + 2.0 * pw.w.numel(),
+                f"dw3x3+pw+head {C:4d}->{pw.cout:4d}->{nc} fused {H:4d}x{W:4d} M={B * H * W:8d}")
     return ("conv2d", 2.0 * B * H * W * C * (9 + pw.cout), 2.0 * (x.numel() + r.numel()) + 2.0 * pw.w.numel(),
             f"dw3x3+pw {C:4d}->{pw.cout:4d} fused {H:4d}x{W:4d} M={B * H * W:8d}")
 

@@ -336,6 +336,21 @@ def test_dwconv_pwconv_fused(lib, C, cout, B, H, W):
     ref = F.silu(F.conv2d(mid, _bf(wp), bp))
     assert y.shape == ref.shape
     assert _rel_err(y, ref) < 8e-3, _rel_err(y, ref)
+    # fused class head: the closing nn.Conv2d(cout, nc, 1) of a Detect.cv3 branch (head.py:56) in the epilogue, fp32
+    # logits written into channels [64, 64 + nc) of the [B, H*W, 68] decode buffer; nothing else of that buffer is touched
+    for nc in (1, 2, 4):
+        wh = torch.randn((nc, cout), generator=gen) * math.sqrt(1.0 / cout)
+        bh = torch.randn(nc, generator=gen) * 0.5
+        buf = torch.full((B, H * W, 68), 7.0, device=DEV)
+        view = buf.view(B, H, W, 68).permute(0, 3, 1, 2)[:, 64:64 + nc]
+        r = ops.dwconv_pwconv(_fmap(x), dw_w, bd.to(DEV), pw, head=(wh.to(DEV), bh.to(DEV), view))
+        assert r is None
+        ref_h = F.conv2d(ref, wh.view(nc, cout, 1, 1), bh)                    # on the fp32 activations
+        got = buf.view(B, H, W, 68)[..., 64:64 + nc].permute(0, 3, 1, 2).cpu()
+        assert float((got - ref_h).abs().max()) < 2e-2 * max(1.0, float(ref_h.abs().max())), float((got - ref_h).abs().max())
+        rest = buf.clone()
+        rest.view(B, H, W, 68)[..., 64:64 + nc] = 7.0
+        assert bool((rest == 7.0).all())
 
 
 @pytest.mark.parametrize("c,B,H,W", [(32, 2, 20, 20), (256, 3, 20, 20), (128, 2, 40, 40), (64, 2, 13, 27), (256, 1, 5, 3),
