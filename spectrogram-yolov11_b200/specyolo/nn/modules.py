@@ -172,7 +172,7 @@ class Bottleneck(nn.Module):
     def forward(self, x, out=None):
         x = _as_fmap(x)
         p1, p2 = self.cv1.packed(), self.cv2.packed()
-        if ops.bottleneck_ok(x, p1, p2):       # thin 3x3 pairs: one kernel, the intermediate never leaves the SM
+        if ops.bottleneck_ok(x, p1, p2, prefer=True):       # thin 3x3 pairs: one kernel, the intermediate never leaves the SM
             return ops.bottleneck(x, p1, p2, self.add, out)
         return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
 

@@ -306,13 +306,19 @@ def dwconv_pwconv(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, pw: P
     return out
 
 
-def bottleneck_ok(x: torch.Tensor, pc1: PackedConv, pc2: PackedConv) -> bool:
-    """Shapes the fused Bottleneck kernel takes (specyolo_bottleneck_ok): two dense 3x3 / s1 / p1 SiLU convs, C -> Cmid -> C."""
+def bottleneck_ok(x: torch.Tensor, pc1: PackedConv, pc2: PackedConv, prefer: bool = False) -> bool:
+    """Shapes the fused Bottleneck kernel takes (specyolo_bottleneck_ok): two dense 3x3 / s1 / p1 SiLU convs, C -> Cmid -> C.
+    prefer=True (the model's dispatch): additionally only where the fused kernel measured faster than two launches —
+    not for the thinnest pair (32 -> 16 -> 32: 151 us fused against 145 us as two halo-kernel launches at 160^2, batch
+    64; every MMA of either form costs the same ~40 cycles of shared-memory operand reads whatever N is, and the fused
+    form issues 1.7x as many because of the halo recompute)."""
     for pc in (pc1, pc2):
         if pc.k != 3 or pc.s != 1 or pc.p != 1 or pc.d != 1 or pc.g != 1 or pc.g_orig != 1 or pc.act != _lib.ACT_SILU:
             return False
     if x.dtype != torch.bfloat16 or x.shape[1] != pc1.cin or pc1.cout != pc2.cin or pc1.cin != pc1.cin_true or \
             pc2.cin != pc2.cin_true:
+        return False
+    if prefer and pc1.cin == 32 and pc1.cout == 16:
         return False
     return bool(_lib.load().specyolo_bottleneck_ok(pc1.cin, pc1.cout, pc2.cout, pc1.n_pad, pc2.n_pad))
 

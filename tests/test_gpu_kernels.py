@@ -394,8 +394,10 @@ def test_fusion_eschannel(lib, k, H, W, up, c):
     assert _rel_err(got, ref) < 5e-3
 
 
-@pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2)])
+@pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2), (16, 16, 2), (5, 7, 1), (16, 32, 2), (24, 24, 2), (40, 40, 1)])
 def test_psa_attention(lib, H, W, heads):
+    """N = 400 (640^2 input), ragged / tiny / exactly 256 and 512 tokens on the resident-S kernel (N <= 512), 576 and
+    1600 tokens on the two-sweep kernel."""
     from specyolo import ops
 
     gen = torch.Generator().manual_seed(11)
