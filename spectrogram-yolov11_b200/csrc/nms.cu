@@ -7,7 +7,11 @@
 //      ordered block compaction; fused input: the segments written by detect_decode),
 //   1. stable descending sort by score: bitonic sort of 64-bit keys (~score_bits << 32 | index) —
 //      equal scores keep the lower candidate index first, like torchvision's stable sort,
-//   2. greedy suppression in sorted order, 1024 candidates per sweep: every thread tests its box
+//   2. greedy suppression in sorted order.  Up to 768 candidates (every predict() call in practice): all pairwise
+//      "i suppresses j" bits (j behind i in score order) are computed in parallel into an n x n/32 bitmask in shared
+//      memory, then ONE warp walks the candidates in order with the 'removed' set spread over its lanes (lane l = word l)
+//      — torchvision's own CUDA scheme, the same greedy result as the sequential definition.  Beyond that,
+//      1024 candidates per sweep: every thread tests its box
 //      against the kept list (shared memory, <= max_det entries), then the 32 warps resolve their 32
 //      candidates in turn with a warp-level bitmask (ballot + shuffles), publishing newly kept boxes
 //      to the warps behind them.  Stops as soon as max_det boxes are kept (ops.py:313).
@@ -21,9 +25,11 @@
 namespace specyolo {
 
 static constexpr int kNmsThreads = 1024;
-static constexpr int kSmemSort = 8192;   // keys held in shared memory up to this many (padded) entries
-static constexpr int kSmemBoxes = 4096;  // sorted boxes held in shared memory up to this many
+static constexpr int kSmemSort = 4096;   // keys held in shared memory up to this many (padded) entries
+static constexpr int kSmemBoxes = 2048;  // sorted boxes held in shared memory up to this many
 static constexpr int kMaxKeep = 2048;    // upper bound for max_det
+static constexpr int kMaskN = 768;       // candidates up to which the suppression bitmask (n x n/32 words) fits in shared memory
+static constexpr int kMaskWords = kMaskN / 32;
 
 struct NmsWs {
     float4* cand_box;   // [B][cap] xyxy (not offset)
@@ -64,6 +70,7 @@ struct NmsParams {
     specyolo_nms_t a;
     NmsWs ws;
     int nseg;
+    long long* dbg;      // SPECYOLO_NMS_DBG=1: [B][5] cycles at the end of phases 0, 1, sorted boxes, 2, output; [B][5] = n
 };
 
 // torchvision CPU nms_kernel_impl arithmetic, fp32, no contraction
@@ -76,7 +83,18 @@ __device__ __forceinline__ bool iou_gt(const float4& bi, float ai, const float4&
     const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
     const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+    // Disjoint boxes (the overwhelming majority of pairs): quotient 0 (or NaN for a degenerate union) is never > thr >= 0.
+    if (!(inter > 0.f)) return false;
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    // Certain decisions without the IEEE division (~35 instructions, and n^2/2 of them bounded the kernel: 210 k of its
+    // 230 k cycles at n = 409): outside a 1e-4 relative band around thr * union the comparison cannot flip; inside the
+    // band — and for degenerate unions — the exact fp32 quotient is compared with the double threshold as torchvision does.
+    const float q = __fmul_rn(uni, (float)thr);
+    if (uni > 0.f) {
+        if (inter < q * 0.9999f) return false;
+        if (inter > q * 1.0001f) return true;
+    }
+    const float ovr = __fdiv_rn(inter, uni);
     return (double)ovr > thr;
 }
 
@@ -126,6 +144,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     float4* s_kept = s_boxes + kSmemBoxes;                                                    // kMaxKeep
     float* s_kept_area = reinterpret_cast<float*>(s_kept + kMaxKeep);                         // kMaxKeep
     int* s_kept_rank = reinterpret_cast<int*>(s_kept_area + kMaxKeep);                        // kMaxKeep
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_kept_rank + kMaxKeep);                   // kMaskN x kMaskWords
     __shared__ int s_scan[33];
     __shared__ int s_n, s_kept_n, s_new_lo;
 
@@ -133,6 +152,8 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cap = p.ws.cap;
+    const long long t_start = p.dbg ? clock64() : 0;
+#define NMS_MARK(k) do { if (p.dbg && tid == 0) p.dbg[b * 6 + (k)] = clock64() - t_start; } while (0)
     float4* cbox = p.ws.cand_box + (size_t)b * cap;
     float* cconf = p.ws.cand_conf + (size_t)b * cap;
     int* ccls = p.ws.cand_cls + (size_t)b * cap;
@@ -227,6 +248,8 @@ nms_kernel(const __grid_constant__ NmsParams p) {
         }
     }
     __syncthreads();
+    NMS_MARK(0);
+    if (p.dbg && tid == 0) p.dbg[b * 6 + 5] = n;
     if (a.n_cand && tid == 0) a.n_cand[b] = n < a.max_nms ? n : a.max_nms;
 
     int* out_count = a.out_count + b;
@@ -260,6 +283,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
             __syncthreads();
         }
     }
+    NMS_MARK(1);
     // max_nms truncation (ops.py:301-302): keep the max_nms best; candidate indices then refer to
     // the score-sorted list, as in the reference after `x = x[argsort[:max_nms]]`.
     const bool truncated = n > a.max_nms;
@@ -277,10 +301,52 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     }
     if (tid == 0) { s_kept_n = 0; }
     __syncthreads();
+    NMS_MARK(2);
 
     // ---------------- phase 2: greedy suppression ----------------
     const int max_det = a.max_det < kMaxKeep ? a.max_det : kMaxKeep;
     const double thr = a.iou_thres;
+    if (n <= kMaskN) {
+        // bitmask path: word (i, w) holds, for the 32 candidates 32w .. 32w+31 that come AFTER i, whether i suppresses them
+        const int words = (n + 31) >> 5;
+        float* s_area = s_kept_area;                  // areas of the sorted boxes (the kept-area array is unused on this path)
+        for (int r = tid; r < n; r += kNmsThreads) s_area[r] = box_area(sboxes[r]);
+        __syncthreads();
+        // one warp per ROW i of the mask, lane = candidate 32w + lane: box reads are consecutive (a thread per word read
+        // 32 boxes at a 512-byte lane stride: 32-way bank conflicts), box i is loaded once per row, only the words behind i
+        // are visited and there is no index arithmetic in the loop (~20 instructions per word; a flat word loop with a
+        // runtime division spent 108 k cycles here at n = 409)
+        for (int i = warp; i < n; i += kNmsThreads / 32) {
+            const float4 bi = sboxes[i];
+            const float ai = s_area[i];
+            for (int w = i >> 5; w < words; ++w) {
+                const int c = 32 * w + lane;
+                const bool sup = (c > i && c < n) && iou_gt(bi, ai, sboxes[c < n ? c : i], s_area[c < n ? c : i], thr);
+                const uint32_t bits = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) s_mask[i * words + w] = bits;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // walk the candidates in score order; lane l holds word l of the 'removed' set; jump from kept box to kept box
+            uint32_t removed = 0;
+            int kept_n = 0, i = 0;
+            while (i < n) {
+                const int w = i >> 5;
+                const uint32_t rw = __shfl_sync(0xffffffffu, removed, w);
+                uint32_t alive = ~rw & (0xffffffffu << (i & 31));
+                if (w == words - 1 && (n & 31)) alive &= (1u << (n & 31)) - 1u;
+                if (!alive) { i = (w + 1) << 5; continue; }          // warp-uniform
+                i = (w << 5) + __ffs((int)alive) - 1;
+                if (lane == 0) s_kept_rank[kept_n] = i;
+                if (++kept_n >= max_det) break;
+                if (lane < words) removed |= s_mask[i * words + lane];    // (words behind i only: earlier ones are never read again)
+                ++i;
+            }
+            if (lane == 0) s_kept_n = kept_n;
+        }
+        __syncthreads();
+    } else
     for (int base = 0; base < n; base += kNmsThreads) {
         const int r = base + tid;
         bool alive = r < n;
@@ -333,6 +399,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     }
     __syncthreads();
 
+    NMS_MARK(3);
     // ---------------- output ----------------
     const int kept = s_kept_n < max_det ? s_kept_n : max_det;
     for (int k = tid; k < kept; k += kNmsThreads) {
@@ -349,6 +416,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
         if (a.keep_idx) a.keep_idx[(size_t)b * a.max_det + k] = truncated ? r : idx;
     }
     if (tid == 0) *out_count = kept;
+    NMS_MARK(4);
 }
 
 size_t nms_ws_bytes(int B, int nc, int A, int multi_label) {
@@ -377,12 +445,34 @@ int nms_launch(const specyolo_nms_t* a, cudaStream_t stream) {
     nms_ws_layout(a->B, a->nc, a->A, a->multi_label, wsb, &p.ws);
     p.nseg = ceil_div(a->A, SPECYOLO_DECODE_SEG);
     SY_CHECK(p.nseg <= kSmemSort * 2, SPECYOLO_ERR_UNSUPPORTED, "too many anchors");
-    const size_t smem = (size_t)kSmemSort * 8 + (size_t)(kSmemBoxes + kMaxKeep) * 16 + (size_t)kMaxKeep * 8;
+    const size_t smem = (size_t)kSmemSort * 8 + (size_t)(kSmemBoxes + kMaxKeep) * 16 + (size_t)kMaxKeep * 8 +
+                        (size_t)kMaskN * kMaskWords * 4;
     // the attribute is per device: set it on every launch (a host-side table lookup, no device work)
     SY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static long long* dbg_dev = nullptr;
+    const bool dbg = env_flag("SPECYOLO_NMS_DBG");
+    if (dbg) {
+        if (!dbg_dev) SY_CUDA(cudaMalloc(&dbg_dev, 4096 * 6 * sizeof(long long)));
+        SY_CUDA(cudaMemsetAsync(dbg_dev, 0, 4096 * 6 * sizeof(long long), stream));
+        p.dbg = a->B <= 4096 ? dbg_dev : nullptr;
+    }
     SY_CUDA(launch_pdl(nms_kernel, dim3(a->B), dim3(kNmsThreads), smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch();
+    if (dbg && p.dbg) {
+        static long long h[4096 * 6];
+        SY_CUDA(cudaStreamSynchronize(stream));
+        SY_CUDA(cudaMemcpy(h, dbg_dev, (size_t)a->B * 6 * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long mx[6] = {0, 0, 0, 0, 0, 0};
+        int worst = 0;
+        for (int i = 0; i < a->B; ++i) {
+            if (h[i * 6 + 4] > h[worst * 6 + 4]) worst = i;
+            for (int k = 0; k < 6; ++k) mx[k] = h[i * 6 + k] > mx[k] ? h[i * 6 + k] : mx[k];
+        }
+        fprintf(stderr, "[nms dbg] B=%d max n=%lld | cycles at end of: candidates %lld sort %lld sorted boxes %lld suppression %lld output %lld "
+                "(slowest image %d: n=%lld, %lld %lld %lld %lld %lld)\n", a->B, mx[5], mx[0], mx[1], mx[2], mx[3], mx[4], worst, h[worst * 6 + 5],
+                h[worst * 6], h[worst * 6 + 1], h[worst * 6 + 2], h[worst * 6 + 3], h[worst * 6 + 4]);
+    }
     return SPECYOLO_OK;
 }
 
