@@ -123,7 +123,7 @@ EMISSION_DB_RANGE = (-83.0, -23.0)
 # ~1.5 % of the anchors above conf = 0.25 again (17-67 detections per burst) so decode / NMS see a realistic load
 IQ_CLS_BIAS = -1.6
 # same for stock yolo11s (nc = 80) at 1280^2 (~400-1000 candidates per image at 1280^2)
-YOLO11S_1280_CLS_BIAS = -1.75
+YOLO11S_1280_CLS_BIAS = -2.05
 
 
 def synth_iq_emissions(batch: int, length: int = 1 << 20, seed: int = 0) -> torch.Tensor:
