@@ -55,6 +55,12 @@ int specyolo_nchw_to_nhwc_bf16(const void* x, int x_dtype, float scale,
 int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C, int H, int W,
                                    float* y, void* stream);
 
+/* nn.Upsample(None, 2, 'nearest') (torch; cfg yolo11.yaml head layers 11 / 14) on an NHWC bf16 window [B,H,W,C] ->
+ * [B,2H,2W,C], written into a channel window of a wider buffer (y_pixstride): the Upsample -> Concat pair of the stock
+ * YOLO11 neck (ultralytics/nn/modules/conv.py:1810-1820 Concat) without the intermediate tensor. */
+int specyolo_upsample2x(const void* x, int x_pixstride, int B, int H, int W, int C,
+                        void* y, int y_pixstride, void* stream);
+
 /* ---- Conv + BN fold + weight repack ------------------------------------------------------ */
 /* Folds BatchNorm into the conv weights exactly like fuse_conv_and_bn
  * (ultralytics/utils/torch_utils.py:238-265) and repacks OIHW fp32 -> the K-major bf16 layout the

@@ -51,6 +51,7 @@ int letterbox_u8_launch(const uint8_t*, int, int, int, uint8_t*, int, int, int, 
 int match_predictions_launch(const float*, const int*, int, int, const float*, const int*, int, const float*, int, uint8_t*,
                              cudaStream_t);
 int stft_init();
+int upsample2x_launch(const void*, int, int, int, int, int, void*, int, cudaStream_t);
 bool bneck_pair_ok(int, int, int, int, int);
 int bneck_pair_launch(const specyolo_bneck_t*, cudaStream_t);
 
@@ -87,6 +88,14 @@ int specyolo_nhwc_bf16_to_nchw_f32(const void* x, int x_pixstride, int B, int C,
     SY_CHECK(x && y && B > 0 && C > 0 && H > 0 && W > 0 && x_pixstride >= C, SPECYOLO_ERR_INVALID,
              "nhwc_to_nchw: bad arguments");
     return nhwc_to_nchw_launch(x, x_pixstride, B, C, H, W, y, (cudaStream_t)stream);
+}
+
+int specyolo_upsample2x(const void* x, int x_pixstride, int B, int H, int W, int C, void* y, int y_pixstride, void* stream) {
+    SY_CHECK(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && x_pixstride >= C && y_pixstride >= C &&
+                 x_pixstride % 8 == 0 && y_pixstride % 8 == 0 &&
+                 !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15),
+             SPECYOLO_ERR_INVALID, "upsample2x: C and the pixel strides must be multiples of 8, tensors 16-byte aligned");
+    return upsample2x_launch(x, x_pixstride, B, H, W, C, y, y_pixstride, (cudaStream_t)stream);
 }
 
 int specyolo_conv_merge(int cin, int cout, int groups, int k, int stride, int pad, int dil) {

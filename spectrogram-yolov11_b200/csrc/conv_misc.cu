@@ -474,4 +474,43 @@ int nhwc_to_nchw_launch(const void* x, int x_pixstride, int B, int C, int H, int
     return SPECYOLO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// nn.Upsample(None, 2, 'nearest') on an NHWC bf16 window, written straight into a channel window of the consumer's
+// concat buffer (stock YOLO11 necks: Upsample -> Concat, cfg yolo11.yaml head; the Spectrogram cfg reads through the
+// upsample inside Fusion instead).  A thread moves one 16-byte vector (8 channels) of a source pixel to its four
+// destinations; consecutive threads take consecutive vectors of a pixel, so reads and writes are full lines.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_pixstride, int H, int W, int vecs, long total,
+                  __nv_bfloat16* __restrict__ y, int y_pixstride) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vecs);
+        const long pix = i / vecs;                      // source pixel (b, h, w)
+        const int w = (int)(pix % W);
+        const long bh = pix / W;                        // b * H + h
+        const uint4 val = *reinterpret_cast<const uint4*>(x + pix * x_pixstride + v * 8);
+        __nv_bfloat16* d = y + ((bh * 2) * (2L * W) + 2 * w) * y_pixstride + v * 8;     // (b, 2h, 2w)
+        const long row = 2L * W * y_pixstride;
+        *reinterpret_cast<uint4*>(d) = val;
+        *reinterpret_cast<uint4*>(d + y_pixstride) = val;
+        *reinterpret_cast<uint4*>(d + row) = val;
+        *reinterpret_cast<uint4*>(d + row + y_pixstride) = val;
+    }
+}
+
+int upsample2x_launch(const void* x, int x_pixstride, int B, int H, int W, int C, void* y, int y_pixstride,
+                      cudaStream_t stream) {
+    const int vecs = C / 8;
+    const long total = (long)B * H * W * vecs;
+    const long blocks = (total + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 148L * 16 ? blocks : 148L * 16);
+    SY_CUDA(launch_pdl(upsample2x_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
+                       x_pixstride, H, W, vecs, total, reinterpret_cast<__nv_bfloat16*>(y), y_pixstride));
+    SY_LAUNCH_CHECK();
+    count_launch();
+    return SPECYOLO_OK;
+}
+
 }  // namespace specyolo

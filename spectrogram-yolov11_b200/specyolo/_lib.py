@@ -116,6 +116,7 @@ SIGNATURES = {
                                              C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_void_p]),
+    "specyolo_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_fold_pack_conv": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 7 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),
     "specyolo_conv_merge": (C.c_int, [C.c_int] * 7),

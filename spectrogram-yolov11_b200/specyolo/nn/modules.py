@@ -350,13 +350,19 @@ class Concat(nn.Module):
         self.d = dimension
 
     def forward(self, xs: Sequence[torch.Tensor]):
-        xs = [_as_fmap(x) for x in xs]
+        """Fallback form (inputs copied): DetectionModel._run_trunk normally plans the buffer ahead and lets the producers
+        write their channel slices in place (tasks.py `_concat_plan`), so nothing is copied."""
         B, _, H, W = xs[0].shape
-        out = ops.new_act(B, sum(x.shape[1] for x in xs), H, W, xs[0].device)
+        dev = (xs[0].src if isinstance(xs[0], UpsampledView) else xs[0]).device
+        out = ops.new_act(B, sum(x.shape[1] for x in xs), H, W, dev)
         o = 0
         for x in xs:
-            out[:, o: o + x.shape[1]].copy_(x)   # plumbing copy (torch); the fusion cfg has no Concat
-            o += x.shape[1]
+            c = x.shape[1]
+            if isinstance(x, UpsampledView):
+                x.materialise(out=out[:, o: o + c])
+            else:
+                out[:, o: o + c].copy_(_as_fmap(x))   # plumbing copy (torch)
+            o += c
         return out
 
 
@@ -384,13 +390,19 @@ class UpsampledView:
         B, C, H, W = self.src.shape
         return torch.Size((B, C, 2 * H, 2 * W))
 
-    def materialise(self) -> torch.Tensor:
-        s = self.src
+    def materialise(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The upsampled map itself, optionally written into a channel slice of the consumer's concat buffer."""
+        if self.src.shape[1] % 8 == 0:
+            return ops.upsample2x(self.src, out)
+        s = self.src                                   # odd channel counts: torch plumbing
         B, C, H, W = s.shape
-        out = ops.new_act(B, C, 2 * H, 2 * W, s.device)
-        v = out.permute(0, 2, 3, 1).view(B, H, 2, W, 2, C)
+        res = ops.new_act(B, C, 2 * H, 2 * W, s.device)
+        v = res.permute(0, 2, 3, 1).view(B, H, 2, W, 2, C)
         v.copy_(s.permute(0, 2, 3, 1)[:, :, None, :, None, :].expand(B, H, 2, W, 2, C))
-        return out
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 class GCT(nn.Module):

@@ -117,6 +117,7 @@ def parse_model(d: dict, ch: int, verbose: bool = False):
         m_ = nn.Sequential(*(mod(*args) for _ in range(n))) if n > 1 else mod(*args)
         m_.np = sum(x.numel() for x in m_.parameters())
         m_.i, m_.f, m_.type = i, f, m
+        m_.c_out, m_.s_out = c2, s_out          # output channels / cumulative stride (concat planning, _concat_plan)
         save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
         layers.append(m_)
         if i == 0:
@@ -194,11 +195,55 @@ class DetectionModel(nn.Module):
             self._groups = groups
         return self._groups
 
+    def _concat_plan(self):
+        """Concat layers whose buffer can be planned ahead (stock YOLO11 necks: `Upsample -> Concat`, `Conv -> Concat`):
+        {producer layer: (concat layer, channel offset, channels)} for inputs whose producer can write its output straight
+        into the concat buffer's channel slice (`out=`), and {concat layer: [(input layer, offset, channels, how)]}.
+        torch.cat (conv.py:1810-1820) then moves no bytes: the only kernel left is the x2 nearest upsample, which writes
+        into its slice directly."""
+        if getattr(self, "_cplan", None) is None:
+            writers, cats = {}, {}
+            n = len(self.model) - 1
+            takes_out = (Conv, DWConv, DDWConv, C2f, C3, C3k, C3k2, SPPF, C2PSA, Fusion)
+            for i in range(n):
+                m = self.model[i]
+                if not isinstance(m, Concat) or not isinstance(m.f, (list, tuple)):
+                    continue
+                srcs = [(i - 1) if j == -1 else j for j in m.f]
+                if any(getattr(self.model[j], "c_out", None) is None or self.model[j].c_out % 8 for j in srcs):
+                    continue
+                off, entries = 0, []
+                for j in srcs:
+                    pm, c = self.model[j], self.model[j].c_out
+                    if isinstance(pm, Upsample2x):
+                        how = "upsample"
+                    elif isinstance(pm, takes_out) and j not in writers and j != 0 and not (j == 1 and isinstance(self.model[0], Conv)):
+                        how = "inplace"                     # (layers 0 / 1 may run as the fused stem pair: left alone)
+                        writers[j] = (i, off, c)
+                    else:
+                        how = "copy"
+                    entries.append((j, off, c, how))
+                    off += c
+                cats[i] = (entries, off, m.s_out)
+            self._cplan = (writers, cats)
+        return self._cplan
+
     def _run_trunk(self, x):
         """All layers except Detect; returns the list of Detect inputs."""
         y = []
         groups = DetectionModel._parallel_groups(self)      # (self may be the reference's model behind the shim)
         layers = list(self.model[:-1])
+        # concat buffers planned ahead (our own layer classes only; behind the ultralytics shim the reference's Concat runs)
+        plan_ok = isinstance(self, DetectionModel) and x.dim() == 4 and x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0
+        writers, cats = DetectionModel._concat_plan(self) if plan_ok else ({}, {})
+        cat_bufs = {}
+        in_b, in_h, in_w, in_dev = (x.shape[0], x.shape[2], x.shape[3], x.device) if plan_ok else (0, 0, 0, None)
+
+        def cat_buf(ci):
+            if ci not in cat_bufs:
+                _, ctot, s_out = cats[ci]
+                cat_bufs[ci] = ops.new_act(in_b, ctot, in_h // s_out, in_w // s_out, in_dev)
+            return cat_bufs[ci]
         i = 0
         # stem pair: layer 0 writes its output 2x2-blocked and layer 1 (3x3 / s2) reads it as a 2x2 / s1 conv over
         # 4c channels — one 128-byte-row TMA box per tile instead of nine strided boxes (same arithmetic)
@@ -229,9 +274,20 @@ class DetectionModel(nn.Module):
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             if isinstance(x, UpsampledView) and type(m).__name__ != "Fusion":
                 x = x.materialise()
-            if type(m).__name__ == "Concat":
-                x = [t.materialise() if isinstance(t, UpsampledView) else t for t in x]
-            x = m(x)
+            if i in cats:
+                # planned concat: in-place inputs are already there, upsampled inputs are written by the upsample kernel
+                buf = cat_buf(i)
+                for (j, off, c, how), t in zip(cats[i][0], x):
+                    if how == "upsample":
+                        t.materialise(out=buf[:, off: off + c])
+                    elif how == "copy" or t.data_ptr() != buf[:, off: off + c].data_ptr():
+                        buf[:, off: off + c].copy_(t.materialise() if isinstance(t, UpsampledView) else t)
+                x = buf
+            elif i in writers:
+                ci, off, c = writers[i]
+                x = m(x, out=cat_buf(ci)[:, off: off + c])
+            else:
+                x = m(x)       # (the Concat fallback handles UpsampledView inputs itself)
             y.append(x if m.i in self.save else None)
             i += 1
         det = self.model[-1]

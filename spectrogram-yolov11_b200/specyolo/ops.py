@@ -110,6 +110,21 @@ def to_nhwc_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Upsample(None, 2, 'nearest') of an NHWC bf16 feature map, optionally into a channel slice of a concat buffer
+    (specyolo_upsample2x)."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("upsample2x expects bf16")
+    if out is None:
+        out = new_act(B, Cc, 2 * H, 2 * W, x.device)
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, Cc, 2 * H, 2 * W) or out.dtype != torch.bfloat16:
+        raise ValueError("upsample2x: out shape / dtype mismatch")
+    check(_lib.load().specyolo_upsample2x(x.data_ptr(), xpix, B, H, W, Cc, out.data_ptr(), ypix, _lib.stream_ptr()))
+    return out
+
+
 def to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     """NHWC bf16 feature map -> NCHW-contiguous fp32 tensor."""
     B, Cc, H, W, pix = nhwc_meta(x)

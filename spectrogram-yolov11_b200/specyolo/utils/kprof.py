@@ -85,6 +85,7 @@ _WORK = {
     "nms": lambda r, *a, **k: ("nms", 0.0, 0.0, "nms"),
     "iq_to_letterbox": lambda r, iq, *a, **k: ("stft_letterbox", 0.0, 4.0 * iq.numel() + r.numel() * r.element_size(),
                                                f"iq_to_letterbox {tuple(iq.shape)}"),
+    "upsample2x": lambda r, x, out=None: ("layout", 0.0, 2.0 * x.numel() + 2.0 * r.numel(), f"upsample x2 {tuple(x.shape)}"),
     "to_nhwc_bf16": lambda r, x, *a, **k: ("layout", 0.0, x.numel() * x.element_size() + 2.0 * r.numel(), "nchw->nhwc"),
 }
 
