@@ -38,56 +38,66 @@ detect_decode_kernel(const __grid_constant__ DecodeParams p) {
         while (l + 1 < a.nl && anchor >= p.lvl_off[l + 1]) ++l;
         const int local = anchor - p.lvl_off[l];
         const int gw = a.w[l];
-        const float ax = (float)(local % gw) + 0.5f;   // make_anchors: cell centre
-        const float ay = (float)(local / gw) + 0.5f;
         const float* row = a.logits[l] + ((size_t)b * a.h[l] * gw + local) * a.no_stride;
+        const float* cls = row + 4 * a.reg_max;
+        float* ydense = a.y ? a.y + (size_t)b * (4 + a.nc) * p.A + anchor : nullptr;
 
-        // DFL: softmax over reg_max bins, expectation with weights 0..reg_max-1
-        float dist[4];
+        // ---- scores first.  Without the dense output only survivors of the threshold need their box, and >= 97 % of the
+        // anchors fail it: those read just the nc class logits of their row (not the 64 DFL bins) and evaluate ONE sigmoid.
+        // sigmoid is monotonic as computed (expf, 1 + e, reciprocal), so  max_c sigmoid(l_c) == sigmoid(max_c l_c)  as a
+        // number: the threshold decision is bit-identical to the reference order (sigmoid every class, then max,
+        // head.py:100-131 + ops.py:250); survivors then redo the exact loop so that ties pick the reference's class.
+        bool need_box = ydense != nullptr;
+        if (!need_box) {
+            float lmax = __ldg(cls);
+            for (int c = 1; c < a.nc; ++c) lmax = fmaxf(lmax, __ldg(cls + c));
+            need_box = (1.0f / (1.0f + expf(-lmax))) > a.conf_thres;
+        }
+        if (need_box) {
+            for (int c = 0; c < a.nc; ++c) {
+                const float sc = 1.0f / (1.0f + expf(-__ldg(cls + c)));
+                if (ydense) ydense[(size_t)(4 + c) * p.A] = sc;
+                if (sc > conf) { conf = sc; best = c; }   // strict '>' keeps the first maximum (torch.max)
+            }
+            const float ax = (float)(local % gw) + 0.5f;   // make_anchors: cell centre
+            const float ay = (float)(local / gw) + 0.5f;
+            // DFL: softmax over reg_max bins, expectation with weights 0..reg_max-1
+            float dist[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            float v[16];
-            if (a.reg_max == 16) {
+            for (int s = 0; s < 4; ++s) {
+                float v[16];
                 const float4* r4 = reinterpret_cast<const float4*>(row + s * 16);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 t = __ldg(r4 + q);
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
-            }
-            float m = v[0];
+                float m = v[0];
 #pragma unroll
-            for (int k = 1; k < 16; ++k) m = fmaxf(m, v[k]);
-            float sum = 0.f, wsum = 0.f;
+                for (int k = 1; k < 16; ++k) m = fmaxf(m, v[k]);
+                float sum = 0.f, wsum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float e = expf(v[k] - m);
-                sum += e;
-                wsum = fmaf((float)k, e, wsum);
+                for (int k = 0; k < 16; ++k) {
+                    const float e = expf(v[k] - m);
+                    sum += e;
+                    wsum = fmaf((float)k, e, wsum);
+                }
+                dist[s] = wsum / sum;
             }
-            dist[s] = wsum / sum;
-        }
-        // dist2bbox (xywh=True) then * stride
-        const float x1 = ax - dist[0], y1 = ay - dist[1];
-        const float x2 = ax + dist[2], y2 = ay + dist[3];
-        const float st = a.stride[l];
-        cx = (x1 + x2) * 0.5f * st;
-        cy = (y1 + y2) * 0.5f * st;
-        bw = (x2 - x1) * st;
-        bh = (y2 - y1) * st;
-
-        const float* cls = row + 4 * a.reg_max;
-        float* ydense = a.y ? a.y + (size_t)b * (4 + a.nc) * p.A + anchor : nullptr;
-        if (ydense) {
-            ydense[0] = cx;
-            ydense[(size_t)p.A] = cy;
-            ydense[(size_t)2 * p.A] = bw;
-            ydense[(size_t)3 * p.A] = bh;
-        }
-        for (int c = 0; c < a.nc; ++c) {
-            const float sc = 1.0f / (1.0f + expf(-__ldg(cls + c)));
-            if (ydense) ydense[(size_t)(4 + c) * p.A] = sc;
-            if (sc > conf) { conf = sc; best = c; }   // strict '>' keeps the first maximum (torch.max)
+            // dist2bbox (xywh=True) then * stride
+            const float x1 = ax - dist[0], y1 = ay - dist[1];
+            const float x2 = ax + dist[2], y2 = ay + dist[3];
+            const float st = a.stride[l];
+            cx = (x1 + x2) * 0.5f * st;
+            cy = (y1 + y2) * 0.5f * st;
+            bw = (x2 - x1) * st;
+            bh = (y2 - y1) * st;
+            if (ydense) {
+                ydense[0] = cx;
+                ydense[(size_t)p.A] = cy;
+                ydense[(size_t)2 * p.A] = bw;
+                ydense[(size_t)3 * p.A] = bh;
+            }
         }
     }
 

@@ -80,8 +80,12 @@ _WORK = {
     "psa_attention": lambda r, qkv, heads, key_dim, head_dim, *a, **k: (
         "psa_attention", 2.0 * qkv.shape[0] * heads * (qkv.shape[2] * qkv.shape[3]) ** 2 * (key_dim + head_dim),
         2.0 * (qkv.numel() + r.numel()), f"psa_attention N={qkv.shape[2] * qkv.shape[3]} heads={heads}"),
-    "detect_decode": lambda r, logits, *a, **k: ("detect_decode", 0.0, 4.0 * sum(t.numel() for t in logits),
-                                                 "detect_decode"),
+    # with the fused threshold only the class logits of every anchor (and the 64 DFL bins of the few survivors) are read
+    "detect_decode": lambda r, logits, hw, strides, nc, want_dense=True, conf_thres=None: (
+        "detect_decode", 0.0,
+        4.0 * sum(t.numel() for t in logits) if (want_dense or conf_thres is None) else
+        4.0 * sum(t.shape[0] * t.shape[1] * max(nc, 8) for t in logits),       # (a 32-byte sector per row at least)
+        "detect_decode" + ("" if want_dense else " (scores first)")),
     "nms": lambda r, *a, **k: ("nms", 0.0, 0.0, "nms"),
     "iq_to_letterbox": lambda r, iq, *a, **k: ("stft_letterbox", 0.0, 4.0 * iq.numel() + r.numel() * r.element_size(),
                                                f"iq_to_letterbox {tuple(iq.shape)}"),
