@@ -66,6 +66,8 @@ def compare_detections(ref_list, got_list, score_floor: float = 0.30, match_iou:
         "p99_dbox_px": float(np.quantile(dbox, 0.99)) if len(dbox) else 0.0,
         "mean_dbox_px": float(dbox.mean()) if len(dbox) else 0.0,
         "frac_dbox_le_0p5": float((dbox <= 0.5).mean()) if len(dbox) else 1.0,
+        "frac_dbox_le_2": float((dbox <= 2.0).mean()) if len(dbox) else 1.0,
+        "median_dbox_px": float(np.median(dbox)) if len(dbox) else 0.0,
         "max_dscore": float(dscore.max()) if len(dscore) else 0.0,
         "mean_dscore": float(dscore.mean()) if len(dscore) else 0.0,
         "images_with_count_diff": int(sum(1 for c in count_diff if c)),
