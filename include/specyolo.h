@@ -209,6 +209,20 @@ typedef struct {
 size_t specyolo_fusion_ws_bytes(int k, int B, int H, int W, int c);
 int    specyolo_fusion_eschannel(const specyolo_fusion_t* a, void* stream);
 
+/* ---- SobelSpatialAttention (ultralytics/nn/modules/conv.py:1184-1198), the gate of ConvHCA (conv.py:829-844;
+ *      cfg yolo11_fusion_sand3_new_convHCA.yaml backbone layers 3, 5, 7) ------------------------------------------
+ * y = x * sigmoid( cv1( sum_k sobel_k (*) cat(mean_c x, max_c x) ) ).  The three depthwise 3x3 convs (SobelConv,
+ * conv.py:1153-1182: groups = 2, zero padding, no bias) and the 2 -> 1 1x1 conv are linear in the two statistic
+ * planes; the caller passes them folded: w[c*9 + ky*3 + kx] = cv1[0][c] * sum_k sobel_k[c][0][ky][kx]. */
+typedef struct {
+    const void* x; int x_pixstride;   /* bf16 NHWC [B,H,W,C], C % 8 == 0                      */
+    void* y; int y_pixstride;         /* bf16 NHWC, may alias x                               */
+    int B, H, W, C;
+    float w[18];
+    float* mm;                        /* workspace: B * 2 * H * W floats (mean / max planes)  */
+} specyolo_spatial_gate_t;
+int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* stream);
+
 /* ---- PSA attention core (ultralytics/nn/modules/block.py:1922-1933) ----------------------- */
 /* qkv: bf16 NHWC [B,N,heads*(2*kd+hd)] as written by the qkv 1x1 conv; out[b,n,h*hd+d] =
  * sum_j softmax_j(q_n.k_j*scale) v_j[d] + pe(v)[n] where pe is the depthwise 3x3 (+folded BN)

@@ -34,6 +34,7 @@ MODEL_CASES = [
     # fixture name, reference yaml, our cfg name, nc, input H, W, seed
     ("specyolo_s", "yolo11s_fusion_sand3_new.yaml", "yolo11s_fusion_sand3_new.yaml", 2, 96, 128, 0),
     ("yolo11n", "yolo11n.yaml", "yolo11n.yaml", 80, 64, 96, 1),
+    ("specyolo_s_convhca", "yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11s_fusion_sand3_new_convHCA.yaml", 2, 96, 128, 2),
 ]
 
 
@@ -43,7 +44,10 @@ def gen_models():
     import specyolo
     from specyolo.nn.init import synth_images, synth_state_dict
 
+    only = {a[len("model="):] for a in sys.argv[1:] if a.startswith("model=")}     # e.g. `models model=specyolo_s_convhca`
     for name, ref_yaml, cfg, nc, H, W, seed in MODEL_CASES:
+        if only and name not in only:
+            continue
         ref = RefModel(f"{REFERENCE_ROOT}/ultralytics/cfg/models/11/{ref_yaml}", nc=nc, verbose=False).eval()
         mine = specyolo.DetectionModel(cfg, nc=nc)
         sd = synth_state_dict(mine, seed=seed)
@@ -375,7 +379,7 @@ def gen_results():
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"models", "nms", "letterbox", "metrics", "letterbox_u8"}
+    which = {a for a in sys.argv[1:] if "=" not in a} or {"models", "nms", "letterbox", "metrics", "letterbox_u8"}
     if "models" in which:
         gen_models()
     if "nms" in which:

@@ -55,13 +55,15 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
         n = max(round(n * depth), 1) if n > 1 else n  # tasks.py:1085
         c1 = (cin_first if i == 0 else chans[f]) if isinstance(f, int) else None
         L = dict(i=i, f=f, type=m, prefix=f"model.{i}")
-        if m in ("Conv", "C3k2", "SPPF", "C2PSA", "DDWConv"):
+        if m in ("Conv", "ConvHCA", "C3k2", "SPPF", "C2PSA", "DDWConv"):
             c2 = make_divisible(min(args[0], max_ch) * width, 8)  # tasks.py:1088-1089
             rest = list(args[1:])
             if m == "Conv":
                 k = rest[0] if len(rest) > 0 else 1
                 s = rest[1] if len(rest) > 1 else 1
                 L.update(c1=c1, c2=c2, k=k, s=s)
+            elif m == "ConvHCA":  # conv.py:830: k=3, s=2 defaults
+                L.update(c1=c1, c2=c2, k=rest[0] if len(rest) > 0 else 3, s=rest[1] if len(rest) > 1 else 2)
             elif m == "C3k2":
                 c3k = rest[0] if len(rest) > 0 else False
                 e = rest[1] if len(rest) > 1 else 0.5
@@ -198,6 +200,14 @@ class Ref:
     def ddwconv(self, x, p, k, s, d):
         return self.conv(self.conv(x, p + ".conv1", k, s, g=8, d=d), p + ".conv2")
 
+    # ConvHCA (conv.py:829-844) = Conv then SobelSpatialAttention (conv.py:1184-1198) over SobelConv (conv.py:1153-1182)
+    def convhca(self, x, p, k, s):
+        sd = self.sd
+        x1 = self.conv(x, p + ".conv2", k, s)
+        m = torch.cat([x1.mean(1, keepdim=True), x1.max(1, keepdim=True)[0]], 1)
+        e = sum(F.conv2d(m, sd[f"{p}.hca.sobel.convs.{j}.weight"], None, 1, 1, 1, 2) for j in range(3))
+        return x1 * torch.sigmoid(F.conv2d(e, sd[p + ".hca.cv1.weight"]))
+
     # GCT (conv.py:2284-2301)
     def gct(self, x, p, eps=1e-5):
         sd = self.sd
@@ -286,6 +296,8 @@ def forward(graph: List[dict], sd, x: torch.Tensor, strides=(8.0, 16.0, 32.0),
         t, p = L["type"], L["prefix"]
         if t == "Conv":
             x = R.conv(inp, p, L["k"], L["s"])
+        elif t == "ConvHCA":
+            x = R.convhca(inp, p, L["k"], L["s"])
         elif t == "C3k2":
             x = R.c3k2(inp, p, L["n"], L["c3k"])
         elif t == "SPPF":

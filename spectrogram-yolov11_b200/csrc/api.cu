@@ -34,6 +34,7 @@ int nhwc_to_nchw_launch(const void*, int, int, int, int, int, float*, cudaStream
 int sppf_pool_launch(void*, int, int, int, int, int, cudaStream_t);
 size_t fusion_ws_bytes(int, int, int, int, int);
 int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
+int spatial_gate_launch(const specyolo_spatial_gate_t*, cudaStream_t);
 int psa_attention_launch(const void*, int, int, int, int, int, int, int, float, const float*, const float*,
                          void*, int, cudaStream_t);
 int detect_decode_launch(const specyolo_decode_t*, cudaStream_t);
@@ -228,6 +229,12 @@ size_t specyolo_fusion_ws_bytes(int k, int B, int H, int W, int c) { return fusi
 int specyolo_fusion_eschannel(const specyolo_fusion_t* a, void* stream) {
     SY_CHECK(a && a->y && a->alpha && a->gamma && a->beta && a->sab_w, SPECYOLO_ERR_INVALID, "fusion: null pointer");
     return fusion_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->y && a->mm, SPECYOLO_ERR_INVALID, "spatial gate: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, SPECYOLO_ERR_INVALID, "spatial gate: bad sizes");
+    return spatial_gate_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_psa_attention(const void* qkv, int qkv_pixstride, int B, int H, int W, int heads, int key_dim,

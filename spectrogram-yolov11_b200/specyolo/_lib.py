@@ -76,6 +76,14 @@ class FusionArgs(C.Structure):
     ]
 
 
+class SpatialGateArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_pixstride", C.c_int), ("y", C.c_void_p), ("y_pixstride", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("w", C.c_float * 18), ("mm", C.c_void_p),
+    ]
+
+
 class DecodeArgs(C.Structure):
     _fields_ = [
         ("nl", C.c_int), ("logits", C.c_void_p * 4), ("h", C.c_int * 4), ("w", C.c_int * 4),
@@ -116,6 +124,7 @@ SIGNATURES = {
                                              C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_void_p]),
+    "specyolo_sobel_spatial_attention": (C.c_int, [C.POINTER(SpatialGateArgs), C.c_void_p]),
     "specyolo_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_fold_pack_conv": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 7 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -159,6 +159,58 @@ class DDWConv(nn.Module):
         return self.conv2(self.conv1(x), out=out)
 
 
+class SobelConv(nn.Module):
+    """Parameter container of SobelConv (conv.py:1153-1182): three depthwise 3x3 convs (groups = out_channels, no bias)
+    initialised to the Sobel-x, Sobel-x + Sobel-y and Sobel-y kernels; their outputs are summed."""
+
+    def __init__(self, in_channels=1, out_channels=16):
+        super().__init__()
+        sx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]])
+        sy = torch.tensor([[-1.0, -2.0, -1.0], [0.0, 0.0, 0.0], [1.0, 2.0, 1.0]])
+        self.convs = nn.ModuleList()
+        for kern in (sx, sx + sy, sy):
+            conv = nn.Conv2d(in_channels, out_channels, 3, padding=1, groups=out_channels, bias=False)
+            conv.weight = nn.Parameter(kern.view(1, 1, 3, 3).repeat(out_channels, 1, 1, 1))
+            self.convs.append(conv)
+
+
+class SobelSpatialAttention(nn.Module):
+    """x * sigmoid(cv1(sobel(cat(mean_c x, max_c x)))) (conv.py:1184-1198): one statistics pass + one gate pass
+    (csrc/spatial_gate.cu); the seven small linear weights are folded into one 2 x 3 x 3 stencil on the host."""
+
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        assert kernel_size in {3, 7}
+        self.sobel = SobelConv(in_channels=2, out_channels=2)
+        self.cv1 = nn.Conv2d(2, 1, 1, padding=0, bias=False)
+        self._w18 = None
+
+    def stencil(self):
+        ws = [c.weight for c in self.sobel.convs] + [self.cv1.weight]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if getattr(self, "_w18", None) is None or self._w18[0] != key:
+            k = sum(c.weight.detach().float() for c in self.sobel.convs).reshape(2, 9)      # [c][ky*3+kx]
+            w = (self.cv1.weight.detach().float().reshape(2, 1) * k).reshape(18)
+            self._w18 = (key, [float(v) for v in w.cpu()])
+        return self._w18[1]
+
+    def forward(self, x, out=None):
+        return ops.sobel_spatial_attention(_as_fmap(x), self.stencil(), out)
+
+
+class ConvHCA(nn.Module):
+    """Conv(k, s) followed by SobelSpatialAttention (conv.py:829-844; *_convHCA configs, backbone layers 3 / 5 / 7)."""
+
+    def __init__(self, c1, c2, k=3, s=2, d=1, act=True):
+        super().__init__()
+        self.kz, self.stride, self.dilation = k, s, d
+        self.conv2 = Conv(c1, c2, k=k, s=s)
+        self.hca = SobelSpatialAttention(7)
+
+    def forward(self, x, out=None):
+        return self.hca(self.conv2(x, out=out))        # the gate runs in place on the conv's output window
+
+
 class Bottleneck(nn.Module):
     """Two convs with an optional shortcut added in the second conv's epilogue (block.py:713-726)."""
 

@@ -21,16 +21,16 @@ import torch.nn as nn
 import yaml
 
 from .. import ops
-from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, Concat, Conv, DDWConv, Detect, DWConv, Fusion,
+from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, Concat, Conv, ConvHCA, DDWConv, Detect, DWConv, Fusion,
                       Upsample2x, UpsampledView)
 
 CFG_DIR = Path(__file__).resolve().parent.parent / "cfg"
 
-_MODULES = {m.__name__: m for m in (Conv, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA, Concat, Fusion,
+_MODULES = {m.__name__: m for m in (Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA, Concat, Fusion,
                                     Detect)}
-_BASE = {Conv, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA}
+_BASE = {Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA}
 _REPEAT = {C2f, C3, C3k, C3k2, C2PSA}
-_STRIDE2 = {Conv, DWConv, DDWConv}
+_STRIDE2 = {Conv, ConvHCA, DWConv, DDWConv}
 
 
 def make_divisible(x, divisor):
@@ -101,7 +101,7 @@ def parse_model(d: dict, ch: int, verbose: bool = False):
                 if scale in "mlx":
                     args[3] = True
             if mod in _STRIDE2:
-                s = args[3] if len(args) > 3 else (1 if mod is not DDWConv else 2)
+                s = args[3] if len(args) > 3 else (1 if mod not in (DDWConv, ConvHCA) else 2)
                 s_out = s_in * s
         elif mod is Upsample2x:
             c2 = chans[f]

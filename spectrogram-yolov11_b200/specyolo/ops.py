@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, StemPairArgs, StftArgs, check
+from ._lib import BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, SpatialGateArgs, StemPairArgs, StftArgs, check
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -482,6 +482,28 @@ def fusion_eschannel(xs: Sequence[torch.Tensor], upshift: Sequence[int], alpha: 
     a.y, a.y_pixstride = out.data_ptr(), nhwc_meta(out)[4]
     a.ws = ws.data_ptr()
     check(lib.specyolo_fusion_eschannel(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def sobel_spatial_attention(x: torch.Tensor, w18: Sequence[float], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SobelSpatialAttention (conv.py:1184-1198): x * sigmoid(stencil(mean_c x, max_c x)); `w18` is the folded
+    2 x 3 x 3 stencil (see include/specyolo.h).  out=None gates x in place."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("sobel_spatial_attention expects bf16")
+    if out is None:
+        out = x
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, Cc, H, W) or out.dtype != torch.bfloat16:
+        raise ValueError("sobel_spatial_attention: out shape / dtype mismatch")
+    mm = torch.empty((B, 2, H, W), device=x.device, dtype=torch.float32)
+    a = SpatialGateArgs()
+    a.x, a.x_pixstride, a.y, a.y_pixstride = x.data_ptr(), xpix, out.data_ptr(), ypix
+    a.B, a.H, a.W, a.C = B, H, W, Cc
+    for i, v in enumerate(w18):
+        a.w[i] = float(v)
+    a.mm = mm.data_ptr()
+    check(_lib.load().specyolo_sobel_spatial_attention(C.byref(a), _lib.stream_ptr()))
     return out
 
 

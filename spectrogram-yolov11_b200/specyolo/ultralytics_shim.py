@@ -7,7 +7,7 @@ runs libspecyolo (SURVEY 8(b) hook 5).  `install()` rebinds, 
 (`ultralytics.nn.tasks` — where `parse_model` resolves YAML names, tasks.py:1074-1080 — and `ultralytics.nn.modules[.conv /
 .block / .head]`, where the blocks construct their sub-blocks), the classes
 
-    Conv DWConv DDWConv Bottleneck C3 C3k C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
+    Conv DWConv DDWConv ConvHCA SobelSpatialAttention Bottleneck C3 C3k C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
 
 to SUBCLASSES of the reference's own classes: constructor, parameters, `state_dict` keys, `fuse()`, pickling and every
 `isinstance` check stay the reference's; only `forward` changes — CUDA tensors go through the specyolo forward of the same
@@ -37,7 +37,7 @@ _INSTALLED = False
 
 # reference module (relative to ultralytics.nn.modules) -> class names defined there that get a shim
 _WHERE = {
-    "conv": ["Conv", "DWConv", "DDWConv", "Fusion"],
+    "conv": ["Conv", "DWConv", "DDWConv", "Fusion", "ConvHCA", "SobelSpatialAttention"],
     "block": ["Bottleneck", "C3", "C3k", "C2f", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA"],
     "head": ["Detect"],
 }
@@ -198,6 +198,8 @@ def install() -> dict:
     shims["DWConv"] = type("DWConv", (shims["Conv"], ref_dw), {"__doc__": ref_dw.__doc__})
     shims["DDWConv"] = _make_block(sub["conv"].DDWConv, M.DDWConv)
     shims["Fusion"] = _make_block(sub["conv"].Fusion, M.Fusion)
+    shims["SobelSpatialAttention"] = _make_block(sub["conv"].SobelSpatialAttention, M.SobelSpatialAttention, extra=("stencil",))
+    shims["ConvHCA"] = _make_block(sub["conv"].ConvHCA, M.ConvHCA)
     shims["Bottleneck"] = _make_block(sub["block"].Bottleneck, M.Bottleneck)
     shims["C3"] = _make_block(sub["block"].C3, M.C3)
     shims["C2f"] = _make_block(sub["block"].C2f, M.C2f)

@@ -394,6 +394,45 @@ def test_fusion_eschannel(lib, k, H, W, up, c):
     assert _rel_err(got, ref) < 5e-3
 
 
+@pytest.mark.parametrize("B,c,H,W,window", [(2, 128, 80, 80, False), (3, 256, 40, 40, False), (2, 512, 20, 20, False), (1, 64, 7, 9, False),
+                                            (2, 192, 5, 33, True), (1, 8, 3, 3, False), (5, 128, 1, 1, True)])
+def test_sobel_spatial_attention(lib, B, c, H, W, window):
+    """SobelSpatialAttention (conv.py:1184-1198) vs the oracle's restatement on bf16-rounded inputs: every lane-group
+    width (c / 8 = 1 ... 64 vectors per pixel, incl. one that is not a power of two), ragged / single-pixel maps,
+    in place on a channel window of a wider buffer and out of place."""
+    from specyolo import ops
+    from specyolo.nn.modules import SobelSpatialAttention
+
+    gen = torch.Generator().manual_seed(40 + c)
+    x = torch.randn((B, c, H, W), generator=gen)
+    m = SobelSpatialAttention(7)
+    with torch.no_grad():
+        for cv in m.sobel.convs:
+            cv.weight.add_(torch.randn(cv.weight.shape, generator=gen) * 0.3)
+        m.cv1.weight.copy_(torch.randn(m.cv1.weight.shape, generator=gen) * 0.7)
+    xb = _bf(x)
+    mm = torch.cat([xb.mean(1, keepdim=True), xb.max(1, keepdim=True)[0]], 1)
+    e = sum(F.conv2d(mm, cv.weight.detach(), None, 1, 1, 1, 2) for cv in m.sobel.convs)
+    ref = xb * torch.sigmoid(F.conv2d(e, m.cv1.weight.detach()))
+    if window:
+        buf = ops.new_act(B, c + 16, H, W, DEV)
+        buf.zero_()
+        xin = buf[:, 8:8 + c]
+        xin.copy_(x.to(DEV))
+        got = m(xin)                                           # in place on the window
+        assert got.data_ptr() == xin.data_ptr()
+        assert float(buf[:, :8].float().abs().max()) == 0.0 and float(buf[:, 8 + c:].float().abs().max()) == 0.0
+    else:
+        xin = _fmap(x)
+        keep = xin.clone()
+        out = ops.new_act(B, c, H, W, DEV)
+        got = ops.sobel_spatial_attention(xin, m.stencil(), out)
+        assert torch.equal(xin, keep)                          # out of place leaves x alone
+    got = got.float().cpu()
+    assert (got - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())      # one bf16 rounding of the product
+    assert _rel_err(got, ref) < 3e-3
+
+
 @pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2), (16, 16, 2), (5, 7, 1), (16, 32, 2), (24, 24, 2), (40, 40, 1)])
 def test_psa_attention(lib, H, W, heads):
     """N = 400 (640^2 input), ragged / tiny / exactly 256 and 512 tokens on the resident-S kernel (N <= 512), 576 and

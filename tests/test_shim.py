@@ -26,10 +26,10 @@ def _reference():
     return ref_loader.import_reference()
 
 
-def _ref_yolo(ultralytics, sd):
+def _ref_yolo(ultralytics, sd, cfg_name=CFG):
     from ultralytics.nn.tasks import DetectionModel as RefModel
 
-    cfg = Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG
+    cfg = Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / cfg_name
     m = RefModel(str(cfg), nc=2, verbose=False)
     m.load_state_dict(sd, strict=True)
     y = ultralytics.YOLO(str(cfg), task="detect")
@@ -37,11 +37,11 @@ def _ref_yolo(ultralytics, sd):
     return y
 
 
-def _sd():
+def _sd(cfg_name=CFG):
     import specyolo
     from specyolo.nn.init import synth_state_dict
 
-    return synth_state_dict(specyolo.DetectionModel(CFG, nc=2), seed=0)
+    return synth_state_dict(specyolo.DetectionModel(cfg_name, nc=2), seed=0)
 
 
 def test_shim_builds_through_the_reference_and_falls_through_on_cpu(lib):
@@ -115,3 +115,32 @@ def test_reference_predict_with_shim_vs_without(lib):
     s2 = compare_detections(ref, half)                                       # half=True: fp16 input, weights repacked from fp16
     record("shim_reference_api_b16_640_half", s2)
     assert s2["matched_rate"] >= 0.96, s2
+
+
+@pytest.mark.gpu
+def test_reference_predict_with_shim_convhca_variant(lib):
+    """Sibling config yolo11s_fusion_sand3_new_convHCA.yaml (ConvHCA = Conv + SobelSpatialAttention) behind the
+    reference API: the reference's parse_model builds the shim ConvHCA / SobelSpatialAttention, the gate kernel runs."""
+    ultralytics = _reference()
+    from specyolo import _lib
+    from specyolo import ultralytics_shim as shim
+    from specyolo.nn.init import synth_images
+
+    cfg = "yolo11s_fusion_sand3_new_convHCA.yaml"
+    sd = _sd(cfg)
+    x = (synth_images(64, 640, seed=0, dtype=torch.uint8)[:8].float() / 255)
+    stock = _ref_yolo(ultralytics, sd, cfg)
+    ref = [r.boxes.data.cpu().numpy() for r in stock.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+    shims = shim.install()
+    try:
+        y = _ref_yolo(ultralytics, sd, cfg)
+        assert type(y.model.model[3]) is shims["ConvHCA"] and type(y.model.model[3].hca) is shims["SobelSpatialAttention"]
+        n0 = _lib.load().specyolo_launch_count()
+        got = [r.boxes.data.cpu().numpy() for r in y.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+        launches = int(_lib.load().specyolo_launch_count() - n0)
+    finally:
+        shim.uninstall()
+    assert launches > 86, launches                                # 6 more than the base config: 3 x (statistics, gate)
+    stats = compare_detections(ref, got)
+    record("shim_reference_api_convhca_b8_640", stats)
+    assert sum(len(r) for r in ref) > 20 and stats["matched_rate"] >= 0.96, stats

@@ -59,21 +59,20 @@ class CalibRef(yolo_ref.Ref):
 
 def main():
     cases = [("yolo11s_fusion_sand3_new.yaml", "yolo11_fusion_sand3_new.yaml", "s", 2),
-             ("yolo11n.yaml", "yolo11.yaml", "n", 80), ("yolo11s.yaml", "yolo11.yaml", "s", 80)]
+             ("yolo11n.yaml", "yolo11.yaml", "n", 80), ("yolo11s.yaml", "yolo11.yaml", "s", 80),
+             ("yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11_fusion_sand3_new_convHCA.yaml", "s", 2)]
+    only = set(sys.argv[1:])
     for cfg, cfg_file, scale, nc in cases:
+        if only and cfg not in only:
+            continue
         m = specyolo.DetectionModel(cfg, nc=nc)
         d = yaml.safe_load((ROOT / "spectrogram-yolov11_b200" / "specyolo" / "cfg" / cfg_file).read_text())
         g = yolo_ref.parse_graph(d, scale, nc)
         sd = synth_state_dict(m, seed=0, calibrated=False)
         x = synth_images(2, 320, seed=0)
         R = CalibRef(sd)
-        orig_ref = yolo_ref.Ref
-        yolo_ref.Ref = lambda _sd: R
-        try:
-            with torch.no_grad():
-                yolo_ref.forward(g, sd, x)
-        finally:
-            yolo_ref.Ref = orig_ref
+        with torch.no_grad():
+            yolo_ref.forward(g, R, x)          # a prepared Ref is accepted in place of the state_dict
         out = ROOT / "spectrogram-yolov11_b200" / "specyolo" / "cfg" / (Path(cfg).stem + ".synth.json")
         out.write_text(json.dumps({k: round(v, 5) for k, v in R.rms.items()}, indent=0))
         print(cfg, len(R.rms), "convs; max rms", max(R.rms.values()), "min", min(R.rms.values()))
