@@ -1,14 +1,18 @@
 """Image-file ingest: `LoadImagesAndVideos` for image sources, decoded straight into device memory.
 
-Mirrors ultralytics/data/loaders.py:284-448 (constructor arguments, file discovery rules, `(paths, imgs, info)` batches,
-`__len__`), images only: videos and streams are outside the hot path this package rebuilds.  JPEG files are decoded by
+Mirrors ultralytics/data/loaders.py:284-448 (constructor arguments, file discovery rules, images before videos,
+`(paths, imgs, info)` batches that never mix the two, `vid_stride`, `__len__`).  JPEG files are decoded by
 nvJPEG into HBM (`specyolo_jpeg_decode_bgr`: HWC BGR uint8, the layout of `cv2.imread`) — the host only reads the file
 bytes; the pixels never exist in host memory.  Other formats (PNG, BMP, TIFF, WebP ...) have no GPU decoder in this image:
 they are decoded on the host with OpenCV exactly as the reference does (`cv2.imdecode`, loaders.py:406 / patches.py:20)
-and uploaded.  Every image of a batch is then letterboxed by `specyolo_letterbox_u8` (bit-exact with cv2's resize).
+and uploaded.  Video files are demuxed and decoded on the host by `cv2.VideoCapture` as in the reference
+(loaders.py:388-412, 440-446; this image has no NVDEC binding) — grab `vid_stride` frames, retrieve the last — and each
+retrieved frame is uploaded as one more [H, W, 3] BGR uint8 device tensor; live streams (`LoadStreams`) are not rebuilt.
+Every image of a batch is then letterboxed by `specyolo_letterbox_u8` (bit-exact with cv2's resize).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import glob
 import math
@@ -153,40 +157,94 @@ class LoadImagesAndVideos:
                 raise FileNotFoundError(f"{p} does not exist")
         images = [f for f in files if f.split(".")[-1].lower() in IMG_FORMATS]
         videos = [f for f in files if f.split(".")[-1].lower() in VID_FORMATS]
-        if videos:
-            raise NotImplementedError("video sources are outside the path specyolo implements (images only)")
         if world > 1:       # multi-GPU: files are independent, every rank takes a contiguous share, no collective
             from ..dist import shard_range
 
             b, e = shard_range(len(images), rank, world)
             images = images[b:e]
-        self.files = images
-        self.nf = self.ni = len(images)
-        self.video_flag = [False] * self.nf
-        self.mode = "image"
+            b, e = shard_range(len(videos), rank, world)
+            videos = videos[b:e]
+        self.files = images + videos                                   # loaders.py:347-352: images first
+        self.ni = len(images)
+        self.nf = self.ni + len(videos)
+        self.video_flag = [False] * self.ni + [True] * len(videos)
+        self.mode = "video" if self.ni == 0 and videos else "image"
         self.vid_stride = vid_stride
         self.bs = batch
         self.device = device
         self.count = 0
+        self.cap = None
+        self.frame = self.frames = self.fps = 0
         if self.nf == 0 and world == 1:
-            raise FileNotFoundError(f"No images found in {path}. Supported formats are: images: {IMG_FORMATS}")
+            raise FileNotFoundError(f"No images or videos found in {path}. Supported formats are: images: {IMG_FORMATS} "
+                                    f"videos: {VID_FORMATS}")
+        if videos:
+            self._new_video(videos[0])                                 # loaders.py:358-359: fails early on an unreadable file
 
     def __iter__(self):
         self.count = 0
+        if self.cap is not None and self.frame:                        # a second pass starts every video from its first frame
+            self.cap.release()
+            self.cap = None
         return self
 
+    def _new_video(self, path: str) -> None:
+        """loaders.py:440-446."""
+        import cv2
+
+        self.frame = 0
+        self.cap = cv2.VideoCapture(path)
+        self.fps = int(self.cap.get(cv2.CAP_PROP_FPS))
+        if not self.cap.isOpened():
+            raise FileNotFoundError(f"Failed to open video {path}")
+        self.frames = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT) / self.vid_stride)
+
+    def _next_frame(self, paths, imgs, info) -> None:
+        """One step of the reference's video branch (loaders.py:388-412): grab vid_stride frames, keep the last."""
+        path = self.files[self.count]
+        self.mode = "video"
+        if self.cap is None or not self.cap.isOpened():
+            self._new_video(path)
+        ok = False
+        for _ in range(self.vid_stride):
+            ok = self.cap.grab()
+            if not ok:
+                break
+        if ok:
+            ok, im0 = self.cap.retrieve()
+            if ok:
+                self.frame += 1
+                paths.append(path)
+                imgs.append(torch.from_numpy(np.ascontiguousarray(im0)).to(self.device, non_blocking=True))
+                info.append(f"video {self.count + 1}/{self.nf} (frame {self.frame}/{self.frames}) {path}: ")
+                if self.frame == self.frames:                          # the container's frame count is reached
+                    self.count += 1
+                    self.cap.release()
+        else:                                                          # end of stream (or a failed grab): next file
+            self.count += 1
+            self.cap.release()
+            if self.count < self.nf:
+                self._new_video(self.files[self.count])
+
     def __next__(self) -> Tuple[List[str], List[torch.Tensor], List[str]]:
-        if self.count >= self.nf:
-            raise StopIteration
         paths, imgs, info = [], [], []
-        while len(imgs) < self.bs and self.count < self.nf:
-            # the next files of the batch, decoded concurrently: the host part of a JPEG decode (file read + Huffman) runs
-            # on the calling thread and releases the GIL, the library keeps one nvJPEG state per in-flight decode
-            chunk = self.files[self.count:self.count + (self.bs - len(imgs))]
-            stream = torch.cuda.current_stream()
+        while len(imgs) < self.bs:
+            if self.count >= self.nf:
+                if imgs:
+                    return paths, imgs, info                           # last partial batch
+                raise StopIteration
+            if self.video_flag[self.count]:
+                self._next_frame(paths, imgs, info)
+                continue
+            # the next image files of the batch, decoded concurrently: the host part of a JPEG decode (file read + Huffman)
+            # runs on the calling thread and releases the GIL, the library keeps one nvJPEG state per in-flight decode
+            self.mode = "image"
+            chunk = self.files[self.count:min(self.ni, self.count + (self.bs - len(imgs)))]
+            on_gpu = torch.device(self.device).type == "cuda"      # device="cpu": file-discovery / ordering tests only
+            stream = torch.cuda.current_stream() if on_gpu else None
 
             def load(path):
-                with torch.cuda.stream(stream):
+                with (torch.cuda.stream(stream) if on_gpu else contextlib.nullcontext()):
                     try:
                         return imread_device(path, self.device)
                     except ValueError:
@@ -199,8 +257,8 @@ class LoadImagesAndVideos:
                     imgs.append(im0)
                     info.append(f"image {self.count + k + 1}/{self.nf} {path}: ")
             self.count += len(chunk)
-        if not imgs:
-            raise StopIteration
+            if self.count >= self.ni and imgs:                         # loaders.py:431-432: images and frames never share a batch
+                break
         return paths, imgs, info
 
     def __len__(self):

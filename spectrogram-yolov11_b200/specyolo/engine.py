@@ -670,12 +670,13 @@ class YOLO:
             self.predictor = (predictor or DetectionPredictor)(self.model, args)
         if isinstance(source, (str, Path)) or (isinstance(source, (list, tuple)) and source and
                                                all(isinstance(s, (str, Path)) for s in source)):
-            # image files / directory / glob / *.txt list (data/build.py:158-205 -> LoadImagesAndVideos): JPEGs are decoded
-            # by nvJPEG straight into device memory, letterboxed and run batch by batch through the streaming loop
+            # image / video files, directory, glob, *.txt list (data/build.py:158-205 -> LoadImagesAndVideos): JPEGs are decoded
+            # by nvJPEG straight into device memory (video frames: cv2 on the host, uploaded), letterboxed and run batch by
+            # batch through the streaming loop
             from .data import LoadImagesAndVideos
 
             loader = LoadImagesAndVideos([str(s) for s in source] if isinstance(source, (list, tuple)) else str(source),
-                                         batch=int(args.get("batch", 1)))
+                                         batch=int(args.get("batch", 1)), vid_stride=int(args.get("vid_stride", 1)))
             paths: List[str] = []
 
             def batches():

@@ -51,12 +51,88 @@ def test_loader_file_discovery(tmp_path):
     with pytest.raises(FileNotFoundError):
         LoadImagesAndVideos(str(tmp_path / "missing.jpg"))
     (tmp_path / "clip.mp4").write_bytes(b"0")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):                                     # loaders.py:444-445: "Failed to open video"
         LoadImagesAndVideos(str(tmp_path / "clip.mp4"))
+    (tmp_path / "clip.mp4").unlink()
     empty = tmp_path / "empty"
     empty.mkdir()
     with pytest.raises(FileNotFoundError):
         LoadImagesAndVideos(str(empty))
+
+
+def _write_video(path, n, hw=(48, 64), seed=0):
+    h, w = hw
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), 10, (w, h))
+    assert vw.isOpened()
+    for i in range(n):
+        vw.write(_spectrogram_like(h, w, seed * 100 + i))
+    vw.release()
+
+
+@pytest.mark.parametrize("vid_stride,batch", [(1, 4), (2, 3), (3, 2)])
+def test_loader_videos_match_reference(tmp_path, vid_stride, batch):
+    """Video sources (loaders.py:388-412, 440-446): images first, then every vid_stride-th frame of every video, batches
+    that never mix the two — the same (paths, frames, info) sequence as the REAL reference's loader on the same files."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference package not available")
+    ref_loader.import_reference()
+    from ultralytics.data.loaders import LoadImagesAndVideos as RefLoader
+
+    from specyolo.data import LoadImagesAndVideos
+
+    for k in range(3):
+        assert cv2.imwrite(str(tmp_path / f"img_{k}.png"), _spectrogram_like(40 + 8 * k, 56, k))
+    _write_video(tmp_path / "a_clip.avi", 7, seed=1)
+    _write_video(tmp_path / "b_clip.avi", 5, (32, 48), seed=2)
+    mine = LoadImagesAndVideos(str(tmp_path), batch=batch, vid_stride=vid_stride, device="cpu")
+    ref = RefLoader(str(tmp_path), batch=batch, vid_stride=vid_stride)
+    assert mine.files == ref.files and mine.nf == ref.nf and mine.ni == ref.ni and mine.video_flag == ref.video_flag
+    assert len(mine) == len(ref)
+    got, want = list(mine), list(ref)
+    assert len(got) == len(want)
+    for (p1, i1, s1), (p2, i2, s2) in zip(got, want):
+        assert p1 == p2 and s1 == s2
+        assert len(i1) == len(i2)
+        for a, b in zip(i1, i2):
+            assert a.dtype == torch.uint8 and np.array_equal(a.numpy(), b)
+    n_frames = sum(len(p) for p, _, _ in got) - 3
+    assert n_frames == 7 // vid_stride + 5 // vid_stride
+    assert [len(p) for p, _, _ in list(mine)] == [len(p) for p, _, _ in got]      # a second pass restarts the videos
+    shards = [LoadImagesAndVideos(str(tmp_path), batch=2, rank=r, world=2, device="cpu").files for r in range(2)]
+    assert sorted(sum(shards, [])) == sorted(mine.files) and all(any(f.endswith(".avi") for f in s) for s in shards)
+
+
+@pytest.mark.gpu
+def test_predict_from_video(tmp_path):
+    """YOLO.predict(directory with a video, vid_stride=2): one Results per image and per kept frame, equal to predict on
+    the same frames handed over as ndarrays."""
+    import specyolo
+    from specyolo.nn.init import synth_state_dict
+
+    assert cv2.imwrite(str(tmp_path / "img_0.png"), _spectrogram_like(160, 200, 3))
+    _write_video(tmp_path / "clip.avi", 6, (120, 160), seed=4)
+    frames = [cv2.imread(str(tmp_path / "img_0.png"))]
+    cap = cv2.VideoCapture(str(tmp_path / "clip.avi"))
+    k = 0
+    while True:
+        ok, im = cap.read()
+        if not ok:
+            break
+        k += 1
+        if k % 2 == 0:
+            frames.append(im)
+    yolo = specyolo.YOLO("yolo11s_fusion_sand3_new.yaml", nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    res = yolo.predict(str(tmp_path), conf=0.25, iou=0.7, imgsz=160, batch=2, vid_stride=2)
+    assert len(res) == len(frames) == 4
+    assert res[0].path.endswith("img_0.png") and all(r.path.endswith("clip.avi") for r in res[1:])
+    for r, im in zip(res, frames):
+        assert tuple(r.orig_shape) == im.shape[:2]
+        want = yolo.predict([im], conf=0.25, iou=0.7, imgsz=160)[0]
+        assert torch.equal(r.boxes.data, want.boxes.data)
 
 
 @pytest.mark.gpu
