@@ -376,6 +376,59 @@ def gen_results():
     print("results egress", {k: len(v["boxes"]) for k, v in cases.items()})
 
 
+from oracle.loss_ref import loss_case  # noqa: E402
+
+
+LOSS_CASES = [  # name, seed, B, H, W, nc, boxes per image, piled up
+    ("mixed", 0, 3, 160, 192, 2, (5, 0, 9), False),
+    ("dense80", 1, 2, 128, 128, 80, (12, 7), True),
+    ("empty", 2, 2, 96, 96, 2, (0, 0), False),
+    ("tiny_boxes", 3, 2, 128, 160, 3, (6, 6), False),
+]
+
+
+def gen_loss():
+    """loss_cases.npz: the REAL v8DetectionLoss (utils/loss.py:166-275) on seeded head maps: loss items, total, autograd
+    gradients with respect to every head map, and the assigner's targets."""
+    from types import SimpleNamespace
+
+    from ultralytics.nn.tasks import DetectionModel as RefModel
+    from ultralytics.utils.loss import v8DetectionLoss
+
+    out = {}
+    for name, seed, B, H, W, nc, n_gt, dense in LOSS_CASES:
+        model = RefModel(f"{REFERENCE_ROOT}/ultralytics/cfg/models/11/yolo11n.yaml", nc=nc, verbose=False)
+        model.args = SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+        crit = v8DetectionLoss(model)
+        feats, batch = loss_case(seed, B, H, W, nc, n_gt, dense)
+        if name == "tiny_boxes":                      # boxes narrower than a stride-8 cell: fewer than topk anchors inside
+            batch["bboxes"][::2, 2:] = torch.tensor([0.03, 0.45])
+        feats = [f.requires_grad_(True) for f in feats]
+        captured = {}
+        orig = crit.assigner.forward
+
+        def spy(*a, **k):
+            r = orig(*a, **k)
+            captured["r"] = r
+            return r
+
+        crit.assigner.forward = spy
+        total, items = crit(feats, batch)
+        total.backward()
+        _, tb, ts, fg, gi = captured["r"]
+        out[f"{name}.meta"] = np.asarray([seed, B, H, W, nc, int(dense)] + list(n_gt), dtype=np.int64)
+        out[f"{name}.bboxes"] = batch["bboxes"].numpy()
+        out[f"{name}.total"] = total.detach().numpy()
+        out[f"{name}.items"] = items.numpy()
+        for i, f in enumerate(feats):
+            out[f"{name}.grad{i}"] = f.grad.numpy()
+        out[f"{name}.target_scores"] = ts.numpy().astype(np.float32)
+        out[f"{name}.target_boxes"] = tb.numpy().astype(np.float32)      # grid units: the criterion divides the assigner's output by the stride in place (loss.py:266)
+        out[f"{name}.fg"] = fg.numpy()
+        print(name, "items", items.tolist(), "fg", int(fg.sum()), "scored", int((ts.sum(-1) > 0).sum()))
+    np.savez_compressed(GOLD / "loss_cases.npz", **out)
+
+
 if __name__ == "__main__":
     import_reference()
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -396,3 +449,5 @@ if __name__ == "__main__":
         gen_dataset()
     if "results" in which:
         gen_results()
+    if "loss" in which:
+        gen_loss()
