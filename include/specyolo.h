@@ -298,6 +298,28 @@ int specyolo_match_predictions(const float* pred, const int* pred_count, int B, 
                                const float* labels, const int* label_off, int max_labels_per_image,
                                const float* iouv_host, int niou, uint8_t* correct, void* stream);
 
+/* ---- training criterion (first slice) --------------------------------------------------
+ * Replaces v8DetectionLoss.__call__ (ultralytics/utils/loss.py:222-275): TaskAlignedAssigner.forward
+ * (utils/tal.py:57-118), BCEWithLogits class loss, BboxLoss (CIoU, utils/metrics.py:171-228) and DFLoss
+ * (utils/loss.py:66-129) — forward and the gradient with respect to the head outputs.
+ * pred_distri [B, A, 4*reg_max] / pred_scores [B, A, nc]: fp32 logits in the anchor order of make_anchors
+ * (tal.py:334-346: level by level, row-major), i.e. the tensors loss.py:226-231 builds; gt_boxes [B, M, 4] xyxy in
+ * input pixels and gt_labels [B, M], the first gt_count[b] rows of image b valid (loss.py:193-209 + mask_gt :243).
+ * out[6] = box, cls, dfl (each with its gain), (box + cls + dfl) * B, max(target_scores.sum(), 1), positives.
+ * grad_distri / grad_scores (may be NULL): d out[3] / d pred_distri, d out[3] / d pred_scores. */
+typedef struct {
+    int nl; int h[4], w[4]; float stride[4];
+    int B, nc, reg_max;
+    const float* pred_distri; const float* pred_scores;
+    int M; const float* gt_boxes; const int* gt_labels; const int* gt_count;
+    int topk; float alpha, beta, tal_eps;             /* TaskAlignedAssigner(topk=10, alpha=0.5, beta=6.0, eps=1e-9) */
+    float gain_box, gain_cls, gain_dfl;               /* hyp.box, hyp.cls, hyp.dfl                                  */
+    float* out; float* grad_distri; float* grad_scores;
+    void* ws;                                         /* specyolo_det_loss_ws_bytes() bytes, 256-byte aligned        */
+} specyolo_det_loss_t;
+size_t specyolo_det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
+int    specyolo_det_loss(const specyolo_det_loss_t* a, void* stream);
+
 /* ---- image ingest: LetterBox for uint8 images ----------------------------------------
  * Replaces LetterBox.__call__ (ultralytics/data/augment.py:1535-1601: cv2.resize INTER_LINEAR + copyMakeBorder) and the
  * BGR->RGB / HWC->CHW step of BasePredictor.preprocess (ultralytics/engine/predictor.py:125-136), bit-exact with

@@ -35,6 +35,8 @@ int sppf_pool_launch(void*, int, int, int, int, int, cudaStream_t);
 size_t fusion_ws_bytes(int, int, int, int, int);
 int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
 int spatial_gate_launch(const specyolo_spatial_gate_t*, cudaStream_t);
+int det_loss_launch(const specyolo_det_loss_t*, cudaStream_t);
+size_t det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
 int psa_attention_launch(const void*, int, int, int, int, int, int, int, float, const float*, const float*,
                          void*, int, cudaStream_t);
 int detect_decode_launch(const specyolo_decode_t*, cudaStream_t);
@@ -229,6 +231,17 @@ size_t specyolo_fusion_ws_bytes(int k, int B, int H, int W, int c) { return fusi
 int specyolo_fusion_eschannel(const specyolo_fusion_t* a, void* stream) {
     SY_CHECK(a && a->y && a->alpha && a->gamma && a->beta && a->sab_w, SPECYOLO_ERR_INVALID, "fusion: null pointer");
     return fusion_launch(a, (cudaStream_t)stream);
+}
+
+size_t specyolo_det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk) {
+    if (B < 1 || !h || !w || nl < 1 || nl > 4 || M < 0 || topk < 1) return 0;
+    return det_loss_ws_bytes(B, h, w, nl, M, topk);
+}
+
+int specyolo_det_loss(const specyolo_det_loss_t* a, void* stream) {
+    SY_CHECK(a && a->pred_distri && a->pred_scores && a->out && a->ws && a->gt_count, SPECYOLO_ERR_INVALID, "det loss: null pointer");
+    SY_CHECK(a->M == 0 || (a->gt_boxes && a->gt_labels), SPECYOLO_ERR_INVALID, "det loss: ground truth missing");
+    return det_loss_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* stream) {

@@ -84,6 +84,18 @@ class SpatialGateArgs(C.Structure):
     ]
 
 
+class DetLossArgs(C.Structure):
+    _fields_ = [
+        ("nl", C.c_int), ("h", C.c_int * 4), ("w", C.c_int * 4), ("stride", C.c_float * 4),
+        ("B", C.c_int), ("nc", C.c_int), ("reg_max", C.c_int),
+        ("pred_distri", C.c_void_p), ("pred_scores", C.c_void_p),
+        ("M", C.c_int), ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p), ("gt_count", C.c_void_p),
+        ("topk", C.c_int), ("alpha", C.c_float), ("beta", C.c_float), ("tal_eps", C.c_float),
+        ("gain_box", C.c_float), ("gain_cls", C.c_float), ("gain_dfl", C.c_float),
+        ("out", C.c_void_p), ("grad_distri", C.c_void_p), ("grad_scores", C.c_void_p), ("ws", C.c_void_p),
+    ]
+
+
 class DecodeArgs(C.Structure):
     _fields_ = [
         ("nl", C.c_int), ("logits", C.c_void_p * 4), ("h", C.c_int * 4), ("w", C.c_int * 4),
@@ -125,6 +137,8 @@ SIGNATURES = {
     "specyolo_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_void_p]),
     "specyolo_sobel_spatial_attention": (C.c_int, [C.POINTER(SpatialGateArgs), C.c_void_p]),
+    "specyolo_det_loss_ws_bytes": (C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),
+    "specyolo_det_loss": (C.c_int, [C.POINTER(DetLossArgs), C.c_void_p]),
     "specyolo_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_fold_pack_conv": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 7 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -47,3 +47,70 @@ def test_loss_oracle_matches_reference(name):
     from oracle.loss_ref import make_anchors
     _, stride_t = make_anchors([tuple(f.shape[2:]) for f in feats], (8.0, 16.0, 32.0))
     assert np.allclose((ex["target_boxes"] / stride_t).numpy()[scored], want["target_boxes"][scored], atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA criterion (csrc/det_loss.cu through specyolo.utils.loss.v8DetectionLoss) against the same fixtures of the
+# REAL criterion, and against the oracle at a training-size batch.
+# ---------------------------------------------------------------------------------------------------------------------
+class _FakeDetect:
+    def __init__(self, nc):
+        self.nc, self.reg_max, self.stride = nc, 16, torch.tensor([8.0, 16.0, 32.0])
+
+
+class _FakeModel:
+    """What v8DetectionLoss.__init__ reads of a model (loss.py:166-186): model[-1] (Detect), args (hyp), a parameter."""
+
+    def __init__(self, nc):
+        self.model = [_FakeDetect(nc)]
+        self.args = {"box": 7.5, "cls": 0.5, "dfl": 1.5}
+        self._p = torch.zeros(1, device="cuda")
+
+    def parameters(self):
+        return iter([self._p])
+
+
+def _cuda_loss(feats, batch, nc):
+    from specyolo.utils.loss import v8DetectionLoss
+
+    crit = v8DetectionLoss(_FakeModel(nc))
+    f = [x.detach().cuda().requires_grad_(True) for x in feats]
+    total, items = crit(f, batch)
+    total.backward()
+    return total.detach().cpu(), items.cpu(), [x.grad.cpu() for x in f], crit.last_aux.cpu()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_loss_matches_reference_fixture(lib, name):
+    feats, batch, nc, want = load_case(name)
+    total, items, grads, aux = _cuda_loss(feats, batch, nc)
+    assert np.allclose(items.numpy(), want["items"], rtol=1e-4, atol=1e-5), (items, want["items"])
+    assert np.allclose(float(total), float(want["total"]), rtol=1e-4)
+    for i, g in enumerate(grads):
+        w = want[f"grad{i}"]
+        assert np.abs(g.numpy() - w).max() <= 2e-5 * max(1.0, np.abs(w).max()), (i, np.abs(g.numpy() - w).max())
+    assert int(aux[1]) == int((want["target_scores"].sum(-1) > 0).sum())        # positives with a non-zero target score
+
+
+@pytest.mark.gpu
+def test_cuda_loss_training_size_vs_oracle(lib):
+    """B = 16 at 640^2 (8 400 anchors), 0..14 boxes per image, nc = 2: losses and gradients vs the oracle, run-to-run
+    bit-identical results (no floating-point atomics), fp16 head maps (AMP) accepted."""
+    from oracle.loss_ref import detection_loss, loss_case
+
+    n_gt = [(7 * b) % 15 for b in range(16)]
+    feats, batch = loss_case(11, 16, 640, 640, 2, n_gt)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    total_o, items_o, ex = detection_loss(fo, batch, (8.0, 16.0, 32.0), 2)
+    total_o.backward()
+    total, items, grads, aux = _cuda_loss(feats, batch, 2)
+    assert np.allclose(items.numpy(), items_o.numpy(), rtol=1e-4, atol=1e-5), (items, items_o)
+    for g, f in zip(grads, fo):
+        w = f.grad.numpy()
+        assert np.abs(g.numpy() - w).max() <= 2e-5 * max(1.0, np.abs(w).max())
+    assert abs(float(aux[0]) - ex["tss"]) <= 1e-4 * ex["tss"]
+    total2, items2, grads2, _ = _cuda_loss(feats, batch, 2)
+    assert torch.equal(items, items2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))
+    th, ih, gh, _ = _cuda_loss([f.half() for f in feats], batch, 2)
+    assert gh[0].dtype == torch.float16 and np.allclose(ih.numpy(), items_o.numpy(), rtol=2e-2)
