@@ -173,6 +173,23 @@ def _nms_factory(ref_nms):
     return non_max_suppression
 
 
+def _make_criterion(ref_cls):
+    from .utils.loss import criterion_call
+
+    class v8DetectionLoss(ref_cls):
+        """The reference's v8DetectionLoss (utils/loss.py:163-275) with the CUDA criterion behind `__call__` for CUDA
+        head maps (assigner + losses + gradients in six launches, csrc/det_loss.cu); CPU tensors run the reference."""
+
+        def __call__(self, preds, batch):
+            feats = preds[1] if isinstance(preds, tuple) else preds
+            if feats[0].is_cuda and type(self.assigner).__name__ == "TaskAlignedAssigner":
+                return criterion_call(self, preds, batch)
+            return ref_cls.__call__(self, preds, batch)
+
+    v8DetectionLoss.__module__ = "specyolo.ultralytics_shim"
+    return v8DetectionLoss
+
+
 def _set(obj, name, value):
     _SAVED.append((obj, name, getattr(obj, name)))
     setattr(obj, name, value)
@@ -223,6 +240,9 @@ def install() -> dict:
                 _set(space, name, cls)
     _set(uops, "non_max_suppression", _nms_factory(uops.non_max_suppression))
     _set(tasks.BaseModel, "_predict_once", _predict_once_factory(tasks.BaseModel._predict_once))
+    # training: DetectionModel.init_criterion (tasks.py:~395) resolves v8DetectionLoss from the tasks namespace
+    shims["v8DetectionLoss"] = _make_criterion(tasks.v8DetectionLoss)
+    _set(tasks, "v8DetectionLoss", shims["v8DetectionLoss"])
     _INSTALLED = True
     return shims
 

@@ -118,17 +118,26 @@ class v8DetectionLoss:
         self.tal = (tal_topk, 0.5, 6.0, 1e-9)                       # TaskAlignedAssigner(topk, num_classes, alpha=0.5, beta=6.0)
 
     def __call__(self, preds, batch):
-        feats = preds[1] if isinstance(preds, tuple) else preds
-        B = feats[0].shape[0]
-        cat = torch.cat([xi.view(B, self.no, -1) for xi in feats], 2)
-        pred_distri = cat[:, : self.reg_max * 4].permute(0, 2, 1).contiguous()
-        pred_scores = cat[:, self.reg_max * 4:].permute(0, 2, 1).contiguous()
-        hw = [tuple(int(v) for v in f.shape[2:]) for f in feats]
-        strides = [float(s) for s in self.stride]
-        img_hw = (hw[0][0] * strides[0], hw[0][1] * strides[0])
-        gt_boxes, gt_labels, gt_count, M = pack_targets(batch, B, img_hw, pred_distri.device)
-        gains = (_hyp(self.hyp, "box", 7.5), _hyp(self.hyp, "cls", 0.5), _hyp(self.hyp, "dfl", 1.5))
-        total, items, aux = _DetLossFn.apply(pred_distri, pred_scores, hw, strides, gt_boxes, gt_labels, gt_count, M,
-                                             self.reg_max, self.tal, gains)
-        self.last_aux = aux                                          # (max(target_scores.sum(), 1), number of positives)
-        return total, items
+        return criterion_call(self, preds, batch)
+
+
+def criterion_call(self, preds, batch):
+    """v8DetectionLoss.__call__ (loss.py:222-275) on the CUDA criterion.  `self` is this module's v8DetectionLoss or the
+    REFERENCE's own instance (specyolo.ultralytics_shim): only attributes both have are read (stride, nc, reg_max, no, hyp,
+    and the assigner's topk / alpha / beta / eps)."""
+    feats = preds[1] if isinstance(preds, tuple) else preds
+    B = feats[0].shape[0]
+    cat = torch.cat([xi.view(B, self.no, -1) for xi in feats], 2)
+    pred_distri = cat[:, : self.reg_max * 4].permute(0, 2, 1).contiguous()
+    pred_scores = cat[:, self.reg_max * 4:].permute(0, 2, 1).contiguous()
+    hw = [tuple(int(v) for v in f.shape[2:]) for f in feats]
+    strides = [float(s) for s in self.stride]
+    img_hw = (hw[0][0] * strides[0], hw[0][1] * strides[0])
+    gt_boxes, gt_labels, gt_count, M = pack_targets(batch, B, img_hw, pred_distri.device)
+    gains = (_hyp(self.hyp, "box", 7.5), _hyp(self.hyp, "cls", 0.5), _hyp(self.hyp, "dfl", 1.5))
+    asg = getattr(self, "assigner", None)
+    tal = getattr(self, "tal", None) or (asg.topk, asg.alpha, asg.beta, asg.eps)
+    total, items, aux = _DetLossFn.apply(pred_distri, pred_scores, hw, strides, gt_boxes, gt_labels, gt_count, M,
+                                         self.reg_max, tal, gains)
+    self.last_aux = aux                                          # (max(target_scores.sum(), 1), number of positives)
+    return total, items

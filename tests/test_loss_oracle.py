@@ -35,7 +35,7 @@ def test_loss_oracle_matches_reference(name):
     total, items, ex = detection_loss(feats, batch, (8.0, 16.0, 32.0), nc)
     total.backward()
     assert np.allclose(items.numpy(), want["items"], rtol=2e-5, atol=1e-6), (items, want["items"])
-    assert np.allclose(float(total), float(want["total"]), rtol=2e-5)
+    assert np.allclose(float(total.detach()), float(want["total"]), rtol=2e-5)
     for i, f in enumerate(feats):
         g, w = f.grad.numpy(), want[f"grad{i}"]
         assert np.abs(g - w).max() <= 1e-5 * max(1.0, np.abs(w).max()), (i, np.abs(g - w).max())

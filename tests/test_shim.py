@@ -144,3 +144,45 @@ def test_reference_predict_with_shim_convhca_variant(lib):
     stats = compare_detections(ref, got)
     record("shim_reference_api_convhca_b8_640", stats)
     assert sum(len(r) for r in ref) > 20 and stats["matched_rate"] >= 0.96, stats
+
+
+@pytest.mark.gpu
+def test_reference_training_loss_with_shim_criterion(lib):
+    """SURVEY 8 f2, first slice behind the reference API: `DetectionModel.loss(batch)` (tasks.py:305-322) of the REFERENCE
+    model in training mode on the GPU, stock criterion vs the CUDA criterion bound in by the shim — same loss items, same
+    parameter gradients (the forward / backward of the network itself is the reference's PyTorch code in both runs)."""
+    ultralytics = _reference()
+    from types import SimpleNamespace
+
+    from oracle.loss_ref import loss_case
+    from specyolo import _lib
+    from specyolo import ultralytics_shim as shim
+    from specyolo.nn.init import synth_images
+
+    y = _ref_yolo(ultralytics, _sd())
+    model = y.model.cuda().train()
+    model.args = SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+    _, batch = loss_case(21, 4, 256, 256, 2, (5, 0, 9, 3))
+    batch["img"] = synth_images(4, 256, seed=9).cuda()
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        model.criterion = None
+        loss, items = model.loss(batch)
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        return float(loss.detach()), items.cpu(), grads, type(model.criterion)
+
+    l0, i0, g0, c0 = run()
+    shims = shim.install()
+    try:
+        n0 = _lib.load().specyolo_launch_count()
+        l1, i1, g1, c1 = run()
+        launches = int(_lib.load().specyolo_launch_count() - n0)
+    finally:
+        shim.uninstall()
+    assert c1 is shims["v8DetectionLoss"] and c0 is not c1 and launches == 6, (c0, c1, launches)
+    assert np.allclose(i1.numpy(), i0.numpy(), rtol=2e-4, atol=1e-5) and abs(l1 - l0) <= 2e-4 * abs(l0), (i0, i1)
+    assert g0.keys() == g1.keys() and len(g0) > 250
+    worst = max(float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-12)) for k in g0)
+    assert worst < 5e-3, worst          # cuDNN backward is not bit-reproducible run to run; the criterion's own gradients agree to 2e-5
