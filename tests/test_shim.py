@@ -168,21 +168,30 @@ def test_reference_training_loss_with_shim_criterion(lib):
     def run():
         model.zero_grad(set_to_none=True)
         model.criterion = None
-        loss, items = model.loss(batch)
+        preds = model.forward(batch["img"])
+        for p in preds:
+            p.retain_grad()
+        loss, items = model.loss(batch, preds)
         loss.backward()
         grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
-        return float(loss.detach()), items.cpu(), grads, type(model.criterion)
+        return float(loss.detach()), items.cpu(), grads, [p.grad.clone() for p in preds], type(model.criterion)
 
-    l0, i0, g0, c0 = run()
+    l0, i0, g0, pg0, c0 = run()
     shims = shim.install()
     try:
         n0 = _lib.load().specyolo_launch_count()
-        l1, i1, g1, c1 = run()
+        l1, i1, g1, pg1, c1 = run()
         launches = int(_lib.load().specyolo_launch_count() - n0)
     finally:
         shim.uninstall()
     assert c1 is shims["v8DetectionLoss"] and c0 is not c1 and launches == 6, (c0, c1, launches)
-    assert np.allclose(i1.numpy(), i0.numpy(), rtol=2e-4, atol=1e-5) and abs(l1 - l0) <= 2e-4 * abs(l0), (i0, i1)
+    assert np.allclose(i1.numpy(), i0.numpy(), rtol=1e-5, atol=1e-6) and abs(l1 - l0) <= 1e-5 * abs(l0), (i0, i1)
+    for a, b in zip(pg0, pg1):                                   # d loss / d head maps: the criterion's own output
+        assert float((a - b).norm() / a.norm()) < 1e-5
+    # parameter gradients: the network's backward is the reference's cuDNN code in both runs and is not bit-reproducible
+    # (stock vs stock differs by ~2e-3 rel-L2 on most tensors and by > 1 on the three BatchNorm biases in front of the
+    # softmax-invariant attention inputs whose true gradient is ~0), so the comparison is over all parameters together
     assert g0.keys() == g1.keys() and len(g0) > 250
-    worst = max(float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-12)) for k in g0)
-    assert worst < 5e-3, worst          # cuDNN backward is not bit-reproducible run to run; the criterion's own gradients agree to 2e-5
+    num = sum(float((g1[k] - g0[k]).double().pow(2).sum()) for k in g0) ** 0.5
+    den = sum(float(g0[k].double().pow(2).sum()) for k in g0) ** 0.5
+    assert num / den < 5e-3, num / den
