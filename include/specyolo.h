@@ -320,6 +320,15 @@ typedef struct {
 size_t specyolo_det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
 int    specyolo_det_loss(const specyolo_det_loss_t* a, void* stream);
 
+/* ModelEMA.update (ultralytics/utils/torch_utils.py:514-524): ema[t][i] = ema[t][i] * d + model[t][i] * one_minus_d for
+ * every fp32 tensor t of the state_dict, in one launch over a chunk list, with the reference's roundings (three fp32
+ * roundings per element, no FMA), so the result is bit-identical to the Python loop.  All tables are DEVICE arrays:
+ * ema / model [n] device pointers, numel [n], chunk_tensor / chunk_off [nchunks] (chunk c covers elements
+ * [chunk_off[c], min(chunk_off[c] + chunk, numel[chunk_tensor[c]])) of tensor chunk_tensor[c]). */
+int specyolo_ema_update(float* const* ema, const float* const* model, const long long* numel,
+                        const int* chunk_tensor, const long long* chunk_off, int nchunks, int chunk,
+                        float d, float one_minus_d, void* stream);
+
 /* ---- image ingest: LetterBox for uint8 images ----------------------------------------
  * Replaces LetterBox.__call__ (ultralytics/data/augment.py:1535-1601: cv2.resize INTER_LINEAR + copyMakeBorder) and the
  * BGR->RGB / HWC->CHW step of BasePredictor.preprocess (ultralytics/engine/predictor.py:125-136), bit-exact with

@@ -36,6 +36,7 @@ size_t fusion_ws_bytes(int, int, int, int, int);
 int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
 int spatial_gate_launch(const specyolo_spatial_gate_t*, cudaStream_t);
 int det_loss_launch(const specyolo_det_loss_t*, cudaStream_t);
+int ema_update_launch(float* const*, const float* const*, const long long*, const int*, const long long*, int, int, float, float, cudaStream_t);
 size_t det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
 int psa_attention_launch(const void*, int, int, int, int, int, int, int, float, const float*, const float*,
                          void*, int, cudaStream_t);
@@ -242,6 +243,12 @@ int specyolo_det_loss(const specyolo_det_loss_t* a, void* stream) {
     SY_CHECK(a && a->pred_distri && a->pred_scores && a->out && a->ws && a->gt_count, SPECYOLO_ERR_INVALID, "det loss: null pointer");
     SY_CHECK(a->M == 0 || (a->gt_boxes && a->gt_labels), SPECYOLO_ERR_INVALID, "det loss: ground truth missing");
     return det_loss_launch(a, (cudaStream_t)stream);
+}
+
+int specyolo_ema_update(float* const* ema, const float* const* model, const long long* numel, const int* chunk_tensor,
+                        const long long* chunk_off, int nchunks, int chunk, float d, float one_minus_d, void* stream) {
+    SY_CHECK(nchunks == 0 || (ema && model && numel && chunk_tensor && chunk_off), SPECYOLO_ERR_INVALID, "ema: null pointer");
+    return ema_update_launch(ema, model, numel, chunk_tensor, chunk_off, nchunks, chunk, d, one_minus_d, (cudaStream_t)stream);
 }
 
 int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* stream) {

@@ -139,6 +139,7 @@ SIGNATURES = {
     "specyolo_sobel_spatial_attention": (C.c_int, [C.POINTER(SpatialGateArgs), C.c_void_p]),
     "specyolo_det_loss_ws_bytes": (C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),
     "specyolo_det_loss": (C.c_int, [C.POINTER(DetLossArgs), C.c_void_p]),
+    "specyolo_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "specyolo_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "specyolo_fold_pack_conv": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 7 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),

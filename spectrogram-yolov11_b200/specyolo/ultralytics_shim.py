@@ -190,6 +190,24 @@ def _make_criterion(ref_cls):
     return v8DetectionLoss
 
 
+def _make_ema(ref_cls):
+    from .utils.torch_utils import _de_parallel, ema_update
+
+    class ModelEMA(ref_cls):
+        """The reference's ModelEMA (utils/torch_utils.py:495-530) with `update` as one CUDA launch (csrc/ema.cu),
+        bit-identical to its Python loop; CPU / fp16 entries keep the reference arithmetic."""
+
+        def update(self, model):
+            if self.enabled:
+                self.updates += 1
+                d = self.decay(self.updates)
+                self._specyolo_plan = ema_update(self.ema.state_dict, _de_parallel(model).state_dict(), d,
+                                                 getattr(self, "_specyolo_plan", None))
+
+    ModelEMA.__module__ = "specyolo.ultralytics_shim"
+    return ModelEMA
+
+
 def _set(obj, name, value):
     _SAVED.append((obj, name, getattr(obj, name)))
     setattr(obj, name, value)
@@ -243,6 +261,9 @@ def install() -> dict:
     # training: DetectionModel.init_criterion (tasks.py:~395) resolves v8DetectionLoss from the tasks namespace
     shims["v8DetectionLoss"] = _make_criterion(tasks.v8DetectionLoss)
     _set(tasks, "v8DetectionLoss", shims["v8DetectionLoss"])
+    trainer = importlib.import_module("ultralytics.engine.trainer")     # BaseTrainer._setup_train: self.ema = ModelEMA(self.model)
+    shims["ModelEMA"] = _make_ema(trainer.ModelEMA)
+    _set(trainer, "ModelEMA", shims["ModelEMA"])
     _INSTALLED = True
     return shims
 

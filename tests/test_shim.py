@@ -195,3 +195,56 @@ def test_reference_training_loss_with_shim_criterion(lib):
     num = sum(float((g1[k] - g0[k]).double().pow(2).sum()) for k in g0) ** 0.5
     den = sum(float(g0[k].double().pow(2).sum()) for k in g0) ** 0.5
     assert num / den < 5e-3, num / den
+
+
+@pytest.mark.gpu
+def test_model_ema_update_bit_identical(lib):
+    """ModelEMA.update (torch_utils.py:514-524): the one-launch CUDA update (specyolo.utils.torch_utils.ModelEMA and the
+    shim's subclass of the reference class) leaves every state_dict entry bit-identical to the reference's Python loop."""
+    ultralytics = _reference()
+    import time
+
+    from ultralytics.utils.torch_utils import ModelEMA as RefEMA
+
+    from specyolo import _lib
+    from specyolo import ultralytics_shim as shim
+    from specyolo.utils.torch_utils import ModelEMA as MyEMA
+
+    model = _ref_yolo(ultralytics, _sd()).model.cuda().train()
+    ref, mine = RefEMA(model), MyEMA(model)
+    shims = shim.install()
+    try:
+        import ultralytics.engine.trainer as rtrainer
+
+        assert rtrainer.ModelEMA is shims["ModelEMA"] and issubclass(shims["ModelEMA"], RefEMA)
+        shimmed = rtrainer.ModelEMA(model)
+    finally:
+        shim.uninstall()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    t_ref = t_mine = 0.0
+    for step in range(4):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn(p.shape, generator=g, device="cuda") * 0.01)
+            for b in model.buffers():
+                if b.dtype.is_floating_point:
+                    b.add_(torch.rand(b.shape, generator=g, device="cuda") * 0.01)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ref.update(model)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        n0 = _lib.load().specyolo_launch_count()
+        mine.update(model)
+        launches = int(_lib.load().specyolo_launch_count() - n0)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        shimmed.update(model)
+        if step:
+            t_ref += t1 - t0
+            t_mine += t2 - t1
+        assert launches == 1
+        a, b, c = ref.ema.state_dict(), mine.ema.state_dict(), shimmed.ema.state_dict()
+        assert a.keys() == b.keys() == c.keys()
+        for k in a:
+            assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), (step, k)
+    assert ref.updates == mine.updates == shimmed.updates == 4
+    record("ema_update_timing", {"reference_python_loop_ms": t_ref / 3 * 1e3, "specyolo_one_launch_ms": t_mine / 3 * 1e3,
+                                 "tensors": sum(1 for v in ref.ema.state_dict().values() if v.dtype.is_floating_point)})
