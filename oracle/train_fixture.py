@@ -91,6 +91,8 @@ def main() -> None:
     ap.add_argument("--images", type=int, default=256)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--imgsz", type=int, default=640)
+    ap.add_argument("--shim", action="store_true",
+                    help="bind specyolo's CUDA criterion + EMA update into the reference trainer (specyolo.ultralytics_shim)")
     a = ap.parse_args()
 
     import ref_loader
@@ -101,9 +103,17 @@ def main() -> None:
     # host-side conveniences that need the network / matplotlib (absent here): the label font and the AMP self-test
     ck.check_font = du.check_font = lambda *a, **k: None
 
+    if a.shim:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spectrogram-yolov11_b200"))
+        from specyolo import ultralytics_shim
+        ultralytics_shim.install()
+
     work = tempfile.mkdtemp(prefix="specyolo_trainfix_")
     data = write_dataset(os.path.join(work, "data"), a.images, 16)
     model = YOLO(a.cfg)
+    import time
+    stamps = []
+    model.add_callback("on_train_batch_end", lambda trainer: stamps.append(time.perf_counter()))
     device = a.device if a.device == "cpu" else int(a.device)
     model.train(data=data, epochs=a.epochs, imgsz=a.imgsz, batch=a.batch, device=device, workers=0, amp=False,
                 plots=False, val=False, project=os.path.join(work, "runs"), name="fix", exist_ok=True, pretrained=False,
@@ -114,6 +124,10 @@ def main() -> None:
     shutil.copyfile(last, a.out)
 
     print(f"checkpoint {a.out} ({os.path.getsize(a.out) / 1e6:.1f} MB)")
+    if len(stamps) > 12:
+        dt = np.diff(np.asarray(stamps))[10:]          # skip the first iterations (cuDNN autotune, allocator warm-up)
+        print(f"train step ({'shim: CUDA criterion + EMA' if a.shim else 'stock reference'}): median {np.median(dt) * 1e3:.1f} ms, "
+              f"mean {dt.mean() * 1e3:.1f} ms over {len(dt)} iterations, batch {a.batch}, imgsz {a.imgsz}")
     shutil.rmtree(work, ignore_errors=True)
 
 

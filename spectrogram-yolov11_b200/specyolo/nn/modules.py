@@ -13,6 +13,7 @@ call and hands channel-slice views to the producing convs (`out=`).
 from __future__ import annotations
 
 import math
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -159,6 +160,15 @@ class DDWConv(nn.Module):
         return self.conv2(self.conv1(x), out=out)
 
 
+def tensor_version(t: torch.Tensor) -> int:
+    """In-place modification counter of a tensor, for cache keys; tensors created under torch.inference_mode (the
+    reference fuses its models inside `smart_inference_mode`) do not track one — and cannot be modified in place either."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 class SobelConv(nn.Module):
     """Parameter container of SobelConv (conv.py:1153-1182): three depthwise 3x3 convs (groups = out_channels, no bias)
     initialised to the Sobel-x, Sobel-x + Sobel-y and Sobel-y kernels; their outputs are summed."""
@@ -187,7 +197,7 @@ class SobelSpatialAttention(nn.Module):
 
     def stencil(self):
         ws = [c.weight for c in self.sobel.convs] + [self.cv1.weight]
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        key = tuple((w.data_ptr(), tensor_version(w)) for w in ws)
         if getattr(self, "_w18", None) is None or self._w18[0] != key:
             k = sum(c.weight.detach().float() for c in self.sobel.convs).reshape(2, 9)      # [c][ky*3+kx]
             w = (self.cv1.weight.detach().float().reshape(2, 1) * k).reshape(18)
@@ -519,35 +529,40 @@ class DFL(nn.Module):
 class _HeadConv(nn.Conv2d):
     """Plain nn.Conv2d(c, n, 1) with bias ending each Detect branch; fp32 output into the decode buffer."""
 
-    _packed = None
-
     def packed(self):
-        if self._packed is None:
-            self._packed = ops.fold_pack(self.weight, self.bias, None, 0.0, 1, 0, 1, 1, act=False)
-        return self._packed
+        return head_packed(self)
 
-    def _apply(self, fn, *a, **k):
-        self._packed = self._f32 = None
-        return super()._apply(fn, *a, **k)
 
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = self._f32 = None
-        return super()._load_from_state_dict(*a, **k)
+# Weight packs of the plain nn.Conv2d tails live OUTSIDE the modules (weakly keyed by the module, validated against the
+# identity of its parameters): the tails of a reference model bound in by the shim are stock torch modules, and nothing of
+# this package may end up in their __dict__ — the reference's trainer pickles them into its checkpoints.
+_TAIL_CACHE: "weakref.WeakKeyDictionary[nn.Module, dict]" = weakref.WeakKeyDictionary()
+
+
+def _tail_entry(conv: nn.Conv2d) -> dict:
+    w, b = conv.weight, conv.bias
+    key = (w.data_ptr(), tensor_version(w), w.dtype, w.device, None if b is None else (b.data_ptr(), tensor_version(b)))
+    e = _TAIL_CACHE.get(conv)
+    if e is None or e["key"] != key:
+        e = _TAIL_CACHE[conv] = {"key": key}
+    return e
 
 
 def head_packed(conv: nn.Conv2d) -> ops.PackedConv:
-    """Packed weights of the plain nn.Conv2d(c, n, 1) (with bias) that ends a Detect branch; cached on the module."""
-    if getattr(conv, "_packed", None) is None:
-        conv._packed = ops.fold_pack(conv.weight, conv.bias, None, 0.0, 1, 0, 1, 1, act=False)
-    return conv._packed
+    """Packed weights of the plain nn.Conv2d(c, n, 1) (with bias) that ends a Detect branch; cached per module."""
+    e = _tail_entry(conv)
+    if "packed" not in e:
+        e["packed"] = ops.fold_pack(conv.weight, conv.bias, None, 0.0, 1, 0, 1, 1, act=False)
+    return e["packed"]
 
 
 def head_f32(conv: nn.Conv2d):
     """(w [n, c] fp32, b [n] fp32) of a plain 1x1 nn.Conv2d for the fused class head of ops.dwconv_pwconv; cached."""
-    if getattr(conv, "_f32", None) is None or conv._f32[0].device != conv.weight.device:
-        conv._f32 = (conv.weight.detach().float().reshape(conv.out_channels, conv.in_channels).contiguous(),
-                     conv.bias.detach().float().contiguous())
-    return conv._f32
+    e = _tail_entry(conv)
+    if "f32" not in e:
+        e["f32"] = (conv.weight.detach().float().reshape(conv.out_channels, conv.in_channels).contiguous(),
+                    conv.bias.detach().float().contiguous())
+    return e["f32"]
 
 
 class Detect(nn.Module):

@@ -9,8 +9,9 @@ runs libspecyolo (SURVEY 8(b) hook 5).  `install()` rebinds, 
 
     Conv DWConv DDWConv ConvHCA SobelSpatialAttention Bottleneck C3 C3k C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
 
-to SUBCLASSES of the reference's own classes: constructor, parameters, `state_dict` keys, `fuse()`, pickling and every
-`isinstance` check stay the reference's; only `forward` changes — CUDA tensors go through the specyolo forward of the same
+to SUBCLASSES of the reference's own classes: constructor, parameters, `state_dict` keys, `fuse()` and every `isinstance`
+check stay the reference's, and instances pickle as the reference's classes without this package's caches (a checkpoint the
+reference trainer writes with the shim installed loads in a plain reference install); only `forward` changes — CUDA tensors go through the specyolo forward of the same
 block (the code in specyolo/nn/modules.py, which touches only attributes the reference classes have), anything else
 (the 256 x 256 CPU stride probe of DetectionModel.__init__, tasks.py:365; training mode) falls through to the reference's
 PyTorch definition.  `ultralytics.utils.ops.non_max_suppression` is rebound to the NMS kernel for CUDA predictions, and
@@ -43,6 +44,28 @@ _WHERE = {
 }
 
 
+# attributes this package caches on module instances (weight packs, folded stencils, cache keys)
+_CACHE_ATTRS = ("_packed", "_packed_blocked", "_folded_dw", "_shim_key", "_pe_f32", "_pe_key", "_w18", "_specyolo_plan")
+
+
+def _as_reference_class(cls) -> None:
+    """Make instances pickle / deepcopy as the REFERENCE's class: the trainer saves `deepcopy(ema.ema).half()` with
+    torch.save (engine/trainer.py:500-530), and a checkpoint written while the shim is installed must load in a plain
+    reference install.  The shim class takes the module path and name of the class it derives from (where it is bound
+    while installed, so pickle's identity check holds) and drops this package's caches from the pickled state."""
+    ref = next(b for b in cls.__mro__[1:] if b.__module__.startswith("ultralytics.") and not getattr(b, "_specyolo_shim_class", False))
+    cls._specyolo_shim_class = True
+    cls.__module__, cls.__qualname__, cls.__name__ = ref.__module__, ref.__qualname__, ref.__name__
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in _CACHE_ATTRS:
+            state.pop(k, None)
+        return state
+
+    cls.__getstate__ = __getstate__
+
+
 def _is_cuda(x) -> bool:
     t = x[0] if isinstance(x, (list, tuple)) else x
     t = getattr(t, "src", t)                      # UpsampledView
@@ -54,7 +77,7 @@ def _weights_key(mod: nn.Module):
     (model.to(), .half(), BaseModel.fuse()), and none of that goes through specyolo's own invalidation hooks."""
     c = getattr(mod, "conv", mod)
     w = c.weight
-    return (w.data_ptr(), w._version, w.dtype, w.device, hasattr(mod, "bn"), None if c.bias is None else c.bias.data_ptr())
+    return (w.data_ptr(), M.tensor_version(w), w.dtype, w.device, hasattr(mod, "bn"), None if c.bias is None else c.bias.data_ptr())
 
 
 def _fresh(mod: nn.Module, attrs):
@@ -123,9 +146,7 @@ def _make_detect(ref_cls):
 
         def forward(self, x):
             if _is_cuda(x) and not self.training and not self.end2end and not self.export:
-                for br in list(self.cv2) + list(self.cv3):     # plain nn.Conv2d tails: drop packs of moved / cast weights
-                    _fresh(br[-1], ("_packed", "_f32"))
-                return mine.forward(self, x)
+                return mine.forward(self, x)        # (the plain nn.Conv2d tails are packed outside the modules: _TAIL_CACHE)
             return ref_cls.forward(self, x)
 
     return _ShimDetect
@@ -186,7 +207,6 @@ def _make_criterion(ref_cls):
                 return criterion_call(self, preds, batch)
             return ref_cls.__call__(self, preds, batch)
 
-    v8DetectionLoss.__module__ = "specyolo.ultralytics_shim"
     return v8DetectionLoss
 
 
@@ -204,7 +224,6 @@ def _make_ema(ref_cls):
                 self._specyolo_plan = ema_update(self.ema.state_dict, _de_parallel(model).state_dict(), d,
                                                  getattr(self, "_specyolo_plan", None))
 
-    ModelEMA.__module__ = "specyolo.ultralytics_shim"
     return ModelEMA
 
 
@@ -248,8 +267,7 @@ def install() -> dict:
     shims["C3k"] = _make_block(sub["block"].C3k, M.C3k)
     shims["C3k2"] = _make_block(sub["block"].C3k2, M.C3k2)
     for cls in shims.values():
-        cls.__module__ = "specyolo.ultralytics_shim"
-        cls.__qualname__ = cls.__name__ = cls.__name__.replace("_Shim", "")
+        _as_reference_class(cls)
 
     # the blocks build their sub-blocks from their own module's globals; parse_model from tasks' globals
     for space in [tasks, mods, *sub.values()]:
@@ -260,10 +278,13 @@ def install() -> dict:
     _set(tasks.BaseModel, "_predict_once", _predict_once_factory(tasks.BaseModel._predict_once))
     # training: DetectionModel.init_criterion (tasks.py:~395) resolves v8DetectionLoss from the tasks namespace
     shims["v8DetectionLoss"] = _make_criterion(tasks.v8DetectionLoss)
-    _set(tasks, "v8DetectionLoss", shims["v8DetectionLoss"])
     trainer = importlib.import_module("ultralytics.engine.trainer")     # BaseTrainer._setup_train: self.ema = ModelEMA(self.model)
     shims["ModelEMA"] = _make_ema(trainer.ModelEMA)
-    _set(trainer, "ModelEMA", shims["ModelEMA"])
+    for name, spaces in (("v8DetectionLoss", (tasks, importlib.import_module("ultralytics.utils.loss"))),
+                         ("ModelEMA", (trainer, importlib.import_module("ultralytics.utils.torch_utils")))):
+        _as_reference_class(shims[name])
+        for space in spaces:
+            _set(space, name, shims[name])
     _INSTALLED = True
     return shims
 

@@ -63,7 +63,7 @@ def test_shim_builds_through_the_reference_and_falls_through_on_cpu(lib):
     try:
         assert rtasks.Conv is shims["Conv"] and rblock.Bottleneck is shims["Bottleneck"] and rconv.Conv is shims["Conv"]
         for name, cls in shims.items():
-            base = [b for b in cls.__mro__[1:] if b.__module__.startswith("ultralytics.")]
+            base = [b for b in cls.__mro__[1:] if b.__module__.startswith("ultralytics.") and b not in shims.values()]
             assert base and base[0].__name__ == name, name                  # a subclass of the reference's own class
         y = _ref_yolo(ultralytics, sd)                                      # parse_model + CPU stride probe with the shims bound
         assert type(y.model.model[0]) is shims["Conv"] and type(y.model.model[-1]) is shims["Detect"]
@@ -74,8 +74,22 @@ def test_shim_builds_through_the_reference_and_falls_through_on_cpu(lib):
         for a, b in zip(res, res_plain):
             assert torch.equal(a.boxes.data, b.boxes.data)
         assert sum(len(r.boxes) for r in res) > 0
+        # what the reference trainer does to write a checkpoint (engine/trainer.py:500-530): deepcopy + half + torch.save
+        import io
+        from copy import deepcopy
+
+        y.model.model[0]._packed = object()                                 # a cache of this package: must not be pickled
+        buf = io.BytesIO()
+        want = {k: (v.half() if v.is_floating_point() else v.clone()) for k, v in y.model.state_dict().items()}   # (fused by predict)
+        torch.save({"model": deepcopy(y.model).half()}, buf)
+        blob = buf.getvalue()
     finally:
         shim.uninstall()
+    loaded = torch.load(io.BytesIO(blob), map_location="cpu", weights_only=False)["model"]      # plain reference classes again
+    assert type(loaded.model[0]) is rtasks.Conv and type(loaded.model[-1]) is rtasks.Detect and type(loaded.model[3]) is rtasks.Conv
+    assert not hasattr(loaded.model[0], "_packed") and b"specyolo" not in blob
+    got = loaded.state_dict()
+    assert list(got.keys()) == list(want.keys()) and all(torch.equal(got[k], want[k]) for k in want)
     assert (rtasks.Conv, rtasks.C3k2, rtasks.Detect, rops.non_max_suppression, rtasks.BaseModel._predict_once) == orig
 
 
