@@ -394,8 +394,10 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
                              ("the unmodified reference's YOLO.predict(device='cpu') from oracle/_ref (fp32, BN fused, "
                               "torchvision NMS)" if kind == "reference" else
                               "oracle port (PyTorch CPU fp32 forward with BN folded + numpy NMS)")}
+        crit = None
         if world == 1 and not args.no_extra:
             lib_bar = library_bar(sd, x_dev, dev)
+            crit = train_criterion_bar(dev, B)
         line = {
             "metric": METRIC, "value": world * B * args.steps / t_max, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps,
@@ -414,11 +416,60 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "roofline": roof, "stages": stages, "clocks": clocks, "cpu_baseline": cpu,
-            "c3": c3, "c4": c4, "library_bar": lib_bar,
+            "c3": c3, "c4": c4, "library_bar": lib_bar, "train_criterion": crit,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_criterion_bar(dev, BATCH):
+    """SURVEY 8 f2, first slice: the detection criterion of a training step (v8DetectionLoss: assigner + BCE / CIoU / DFL,
+    forward + backward into the head maps) at the bench's batch — specyolo_det_loss (six launches) against the reference's
+    own criterion in PyTorch eager on the same GPU (oracle/_ref), same seeded head maps and labels."""
+    import torch
+
+    out = {"unit": "ms per forward+backward", "batch": BATCH, "imgsz": IMGSZ, "nc": NC, "boxes_per_image": 8}
+    try:
+        from types import SimpleNamespace
+
+        from oracle.loss_ref import loss_case
+        from specyolo.utils.loss import v8DetectionLoss
+
+        feats, batch = loss_case(5, BATCH, IMGSZ, IMGSZ, NC, [8] * BATCH)
+        f = [x.to(dev).requires_grad_(True) for x in feats]
+        fake = SimpleNamespace(model=[SimpleNamespace(nc=NC, reg_max=16, stride=torch.tensor([8.0, 16.0, 32.0]))],
+                               args={"box": 7.5, "cls": 0.5, "dfl": 1.5}, parameters=lambda: iter([torch.zeros(1, device=dev)]))
+
+        def timeit(c, reps=10):
+            def step():
+                for x in f:
+                    x.grad = None
+                total, items = c(f, batch)
+                total.backward()
+                return items
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                items = step()
+            torch.cuda.synchronize()
+            return 1e3 * (time.perf_counter() - t0) / reps, [float(v) for v in items]
+
+        out["specyolo"], out["loss_items"] = timeit(v8DetectionLoss(fake))
+        out["what"] = "host wall clock per call incl. torch cat / permute glue, label packing and autograd"
+        from oracle import ref_loader
+
+        if ref_loader.reference_available():
+            ref_loader.import_reference()
+            from ultralytics.utils.loss import v8DetectionLoss as RefLoss
+
+            out["reference_eager"], out["reference_loss_items"] = timeit(RefLoss(SimpleNamespace(
+                model=fake.model, args=SimpleNamespace(box=7.5, cls=0.5, dfl=1.5), parameters=fake.parameters)))
+    except Exception as ex:      # an extra key must never take the bench line down
+        out["error"] = f"{type(ex).__name__}: {ex}"[:200]
+    return out
 
 
 def library_bar(sd, x_dev, dev):
