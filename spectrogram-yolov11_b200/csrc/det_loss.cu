@@ -130,32 +130,40 @@ __device__ __forceinline__ D4 ciou_grad(float px1, float py1, float px2, float p
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// four lanes per anchor (lane = box side): a warp reads 2 KB of consecutive logits per step and clears the same span of
+// the gradient (thread-per-anchor reads were 256-byte strided: 7 % of the DRAM bandwidth under ncu)
 __global__ void __launch_bounds__(kLossThreads)
 loss_decode_kernel(const __grid_constant__ LossParams p) {
     const specyolo_det_loss_t& a = p.a;
-    const long i = (long)blockIdx.x * kLossThreads + threadIdx.x;
-    if (i >= (long)a.B * p.A) return;
-    const int anc = (int)(i % p.A);
-    float ax, ay, st;
-    anchor_geom(p, anc, ax, ay, st);
-    const float* row = a.pred_distri + i * (4 * a.reg_max);
-    float dist[4];
-    for (int s = 0; s < 4; ++s) {
+    const long t = (long)blockIdx.x * kLossThreads + threadIdx.x;
+    const long i = t >> 2;                       // (image, anchor)
+    const int side = (int)(t & 3);
+    const bool live = i < (long)a.B * p.A;       // whole groups of four lanes are live or not
+    float dist = 0.f;
+    if (live) {
+        const float* row = a.pred_distri + i * (4 * a.reg_max) + side * a.reg_max;
         float mx = -FLT_MAX;
-        for (int j = 0; j < a.reg_max; ++j) mx = fmaxf(mx, row[s * a.reg_max + j]);
+        for (int j = 0; j < a.reg_max; ++j) mx = fmaxf(mx, row[j]);
         float den = 0.f, num = 0.f;
         for (int j = 0; j < a.reg_max; ++j) {
-            const float e = expf(row[s * a.reg_max + j] - mx);
+            const float e = expf(row[j] - mx);
             den += e;
             num += e * (float)j;
         }
-        dist[s] = num / den;
+        dist = num / den;
+        if (a.grad_distri) {
+            float* g = a.grad_distri + i * (4 * a.reg_max) + side * a.reg_max;
+            for (int j = 0; j < a.reg_max; ++j) g[j] = 0.f;
+        }
     }
-    reinterpret_cast<float4*>(p.box)[i] = make_float4(ax - dist[0], ay - dist[1], ax + dist[2], ay + dist[3]);
-    p.amap[i] = -1;
-    if (a.grad_distri) {
-        float4* g = reinterpret_cast<float4*>(a.grad_distri + i * (4 * a.reg_max));
-        for (int j = 0; j < a.reg_max; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int base = (threadIdx.x & 31) & ~3;
+    const float d0 = __shfl_sync(0xffffffffu, dist, base), d1 = __shfl_sync(0xffffffffu, dist, base + 1);
+    const float d2 = __shfl_sync(0xffffffffu, dist, base + 2), d3 = __shfl_sync(0xffffffffu, dist, base + 3);
+    if (live && side == 0) {
+        float ax, ay, st;
+        anchor_geom(p, (int)(i % p.A), ax, ay, st);
+        reinterpret_cast<float4*>(p.box)[i] = make_float4(ax - d0, ay - d1, ax + d2, ay + d3);
+        p.amap[i] = -1;
     }
 }
 
@@ -560,7 +568,7 @@ int det_loss_launch(const specyolo_det_loss_t* a, cudaStream_t stream) {
     p.fg_blocks = a->M > 0 ? L.fg_blocks : 0;
     p.cls_blocks = L.cls_blocks;
 
-    const unsigned nblk = (unsigned)(((long)a->B * A + kLossThreads - 1) / kLossThreads);
+    const unsigned nblk = (unsigned)(((long)a->B * A * 4 + kLossThreads - 1) / kLossThreads);
     loss_decode_kernel<<<nblk, kLossThreads, 0, stream>>>(p);
     count_launch();
     if (a->M > 0) {
