@@ -16,34 +16,57 @@
 // the IQ samples of those frames (each sample read once per CTA, coalesced 8-byte lanes) plus one
 // write of the bf16 image: 8.39 + 2.46 MB per burst = the roofline of SURVEY 8(d).
 //
-// CTA = 256 threads = 8 warps, 16 output columns = up to 32 frames, 4 per warp.  A warp computes one
-// 1024-point FFT as 32 x 32 (four-step): 32-point FFT in registers, twiddle, transpose through a
-// padded shared-memory tile, second 32-point FFT in registers.
+// CTA = 128 threads = 4 warps, 16 output columns.  A WARP OWNS AN OUTPUT COLUMN: it transforms the column's two frames
+// (bilinear taps t0, t0+1) TOGETHER, every register pair holding the same element of frame 0 and frame 1, so the whole
+// transform — 32 x 32 four-step: 32-point radix-2 FFT in registers, twiddle, transpose through a padded shared-memory
+// tile, second 32-point FFT — runs on packed fp32 pairs (add/sub/mul/fma.f32x2: one issue slot per two butterflies,
+// twiddle constants shared by both halves).  The kernel is issue-bound (round 1: 4.6 k warp instructions per frame at
+// one frame per warp, scalar), hence: powers -> shared memory, log2 only for the 2 x new_h bins the vertical taps read,
+// row / column tap tables built once per CTA (the double-precision geometry used to be redone per frame and per
+// pixel), window and (lane, k1) twiddles read from shared-memory tables laid out for the packed operands, padding
+// written with 16-byte stores.
 #include "common.h"
 
 namespace specyolo {
 
 static constexpr int NFFT = 1024;
-static constexpr int kCols = 16;      // output columns per CTA
-static constexpr int kFrames = 2 * kCols;
+static constexpr int kCols = 16;       // output columns per CTA
+static constexpr int kWarps = 4;
+static constexpr int kThreads = kWarps * 32;
+static constexpr int kTilePitch = 33;  // float2 entries per tile row (conflict-free 8-byte rows and columns)
 
 __host__ __device__ constexpr int bitrev5(int v) {
     return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
 }
 
-// In-register radix-2 DIF FFT of 32 complex points; X[k] ends up in x[bitrev5(k)].
-__device__ __forceinline__ void fft32(float2 (&x)[32]) {
-    // W32^j = exp(-2 pi i j / 32), j = 0..15: literal constants for the unrolled butterflies (W^0 = 1 and W^8 = -i are
-    // special-cased below: 46 of the 80 butterflies of a 32-point FFT need no multiplication)
-    constexpr float kW32c[16] = {
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};\n\t"
+        "sub.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+// W32^j = exp(-2 pi i j / 32), j = 0..15
+__device__ constexpr float kW32c[16] = {
     1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f,
     3.826834324e-01f, 1.950903220e-01f, 0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
     -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
-    constexpr float kW32s[16] = {
+__device__ constexpr float kW32s[16] = {
     -0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f,
     -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f,
     -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
 
+// In-register radix-2 DIF FFT of 32 complex points of TWO frames at once: re[i] = (Re x0[i], Re x1[i]), im likewise;
+// X[k] ends up in element bitrev5(k).  46 of the 80 butterflies need no multiplication (W^0 = 1, W^8 = -i).
+__device__ __forceinline__ void fft32x2(float2 (&re)[32], float2 (&im)[32]) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         const int half = 16 >> s;
@@ -52,17 +75,21 @@ __device__ __forceinline__ void fft32(float2 (&x)[32]) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
                 const int i0 = g * 2 * half + j, i1 = i0 + half;
-                const float2 a = x[i0], b = x[i1];
-                x[i0] = make_float2(a.x + b.x, a.y + b.y);
-                const float dr = a.x - b.x, di = a.y - b.y;
-                const int tw = j << s;  // W_{2*half}^j = W32^(j * 32/(2*half)) = W32^(j << s)
+                const float2 ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+                re[i0] = fadd2(ar, br);
+                im[i0] = fadd2(ai, bi);
+                const int tw = j << s;  // W_{2*half}^j = W32^(j << s)
                 if (tw == 0) {
-                    x[i1] = make_float2(dr, di);                 // W^0 = 1
-                } else if (tw == 8) {
-                    x[i1] = make_float2(di, -dr);                // W^8 = -i
+                    re[i1] = fsub2(ar, br);
+                    im[i1] = fsub2(ai, bi);
+                } else if (tw == 8) {                              // (dr + i di) * (-i) = di - i dr
+                    re[i1] = fsub2(ai, bi);
+                    im[i1] = fsub2(br, ar);
                 } else {
+                    const float2 dr = fsub2(ar, br), di = fsub2(ai, bi);
                     const float c = kW32c[tw], sn = kW32s[tw];
-                    x[i1] = make_float2(dr * c - di * sn, dr * sn + di * c);
+                    re[i1] = ffma2(di, make_float2(-sn, -sn), fmul2(dr, make_float2(c, c)));
+                    im[i1] = ffma2(dr, make_float2(sn, sn), fmul2(di, make_float2(c, c)));
                 }
             }
         }
@@ -76,8 +103,9 @@ struct StftParams {
     int left, top;         // content origin inside the output
     double sx, sy;         // source/dest scale (T/new_w, nfft/new_h)
     int col_tiles;         // CTAs (per burst) doing content columns
-    int pad_tiles;         // CTAs (per burst) filling padding
-    float db_scale, db_off;  // v = dB*db_scale + db_off
+    int pad_tiles;         // CTAs (per burst) filling padding (first in the grid: they are the longest-running)
+    int out_pitch;         // floats per column of the CTA's staging tile (== 2 mod 32: conflict-free both ways)
+    float db_scale, db_off;  // v = 10 log10(pw) * db_scale + db_off
     const float2* twiddle; // [1024] exp(-2 pi i j / 1024)
 };
 
@@ -86,7 +114,49 @@ __device__ __forceinline__ void store_px(const StftParams& p, size_t idx, float 
     else reinterpret_cast<__nv_bfloat16*>(p.a.out)[idx] = __float2bfloat16_rn(v);
 }
 
-__global__ void __launch_bounds__(256)
+// Everything of one burst's image that lies outside the content rectangle.  The rows above and below the band are two
+// contiguous spans per plane: plain 16-byte store loops shared out over the burst's pad CTAs; the strips left and right
+// of the band go row by row.  (The first version divided 64-bit indices per element and outlasted the transform.)
+__device__ void fill_padding(const StftParams& p, int b, int pt) {
+    const specyolo_stft_t& a = p.a;
+    const int tid = threadIdx.x;
+    const size_t plane = (size_t)a.out_h * a.out_w;
+    const size_t base = (size_t)b * 3 * plane;
+    const int vec = a.out_fp32 ? 4 : 8;            // elements per 16-byte store
+    const int esize = a.out_fp32 ? 4 : 2;
+    const bool vec_ok = a.out_w % vec == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    uint4 fill;
+    if (a.out_fp32) {
+        fill.x = fill.y = fill.z = fill.w = __float_as_uint(a.pad_value);
+    } else {
+        const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a.pad_value));
+        fill.x = fill.y = fill.z = fill.w = h | (h << 16);
+    }
+    const int me = pt * kThreads + tid, nthr = p.pad_tiles * kThreads;
+    for (int s = 0; s < 6; ++s) {                  // (plane, above / below)
+        const int y0 = (s & 1) ? p.top + p.new_h : 0, y1 = (s & 1) ? a.out_h : p.top;
+        if (y1 <= y0) continue;
+        const size_t off = base + (size_t)(s >> 1) * plane + (size_t)y0 * a.out_w;
+        const int n = (y1 - y0) * a.out_w;         // elements of the span
+        if (vec_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + off * esize);
+            const int nv = n / vec;
+#pragma unroll 4
+            for (int i = me; i < nv; i += nthr) dst[i] = fill;
+        } else {
+            for (int i = me; i < n; i += nthr) store_px(p, off + i, a.pad_value);
+        }
+    }
+    if (p.left == 0 && p.new_w == a.out_w) return;
+    const int right0 = p.left + p.new_w, strip = p.left + (a.out_w - right0);   // pad elements per band row
+    for (int rr = pt; rr < 3 * p.new_h; rr += p.pad_tiles) {
+        const int pl = rr / p.new_h, y = p.top + rr % p.new_h;
+        const size_t row = base + (size_t)pl * plane + (size_t)y * a.out_w;
+        for (int i = tid; i < strip; i += kThreads) store_px(p, row + (i < p.left ? i : right0 + (i - p.left)), a.pad_value);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
 stft_letterbox_kernel(const __grid_constant__ StftParams p) {
     extern __shared__ __align__(16) uint8_t st_smem[];
     const specyolo_stft_t& a = p.a;
@@ -94,106 +164,145 @@ stft_letterbox_kernel(const __grid_constant__ StftParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t plane = (size_t)a.out_h * a.out_w;
 
-    if ((int)blockIdx.x >= p.col_tiles) {
-        // ---------------- padding fill ----------------
-        const int pt = blockIdx.x - p.col_tiles;
-        const long total = (long)3 * plane;
-        const long per = (total + p.pad_tiles - 1) / p.pad_tiles;
-        const long lo = pt * per, hi = min(total, lo + per);
-        for (long i = lo + tid; i < hi; i += 256) {
-            const int x = (int)(i % a.out_w);
-            const int y = (int)((i / a.out_w) % a.out_h);
-            const bool inside = (x >= p.left) && (x < p.left + p.new_w) && (y >= p.top) && (y < p.top + p.new_h);
-            if (!inside) store_px(p, (size_t)b * 3 * plane + i, a.pad_value);
-        }
+    if ((int)blockIdx.x < p.pad_tiles) {
+        fill_padding(p, b, blockIdx.x);
         return;
     }
 
-    float2* s_tw = reinterpret_cast<float2*>(st_smem);                       // [1024]
-    float2* s_tile = s_tw + NFFT + warp * (32 * 33);                          // per-warp [32][33]
-    float* s_u = reinterpret_cast<float*>(s_tw + NFFT + 8 * (32 * 33));       // [kFrames][new_h]
-    for (int i = tid; i < NFFT; i += 256) s_tw[i] = p.twiddle[i];
-    __syncthreads();
+    // shared memory: per-warp transpose tile | (register, lane) twiddles | window | row taps | column taps | staging
+    float2* s_tile = reinterpret_cast<float2*>(st_smem) + warp * (32 * kTilePitch);     // [32][33] (frame 0, frame 1) of one component
+    float4* s_tw2 = reinterpret_cast<float4*>(reinterpret_cast<float2*>(st_smem) + kWarps * (32 * kTilePitch));  // [32][32] {wr, wr, wi, wi}
+    float* s_win = reinterpret_cast<float*>(s_tw2 + 32 * 32);                            // [1024]
+    int2* s_rowtab = reinterpret_cast<int2*>(s_win + NFFT);                              // [new_h] {r0 | r1 << 16, wy}
+    int2* s_coltab = s_rowtab + p.new_h;                                                 // [kCols] {t0, wx}
+    float* s_out = reinterpret_cast<float*>(s_coltab + kCols);                           // [kCols][out_pitch]
 
-    const int x0 = blockIdx.x * kCols;                 // first content column of this CTA
+    const int x0 = ((int)blockIdx.x - p.pad_tiles) * kCols;   // first content column of this CTA
     const int ncols = min(kCols, p.new_w - x0);
-    const float* iq = a.iq + (size_t)b * a.L * 2;
-
-    for (int f = warp; f < 2 * ncols; f += 8) {
-        // frame index of tap (f&1) of column x0 + f/2
-        const int xs = x0 + (f >> 1);
-        double fx = ((double)xs + 0.5) * p.sx - 0.5;
+    for (int i = tid; i < 32 * 32; i += kThreads) {
+        const int pp = i >> 5, n2 = i & 31;                   // register pp of lane n2 holds Y[k1 = bitrev5(pp)][n2]
+        const float2 w = p.twiddle[(n2 * bitrev5(pp)) & (NFFT - 1)];
+        s_tw2[i] = make_float4(w.x, w.x, w.y, w.y);
+    }
+    for (int i = tid; i < NFFT; i += kThreads) s_win[i] = 0.5f - 0.5f * p.twiddle[i].x;   // periodic Hann
+    for (int ys = tid; ys < p.new_h; ys += kThreads) {
+        double fy = ((double)ys + 0.5) * p.sy - 0.5;
+        if (fy < 0.0) fy = 0.0;
+        int r0 = (int)floor(fy);
+        if (r0 > NFFT - 1) r0 = NFFT - 1;
+        const int r1 = min(r0 + 1, NFFT - 1);
+        s_rowtab[ys] = make_int2(r0 | (r1 << 16), __float_as_int((float)(fy - (double)r0)));
+    }
+    if (tid < kCols) {
+        double fx = ((double)(x0 + tid) + 0.5) * p.sx - 0.5;
         if (fx < 0.0) fx = 0.0;
         int t0 = (int)floor(fx);
         if (t0 > p.T - 1) t0 = p.T - 1;
-        const int t = (f & 1) ? min(t0 + 1, p.T - 1) : t0;
+        s_coltab[tid] = make_int2(t0, __float_as_int((float)(fx - (double)t0)));
+    }
+    __syncthreads();
+
+    const float2* iq = reinterpret_cast<const float2*>(a.iq) + (size_t)b * a.L;
+    const float lg_scale = 3.010299956639812f * p.db_scale;   // 10 log10(pw) = 3.0103 log2(pw)
+
+#pragma unroll 1
+    for (int c = warp; c < ncols; c += kWarps) {
+        const int t0 = s_coltab[c].x;
+        const float wx = __int_as_float(s_coltab[c].y);
+        const int t1 = min(t0 + 1, p.T - 1);
+        const float2* src0 = iq + (size_t)t0 * a.hop;
+        const float2* src1 = iq + (size_t)t1 * a.hop;
 
         // ---- stage A: lane = n2, register = n1; x[n1] = w[n] s[n], n = 32 n1 + n2 ----
-        float2 x[32];
-        const float2* src = reinterpret_cast<const float2*>(iq) + (size_t)t * a.hop;
+        float2 re[32], im[32];
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
             const int n = 32 * n1 + lane;
-            const float2 s = __ldg(src + n);
-            const float w = 0.5f - 0.5f * s_tw[n].x;   // periodic Hann from cos(2 pi n / N)
-            x[n1] = make_float2(s.x * w, s.y * w);
+            const float2 s0 = __ldg(src0 + n), s1 = __ldg(src1 + n);
+            const float w = s_win[n];
+            re[n1] = make_float2(s0.x * w, s1.x * w);
+            im[n1] = make_float2(s0.y * w, s1.y * w);
         }
-        fft32(x);
+        fft32x2(re, im);
         __syncwarp();
-        // twiddle W1024^(n2*k1), write T[k1][n2]
+        // twiddle W1024^(n2*k1), then the 32 x 32 transpose (register k1 of lane n2 -> register n2 of lane k1), real parts
+        // of both frames first, then the imaginary parts, through an 8-byte-entry tile (register pairs move as they are;
+        // a 16-byte tile would cost the third resident CTA)
 #pragma unroll
         for (int pp = 0; pp < 32; ++pp) {
-            const int k1 = bitrev5(pp);
-            const float2 w = s_tw[(lane * k1) & (NFFT - 1)];
-            const float2 v = x[pp];
-            s_tile[k1 * 33 + lane] = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+            const float4 w = s_tw2[pp * 32 + lane];
+            const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+            const float2 vr = fsub2(fmul2(re[pp], wr), fmul2(im[pp], wi));
+            im[pp] = ffma2(im[pp], wr, fmul2(re[pp], wi));
+            re[pp] = vr;
         }
-        __syncwarp();
-        // ---- stage B: lane = k1, register = n2 ----
 #pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) x[n2] = s_tile[lane * 33 + n2];
-        fft32(x);
+        for (int pp = 0; pp < 32; ++pp) s_tile[bitrev5(pp) * kTilePitch + lane] = re[pp];
         __syncwarp();
-        // power -> normalised dB, row r = (k + 512) mod 1024, k = k1 + 32 k2
-        float* s_row = reinterpret_cast<float*>(s_tile);
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) re[n2] = s_tile[lane * kTilePitch + n2];   // stage B: lane = k1, register = n2
+        __syncwarp();
+#pragma unroll
+        for (int pp = 0; pp < 32; ++pp) s_tile[bitrev5(pp) * kTilePitch + lane] = im[pp];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) im[n2] = s_tile[lane * kTilePitch + n2];
+        fft32x2(re, im);
+        __syncwarp();
+        // powers of both frames, row r = (k + 512) mod 1024, k = k1 + 32 k2
+        float2* s_pow = s_tile;                                 // [1024] (frame 0, frame 1)
 #pragma unroll
         for (int pp = 0; pp < 32; ++pp) {
-            const int k2 = bitrev5(pp);
-            const int k = lane + 32 * k2;
-            const float pw = fmaxf(x[pp].x * x[pp].x + x[pp].y * x[pp].y, 1e-20f);
-            // 10*log10(pw) = 3.0102999566 * log2(pw)
-            float v = fmaf(__log2f(pw) * 3.010299956639812f, p.db_scale, p.db_off);
-            v = fminf(fmaxf(v, 0.f), 1.f);
-            s_row[(k + NFFT / 2) & (NFFT - 1)] = v;
+            const int k = lane + 32 * bitrev5(pp);
+            s_pow[(k + NFFT / 2) & (NFFT - 1)] = ffma2(re[pp], re[pp], fmul2(im[pp], im[pp]));
         }
         __syncwarp();
-        // vertical bilinear taps for every output row of the content band
+        // normalised dB of the bins the vertical taps touch, vertical taps of both frames, horizontal tap
+        float* s_col = s_out + c * p.out_pitch;
         for (int ys = lane; ys < p.new_h; ys += 32) {
-            double fy = ((double)ys + 0.5) * p.sy - 0.5;
-            if (fy < 0.0) fy = 0.0;
-            int r0 = (int)floor(fy);
-            if (r0 > NFFT - 1) r0 = NFFT - 1;
-            const int r1 = min(r0 + 1, NFFT - 1);
-            const float wy = (float)(fy - (double)r0);
-            s_u[f * p.new_h + ys] = s_row[r0] + wy * (s_row[r1] - s_row[r0]);
+            const int2 rt = s_rowtab[ys];
+            const float wy = __int_as_float(rt.y);
+            const float2 p0 = s_pow[rt.x & 0xffff], p1 = s_pow[rt.x >> 16];
+            const float a0 = __saturatef(fmaf(__log2f(fmaxf(p0.x, 1e-20f)), lg_scale, p.db_off));
+            const float a1 = __saturatef(fmaf(__log2f(fmaxf(p1.x, 1e-20f)), lg_scale, p.db_off));
+            const float b0 = __saturatef(fmaf(__log2f(fmaxf(p0.y, 1e-20f)), lg_scale, p.db_off));
+            const float b1 = __saturatef(fmaf(__log2f(fmaxf(p1.y, 1e-20f)), lg_scale, p.db_off));
+            const float u0 = a0 + wy * (a1 - a0), u1 = b0 + wy * (b1 - b0);
+            s_col[ys] = u0 + wx * (u1 - u0);
         }
         __syncwarp();
     }
     __syncthreads();
 
-    // ---- horizontal taps + store (col fastest so a half-warp writes one 32/64-byte run) ----
-    for (int i = tid; i < p.new_h * kCols; i += 256) {
+    // ---- store (column fastest so a half-warp writes one 32/64-byte run), 3 identical channels ----
+    const size_t obase = (size_t)b * 3 * plane + (size_t)p.top * a.out_w + (p.left + x0);
+    if (!a.out_fp32 && ((p.left + x0) & 1) == 0 && (a.out_w & 1) == 0) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+        for (int i = tid; i < p.new_h * (kCols / 2); i += kThreads) {
+            const int c = (i % (kCols / 2)) * 2, ys = i / (kCols / 2);
+            if (c >= ncols) continue;
+            const size_t o = obase + (size_t)ys * a.out_w + c;
+            const float v0 = s_out[c * p.out_pitch + ys];
+            if (c + 1 < ncols) {
+                const float v1 = s_out[(c + 1) * p.out_pitch + ys];
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                *reinterpret_cast<__nv_bfloat162*>(out + o) = h;
+                *reinterpret_cast<__nv_bfloat162*>(out + o + plane) = h;
+                *reinterpret_cast<__nv_bfloat162*>(out + o + 2 * plane) = h;
+            } else {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v0);
+                out[o] = h;
+                out[o + plane] = h;
+                out[o + 2 * plane] = h;
+            }
+        }
+        return;
+    }
+    for (int i = tid; i < p.new_h * kCols; i += kThreads) {
         const int c = i % kCols, ys = i / kCols;
         if (c >= ncols) continue;
-        const int xs = x0 + c;
-        double fx = ((double)xs + 0.5) * p.sx - 0.5;
-        if (fx < 0.0) fx = 0.0;
-        int t0 = (int)floor(fx);
-        if (t0 > p.T - 1) t0 = p.T - 1;
-        const float wx = (float)(fx - (double)t0);
-        const float u0 = s_u[(2 * c) * p.new_h + ys], u1 = s_u[(2 * c + 1) * p.new_h + ys];
-        const float v = u0 + wx * (u1 - u0);
-        const size_t o = (size_t)b * 3 * plane + (size_t)(p.top + ys) * a.out_w + (p.left + xs);
+        const float v = s_out[c * p.out_pitch + ys];
+        const size_t o = obase + (size_t)ys * a.out_w + c;
         store_px(p, o, v);
         store_px(p, o + plane, v);
         store_px(p, o + 2 * plane, v);
@@ -249,10 +358,12 @@ int stft_launch(const specyolo_stft_t* a, cudaStream_t stream) {
     p.db_scale = 1.0f / (a->db_max - a->db_min);
     p.db_off = (float)((-pref_db - a->db_min) / (a->db_max - a->db_min));
     p.col_tiles = ceil_div(p.new_w, kCols);
-    p.pad_tiles = 8;
+    p.pad_tiles = 16;
+    p.out_pitch = p.new_h + ((2 - p.new_h) & 31);
     p.twiddle = g_twiddle;
 
-    const size_t smem = (size_t)NFFT * 8 + (size_t)8 * 32 * 33 * 8 + (size_t)kFrames * p.new_h * 4;
+    const size_t smem = (size_t)kWarps * 32 * kTilePitch * 8 + (size_t)32 * 32 * 16 + (size_t)NFFT * 4 +
+                        (size_t)p.new_h * 8 + (size_t)kCols * 8 + (size_t)kCols * p.out_pitch * 4;
     SY_CHECK(smem <= 220 * 1024, SPECYOLO_ERR_UNSUPPORTED, "content band too tall for shared memory");
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -260,7 +371,7 @@ int stft_launch(const specyolo_stft_t* a, cudaStream_t stream) {
         attr_smem = smem;
     }
     dim3 grid((unsigned)(p.col_tiles + p.pad_tiles), (unsigned)a->B);
-    stft_letterbox_kernel<<<grid, 256, smem, stream>>>(p);
+    stft_letterbox_kernel<<<grid, kThreads, smem, stream>>>(p);
     SY_LAUNCH_CHECK();
     count_launch();
     return SPECYOLO_OK;

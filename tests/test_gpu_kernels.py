@@ -587,6 +587,27 @@ def test_stft_letterbox(lib):
     assert np.abs(got_bf - ref).max() < 8e-3
 
 
+@pytest.mark.parametrize("L,hop,out_hw", [
+    (50_000, 200, (250, 333)),      # odd output width (scalar stores, scalar padding), hop not a multiple of 32
+    (1024, 256, (1024, 8)),         # a single frame -> one content column, all 1024 bins as rows (no vertical resampling)
+    (3000, 96, (640, 640)),         # 21 frames stretched over a 640-row band (tallest staging tile)
+    (200_000, 256, (320, 1288)),    # wide output, fp32 vector padding with a partial last column tile
+])
+def test_stft_letterbox_ragged(lib, L, hop, out_hw):
+    """Geometries off the north-star path: every store / padding variant of the kernel against the float64 oracle."""
+    from oracle import stft_ref
+    from specyolo import ops
+    from specyolo.nn.init import synth_iq
+
+    iq = synth_iq(3, L, seed=L % 97)
+    ref = stft_ref.iq_to_letterbox(iq.numpy(), hop=hop, out_hw=out_hw)
+    got = ops.iq_to_letterbox(iq.to(DEV), hop=hop, out_hw=out_hw, out_dtype=torch.float32).cpu().numpy()
+    err = np.abs(got - ref)
+    assert err.max() < 5e-3 and np.mean(err > 1e-4) < 1e-3, (err.max(), np.mean(err > 1e-4))
+    got_bf = ops.iq_to_letterbox(iq.to(DEV), hop=hop, out_hw=out_hw, out_dtype=torch.bfloat16).float().cpu().numpy()
+    assert np.abs(got_bf - ref).max() < 8e-3
+
+
 def test_stft_letterbox_full_burst(lib):
     """North-star geometry: 2^20 samples, hop 256 -> 1024 x 4093 -> 160 x 640 band."""
     from oracle import stft_ref
