@@ -223,6 +223,23 @@ typedef struct {
 } specyolo_spatial_gate_t;
 int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* stream);
 
+/* ---- MSCSpatialAttention (ultralytics/nn/modules/conv.py:1200-1243), the inner block of C3x (block.py:522-529;
+ *      cfg yolo11_fusion_sand3_new_OMN.yaml head layer 21) -----------------------------------------------------
+ * mm = cat(mean_c x, max_c x);  s = relu(cv1(mm)) + relu(cv2(mm))  (2 -> 1 convs, 31x31 and 3x3, zero padding, no
+ * bias);  g = relu(fc(mean_hw(x * s)));  y = x * s * g + x.  Four launches, x read three times. */
+typedef struct {
+    const void* x; int x_pixstride;   /* bf16 NHWC [B,H,W,C], C % 8 == 0, C <= 512            */
+    void* y; int y_pixstride;         /* bf16 NHWC, may alias x                               */
+    int B, H, W, C;
+    const float* w_big; int k_big;    /* device [2][k_big][k_big] (cv1.0.weight), k_big == 31 */
+    const float* w_small;             /* device [2][3][3]         (cv2.0.weight)              */
+    const float* fc_w;                /* device [C][C] (out, in)  (fc.weight)                 */
+    const float* fc_b;                /* device [C]               (fc.bias)                   */
+    float* ws;                        /* workspace, specyolo_msc_ws_bytes() bytes             */
+} specyolo_msc_gate_t;
+size_t specyolo_msc_ws_bytes(int B, int H, int W, int C);
+int    specyolo_msc_spatial_attention(const specyolo_msc_gate_t* a, void* stream);
+
 /* ---- PSA attention core (ultralytics/nn/modules/block.py:1922-1933) ----------------------- */
 /* qkv: bf16 NHWC [B,N,heads*(2*kd+hd)] as written by the qkv 1x1 conv; out[b,n,h*hd+d] =
  * sum_j softmax_j(q_n.k_j*scale) v_j[d] + pe(v)[n] where pe is the depthwise 3x3 (+folded BN)

@@ -55,7 +55,7 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
         n = max(round(n * depth), 1) if n > 1 else n  # tasks.py:1085
         c1 = (cin_first if i == 0 else chans[f]) if isinstance(f, int) else None
         L = dict(i=i, f=f, type=m, prefix=f"model.{i}")
-        if m in ("Conv", "ConvHCA", "C3k2", "SPPF", "C2PSA", "DDWConv"):
+        if m in ("Conv", "ConvHCA", "C3k2", "C3x", "SPPF", "C2PSA", "DDWConv"):
             c2 = make_divisible(min(args[0], max_ch) * width, 8)  # tasks.py:1088-1089
             rest = list(args[1:])
             if m == "Conv":
@@ -70,6 +70,8 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
                 if scale in "mlx":
                     c3k = True  # tasks.py:1098-1101
                 L.update(c1=c1, c2=c2, n=n, c3k=c3k, e=e)
+            elif m == "C3x":  # block.py:522-529: C3(c1, c2, n, shortcut, g, e=0.5) with m = MSCSpatialAttention(c_)
+                L.update(c1=c1, c2=c2, n=n)
             elif m == "SPPF":
                 L.update(c1=c1, c2=c2, k=rest[0] if rest else 5)
             elif m == "C2PSA":
@@ -208,6 +210,20 @@ class Ref:
         e = sum(F.conv2d(m, sd[f"{p}.hca.sobel.convs.{j}.weight"], None, 1, 1, 1, 2) for j in range(3))
         return x1 * torch.sigmoid(F.conv2d(e, sd[p + ".hca.cv1.weight"]))
 
+    # MSCSpatialAttention (conv.py:1200-1243); x8 and x9 are the same tensor there
+    def msc(self, x, p):
+        sd = self.sd
+        x1 = torch.cat([x.mean(1, keepdim=True), x.max(1, keepdim=True)[0]], 1)
+        x2 = F.relu(F.conv2d(x1, sd[p + ".cv1.0.weight"], None, 1, 15))
+        x3 = F.relu(F.conv2d(x1, sd[p + ".cv2.0.weight"], None, 1, 1))
+        x4, x5 = x * x2, x * x3
+        x8 = F.relu(F.conv2d((x4 + x5).mean((2, 3), keepdim=True), sd[p + ".fc.weight"], sd[p + ".fc.bias"]))
+        return x4 * x8 + x5 * x8 + x
+
+    # C3x (block.py:522-529) = C3.forward (block.py:501-504) with m = MSCSpatialAttention
+    def c3x(self, x, p):
+        return self.conv(torch.cat((self.msc(self.conv(x, p + ".cv1"), p + ".m"), self.conv(x, p + ".cv2")), 1), p + ".cv3")
+
     # GCT (conv.py:2284-2301)
     def gct(self, x, p, eps=1e-5):
         sd = self.sd
@@ -300,6 +316,8 @@ def forward(graph: List[dict], sd, x: torch.Tensor, strides=(8.0, 16.0, 32.0),
             x = R.convhca(inp, p, L["k"], L["s"])
         elif t == "C3k2":
             x = R.c3k2(inp, p, L["n"], L["c3k"])
+        elif t == "C3x":
+            x = R.c3x(inp, p)
         elif t == "SPPF":
             x = R.sppf(inp, p, L["k"])
         elif t == "C2PSA":

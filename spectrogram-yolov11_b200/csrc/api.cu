@@ -35,6 +35,8 @@ int sppf_pool_launch(void*, int, int, int, int, int, cudaStream_t);
 size_t fusion_ws_bytes(int, int, int, int, int);
 int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
 int spatial_gate_launch(const specyolo_spatial_gate_t*, cudaStream_t);
+int msc_gate_launch(const specyolo_msc_gate_t*, cudaStream_t);
+size_t msc_ws_bytes(int, int, int, int);
 int det_loss_launch(const specyolo_det_loss_t*, cudaStream_t);
 int ema_update_launch(float* const*, const float* const*, const long long*, const int*, const long long*, int, int, float, float, cudaStream_t);
 size_t det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
@@ -255,6 +257,14 @@ int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* str
     SY_CHECK(a && a->x && a->y && a->mm, SPECYOLO_ERR_INVALID, "spatial gate: null pointer");
     SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, SPECYOLO_ERR_INVALID, "spatial gate: bad sizes");
     return spatial_gate_launch(a, (cudaStream_t)stream);
+}
+
+size_t specyolo_msc_ws_bytes(int B, int H, int W, int C) { return msc_ws_bytes(B, H, W, C); }
+
+int specyolo_msc_spatial_attention(const specyolo_msc_gate_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->y && a->ws && a->w_big && a->w_small && a->fc_w && a->fc_b, SPECYOLO_ERR_INVALID, "msc gate: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, SPECYOLO_ERR_INVALID, "msc gate: bad sizes");
+    return msc_gate_launch(a, (cudaStream_t)stream);
 }
 
 int specyolo_psa_attention(const void* qkv, int qkv_pixstride, int B, int H, int W, int heads, int key_dim,

@@ -266,6 +266,46 @@ class C3(nn.Module):
         return self.cv3(cat, out=out)
 
 
+class MSCSpatialAttention(nn.Module):
+    """x * s * g + x with s = relu(conv31(mm)) + relu(conv3(mm)) over the channel mean / max planes and
+    g = relu(fc(mean_hw(x * s))) (conv.py:1200-1243; x8 == x9 there): csrc/spatial_gate.cu, four launches."""
+
+    def __init__(self, c1, kernel_size=7):
+        super().__init__()
+        self.cv1 = nn.Sequential(nn.Conv2d(2, 1, (31, 31), padding=(15, 15), bias=False), nn.ReLU())
+        self.cv2 = nn.Sequential(nn.Conv2d(2, 1, (3, 3), padding=(1, 1), bias=False), nn.ReLU())
+        self.fc = nn.Conv2d(c1, c1, 1, 1, 0, bias=True)
+        self._f32 = None
+
+    def weights_f32(self):
+        ws = (self.cv1[0].weight, self.cv2[0].weight, self.fc.weight, self.fc.bias)
+        key = tuple((w.data_ptr(), tensor_version(w)) for w in ws)
+        if getattr(self, "_f32", None) is None or self._f32[0] != key:
+            self._f32 = (key, tuple(w.detach().float().contiguous() for w in ws))
+        return self._f32[1]
+
+    def forward(self, x, out=None):
+        return ops.msc_spatial_attention(_as_fmap(x), *self.weights_f32(), out=out)
+
+
+class C3x(C3):
+    """C3 whose inner block is ONE MSCSpatialAttention (block.py:522-529; *_OMN configs, head layer 21)."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        self.c_ = int(c2 * e)
+        self.m = MSCSpatialAttention(self.c_)
+
+    def forward(self, x, out=None):
+        x = _as_fmap(x)
+        B, _, H, W = x.shape
+        c_ = self.cv1.conv.out_channels
+        cat = ops.new_act(B, 2 * c_, H, W, x.device)
+        self.m(self.cv1(x), out=cat[:, : c_])
+        self.cv2(x, out=cat[:, c_:])
+        return self.cv3(cat, out=out)
+
+
 class C3k(C3):
     """C3 with k x k bottlenecks (block.py:1672-1680)."""
 

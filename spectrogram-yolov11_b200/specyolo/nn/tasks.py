@@ -21,15 +21,15 @@ import torch.nn as nn
 import yaml
 
 from .. import ops
-from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, Concat, Conv, ConvHCA, DDWConv, Detect, DWConv, Fusion,
-                      Upsample2x, UpsampledView)
+from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, C3x, Concat, Conv, ConvHCA, DDWConv, Detect, DWConv,
+                      Fusion, Upsample2x, UpsampledView)
 
 CFG_DIR = Path(__file__).resolve().parent.parent / "cfg"
 
-_MODULES = {m.__name__: m for m in (Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA, Concat, Fusion,
-                                    Detect)}
-_BASE = {Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, SPPF, C2PSA}
-_REPEAT = {C2f, C3, C3k, C3k2, C2PSA}
+_MODULES = {m.__name__: m for m in (Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3x, SPPF, C2PSA, Concat,
+                                    Fusion, Detect)}
+_BASE = {Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3x, SPPF, C2PSA}
+_REPEAT = {C2f, C3, C3k, C3k2, C3x, C2PSA}
 _STRIDE2 = {Conv, ConvHCA, DWConv, DDWConv}
 
 

@@ -15,7 +15,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, NmsArgs, SpatialGateArgs, StemPairArgs, StftArgs, check
+from ._lib import (BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, MscGateArgs, NmsArgs, SpatialGateArgs, StemPairArgs,
+                   StftArgs, check)
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -504,6 +505,33 @@ def sobel_spatial_attention(x: torch.Tensor, w18: Sequence[float], out: Optional
         a.w[i] = float(v)
     a.mm = mm.data_ptr()
     check(_lib.load().specyolo_sobel_spatial_attention(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def msc_spatial_attention(x: torch.Tensor, w_big: torch.Tensor, w_small: torch.Tensor, fc_w: torch.Tensor, fc_b: torch.Tensor,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MSCSpatialAttention (conv.py:1200-1243): y = x * s * g + x with s = relu(cv1(mm)) + relu(cv2(mm)) over the channel
+    mean / max planes mm and g = relu(fc(mean_hw(x * s))).  Weights are fp32 device tensors: w_big [1,2,31,31],
+    w_small [1,2,3,3], fc_w [C,C,1,1], fc_b [C].  out=None runs in place."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("msc_spatial_attention expects bf16")
+    if out is None:
+        out = x
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, Cc, H, W) or out.dtype != torch.bfloat16:
+        raise ValueError("msc_spatial_attention: out shape / dtype mismatch")
+    for t, n in ((w_big, 2 * w_big.shape[-1] ** 2), (w_small, 18), (fc_w, Cc * Cc), (fc_b, Cc)):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or t.device != x.device:
+            raise ValueError("msc_spatial_attention: weights must be contiguous fp32 tensors on x's device")
+    lib = _lib.load()
+    ws = torch.empty(lib.specyolo_msc_ws_bytes(B, H, W, Cc), device=x.device, dtype=torch.uint8)
+    a = MscGateArgs()
+    a.x, a.x_pixstride, a.y, a.y_pixstride = x.data_ptr(), xpix, out.data_ptr(), ypix
+    a.B, a.H, a.W, a.C = B, H, W, Cc
+    a.w_big, a.k_big, a.w_small = w_big.data_ptr(), int(w_big.shape[-1]), w_small.data_ptr()
+    a.fc_w, a.fc_b, a.ws = fc_w.data_ptr(), fc_b.data_ptr(), ws.data_ptr()
+    check(lib.specyolo_msc_spatial_attention(C.byref(a), _lib.stream_ptr()))
     return out
 
 

@@ -7,7 +7,7 @@ runs libspecyolo (SURVEY 8(b) hook 5).  `install()` rebinds, 
 (`ultralytics.nn.tasks` — where `parse_model` resolves YAML names, tasks.py:1074-1080 — and `ultralytics.nn.modules[.conv /
 .block / .head]`, where the blocks construct their sub-blocks), the classes
 
-    Conv DWConv DDWConv ConvHCA SobelSpatialAttention Bottleneck C3 C3k C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
+    Conv DWConv DDWConv ConvHCA SobelSpatialAttention MSCSpatialAttention Bottleneck C3 C3k C3x C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
 
 to SUBCLASSES of the reference's own classes: constructor, parameters, `state_dict` keys, `fuse()` and every `isinstance`
 check stay the reference's, and instances pickle as the reference's classes without this package's caches (a checkpoint the
@@ -38,14 +38,14 @@ _INSTALLED = False
 
 # reference module (relative to ultralytics.nn.modules) -> class names defined there that get a shim
 _WHERE = {
-    "conv": ["Conv", "DWConv", "DDWConv", "Fusion", "ConvHCA", "SobelSpatialAttention"],
-    "block": ["Bottleneck", "C3", "C3k", "C2f", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA"],
+    "conv": ["Conv", "DWConv", "DDWConv", "Fusion", "ConvHCA", "SobelSpatialAttention", "MSCSpatialAttention"],
+    "block": ["Bottleneck", "C3", "C3k", "C3x", "C2f", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA"],
     "head": ["Detect"],
 }
 
 
 # attributes this package caches on module instances (weight packs, folded stencils, cache keys)
-_CACHE_ATTRS = ("_packed", "_packed_blocked", "_folded_dw", "_shim_key", "_pe_f32", "_pe_key", "_w18", "_specyolo_plan")
+_CACHE_ATTRS = ("_packed", "_packed_blocked", "_folded_dw", "_shim_key", "_pe_f32", "_pe_key", "_w18", "_f32", "_specyolo_plan")
 
 
 def _as_reference_class(cls) -> None:
@@ -254,6 +254,7 @@ def install() -> dict:
     shims["Fusion"] = _make_block(sub["conv"].Fusion, M.Fusion)
     shims["SobelSpatialAttention"] = _make_block(sub["conv"].SobelSpatialAttention, M.SobelSpatialAttention, extra=("stencil",))
     shims["ConvHCA"] = _make_block(sub["conv"].ConvHCA, M.ConvHCA)
+    shims["MSCSpatialAttention"] = _make_block(sub["conv"].MSCSpatialAttention, M.MSCSpatialAttention, extra=("weights_f32",))
     shims["Bottleneck"] = _make_block(sub["block"].Bottleneck, M.Bottleneck)
     shims["C3"] = _make_block(sub["block"].C3, M.C3)
     shims["C2f"] = _make_block(sub["block"].C2f, M.C2f)
@@ -266,6 +267,7 @@ def install() -> dict:
     # C3k derives from C3 and C3k2 from C2f in the reference: subclass the reference class AND take the shim forward
     shims["C3k"] = _make_block(sub["block"].C3k, M.C3k)
     shims["C3k2"] = _make_block(sub["block"].C3k2, M.C3k2)
+    shims["C3x"] = _make_block(sub["block"].C3x, M.C3x)
     for cls in shims.values():
         _as_reference_class(cls)
 

@@ -433,6 +433,47 @@ def test_sobel_spatial_attention(lib, B, c, H, W, window):
     assert _rel_err(got, ref) < 3e-3
 
 
+@pytest.mark.parametrize("B,c,H,W,window", [(2, 64, 80, 80, False), (3, 128, 40, 40, False), (2, 256, 20, 20, True), (1, 64, 7, 9, False),
+                                            (2, 200, 33, 70, False), (1, 8, 3, 3, True), (4, 512, 17, 5, False), (3, 64, 1, 1, False)])
+def test_msc_spatial_attention(lib, B, c, H, W, window):
+    """MSCSpatialAttention (conv.py:1200-1243) vs the oracle's restatement on bf16-rounded inputs: the 80 x 80 x 64 shape of
+    the *_OMN config, every lane-group width (one, two vectors per lane; a channel count that is not a power of two), maps
+    smaller than the 31 x 31 kernel, ragged tiles, in place on a channel window of a wider buffer and out of place."""
+    from oracle.yolo_ref import Ref
+    from specyolo import ops
+    from specyolo.nn.modules import MSCSpatialAttention
+
+    gen = torch.Generator().manual_seed(70 + c)
+    x = torch.randn((B, c, H, W), generator=gen) * 0.8 + 0.1
+    m = MSCSpatialAttention(c)
+    with torch.no_grad():
+        m.cv1[0].weight.copy_(torch.randn(m.cv1[0].weight.shape, generator=gen) * 0.05)
+        m.cv2[0].weight.copy_(torch.randn(m.cv2[0].weight.shape, generator=gen) * 0.4)
+        m.fc.weight.copy_(torch.randn(m.fc.weight.shape, generator=gen) * (2.0 / c) ** 0.5)
+        m.fc.bias.copy_(torch.randn(m.fc.bias.shape, generator=gen) * 0.2 + 0.3)
+    ref = Ref({"m." + k: v for k, v in m.state_dict().items()}).msc(_bf(x), "m")
+    m.to(DEV)
+    if window:
+        buf = ops.new_act(B, c + 16, H, W, DEV)
+        buf.zero_()
+        xin = buf[:, 8:8 + c]
+        xin.copy_(x.to(DEV))
+        got = m(xin)                                           # in place on the window
+        assert got.data_ptr() == xin.data_ptr()
+        assert float(buf[:, :8].float().abs().max()) == 0.0 and float(buf[:, 8 + c:].float().abs().max()) == 0.0
+    else:
+        xin = _fmap(x)
+        keep = xin.clone()
+        out = ops.new_act(B, c, H, W, DEV)
+        got = m(xin, out=out)
+        assert torch.equal(xin, keep)                          # out of place leaves x alone
+        again = m(xin, out=ops.new_act(B, c, H, W, DEV))
+        assert torch.equal(got, again)                         # fixed-order reductions: bit-identical run to run
+    got = got.float().cpu()
+    assert (got - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item())      # one bf16 rounding of the result
+    assert _rel_err(got, ref) < 3e-3
+
+
 @pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2), (16, 16, 2), (5, 7, 1), (16, 32, 2), (24, 24, 2), (40, 40, 1)])
 def test_psa_attention(lib, H, W, heads):
     """N = 400 (640^2 input), ragged / tiny / exactly 256 and 512 tokens on the resident-S kernel (N <= 512), 576 and
