@@ -240,6 +240,24 @@ typedef struct {
 size_t specyolo_msc_ws_bytes(int B, int H, int W, int C);
 int    specyolo_msc_spatial_attention(const specyolo_msc_gate_t* a, void* stream);
 
+/* ---- BottleNect + FGM (ultralytics/nn/modules/block.py:782-861), the inner block of C3k2GC (block.py:1706-1714;
+ *      cfg yolo11_fusion_sand3_new_GC.yaml backbone layer 2).  The reference runs two torch.fft (cuFFT) round trips;
+ *      see csrc/bottlenect.cu for the algebra.  All weights are fp32 device arrays, 1x1 convs as [C][C] (out, in). --- */
+typedef struct {
+    const void* x; int x_pixstride;   /* bf16 NHWC [B,H,W,C], C in {16, 32}                    */
+    void* y; int y_pixstride;         /* bf16 NHWC, may alias x                                */
+    int B, H, W, C;                   /* H, W: prime factors <= 7, plane must fit shared memory */
+    const float* in_w;  const float* in_b;     /* in_conv.0                                    */
+    const float* fac_w; const float* fac_b;    /* fac_conv                                     */
+    const float* sca_w; const float* sca_b;    /* conv                                         */
+    const float* dw1_w; const float* dw1_b;    /* fgm.dwconv1                                  */
+    const float* dw2_w; const float* dw2_b;    /* fgm.dwconv2                                  */
+    const float* alpha; const float* beta;     /* fgm.alpha, fgm.beta [C]                      */
+    float* ws;                        /* workspace, specyolo_bottlenect_ws_bytes() bytes       */
+} specyolo_bottlenect_t;
+size_t specyolo_bottlenect_ws_bytes(int B, int H, int W, int C);
+int    specyolo_bottlenect(const specyolo_bottlenect_t* a, void* stream);
+
 /* ---- PSA attention core (ultralytics/nn/modules/block.py:1922-1933) ----------------------- */
 /* qkv: bf16 NHWC [B,N,heads*(2*kd+hd)] as written by the qkv 1x1 conv; out[b,n,h*hd+d] =
  * sum_j softmax_j(q_n.k_j*scale) v_j[d] + pe(v)[n] where pe is the depthwise 3x3 (+folded BN)

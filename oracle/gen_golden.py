@@ -36,6 +36,7 @@ MODEL_CASES = [
     ("yolo11n", "yolo11n.yaml", "yolo11n.yaml", 80, 64, 96, 1),
     ("specyolo_s_convhca", "yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11s_fusion_sand3_new_convHCA.yaml", 2, 96, 128, 2),
     ("specyolo_s_omn", "yolo11s_fusion_sand3_new_OMN.yaml", "yolo11s_fusion_sand3_new_OMN.yaml", 2, 96, 128, 3),
+    ("specyolo_s_gc", "yolo11s_fusion_sand3_new_GC.yaml", "yolo11s_fusion_sand3_new_GC.yaml", 2, 96, 128, 4),
 ]
 
 

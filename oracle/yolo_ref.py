@@ -55,7 +55,7 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
         n = max(round(n * depth), 1) if n > 1 else n  # tasks.py:1085
         c1 = (cin_first if i == 0 else chans[f]) if isinstance(f, int) else None
         L = dict(i=i, f=f, type=m, prefix=f"model.{i}")
-        if m in ("Conv", "ConvHCA", "C3k2", "C3x", "SPPF", "C2PSA", "DDWConv"):
+        if m in ("Conv", "ConvHCA", "C3k2", "C3k2GC", "C3x", "SPPF", "C2PSA", "DDWConv"):
             c2 = make_divisible(min(args[0], max_ch) * width, 8)  # tasks.py:1088-1089
             rest = list(args[1:])
             if m == "Conv":
@@ -70,6 +70,11 @@ def parse_graph(d: dict, scale: str, nc: int | None = None, ch: int = 3) -> List
                 if scale in "mlx":
                     c3k = True  # tasks.py:1098-1101
                 L.update(c1=c1, c2=c2, n=n, c3k=c3k, e=e)
+            elif m == "C3k2GC":  # block.py:1706-1714; tasks.py:1110-1112 forces c3k for m/l/x (C3kGC: not restated)
+                c3k = (rest[0] if len(rest) > 0 else False) or scale in "mlx"
+                if c3k:
+                    raise NotImplementedError("oracle does not restate C3kGC")
+                L.update(c1=c1, c2=c2, n=n, e=rest[1] if len(rest) > 1 else 0.5)
             elif m == "C3x":  # block.py:522-529: C3(c1, c2, n, shortcut, g, e=0.5) with m = MSCSpatialAttention(c_)
                 L.update(c1=c1, c2=c2, n=n)
             elif m == "SPPF":
@@ -210,6 +215,26 @@ class Ref:
         e = sum(F.conv2d(m, sd[f"{p}.hca.sobel.convs.{j}.weight"], None, 1, 1, 1, 2) for j in range(3))
         return x1 * torch.sigmoid(F.conv2d(e, sd[p + ".hca.cv1.weight"]))
 
+    # BottleNect (block.py:782-836) with FGM (block.py:838-861); torch.fft on the CPU where the reference calls cuFFT
+    def bottlenect(self, x, p):
+        sd = self.sd
+        out = F.gelu(F.conv2d(x, sd[p + ".in_conv.0.weight"], sd[p + ".in_conv.0.bias"]))
+        x_att = F.conv2d(out.mean((2, 3), keepdim=True), sd[p + ".fac_conv.weight"], sd[p + ".fac_conv.bias"])
+        x_fca = torch.abs(torch.fft.ifft2(x_att * torch.fft.fft2(out, norm="backward"), dim=(-2, -1), norm="backward"))
+        x_att = F.conv2d(x_fca.mean((2, 3), keepdim=True), sd[p + ".conv.weight"], sd[p + ".conv.bias"])
+        x_sca = x_att * x_fca
+        x1 = F.conv2d(x_sca, sd[p + ".fgm.dwconv1.weight"], sd[p + ".fgm.dwconv1.bias"])
+        x2 = F.conv2d(x_sca, sd[p + ".fgm.dwconv2.weight"], sd[p + ".fgm.dwconv2.bias"])
+        o = torch.abs(torch.fft.ifft2(x1 * torch.fft.fft2(x2, norm="backward"), dim=(-2, -1), norm="backward"))
+        return F.relu(o * sd[p + ".fgm.alpha"] + x_sca * sd[p + ".fgm.beta"])
+
+    # C3k2GC (block.py:1706-1714) = C2f.forward (block.py:459-464) over BottleNect blocks
+    def c3k2gc(self, x, p, n):
+        y = list(self.conv(x, p + ".cv1").chunk(2, 1))
+        for j in range(n):
+            y.append(self.bottlenect(y[-1], f"{p}.m.{j}"))
+        return self.conv(torch.cat(y, 1), p + ".cv2")
+
     # MSCSpatialAttention (conv.py:1200-1243); x8 and x9 are the same tensor there
     def msc(self, x, p):
         sd = self.sd
@@ -316,6 +341,8 @@ def forward(graph: List[dict], sd, x: torch.Tensor, strides=(8.0, 16.0, 32.0),
             x = R.convhca(inp, p, L["k"], L["s"])
         elif t == "C3k2":
             x = R.c3k2(inp, p, L["n"], L["c3k"])
+        elif t == "C3k2GC":
+            x = R.c3k2gc(inp, p, L["n"])
         elif t == "C3x":
             x = R.c3x(inp, p)
         elif t == "SPPF":

@@ -37,6 +37,8 @@ int fusion_launch(const specyolo_fusion_t*, cudaStream_t);
 int spatial_gate_launch(const specyolo_spatial_gate_t*, cudaStream_t);
 int msc_gate_launch(const specyolo_msc_gate_t*, cudaStream_t);
 size_t msc_ws_bytes(int, int, int, int);
+int bottlenect_launch(const specyolo_bottlenect_t*, cudaStream_t);
+size_t bottlenect_ws_bytes(int, int, int, int);
 int det_loss_launch(const specyolo_det_loss_t*, cudaStream_t);
 int ema_update_launch(float* const*, const float* const*, const long long*, const int*, const long long*, int, int, float, float, cudaStream_t);
 size_t det_loss_ws_bytes(int B, const int* h, const int* w, int nl, int M, int topk);
@@ -257,6 +259,15 @@ int specyolo_sobel_spatial_attention(const specyolo_spatial_gate_t* a, void* str
     SY_CHECK(a && a->x && a->y && a->mm, SPECYOLO_ERR_INVALID, "spatial gate: null pointer");
     SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, SPECYOLO_ERR_INVALID, "spatial gate: bad sizes");
     return spatial_gate_launch(a, (cudaStream_t)stream);
+}
+
+size_t specyolo_bottlenect_ws_bytes(int B, int H, int W, int C) { return bottlenect_ws_bytes(B, H, W, C); }
+
+int specyolo_bottlenect(const specyolo_bottlenect_t* a, void* stream) {
+    SY_CHECK(a && a->x && a->y && a->ws && a->in_w && a->in_b && a->fac_w && a->fac_b && a->sca_w && a->sca_b && a->dw1_w &&
+             a->dw1_b && a->dw2_w && a->dw2_b && a->alpha && a->beta, SPECYOLO_ERR_INVALID, "BottleNect: null pointer");
+    SY_CHECK(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, SPECYOLO_ERR_INVALID, "BottleNect: bad sizes");
+    return bottlenect_launch(a, (cudaStream_t)stream);
 }
 
 size_t specyolo_msc_ws_bytes(int B, int H, int W, int C) { return msc_ws_bytes(B, H, W, C); }

@@ -93,6 +93,17 @@ class MscGateArgs(C.Structure):
     ]
 
 
+class BottleNectArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_pixstride", C.c_int), ("y", C.c_void_p), ("y_pixstride", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("in_w", C.c_void_p), ("in_b", C.c_void_p), ("fac_w", C.c_void_p), ("fac_b", C.c_void_p),
+        ("sca_w", C.c_void_p), ("sca_b", C.c_void_p), ("dw1_w", C.c_void_p), ("dw1_b", C.c_void_p),
+        ("dw2_w", C.c_void_p), ("dw2_b", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p),
+        ("ws", C.c_void_p),
+    ]
+
+
 class DetLossArgs(C.Structure):
     _fields_ = [
         ("nl", C.c_int), ("h", C.c_int * 4), ("w", C.c_int * 4), ("stride", C.c_float * 4),
@@ -146,6 +157,8 @@ SIGNATURES = {
     "specyolo_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_void_p]),
     "specyolo_sobel_spatial_attention": (C.c_int, [C.POINTER(SpatialGateArgs), C.c_void_p]),
+    "specyolo_bottlenect_ws_bytes": (C.c_size_t, [C.c_int] * 4),
+    "specyolo_bottlenect": (C.c_int, [C.POINTER(BottleNectArgs), C.c_void_p]),
     "specyolo_msc_ws_bytes": (C.c_size_t, [C.c_int] * 4),
     "specyolo_msc_spatial_attention": (C.c_int, [C.POINTER(MscGateArgs), C.c_void_p]),
     "specyolo_det_loss_ws_bytes": (C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),

@@ -346,6 +346,59 @@ class C3k2(C2f):
             C3k(self.c, self.c, 2, shortcut, g) if c3k else Bottleneck(self.c, self.c, shortcut, g) for _ in range(n))
 
 
+class FGM(nn.Module):
+    """Parameter container of FGM (block.py:838-861): out = |ifft2(dwconv1(x) * fft2(dwconv2(x)))| * alpha + x * beta.
+    `conv` is declared by the reference and never used; it is kept for state_dict compatibility."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv = nn.Conv2d(dim, dim * 2, 3, 1, 1)
+        self.dwconv1 = nn.Conv2d(dim, dim, 1, 1, groups=1)
+        self.dwconv2 = nn.Conv2d(dim, dim, 1, 1, groups=1)
+        self.alpha = nn.Parameter(torch.zeros(dim, 1, 1))
+        self.beta = nn.Parameter(torch.ones(dim, 1, 1))
+
+
+class BottleNect(nn.Module):
+    """The block.py BottleNect (block.py:782-836, the one C3k2GC instantiates): 1x1 conv + GELU, the two pooled channel
+    gates around an FFT identity, FGM, ReLU — csrc/bottlenect.cu.  `out_conv` and `dw_11` are declared by the reference and
+    never used; kept for state_dict compatibility."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.in_conv = nn.Sequential(nn.Conv2d(dim, dim, kernel_size=1, padding=0, stride=1), nn.GELU())
+        self.out_conv = nn.Conv2d(dim, dim, kernel_size=1, padding=0, stride=1)
+        self.dw_11 = nn.Conv2d(dim, dim, kernel_size=3, padding=1, stride=1, groups=dim)
+        self.act = nn.ReLU()
+        self.conv = nn.Conv2d(dim, dim, kernel_size=1, padding=0, stride=1, groups=1, bias=True)
+        self.fac_conv = nn.Conv2d(dim, dim, kernel_size=1, padding=0, stride=1, groups=1, bias=True)
+        self.fgm = FGM(dim)
+        self._f32 = None
+
+    def weights_f32(self):
+        ws = (self.in_conv[0].weight, self.in_conv[0].bias, self.fac_conv.weight, self.fac_conv.bias, self.conv.weight,
+              self.conv.bias, self.fgm.dwconv1.weight, self.fgm.dwconv1.bias, self.fgm.dwconv2.weight, self.fgm.dwconv2.bias,
+              self.fgm.alpha, self.fgm.beta)
+        key = tuple((w.data_ptr(), tensor_version(w)) for w in ws)
+        if getattr(self, "_f32", None) is None or self._f32[0] != key:
+            self._f32 = (key, tuple(w.detach().float().contiguous() for w in ws))
+        return self._f32[1]
+
+    def forward(self, x, out=None):
+        return ops.bottlenect(_as_fmap(x), self.weights_f32(), out=out)
+
+
+class C3k2GC(C2f):
+    """C2f whose inner blocks are BottleNect (block.py:1706-1714; *_GC configs, backbone layer 2).  The c3k=True branch
+    (C3kGC, scales m / l / x) is not built."""
+
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, g=1, shortcut=True):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        if c3k:
+            raise NotImplementedError("C3k2GC(c3k=True) (C3kGC, scales m/l/x) is outside the hot path this package implements")
+        self.m = nn.ModuleList(BottleNect(self.c) for _ in range(n))
+
+
 class SPPF(nn.Module):
     """cv1 -> 3 chained 5x5 max-pools -> cat -> cv2 (block.py:179-198)."""
 

@@ -21,15 +21,15 @@ import torch.nn as nn
 import yaml
 
 from .. import ops
-from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, C3x, Concat, Conv, ConvHCA, DDWConv, Detect, DWConv,
+from .modules import (C2PSA, C3, SPPF, Bottleneck, C2f, C3k, C3k2, C3k2GC, C3x, Concat, Conv, ConvHCA, DDWConv, Detect, DWConv,
                       Fusion, Upsample2x, UpsampledView)
 
 CFG_DIR = Path(__file__).resolve().parent.parent / "cfg"
 
-_MODULES = {m.__name__: m for m in (Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3x, SPPF, C2PSA, Concat,
+_MODULES = {m.__name__: m for m in (Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3k2GC, C3x, SPPF, C2PSA, Concat,
                                     Fusion, Detect)}
-_BASE = {Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3x, SPPF, C2PSA}
-_REPEAT = {C2f, C3, C3k, C3k2, C3x, C2PSA}
+_BASE = {Conv, ConvHCA, DWConv, DDWConv, Bottleneck, C2f, C3, C3k, C3k2, C3k2GC, C3x, SPPF, C2PSA}
+_REPEAT = {C2f, C3, C3k, C3k2, C3k2GC, C3x, C2PSA}
 _STRIDE2 = {Conv, ConvHCA, DWConv, DDWConv}
 
 
@@ -100,6 +100,8 @@ def parse_model(d: dict, ch: int, verbose: bool = False):
                 legacy = False
                 if scale in "mlx":
                     args[3] = True
+            if mod is C3k2GC and scale in "mlx":        # tasks.py:1110-1112
+                args[3] = True
             if mod in _STRIDE2:
                 s = args[3] if len(args) > 3 else (1 if mod not in (DDWConv, ConvHCA) else 2)
                 s_out = s_in * s

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (BneckArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, MscGateArgs, NmsArgs, SpatialGateArgs, StemPairArgs,
+from ._lib import (BneckArgs, BottleNectArgs, ConvArgs, DecodeArgs, DwpwArgs, FusionArgs, MscGateArgs, NmsArgs, SpatialGateArgs, StemPairArgs,
                    StftArgs, check)
 
 
@@ -505,6 +505,39 @@ def sobel_spatial_attention(x: torch.Tensor, w18: Sequence[float], out: Optional
         a.w[i] = float(v)
     a.mm = mm.data_ptr()
     check(_lib.load().specyolo_sobel_spatial_attention(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+_BOTTLENECT_FIELDS = ("in_w", "in_b", "fac_w", "fac_b", "sca_w", "sca_b", "dw1_w", "dw1_b", "dw2_w", "dw2_b", "alpha", "beta")
+
+
+def bottlenect(x: torch.Tensor, weights: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BottleNect + FGM (block.py:782-861): relu(|ifft2(x1 * fft2(x2))| * alpha + x_sca * beta), see include/specyolo.h.
+    `weights`: fp32 device tensors in the order in_conv.0 (w, b), fac_conv (w, b), conv (w, b), fgm.dwconv1 (w, b),
+    fgm.dwconv2 (w, b), fgm.alpha, fgm.beta.  out=None runs in place."""
+    B, Cc, H, W, xpix = nhwc_meta(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("bottlenect expects bf16")
+    if out is None:
+        out = x
+    oB, oC, oH, oW, ypix = nhwc_meta(out)
+    if (oB, oC, oH, oW) != (B, Cc, H, W) or out.dtype != torch.bfloat16:
+        raise ValueError("bottlenect: out shape / dtype mismatch")
+    if len(weights) != len(_BOTTLENECT_FIELDS):
+        raise ValueError("bottlenect: 12 weight tensors expected")
+    for t, name in zip(weights, _BOTTLENECT_FIELDS):
+        n = Cc * Cc if name.endswith("_w") else Cc
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or t.device != x.device:
+            raise ValueError(f"bottlenect: {name} must be a contiguous fp32 tensor of {n} elements on x's device")
+    lib = _lib.load()
+    ws = torch.empty(lib.specyolo_bottlenect_ws_bytes(B, H, W, Cc), device=x.device, dtype=torch.uint8)
+    a = BottleNectArgs()
+    a.x, a.x_pixstride, a.y, a.y_pixstride = x.data_ptr(), xpix, out.data_ptr(), ypix
+    a.B, a.H, a.W, a.C = B, H, W, Cc
+    for t, name in zip(weights, _BOTTLENECT_FIELDS):
+        setattr(a, name, t.data_ptr())
+    a.ws = ws.data_ptr()
+    check(lib.specyolo_bottlenect(C.byref(a), _lib.stream_ptr()))
     return out
 
 

@@ -474,6 +474,52 @@ def test_msc_spatial_attention(lib, B, c, H, W, window):
     assert _rel_err(got, ref) < 3e-3
 
 
+@pytest.mark.parametrize("B,c,H,W,window", [(2, 32, 160, 160, False), (3, 32, 24, 32, True), (2, 16, 40, 56, False), (1, 32, 20, 12, False),
+                                            (2, 32, 1, 1, False), (1, 16, 7, 15, True), (2, 32, 96, 128, False)])
+def test_bottlenect_fgm(lib, B, c, H, W, window):
+    """BottleNect + FGM (block.py:782-861) vs the oracle's restatement (torch.fft) on bf16-rounded inputs: the 160 x 160 x 32
+    planes of the *_GC config at 640^2, every radix of the mixed-radix transform (4, 2, 3, 5, 7), an odd number of stages,
+    non-square and single-pixel planes, both channel counts, in place on a channel window and out of place."""
+    from oracle.yolo_ref import Ref
+    from specyolo import ops
+    from specyolo.nn.modules import BottleNect
+
+    gen = torch.Generator().manual_seed(90 + c + H)
+    x = torch.randn((B, c, H, W), generator=gen) * 0.8 + 0.2
+    m = BottleNect(c)
+    with torch.no_grad():
+        for name, prm in m.named_parameters():
+            if name.endswith("alpha"):
+                prm.copy_(torch.rand(prm.shape, generator=gen) * 0.5 + 0.75)
+            elif name.endswith("beta"):
+                prm.copy_(torch.randn(prm.shape, generator=gen) * 0.5)
+            elif name.endswith("bias"):
+                prm.copy_(torch.randn(prm.shape, generator=gen) * 0.3)
+            else:
+                prm.copy_(torch.randn(prm.shape, generator=gen) * (1.5 / prm[0].numel()) ** 0.5)
+    ref = Ref({"m." + k: v for k, v in m.state_dict().items()}).bottlenect(_bf(x), "m")
+    m.to(DEV)
+    if window:
+        buf = ops.new_act(B, c + 16, H, W, DEV)
+        buf.zero_()
+        xin = buf[:, 8:8 + c]
+        xin.copy_(x.to(DEV))
+        got = m(xin)                                           # in place on the window
+        assert got.data_ptr() == xin.data_ptr()
+        assert float(buf[:, :8].float().abs().max()) == 0.0 and float(buf[:, 8 + c:].float().abs().max()) == 0.0
+    else:
+        xin = _fmap(x)
+        keep = xin.clone()
+        out = ops.new_act(B, c, H, W, DEV)
+        got = m(xin, out=out)
+        assert torch.equal(xin, keep)                          # out of place leaves x alone
+        again = m(xin, out=ops.new_act(B, c, H, W, DEV))
+        assert torch.equal(got, again)                         # fixed-order reductions: bit-identical run to run
+    got = got.float().cpu()
+    assert (got - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item())      # one bf16 rounding of the result
+    assert _rel_err(got, ref) < 3e-3
+
+
 @pytest.mark.parametrize("H,W,heads", [(20, 20, 4), (8, 12, 2), (16, 16, 2), (5, 7, 1), (16, 32, 2), (24, 24, 2), (40, 40, 1)])
 def test_psa_attention(lib, H, W, heads):
     """N = 400 (640^2 input), ragged / tiny / exactly 256 and 512 tokens on the resident-S kernel (N <= 512), 576 and

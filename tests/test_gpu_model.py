@@ -53,6 +53,7 @@ def _oracle(cfg_file, scale, nc, sd, x, layers=False):
     ("yolo11n", "yolo11n.yaml", "yolo11.yaml", "n", 80),
     ("specyolo_s_convhca", "yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11_fusion_sand3_new_convHCA.yaml", "s", 2),
     ("specyolo_s_omn", "yolo11s_fusion_sand3_new_OMN.yaml", "yolo11_fusion_sand3_new_OMN.yaml", "s", 2),
+    ("specyolo_s_gc", "yolo11s_fusion_sand3_new_GC.yaml", "yolo11_fusion_sand3_new_GC.yaml", "s", 2),
 ])
 def test_model_vs_golden_reference(lib, name, cfg, cfg_file, scale, nc):
     """CUDA path vs outputs of the REAL reference (fixture) on the fixture's input and seeded weights."""

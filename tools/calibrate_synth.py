@@ -61,7 +61,8 @@ def main():
     cases = [("yolo11s_fusion_sand3_new.yaml", "yolo11_fusion_sand3_new.yaml", "s", 2),
              ("yolo11n.yaml", "yolo11.yaml", "n", 80), ("yolo11s.yaml", "yolo11.yaml", "s", 80),
              ("yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11_fusion_sand3_new_convHCA.yaml", "s", 2),
-             ("yolo11s_fusion_sand3_new_OMN.yaml", "yolo11_fusion_sand3_new_OMN.yaml", "s", 2)]
+             ("yolo11s_fusion_sand3_new_OMN.yaml", "yolo11_fusion_sand3_new_OMN.yaml", "s", 2),
+             ("yolo11s_fusion_sand3_new_GC.yaml", "yolo11_fusion_sand3_new_GC.yaml", "s", 2)]
     only = set(sys.argv[1:])
     for cfg, cfg_file, scale, nc in cases:
         if only and cfg not in only:
