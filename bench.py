@@ -385,6 +385,11 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
         del y4, x4
         torch.cuda.empty_cache()
 
+    # ---- c5: DDP training step (BASELINE configs[4]) ----
+    c5 = None
+    if not args.no_extra:
+        c5 = c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, args.c5_batch)
+
     if rank == 0:
         cpu = lib_bar = None
         if world == 1 and not args.no_cpu_baseline:
@@ -416,11 +421,104 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "roofline": roof, "stages": stages, "clocks": clocks, "cpu_baseline": cpu,
-            "c3": c3, "c4": c4, "library_bar": lib_bar, "train_criterion": crit,
+            "c3": c3, "c4": c4, "c5": c5, "library_bar": lib_bar, "train_criterion": crit,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, batch):
+    """BASELINE configs[4] / SURVEY 8 f2: one data-parallel TRAINING step of the Spectrogram detector on synthetic images and
+    labels, one process per GPU: forward, detection criterion, backward with the NCCL gradient all-reduce of
+    DistributedDataParallel (engine/trainer.py:272-273), gradient clipping + SGD step + EMA update (trainer.py:380-399,
+    590-600), fp32 as the reference trainer runs when its AMP self-check cannot (offline) — under fp16 autocast GCT's sum of squares
+    over an 80 x 80 map overflows and the loss is NaN for the stock criterion as well.  The network's forward / backward are the REFERENCE's own
+    PyTorch modules (oracle/_ref; cuDNN / cuBLAS library kernels — this package has no backward pass); what this package
+    contributes to the step is the criterion (`specyolo_det_loss`) and the EMA update (`specyolo_ema_update`), bound in through
+    `ultralytics_shim.install()`.  Two arms on the same weights and batch: stock and shim.  Max over ranks."""
+    import torch
+
+    out = {"workload": f"spectrogram-yolov11-s nc={NC} DDP training step, batch {batch} per GPU, {IMGSZ}^2, fp32 (cuDNN TF32 convs), SGD + EMA, "
+                       "synthetic images / 8 boxes per image (BASELINE configs[4]); forward / backward = the reference's PyTorch "
+                       "modules (library kernels), criterion + EMA update = this package in the shim arm",
+           "unit": "images/s", "batch_per_gpu": batch, "n_gpus": world,
+           "allreduce": "torch DistributedDataParallel over NCCL" if world > 1 else "none (one GPU)"}
+    try:
+        import copy
+        from types import SimpleNamespace
+
+        import torch.distributed as dist
+
+        from oracle import ref_loader
+        from oracle.loss_ref import loss_case
+        from specyolo import ultralytics_shim as shim
+        from specyolo.nn.init import synth_images
+
+        if not ref_loader.reference_available():
+            out["unavailable"] = "oracle/_ref (the reference package) did not travel to this box"
+            return out
+        ultralytics = ref_loader.import_reference()
+        from ultralytics.nn.tasks import DetectionModel as RefModel
+
+        torch.manual_seed(0)        # a freshly initialised model, as `YOLO(cfg).train()` starts from (the calibrated synthetic
+        base = RefModel(str(Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG), nc=NC, verbose=False)
+        # inference weights overflow fp16 in GCT's sum of squares once BatchNorm switches to batch statistics)
+        _, labels = loss_case(11 + rank, batch, IMGSZ, IMGSZ, NC, [8] * batch)
+        labels = {k: v.to(dev) for k, v in labels.items()}
+        labels["img"] = synth_images(batch, IMGSZ, seed=300 + rank).to(dev)
+        steps, warm = 8, 3
+
+        def arm():
+            from ultralytics.utils.torch_utils import ModelEMA          # the shim rebinds this name while installed
+
+            model = copy.deepcopy(base).to(dev).train()
+            for name, prm in model.named_parameters():                  # trainer.py:236-252: everything trains but the DFL projection
+                prm.requires_grad_(".dfl" not in name)
+            model.args = SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+            model.criterion = None
+            ema = ModelEMA(model)
+            net = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=True)
+                   if world > 1 else model)                        # trainer.py:272-273
+            opt = torch.optim.SGD([q for q in model.parameters() if q.requires_grad], lr=1e-4, momentum=0.937, nesterov=True)
+
+            def step():
+                loss, _items = net(labels)                               # BaseModel.forward(dict) -> self.loss(batch) (tasks.py:100-116)
+                (loss * world).backward()                                # trainer.py:385: loss *= world_size under DDP
+                torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
+                opt.step()
+                opt.zero_grad()
+                ema.update(model)
+                return loss
+
+            for _ in range(warm):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                last = step()
+            barrier()
+            t = max_over_ranks(time.perf_counter() - t0)
+            lv = float(last.detach())
+            del net, opt, ema, model
+            torch.cuda.empty_cache()
+            return t, lv
+
+        t_stock, l_stock = arm()
+        shim.install()
+        try:
+            t_shim, l_shim = arm()
+        finally:
+            shim.uninstall()
+        out.update({"value": world * batch * steps / t_shim, "ms_per_step": 1e3 * t_shim / steps, "steps": steps,
+                    "stock_value": world * batch * steps / t_stock, "stock_ms_per_step": 1e3 * t_stock / steps,
+                    "loss_last_step": {"stock": l_stock, "shim": l_shim},
+                    "timing": "host wall clock between barriers (+ device synchronize), max over ranks"})
+        if world > 1:
+            dist.barrier()
+    except Exception as ex:      # an extra key must never take the bench line down
+        out["error"] = f"{type(ex).__name__}: {ex}"[:300]
+    return out
 
 
 def train_criterion_bar(dev, BATCH):
@@ -542,7 +640,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the resident-input loop")
-    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / library_bar keys")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / c5 / library_bar keys")
+    ap.add_argument("--c5-batch", type=int, default=16, help="images per GPU of the c5 training step (the reference's default batch)")
     ap.add_argument("--iq-bursts", type=int, default=32, help="IQ bursts per GPU per step of the c3 workload")
     ap.add_argument("--c4-batch", type=int, default=128, help="images per GPU per step of the c4 workload (yolo11s 1280^2)")
     args = ap.parse_args()

@@ -113,6 +113,29 @@ def test_layers_vs_oracle(lib):
     assert dsc < 0.03, (dsc, worst)
 
 
+@pytest.mark.parametrize("cfg", ["yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11s_fusion_sand3_new_OMN.yaml", "yolo11s_fusion_sand3_new_GC.yaml"])
+def test_predict_sibling_variants(lib, cfg):
+    """The sibling configs through the product API: CUDA-graph replay == eager == model() + non_max_suppression (their extra
+    kernels allocate workspaces and set shared-memory attributes: both must survive graph capture and replay)."""
+    import specyolo
+    from specyolo.nn.init import synth_images, synth_state_dict
+    from specyolo.utils.ops import non_max_suppression
+
+    yolo = specyolo.YOLO(cfg, nc=2)
+    yolo.load_state_dict(synth_state_dict(yolo.model, seed=0))
+    yolo.to("cuda")
+    x = synth_images(3, 320, seed=9).cuda()
+    res_graph = yolo.predict(x, conf=0.1, iou=0.7)
+    res_graph2 = yolo.predict(x, conf=0.1, iou=0.7)             # replay
+    res_eager = yolo.predict(x, conf=0.1, iou=0.7, use_graph=False)
+    y, _ = yolo.model(x)
+    dense = non_max_suppression(y, 0.1, 0.7)
+    for a, b, c, d in zip(res_graph, res_graph2, res_eager, dense):
+        assert torch.equal(a.boxes.data, b.boxes.data)
+        assert torch.equal(a.boxes.data, c.boxes.data)
+        assert torch.equal(a.boxes.data, _clip(d.cpu(), 320, 320))
+
+
 def test_predict_api_and_fused_path(lib):
     """YOLO(cfg).predict(tensor): CUDA-graph replay == eager fused path == model() + non_max_suppression."""
     import specyolo
