@@ -215,13 +215,32 @@ stft_letterbox_kernel(const __grid_constant__ StftParams p) {
 
         // ---- stage A: lane = n2, register = n1; x[n1] = w[n] s[n], n = 32 n1 + n2 ----
         float2 re[32], im[32];
+        if (c + kWarps < ncols) {                      // next column of this warp: pull its samples towards L2 while this one computes
+            const int tn = s_coltab[c + kWarps].x;
+            const char* nx = reinterpret_cast<const char*>(iq + (size_t)tn * a.hop);
+            const int bytes = (NFFT + a.hop) * 8;      // both frames
+            for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + o));
+        }
+        if (a.hop == 256 && t1 == t0 + 1) {
+            // frame 1 is frame 0 advanced by 256 samples = 8 registers: 40 loads instead of 64
+            float2 raw[40];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            const int n = 32 * n1 + lane;
-            const float2 s0 = __ldg(src0 + n), s1 = __ldg(src1 + n);
-            const float w = s_win[n];
-            re[n1] = make_float2(s0.x * w, s1.x * w);
-            im[n1] = make_float2(s0.y * w, s1.y * w);
+            for (int n1 = 0; n1 < 40; ++n1) raw[n1] = __ldg(src0 + 32 * n1 + lane);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const float w = s_win[32 * n1 + lane];
+                re[n1] = make_float2(raw[n1].x * w, raw[n1 + 8].x * w);
+                im[n1] = make_float2(raw[n1].y * w, raw[n1 + 8].y * w);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int n = 32 * n1 + lane;
+                const float2 s0 = __ldg(src0 + n), s1 = __ldg(src1 + n);
+                const float w = s_win[n];
+                re[n1] = make_float2(s0.x * w, s1.x * w);
+                im[n1] = make_float2(s0.y * w, s1.y * w);
+            }
         }
         fft32x2(re, im);
         __syncwarp();
