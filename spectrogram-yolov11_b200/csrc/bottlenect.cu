@@ -18,8 +18,10 @@
 //                     and writes x_sca, x1, x2 as PLANAR fp32 planes (the transform works plane by plane)
 //   gc_fft_kernel     persistent, one plane at a time, the complex plane resident in shared memory (H x (W+1) x 8 bytes:
 //                     206 KB at 160 x 160): row FFTs, column FFTs, multiply by x1 and conjugate, row FFTs, column FFTs,
-//                     modulus, alpha / beta / relu.  A warp owns a row / column: mixed-radix Stockham autosort stages
-//                     (radix 4, 2, 3, 5, 7) between the strided line in the plane and a per-warp scratch line.
+//                     modulus, alpha / beta / relu.  A warp owns a row / column: sides that are multiples of 32 (<= 256)
+//                     are transformed in registers (M-point DFT per lane + a 32-point transform across the lanes by
+//                     shuffles), any other side by mixed-radix Stockham autosort stages (radix 4, 2, 3, 5, 7) between the
+//                     strided line in the plane and a per-warp scratch line.
 //   gc_pack_kernel    planar fp32 -> bf16 NHWC channel window
 // All reductions run in a fixed order: results are bit-identical run to run.
 #include "common.h"
@@ -265,6 +267,87 @@ __device__ void fft_line(float2* data, int stride, int N, const int* rad, int ns
     }
 }
 
+// ---- register path: lines of N = 32 M points, M <= 8 -------------------------------------------------------------------
+// Lane l holds x[l + 32 j], j < M.  N = M x 32 Cooley-Tukey: an M-point DFT over j in registers, the twiddle
+// W_N^(l k1), then — for each of the M residues k1 — a 32-point radix-2 DIF transform ACROSS the lanes with shuffles; lane l
+// ends up with X[k1 + M * bitrev5(l)], stored to its natural place.  ~3x fewer instructions per line than the Stockham
+// stages (no shared-memory round trip per stage, no index arithmetic), used whenever a plane side is a multiple of 32.
+template <int M>
+__device__ __forceinline__ void fft_line_reg(float2* data, int stride, const float2* tw, int lane) {
+    constexpr int N = 32 * M;
+    float2 v[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) v[j] = data[(lane + 32 * j) * stride];
+    if (M > 1) {
+        // M-point DFT through the (t, M - t) symmetry: X_u = A_u - i B_u, X_{M-u} = A_u + i B_u
+        float2 x[M];
+        x[0] = v[0];
+#pragma unroll
+        for (int t = 1; t < M; ++t) { x[0].x += v[t].x; x[0].y += v[t].y; }
+#pragma unroll
+        for (int u = 1; u <= M / 2; ++u) {
+            float2 A = v[0], B = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 1; t <= (M - 1) / 2; ++t) {
+                const float2 w = tw[((u * t) % M) * 32];            // (cos, -sin)(2 pi u t / M)
+                A.x = fmaf(v[t].x + v[M - t].x, w.x, A.x); A.y = fmaf(v[t].y + v[M - t].y, w.x, A.y);
+                B.x = fmaf(v[t].x - v[M - t].x, -w.y, B.x); B.y = fmaf(v[t].y - v[M - t].y, -w.y, B.y);
+            }
+            if (M % 2 == 0) {                                       // the self-paired middle term: (-1)^u v[M/2]
+                const float sg = (u & 1) ? -1.f : 1.f;
+                A.x = fmaf(sg, v[M / 2].x, A.x); A.y = fmaf(sg, v[M / 2].y, A.y);
+            }
+            x[u] = make_float2(A.x + B.y, A.y - B.x);               // A - i B
+            if (u != M - u) x[M - u] = make_float2(A.x - B.y, A.y + B.x);
+        }
+#pragma unroll
+        for (int u = 0; u < M; ++u) v[u] = u == 0 ? x[0] : cmul(x[u], tw[lane * u]);
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int half = 16 >> s;
+        const bool upper = (lane & half) != 0;
+        const float sg = upper ? -1.f : 1.f;
+        float2 w = make_float2(1.f, 0.f);
+        if (s < 4 && upper) w = tw[((lane & (half - 1)) << s) * M];   // W_32^((l mod half) << s)
+#pragma unroll
+        for (int u = 0; u < M; ++u) {
+            const float ox = __shfl_xor_sync(0xffffffffu, v[u].x, half), oy = __shfl_xor_sync(0xffffffffu, v[u].y, half);
+            const float2 r = make_float2(fmaf(sg, v[u].x, ox), fmaf(sg, v[u].y, oy));   // lower: v + other, upper: other - v
+            v[u] = s < 4 ? cmul(r, w) : r;
+        }
+    }
+    const int k2 = (int)(__brev((unsigned)lane) >> 27);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < M; ++u) data[(u + M * k2) * stride] = v[u];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void fft_line_any(float2* data, int stride, int N, const int* rad, int nst, const float2* tw, float2* scratch, int lane) {
+    if ((N & 31) == 0 && N <= 256) {
+        switch (N >> 5) {
+            case 1: fft_line_reg<1>(data, stride, tw, lane); break;
+            case 2: fft_line_reg<2>(data, stride, tw, lane); break;
+            case 3: fft_line_reg<3>(data, stride, tw, lane); break;
+            case 4: fft_line_reg<4>(data, stride, tw, lane); break;
+            case 5: fft_line_reg<5>(data, stride, tw, lane); break;
+            case 6: fft_line_reg<6>(data, stride, tw, lane); break;
+            case 7: fft_line_reg<7>(data, stride, tw, lane); break;
+            default: fft_line_reg<8>(data, stride, tw, lane); break;
+        }
+    } else {
+        fft_line(data, stride, N, rad, nst, tw, scratch, lane);
+    }
+}
+
+// linear pixel index -> offset in the padded shared-memory plane; y = floor((i + 0.5) / W) in fp32 is exact for the plane
+// sizes that fit shared memory (the quotient sits 0.5 / W away from an integer, fp32 error is < 1e-4 of that)
+__device__ __forceinline__ int plane_index(int i, int W, float inv_w, int pitch) {
+    const int y = (int)(((float)i + 0.5f) * inv_w);
+    return y * pitch + (i - y * W);
+}
+
 __global__ void __launch_bounds__(kFftThreads, 1)
 gc_fft_kernel(const __grid_constant__ GcParams p) {
     const specyolo_bottlenect_t& a = p.a;
@@ -286,35 +369,57 @@ gc_fft_kernel(const __grid_constant__ GcParams p) {
     }
     float2* scr = s_scr + (size_t)warp * p.maxn;
     const int planes = a.B * a.C;
+    const float inv_w = 1.0f / (float)a.W;
     for (int pl = blockIdx.x; pl < planes; pl += gridDim.x) {
         const size_t off = (size_t)pl * p.HW;
         const float al = __ldg(a.alpha + pl % a.C), be = __ldg(a.beta + pl % a.C);
         __syncthreads();                               // twiddles written / previous plane consumed
-        for (int i = tid; i < p.HW; i += kFftThreads) {
-            const int y = i / a.W, x = i - y * a.W;
-            s_plane[(size_t)y * p.pitch + x] = make_float2(__ldg(p.x2 + off + i), 0.f);
+        for (int i0 = tid; i0 < p.HW; i0 += 4 * kFftThreads) {      // four global loads in flight per thread
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = i0 + u * kFftThreads < p.HW ? __ldg(p.x2 + off + i0 + u * kFftThreads) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kFftThreads;
+                if (i < p.HW) s_plane[plane_index(i, a.W, inv_w, p.pitch)] = make_float2(g[u], 0.f);
+            }
         }
         __syncthreads();
         for (int pass = 0; pass < 2; ++pass) {
-            for (int y = warp; y < a.H; y += kFftWarps) fft_line(s_plane + (size_t)y * p.pitch, 1, a.W, p.rad_w, p.nst_w, s_tww, scr, lane);
+            for (int y = warp; y < a.H; y += kFftWarps) fft_line_any(s_plane + (size_t)y * p.pitch, 1, a.W, p.rad_w, p.nst_w, s_tww, scr, lane);
             __syncthreads();
-            for (int x = warp; x < a.W; x += kFftWarps) fft_line(s_plane + x, p.pitch, a.H, p.rad_h, p.nst_h, s_twh, scr, lane);
+            for (int x = warp; x < a.W; x += kFftWarps) fft_line_any(s_plane + x, p.pitch, a.H, p.rad_h, p.nst_h, s_twh, scr, lane);
             __syncthreads();
             if (pass == 0) {                           // Y = x1 * fft2(x2); |ifft2(Y)| = |fft2(conj Y)| / (H W)
-                for (int i = tid; i < p.HW; i += kFftThreads) {
-                    const int y = i / a.W, x = i - y * a.W;
-                    const float m = __ldg(p.x1 + off + i);
-                    float2& z = s_plane[(size_t)y * p.pitch + x];
-                    z = make_float2(m * z.x, -m * z.y);
+                for (int i0 = tid; i0 < p.HW; i0 += 4 * kFftThreads) {
+                    float g[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) g[u] = i0 + u * kFftThreads < p.HW ? __ldg(p.x1 + off + i0 + u * kFftThreads) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kFftThreads;
+                        if (i < p.HW) {
+                            float2& z = s_plane[plane_index(i, a.W, inv_w, p.pitch)];
+                            z = make_float2(g[u] * z.x, -g[u] * z.y);
+                        }
+                    }
                 }
                 __syncthreads();
             }
         }
-        for (int i = tid; i < p.HW; i += kFftThreads) {
-            const int y = i / a.W, x = i - y * a.W;
-            const float2 z = s_plane[(size_t)y * p.pitch + x];
-            const float o = sqrtf(z.x * z.x + z.y * z.y) * p.inv_hw;
-            p.xs[off + i] = fmaxf(fmaf(o, al, p.xs[off + i] * be), 0.f);
+        for (int i0 = tid; i0 < p.HW; i0 += 4 * kFftThreads) {
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = i0 + u * kFftThreads < p.HW ? p.xs[off + i0 + u * kFftThreads] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kFftThreads;
+                if (i < p.HW) {
+                    const float2 z = s_plane[plane_index(i, a.W, inv_w, p.pitch)];
+                    const float o = sqrtf(z.x * z.x + z.y * z.y) * p.inv_hw;
+                    p.xs[off + i] = fmaxf(fmaf(o, al, g[u] * be), 0.f);
+                }
+            }
         }
     }
 }
