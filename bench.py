@@ -455,11 +455,18 @@ def c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, batch):
         from specyolo import ultralytics_shim as shim
         from specyolo.nn.init import synth_images
 
-        if not ref_loader.reference_available():
-            out["unavailable"] = "oracle/_ref (the reference package) did not travel to this box"
+        # every rank must take the same path through the collectives below: agree first on whether the leg can run at all
+        ready, why = 1.0, ""
+        try:
+            if not ref_loader.reference_available():
+                raise RuntimeError("oracle/_ref (the reference package) did not travel to this box")
+            ultralytics = ref_loader.import_reference()
+            from ultralytics.nn.tasks import DetectionModel as RefModel
+        except Exception as ex:
+            ready, why = 0.0, f"{type(ex).__name__}: {ex}"[:200]
+        if -max_over_ranks(-ready) < 1.0:                               # min over ranks
+            out["unavailable"] = why or "the reference package is missing on another rank"
             return out
-        ultralytics = ref_loader.import_reference()
-        from ultralytics.nn.tasks import DetectionModel as RefModel
 
         torch.manual_seed(0)        # a freshly initialised model, as `YOLO(cfg).train()` starts from (the calibrated synthetic
         base = RefModel(str(Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG), nc=NC, verbose=False)
