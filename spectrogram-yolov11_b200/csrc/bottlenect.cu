@@ -74,15 +74,17 @@ __device__ __forceinline__ void gc_stage_tile(const __nv_bfloat16* xb, int pixst
     dst[1] = make_float4(__uint_as_float(w[2] << 16), __uint_as_float(w[2] & 0xffff0000u), __uint_as_float(w[3] << 16), __uint_as_float(w[3] & 0xffff0000u));
 }
 
+// packed pairs (FFMA2): the mat-vecs are issue-bound; two partial sums, added in a fixed order
 template <int C>
 __device__ __forceinline__ float gc_dot(const float (&w)[C], float bias, const float* x) {
-    float t = bias;
+    float2 t0 = make_float2(bias, 0.f), t1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < C; j += 4) {
         const float4 v = *reinterpret_cast<const float4*>(x + j);
-        t = fmaf(w[j], v.x, t); t = fmaf(w[j + 1], v.y, t); t = fmaf(w[j + 2], v.z, t); t = fmaf(w[j + 3], v.w, t);
+        t0 = ffma2(make_float2(w[j], w[j + 1]), make_float2(v.x, v.y), t0);
+        t1 = ffma2(make_float2(w[j + 2], w[j + 3]), make_float2(v.z, v.w), t1);
     }
-    return t;
+    return (t0.x + t1.x) + (t0.y + t1.y);
 }
 
 template <int C>
@@ -472,7 +474,7 @@ size_t bottlenect_ws_bytes(int B, int H, int W, int C) {
     return ((size_t)B * gc_nchunk((int)HW) * 2 * C + 3 * (size_t)B * C * HW) * sizeof(float);
 }
 
-static size_t g_fft_attr_smem[64] = {0};
+static size_t g_fft_attr_smem[kMaxDevices] = {0};
 
 template <int C>
 static int bottlenect_launch_t(GcParams& p, cudaStream_t stream) {
@@ -485,12 +487,7 @@ static int bottlenect_launch_t(GcParams& p, cudaStream_t stream) {
     gc_prep_kernel<C><<<dim3((unsigned)per_img, (unsigned)a.B), kGcThreads, 0, stream>>>(p);
     count_launch();
     const size_t smem = gc_fft_smem(a.H, a.W);
-    int dev = 0;
-    SY_CUDA(cudaGetDevice(&dev));
-    if (smem > g_fft_attr_smem[dev & 63]) {            // one cache for both channel-count instantiations of this launcher
-        SY_CUDA(cudaFuncSetAttribute(gc_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_fft_attr_smem[dev & 63] = smem;
-    }
+    SY_CUDA(ensure_dynamic_smem(gc_fft_kernel, smem, g_fft_attr_smem));   // one cache for both channel-count instantiations
     const int planes = a.B * a.C;
     gc_fft_kernel<<<(unsigned)min(planes, sm_count()), kFftThreads, smem, stream>>>(p);
     count_launch();

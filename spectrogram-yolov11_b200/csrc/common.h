@@ -31,6 +31,23 @@ void set_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: `cache` is the caller's
+// `static size_t [kMaxDevices]` of what has been set so far (the attribute is raised, never lowered).
+static constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t* cache) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = cache[dev % kMaxDevices];
+    if (bytes > have) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) have = bytes;
+    }
+    return e;
+}
+
 // Launch check used after every kernel launch (does not synchronise).
 #define SY_LAUNCH_CHECK()                                                               \
     do {                                                                                \

@@ -573,11 +573,8 @@ int det_loss_launch(const specyolo_det_loss_t* a, cudaStream_t stream) {
     count_launch();
     if (a->M > 0) {
         const size_t smem_c = (size_t)A * 4;
-        static size_t attr_c = 0;
-        if (smem_c > 48 * 1024 && smem_c > attr_c) {
-            SY_CUDA(cudaFuncSetAttribute(tal_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-            attr_c = smem_c;
-        }
+        static size_t attr_c[kMaxDevices] = {0};
+        SY_CUDA(ensure_dynamic_smem(tal_candidates_kernel, smem_c, attr_c));
         tal_candidates_kernel<<<dim3((unsigned)a->M, (unsigned)a->B), kLossThreads, smem_c, stream>>>(p);
         count_launch();
     }

@@ -91,11 +91,8 @@ int match_predictions_launch(const float* pred, const int* pred_count, int B, in
     p.pred = pred; p.pred_count = pred_count; p.B = B; p.max_det = max_det;
     p.labels = labels; p.label_off = label_off; p.niou = niou; p.correct = correct;
     for (int i = 0; i < niou; ++i) p.iouv[i] = iouv[i];
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        SY_CUDA(cudaFuncSetAttribute(match_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static size_t attr_smem[kMaxDevices] = {0};
+    SY_CUDA(ensure_dynamic_smem(match_predictions_kernel, smem, attr_smem));
     SY_CUDA(launch_pdl(match_predictions_kernel, dim3((unsigned)B), dim3(kMatchThreads), smem, stream, p));
     SY_LAUNCH_CHECK();
     count_launch();

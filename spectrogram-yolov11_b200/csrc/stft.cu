@@ -384,11 +384,8 @@ int stft_launch(const specyolo_stft_t* a, cudaStream_t stream) {
     const size_t smem = (size_t)kWarps * 32 * kTilePitch * 8 + (size_t)32 * 32 * 16 + (size_t)NFFT * 4 +
                         (size_t)p.new_h * 8 + (size_t)kCols * 8 + (size_t)kCols * p.out_pitch * 4;
     SY_CHECK(smem <= 220 * 1024, SPECYOLO_ERR_UNSUPPORTED, "content band too tall for shared memory");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        SY_CUDA(cudaFuncSetAttribute(stft_letterbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static size_t attr_smem[kMaxDevices] = {0};
+    SY_CUDA(ensure_dynamic_smem(stft_letterbox_kernel, smem, attr_smem));
     dim3 grid((unsigned)(p.col_tiles + p.pad_tiles), (unsigned)a->B);
     stft_letterbox_kernel<<<grid, kThreads, smem, stream>>>(p);
     SY_LAUNCH_CHECK();

@@ -14,7 +14,8 @@ PY
 tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"; cat gpurun_out/bench_ref.json
 if [ "$1" = "ncu" ]; then
-python bench.py --steps 2 --warmup 3 > gpurun_out/plain_bench.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1
+# (--no-extra: the c3 / c4 / c5 / library legs run after the timed region and would only add thousands of library launches)
+python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "ncu exit $?"; tail -2 gpurun_out/ncu_launches.log; wc -l gpurun_out/launches.csv
 fi
