@@ -450,10 +450,9 @@ def c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, batch):
 
         import torch.distributed as dist
 
-        from oracle import ref_loader
-        from oracle.loss_ref import loss_case
+        from oracle import ref_loader                       # comparison / host leg: the REFERENCE's modules are the network
         from specyolo import ultralytics_shim as shim
-        from specyolo.nn.init import synth_images
+        from specyolo.nn.init import synth_det_batch, synth_images
 
         # every rank must take the same path through the collectives below: agree first on whether the leg can run at all
         ready, why = 1.0, ""
@@ -471,8 +470,7 @@ def c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, batch):
         torch.manual_seed(0)        # a freshly initialised model, as `YOLO(cfg).train()` starts from (the calibrated synthetic
         base = RefModel(str(Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG), nc=NC, verbose=False)
         # inference weights overflow fp16 in GCT's sum of squares once BatchNorm switches to batch statistics)
-        _, labels = loss_case(11 + rank, batch, IMGSZ, IMGSZ, NC, [8] * batch)
-        labels = {k: v.to(dev) for k, v in labels.items()}
+        labels = {k: v.to(dev) for k, v in synth_det_batch(batch, IMGSZ, NC, 8, seed=11 + rank).items()}
         labels["img"] = synth_images(batch, IMGSZ, seed=300 + rank).to(dev)
         steps, warm = 8, 3
 
@@ -538,10 +536,10 @@ def train_criterion_bar(dev, BATCH):
     try:
         from types import SimpleNamespace
 
-        from oracle.loss_ref import loss_case
+        from specyolo.nn.init import synth_det_batch
         from specyolo.utils.loss import v8DetectionLoss
 
-        feats, batch = loss_case(5, BATCH, IMGSZ, IMGSZ, NC, [8] * BATCH)
+        feats, batch = synth_det_batch(BATCH, IMGSZ, NC, 8, seed=5, head_maps=True)
         f = [x.to(dev).requires_grad_(True) for x in feats]
         fake = SimpleNamespace(model=[SimpleNamespace(nc=NC, reg_max=16, stride=torch.tensor([8.0, 16.0, 32.0]))],
                                args={"box": 7.5, "cls": 0.5, "dfl": 1.5}, parameters=lambda: iter([torch.zeros(1, device=dev)]))

@@ -69,6 +69,27 @@ def synth_state_dict(model: torch.nn.Module, seed: int = 0, cls_bias: float | No
     return out
 
 
+def synth_det_batch(batch: int, size: int = 640, nc: int = 2, boxes_per_image: int = 8, seed: int = 0, head_maps: bool = False):
+    """Synthetic detection labels in the reference's collated-batch format (`batch_idx` [n], `cls` [n, 1], `bboxes` [n, 4]
+    normalised xywh; data/dataset.py:232-252) and, on request, seeded Detect head maps `[B, 64 + nc, size/s, size/s]` for
+    s = 8, 16, 32 whose decoded boxes span a few grid cells (inputs of the criterion benchmark).  Bench / demo data only."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    n = batch * boxes_per_image
+    wh = torch.rand((n, 2), generator=g) * 0.5 + 0.04
+    ctr = torch.rand((n, 2), generator=g) * (1 - wh) + wh / 2
+    labels = {"batch_idx": torch.arange(batch, dtype=torch.float32).repeat_interleave(boxes_per_image),
+              "cls": torch.randint(0, nc, (n, 1), generator=g).float(), "bboxes": torch.cat((ctr, wh), 1)}
+    if not head_maps:
+        return labels
+    feats = []
+    for s in (8, 16, 32):
+        f = torch.randn((batch, 64 + nc, size // s, size // s), generator=g)
+        f[:, :64] *= 2.0
+        f[:, 64:] = f[:, 64:] * 1.5 - 2.0
+        feats.append(f)
+    return feats, labels
+
+
 def synth_images(batch: int, size: int = 640, seed: int = 0, dtype=torch.float32) -> torch.Tensor:
     """Spectrogram-like frames: noise floor + a few bright axis-aligned rectangles."""
     g = torch.Generator().manual_seed(1000 + seed)
