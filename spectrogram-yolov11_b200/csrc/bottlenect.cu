@@ -500,6 +500,7 @@ static int bottlenect_launch_t(GcParams& p, cudaStream_t stream) {
 
 int bottlenect_launch(const specyolo_bottlenect_t* a, cudaStream_t stream) {
     SY_CHECK(a->C == 16 || a->C == 32, SPECYOLO_ERR_UNSUPPORTED, "BottleNect: 16 or 32 channels (scales n, s of the *_GC config), got %d", a->C);
+    SY_CHECK(a->B <= 65535, SPECYOLO_ERR_UNSUPPORTED, "BottleNect: batch %d exceeds the grid limit", a->B);
     SY_CHECK(a->x_pixstride % 8 == 0 && a->y_pixstride % 8 == 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->C,
              SPECYOLO_ERR_INVALID, "BottleNect: pixel strides must be multiples of 8 elements and >= C");
     SY_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->y)) & 15) == 0, SPECYOLO_ERR_INVALID,

@@ -432,6 +432,7 @@ static void msc_launch_t(const MscParams& p, const GateParams& gp, cudaStream_t 
 
 int msc_gate_launch(const specyolo_msc_gate_t* a, cudaStream_t stream) {
     SY_CHECK(a->C % 8 == 0 && a->C >= 8 && a->C <= 512, SPECYOLO_ERR_UNSUPPORTED, "msc gate: C must be a multiple of 8, <= 512 (got %d)", a->C);
+    SY_CHECK(a->B <= 65535, SPECYOLO_ERR_UNSUPPORTED, "msc gate: batch %d exceeds the grid limit", a->B);
     SY_CHECK(a->k_big == kMscK, SPECYOLO_ERR_UNSUPPORTED, "msc gate: only the reference's 31 x 31 kernel is built (got %d)", a->k_big);
     SY_CHECK(a->x_pixstride % 8 == 0 && a->y_pixstride % 8 == 0 && a->x_pixstride >= a->C && a->y_pixstride >= a->C,
              SPECYOLO_ERR_INVALID, "msc gate: pixel strides must be multiples of 8 elements and >= C");

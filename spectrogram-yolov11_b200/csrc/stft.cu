@@ -218,7 +218,7 @@ stft_letterbox_kernel(const __grid_constant__ StftParams p) {
         if (c + kWarps < ncols) {                      // next column of this warp: pull its samples towards L2 while this one computes
             const int tn = s_coltab[c + kWarps].x;
             const char* nx = reinterpret_cast<const char*>(iq + (size_t)tn * a.hop);
-            const int bytes = (NFFT + a.hop) * 8;      // both frames
+            const int bytes = (int)min((long)(NFFT + a.hop), (long)a.L - (long)tn * a.hop) * 8;   // both frames, inside the burst
             for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + o));
         }
         if (a.hop == 256 && t1 == t0 + 1) {

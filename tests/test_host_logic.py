@@ -48,7 +48,9 @@ def test_state_dict_keys_match_reference():
     import specyolo
 
     for mine_cfg, ref_cfg, nc in [("yolo11s_fusion_sand3_new.yaml", "yolo11s_fusion_sand3_new.yaml", 2), ("yolo11n.yaml", "yolo11n.yaml", 80),
-                                  ("yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11s_fusion_sand3_new_convHCA.yaml", 2)]:
+                                  ("yolo11s_fusion_sand3_new_convHCA.yaml", "yolo11s_fusion_sand3_new_convHCA.yaml", 2),
+                                  ("yolo11s_fusion_sand3_new_OMN.yaml", "yolo11s_fusion_sand3_new_OMN.yaml", 2),
+                                  ("yolo11s_fusion_sand3_new_GC.yaml", "yolo11s_fusion_sand3_new_GC.yaml", 2)]:
         r = Ref(f"/root/reference/ultralytics/cfg/models/11/{ref_cfg}", nc=nc, verbose=False).state_dict()
         m = specyolo.DetectionModel(mine_cfg, nc=nc).state_dict()
         assert list(r.keys()) == list(m.keys())
