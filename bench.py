@@ -403,6 +403,8 @@ def run_product_arm(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_extra:
             lib_bar = library_bar(sd, x_dev, dev)
             crit = train_criterion_bar(dev, B)
+            if c5 is not None and "value" in c5:
+                c5["cuda_graph"] = c5_graph_subprocess(args.c5_batch, local_rank)
         line = {
             "metric": METRIC, "value": world * B * args.steps / t_max, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps,
@@ -526,6 +528,101 @@ def c5_train_step(sd, dev, rank, world, barrier, max_over_ranks, batch):
     return out
 
 
+def c5_graph_worker(batch: int, local_rank: int):
+    """`bench.py --c5-graph`: the c5 training step of ONE GPU as a single CUDA graph — forward of the reference's modules,
+    this package's criterion on pre-packed static targets (`pack_batch_targets`: no host work, no host synchronisation),
+    backward, gradient clipping and the SGD step captured once and replayed; the EMA update (its decay changes per step) runs
+    eagerly after each replay.  The reference's own criterion cannot be captured (`if fg_mask.sum()`, `max(target_scores
+    .sum(), 1)` and the per-image loop of `preprocess` synchronise with the host).  Run as a SEPARATE PROCESS by the parent
+    bench so that a capture failure can never take the bench line down; prints one JSON object."""
+    import copy
+    from types import SimpleNamespace
+
+    import torch
+
+    out = {}
+    try:
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        from oracle import ref_loader                       # host leg: the REFERENCE's modules are the network
+        from specyolo import ultralytics_shim as shim
+        from specyolo.nn.init import synth_det_batch, synth_images
+        from specyolo.utils.loss import pack_batch_targets
+
+        ultralytics = ref_loader.import_reference()
+        from ultralytics.nn.tasks import DetectionModel as RefModel
+
+        torch.manual_seed(0)
+        base = RefModel(str(Path(ultralytics.__file__).parent / "cfg" / "models" / "11" / CFG), nc=NC, verbose=False)
+        labels = synth_det_batch(batch, IMGSZ, NC, 8, seed=11)
+        gbatch = {k: v.to(dev) for k, v in labels.items()}
+        gbatch["img"] = synth_images(batch, IMGSZ, seed=300).to(dev)
+        gbatch["packed_targets"] = pack_batch_targets(labels, batch, (IMGSZ, IMGSZ), dev, max_boxes=8)
+        shim.install()
+        from ultralytics.utils.torch_utils import ModelEMA
+
+        model = copy.deepcopy(base).to(dev).train()
+        for name, prm in model.named_parameters():
+            prm.requires_grad_(".dfl" not in name)
+        model.args = SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+        model.criterion = None
+        ema = ModelEMA(model)
+        params = [q for q in model.parameters() if q.requires_grad]
+        opt = torch.optim.SGD(params, lr=1e-4, momentum=0.937, nesterov=True)
+
+        def step_body():
+            loss, _items = model(gbatch)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, max_norm=10.0)
+            opt.step()
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                                            # warm-up: cuDNN plans, criterion caches, momentum buffers
+                opt.zero_grad(set_to_none=True)
+                step_body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = step_body()
+        steps = 20
+        for _ in range(3):
+            graph.replay()
+            ema.update(model)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            graph.replay()
+            ema.update(model)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        out = {"value": batch * steps / t, "ms_per_step": 1e3 * t / steps, "steps": steps, "loss_last_step": float(static_loss.detach()),
+               "what": "forward + criterion + backward + clip + SGD step replayed as one CUDA graph, EMA update eager; one GPU"}
+    except Exception as ex:
+        out = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    print("C5GRAPH " + json.dumps(out), flush=True)
+
+
+def c5_graph_subprocess(batch: int, local_rank: int):
+    """Runs c5_graph_worker in its own process (bounded time); returns its JSON object or an error record."""
+    import subprocess
+
+    try:
+        r = subprocess.run([sys.executable, str(Path(__file__).resolve()), "--c5-graph", "--c5-batch", str(batch)],
+                           capture_output=True, text=True, timeout=240,
+                           env={**os.environ, "LOCAL_RANK": str(local_rank), "WORLD_SIZE": "1", "RANK": "0"})
+        for ln in r.stdout.splitlines():
+            if ln.startswith("C5GRAPH "):
+                return json.loads(ln[len("C5GRAPH "):])
+        return {"error": f"worker exited {r.returncode}: {(r.stderr or '')[-200:]}"}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {ex}"[:200]}
+
+
 def train_criterion_bar(dev, BATCH):
     """SURVEY 8 f2, first slice: the detection criterion of a training step (v8DetectionLoss: assigner + BCE / CIoU / DFL,
     forward + backward into the head maps) at the bench's batch — specyolo_det_loss (six launches) against the reference's
@@ -647,12 +744,16 @@ def main():
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the resident-input loop")
     ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / c5 / library_bar keys")
     ap.add_argument("--c5-batch", type=int, default=16, help="images per GPU of the c5 training step (the reference's default batch)")
+    ap.add_argument("--c5-graph", action="store_true", help="(internal) run only the CUDA-graph arm of c5 and print its JSON object")
     ap.add_argument("--iq-bursts", type=int, default=32, help="IQ bursts per GPU per step of the c3 workload")
     ap.add_argument("--c4-batch", type=int, default=128, help="images per GPU per step of the c4 workload (yolo11s 1280^2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.c5_graph:
+        c5_graph_worker(args.c5_batch, local_rank)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return

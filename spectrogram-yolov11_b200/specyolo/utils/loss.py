@@ -104,6 +104,22 @@ def pack_targets(batch: Dict[str, torch.Tensor], B: int, img_hw: Tuple[float, fl
     return gt_boxes.to(device), gt_labels.to(device), count.to(torch.int32).to(device), M
 
 
+def pack_batch_targets(batch: Dict[str, torch.Tensor], B: int, img_hw: Tuple[float, float], device, max_boxes: int = 0):
+    """`pack_targets` ahead of the criterion call, with the per-image slot count padded up to `max_boxes`: put the result
+    under `batch["packed_targets"]` and the criterion does no host work and no host synchronisation at all — which is
+    what lets a whole training step (forward, criterion, backward, optimizer) be captured in ONE CUDA graph: the packed
+    tensors are static buffers, refill them in place (`copy_`) between replays.  `max_boxes` must not be smaller than the
+    largest number of boxes of any image that will ever be copied in."""
+    gt_boxes, gt_labels, gt_count, M = pack_targets(batch, B, img_hw, device)
+    if max_boxes > M:
+        gb = torch.zeros((B, max_boxes, 4), dtype=torch.float32, device=gt_boxes.device)
+        gl = torch.zeros((B, max_boxes), dtype=torch.int32, device=gt_boxes.device)
+        gb[:, : gt_boxes.shape[1]] = gt_boxes
+        gl[:, : gt_labels.shape[1]] = gt_labels
+        gt_boxes, gt_labels, M = gb, gl, max_boxes
+    return gt_boxes, gt_labels, gt_count, M
+
+
 class v8DetectionLoss:
     """Criterion class for computing training losses (ultralytics/utils/loss.py:163-275)."""
 
@@ -131,9 +147,12 @@ def criterion_call(self, preds, batch):
     pred_distri = cat[:, : self.reg_max * 4].permute(0, 2, 1).contiguous()
     pred_scores = cat[:, self.reg_max * 4:].permute(0, 2, 1).contiguous()
     hw = [tuple(int(v) for v in f.shape[2:]) for f in feats]
-    strides = [float(s) for s in self.stride]
+    strides = getattr(self, "_strides_host", None)               # `stride` is a (device) tensor on the reference's criterion:
+    if strides is None:                                          # read it once — float(tensor) is a host synchronisation
+        strides = self._strides_host = [float(s) for s in self.stride]
     img_hw = (hw[0][0] * strides[0], hw[0][1] * strides[0])
-    gt_boxes, gt_labels, gt_count, M = pack_targets(batch, B, img_hw, pred_distri.device)
+    packed = batch.get("packed_targets") if isinstance(batch, dict) else None
+    gt_boxes, gt_labels, gt_count, M = packed if packed is not None else pack_targets(batch, B, img_hw, pred_distri.device)
     gains = (_hyp(self.hyp, "box", 7.5), _hyp(self.hyp, "cls", 0.5), _hyp(self.hyp, "dfl", 1.5))
     asg = getattr(self, "assigner", None)
     tal = getattr(self, "tal", None) or (asg.topk, asg.alpha, asg.beta, asg.eps)
