@@ -114,3 +114,57 @@ def test_cuda_loss_training_size_vs_oracle(lib):
     assert torch.equal(items, items2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))
     th, ih, gh, _ = _cuda_loss([f.half() for f in feats], batch, 2)
     assert gh[0].dtype == torch.float16 and np.allclose(ih.numpy(), items_o.numpy(), rtol=2e-2)
+
+
+@pytest.mark.gpu
+def test_cuda_loss_packed_targets_and_graph_capture(lib):
+    """`pack_batch_targets` (static target buffers padded to a fixed number of slots per image): the same losses and gradients
+    as the plain batch (the padding changes the reduction layout: last-ulp differences only); with them the criterion makes
+    no host round trip, so forward + backward capture into a CUDA graph whose replays are bit-identical to the eager call, and
+    refilling the static buffers between replays switches the labels."""
+    from oracle.loss_ref import loss_case
+    from specyolo.utils.loss import pack_batch_targets, v8DetectionLoss
+
+    B, nc = 8, 2
+    feats, batch_a = loss_case(31, B, 320, 320, nc, [(5 * b) % 9 for b in range(B)])
+    _, batch_b = loss_case(32, B, 320, 320, nc, [(3 * b + 1) % 7 for b in range(B)])
+    crit = v8DetectionLoss(_FakeModel(nc))
+    f = [x.detach().cuda().requires_grad_(True) for x in feats]
+
+    def eager(batch):
+        for x in f:
+            x.grad = None
+        total, items = crit(f, batch)
+        total.backward()
+        return items.cpu(), [x.grad.cpu().clone() for x in f]
+
+    def close(got, want):
+        return np.allclose(got[0].numpy(), want[0].numpy(), rtol=1e-5, atol=1e-6) and all(
+            float((g - w).abs().max()) <= 1e-5 * max(1.0, float(w.abs().max())) for g, w in zip(got[1], want[1]))
+
+    packed = pack_batch_targets(batch_a, B, (320, 320), "cuda", max_boxes=12)
+    assert packed[0].shape == (B, 12, 4) and packed[1].shape == (B, 12) and packed[3] == 12
+    static = dict(batch_a, packed_targets=packed)
+    plain_a, plain_b = eager(batch_a), eager(batch_b)
+    padded_a = eager(static)
+    assert close(padded_a, plain_a)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eager(static)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    for x in f:
+        x.grad = None
+    with torch.cuda.graph(graph):
+        total_g, items_g = crit(f, static)
+        total_g.backward()
+    graph.replay()
+    assert torch.equal(items_g.cpu(), padded_a[0]) and all(torch.equal(x.grad.cpu(), g) for x, g in zip(f, padded_a[1]))
+    nb = pack_batch_targets(batch_b, B, (320, 320), "cuda", max_boxes=12)
+    for dst, src in zip(packed[:3], nb[:3]):
+        dst.copy_(src)                                             # new labels into the same buffers
+    graph.replay()
+    assert close((items_g.cpu(), [x.grad.cpu() for x in f]), plain_b)
+    assert not close((items_g.cpu(), [x.grad.cpu() for x in f]), plain_a)
