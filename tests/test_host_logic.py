@@ -107,3 +107,25 @@ def test_bench_reference_arm_runs_on_cpu():
     vendored = (ROOT / "oracle" / "_ref" / "ultralytics" / "__init__.py").is_file()
     assert line["cpu_baseline"]["kind"] == ("reference" if vendored else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "images/s"
+
+
+def test_pack_batch_targets_pads_to_static_slots():
+    """Host side of the graph-capturable criterion call: targets grouped by image, normalised xywh -> xyxy pixels, padded to
+    a fixed number of slots per image (static buffers), counts unchanged."""
+    from specyolo.nn.init import synth_det_batch
+    from specyolo.utils.loss import pack_batch_targets, pack_targets
+
+    batch = synth_det_batch(4, 320, nc=3, boxes_per_image=5, seed=1)
+    keep = torch.tensor([True] * 20)
+    keep[[2, 3, 11]] = False                                   # ragged: 3, 5, 4, 5 boxes
+    batch = {k: v[keep] for k, v in batch.items()}
+    b0, l0, c0, m0 = pack_targets(batch, 4, (320, 320), "cpu")
+    assert m0 == 5 and c0.tolist() == [3, 5, 4, 5] and b0.shape == (4, 5, 4)
+    b1, l1, c1, m1 = pack_batch_targets(batch, 4, (320, 320), "cpu", max_boxes=9)
+    assert m1 == 9 and b1.shape == (4, 9, 4) and l1.shape == (4, 9) and torch.equal(c1, c0)
+    assert torch.equal(b1[:, :5], b0) and torch.equal(l1[:, :5], l0) and float(b1[:, 5:].abs().sum()) == 0.0
+    xywh = batch["bboxes"][batch["batch_idx"] == 1] * 320
+    want = torch.cat((xywh[:, :2] - xywh[:, 2:] / 2, xywh[:, :2] + xywh[:, 2:] / 2), 1)
+    assert torch.allclose(b1[1, :5], want)
+    b2, _, _, m2 = pack_batch_targets(batch, 4, (320, 320), "cpu", max_boxes=3)      # never shrinks below the data
+    assert m2 == 5 and torch.equal(b2, b0)
