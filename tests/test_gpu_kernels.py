@@ -585,6 +585,30 @@ def test_detect_decode(lib, nc, hw):
         assert torch.equal(rows, exp)
 
 
+@pytest.mark.parametrize("nc", [2, 16, 17, 21, 80])
+def test_detect_decode_scores_first(lib, nc):
+    """The candidate path without the dense output (what `predict` runs): class maxima first — gathered cooperatively by
+    eight lanes per anchor for nc >= 16 —, boxes only for survivors.  Candidates must equal, bit for bit and in anchor order,
+    those of the dense path; row padding beyond nc (garbage here) must never be read as a class."""
+    from specyolo import ops
+
+    gen = torch.Generator().manual_seed(50 + nc)
+    B, hw, strides, conf = 3, [(20, 28), (10, 14), (5, 7)], [8.0, 16.0, 32.0], 0.25
+    no_stride = (64 + nc + 3) // 4 * 4 + 4                      # at least one whole padding vector per row
+    bufs = _rand_head_logits(gen, B, hw, nc, no_stride)
+    for t in bufs:
+        t[..., 64 + nc:] = 50.0
+    dev = [t.to(DEV) for t in bufs]
+    _, cand_d, seg_d = ops.detect_decode(dev, hw, strides, nc, want_dense=True, conf_thres=conf)
+    _, cand_s, seg_s = ops.detect_decode(dev, hw, strides, nc, want_dense=False, conf_thres=conf)
+    assert torch.equal(seg_d, seg_s) and int(seg_s.sum()) > 20
+    seg = seg_s.cpu()
+    for b in range(B):
+        for q in range(seg.shape[1]):
+            n = int(seg[b, q])
+            assert torch.equal(cand_d[b, q, :n], cand_s[b, q, :n])
+
+
 def _nms_inputs(gen, B, nc, A, dup=True):
     xy = torch.rand((B, 2, A), generator=gen) * 600 + 20
     wh = torch.rand((B, 2, A), generator=gen) * 192 + 8
