@@ -7,7 +7,7 @@ runs libspecyolo (SURVEY 8(b) hook 5).  `install()` rebinds, 
 (`ultralytics.nn.tasks` — where `parse_model` resolves YAML names, tasks.py:1074-1080 — and `ultralytics.nn.modules[.conv /
 .block / .head]`, where the blocks construct their sub-blocks), the classes
 
-    Conv DWConv DDWConv ConvHCA SobelSpatialAttention MSCSpatialAttention Bottleneck C3 C3k C3x C2f C3k2 SPPF Attention PSABlock C2PSA Fusion Detect
+    Conv DWConv DDWConv ConvHCA SobelSpatialAttention MSCSpatialAttention Bottleneck BottleNect C3 C3k C3x C2f C3k2 C3k2GC SPPF Attention PSABlock C2PSA Fusion Detect
 
 to SUBCLASSES of the reference's own classes: constructor, parameters, `state_dict` keys, `fuse()` and every `isinstance`
 check stay the reference's, and instances pickle as the reference's classes without this package's caches (a checkpoint the
@@ -39,7 +39,7 @@ _INSTALLED = False
 # reference module (relative to ultralytics.nn.modules) -> class names defined there that get a shim
 _WHERE = {
     "conv": ["Conv", "DWConv", "DDWConv", "Fusion", "ConvHCA", "SobelSpatialAttention", "MSCSpatialAttention"],
-    "block": ["Bottleneck", "C3", "C3k", "C3x", "C2f", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA"],
+    "block": ["Bottleneck", "C3", "C3k", "C3x", "C2f", "C3k2", "C3k2GC", "BottleNect", "SPPF", "Attention", "PSABlock", "C2PSA"],
     "head": ["Detect"],
 }
 
@@ -268,6 +268,8 @@ def install() -> dict:
     shims["C3k"] = _make_block(sub["block"].C3k, M.C3k)
     shims["C3k2"] = _make_block(sub["block"].C3k2, M.C3k2)
     shims["C3x"] = _make_block(sub["block"].C3x, M.C3x)
+    shims["BottleNect"] = _make_block(sub["block"].BottleNect, M.BottleNect, extra=("weights_f32",))
+    shims["C3k2GC"] = _make_block(sub["block"].C3k2GC, M.C3k2GC)
     for cls in shims.values():
         _as_reference_class(cls)
 

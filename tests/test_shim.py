@@ -189,6 +189,35 @@ def test_reference_predict_with_shim_omn_variant(lib):
 
 
 @pytest.mark.gpu
+def test_reference_predict_with_shim_gc_variant(lib):
+    """Sibling config yolo11s_fusion_sand3_new_GC.yaml (C3k2GC = C2f around BottleNect / FGM, the cuFFT block) behind the
+    reference API: the reference's parse_model builds the shim classes, the FFT kernels run in place of torch.fft."""
+    ultralytics = _reference()
+    from specyolo import _lib
+    from specyolo import ultralytics_shim as shim
+    from specyolo.nn.init import synth_images
+
+    cfg = "yolo11s_fusion_sand3_new_GC.yaml"
+    sd = _sd(cfg)
+    x = (synth_images(64, 640, seed=0, dtype=torch.uint8)[:8].float() / 255)
+    stock = _ref_yolo(ultralytics, sd, cfg)
+    ref = [r.boxes.data.cpu().numpy() for r in stock.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+    shims = shim.install()
+    try:
+        y = _ref_yolo(ultralytics, sd, cfg)
+        assert type(y.model.model[2]) is shims["C3k2GC"] and type(y.model.model[2].m[0]) is shims["BottleNect"]
+        n0 = _lib.load().specyolo_launch_count()
+        got = [r.boxes.data.cpu().numpy() for r in y.predict(x, device=0, conf=0.25, iou=0.7, verbose=False)]
+        launches = int(_lib.load().specyolo_launch_count() - n0)
+    finally:
+        shim.uninstall()
+    assert launches > 86, launches
+    stats = compare_detections(ref, got)
+    record("shim_reference_api_gc_b8_640", stats)
+    assert sum(len(r) for r in ref) > 20 and stats["matched_rate"] >= 0.96, stats
+
+
+@pytest.mark.gpu
 def test_reference_training_loss_with_shim_criterion(lib):
     """SURVEY 8 f2, first slice behind the reference API: `DetectionModel.loss(batch)` (tasks.py:305-322) of the REFERENCE
     model in training mode on the GPU, stock criterion vs the CUDA criterion bound in by the shim — same loss items, same
