@@ -2,7 +2,7 @@
 # Profiles for profiles/: launch list of the bench command, DRAM traffic of the conv kernels, full captures of the top kernels
 mkdir -p gpurun_out
 python tools/profile_layers.py 64 > gpurun_out/layers_b64_cur.txt 2>&1 && \
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_|dwpw_kernel|stem_pair_kernel" --csv --log-file gpurun_out/conv_traffic.csv python tools/profile_layers.py 64 > gpurun_out/ncu_traffic.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_|dwpw_kernel|stem_pair_kernel|bneck_pair_kernel" --csv --log-file gpurun_out/conv_traffic.csv python tools/profile_layers.py 64 > gpurun_out/ncu_traffic.log 2>&1
 echo "traffic exit $?"; wc -l gpurun_out/conv_traffic.csv
 python tools/one_conv.py 64 64 3 1 80 80 64 5 > gpurun_out/p.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"conv_halo" -s 3 -c 1 -o gpurun_out/prof_halo_64_64_k3_80 -f python tools/one_conv.py 64 64 3 1 80 80 64 5 > gpurun_out/n1.log 2>&1

@@ -9,7 +9,7 @@ ki, mi, vi, ui, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.ind
 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "usecond": 1e3, "nsecond": 1.0, "msecond": 1e6}
 launches = {}
 for r in rows:
-    if not any(t in r[ki] for t in ("conv_", "dwpw_kernel", "stem_pair_kernel")):
+    if not any(t in r[ki] for t in ("conv_", "dwpw_kernel", "stem_pair_kernel", "bneck_pair_kernel")):
         continue
     d = launches.setdefault(int(r[ii]), {"name": re.sub(r"\(.*", "", r[ki]).replace("specyolo::", "").replace("void ", "")})
     d[r[mi]] = float(r[vi].replace(",", "")) * unit.get(r[ui], 1.0)
