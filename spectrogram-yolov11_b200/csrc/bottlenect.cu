@@ -16,7 +16,7 @@
 //   gc_stats_kernel   per (image, pixel chunk): sum_hw(out), sum_hw(|out|) per channel, fixed-order partials
 //   gc_prep_kernel    every CTA folds the partials of its image into q (two C x C mat-vecs), then per pixel recomputes out
 //                     and writes x_sca, x1, x2 as PLANAR fp32 planes (the transform works plane by plane)
-//   gc_fft_kernel     persistent, one plane at a time, the complex plane resident in shared memory (H x (W+1) x 8 bytes:
+//   gc_fft_kernel     persistent (32 warps), one plane at a time, the complex plane resident in shared memory (H x (W+1) x 8 bytes:
 //                     206 KB at 160 x 160): row FFTs, column FFTs, multiply by x1 and conjugate, row FFTs, column FFTs,
 //                     modulus, alpha / beta / relu.  A warp owns a row / column: sides that are multiples of 32 (<= 256)
 //                     are transformed in registers (M-point DFT per lane + a 32-point transform across the lanes by
@@ -30,7 +30,7 @@
 namespace specyolo {
 
 static constexpr int kGcThreads = 256;
-static constexpr int kFftThreads = 512;
+static constexpr int kFftThreads = 1024;
 static constexpr int kFftWarps = kFftThreads / 32;
 static constexpr int kMaxStages = 8;
 
@@ -464,9 +464,16 @@ static bool gc_factor(int n, int* rad, int* nst) {
     return n == 1;
 }
 
+static bool gc_reg_path(int n) { return (n & 31) == 0 && n <= 256; }
+
+// per-warp scratch lines exist only when a side takes the Stockham path
+static int gc_scratch_len(int H, int W) {
+    const int a = gc_reg_path(W) ? 0 : W, b = gc_reg_path(H) ? 0 : H;
+    return a > b ? a : b;
+}
+
 static size_t gc_fft_smem(int H, int W) {
-    const int maxn = H > W ? H : W;
-    return ((size_t)H * (W + 1) + (size_t)kFftWarps * maxn + W + H) * sizeof(float2);
+    return ((size_t)H * (W + 1) + (size_t)kFftWarps * gc_scratch_len(H, W) + W + H) * sizeof(float2);
 }
 
 size_t bottlenect_ws_bytes(int B, int H, int W, int C) {
@@ -511,7 +518,7 @@ int bottlenect_launch(const specyolo_bottlenect_t* a, cudaStream_t stream) {
     p.inv_hw = 1.0f / (float)p.HW;
     p.nchunk = gc_nchunk(p.HW);
     p.pitch = a->W + 1;
-    p.maxn = a->H > a->W ? a->H : a->W;
+    p.maxn = gc_scratch_len(a->H, a->W);
     SY_CHECK(gc_factor(a->W, p.rad_w, &p.nst_w) && gc_factor(a->H, p.rad_h, &p.nst_h), SPECYOLO_ERR_UNSUPPORTED,
              "BottleNect: plane %d x %d has a prime factor above 7", a->H, a->W);
     SY_CHECK(gc_fft_smem(a->H, a->W) <= 227 * 1024, SPECYOLO_ERR_UNSUPPORTED,
