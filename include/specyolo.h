@@ -246,7 +246,7 @@ int    specyolo_msc_spatial_attention(const specyolo_msc_gate_t* a, void* stream
 typedef struct {
     const void* x; int x_pixstride;   /* bf16 NHWC [B,H,W,C], C in {16, 32}                    */
     void* y; int y_pixstride;         /* bf16 NHWC, may alias x                                */
-    int B, H, W, C;                   /* H, W: prime factors <= 7, plane must fit shared memory */
+    int B, H, W, C;                   /* H, W: prime factors <= 19, plane must fit shared memory */
     const float* in_w;  const float* in_b;     /* in_conv.0                                    */
     const float* fac_w; const float* fac_b;    /* fac_conv                                     */
     const float* sca_w; const float* sca_b;    /* conv                                         */

@@ -20,7 +20,7 @@
 //                     206 KB at 160 x 160): row FFTs, column FFTs, multiply by x1 and conjugate, row FFTs, column FFTs,
 //                     modulus, alpha / beta / relu.  A warp owns a row / column: sides that are multiples of 32 (<= 256)
 //                     are transformed in registers (M-point DFT per lane + a 32-point transform across the lanes by
-//                     shuffles), any other side by mixed-radix Stockham autosort stages (radix 4, 2, 3, 5, 7) between the
+//                     shuffles), any other side by mixed-radix Stockham autosort stages (radix 4, 2 and the odd primes up to 19) between the
 //                     strided line in the plane and a per-warp scratch line.
 //   gc_pack_kernel    planar fp32 -> bf16 NHWC channel window
 // All reductions run in a fixed order: results are bit-identical run to run.
@@ -246,6 +246,15 @@ __device__ __forceinline__ void fft_stage(const float2* src, int ss, float2* dst
     }
 }
 
+// Radices 11 ... 19 (352 / 416 / 544 / 608-pixel inputs: plane sides 88, 104, 136, 152): kept out of line so that their
+// register appetite (19 complex values + accumulators) does not shape the allocation of the common path.
+__device__ __noinline__ void fft_stage_big(int R, const float2* src, int ss, float2* dst, int ds, int N, int Ns, const float2* tw, int lane) {
+    if (R == 11) fft_stage<11>(src, ss, dst, ds, N, Ns, tw, lane);
+    else if (R == 13) fft_stage<13>(src, ss, dst, ds, N, Ns, tw, lane);
+    else if (R == 17) fft_stage<17>(src, ss, dst, ds, N, Ns, tw, lane);
+    else fft_stage<19>(src, ss, dst, ds, N, Ns, tw, lane);
+}
+
 // In-place forward DFT of the line `data` (element stride `stride`) through the warp's scratch line.
 __device__ void fft_line(float2* data, int stride, int N, const int* rad, int nst, const float2* tw, float2* scratch, int lane) {
     float2* src = data; int ss = stride;
@@ -257,7 +266,8 @@ __device__ void fft_line(float2* data, int stride, int N, const int* rad, int ns
         else if (R == 2) fft_stage<2>(src, ss, dst, ds, N, Ns, tw, lane);
         else if (R == 3) fft_stage<3>(src, ss, dst, ds, N, Ns, tw, lane);
         else if (R == 5) fft_stage<5>(src, ss, dst, ds, N, Ns, tw, lane);
-        else fft_stage<7>(src, ss, dst, ds, N, Ns, tw, lane);
+        else if (R == 7) fft_stage<7>(src, ss, dst, ds, N, Ns, tw, lane);
+        else fft_stage_big(R, src, ss, dst, ds, N, Ns, tw, lane);
         __syncwarp();
         float2* t = src; src = dst; dst = t;
         const int ti = ss; ss = ds; ds = ti;
@@ -457,8 +467,8 @@ static int gc_nchunk(int HW) {
 static bool gc_factor(int n, int* rad, int* nst) {
     int k = 0;
     while (n % 4 == 0 && k < kMaxStages) { rad[k++] = 4; n /= 4; }
-    const int primes[4] = {2, 3, 5, 7};
-    for (int q = 0; q < 4; ++q)
+    const int primes[8] = {2, 3, 5, 7, 11, 13, 17, 19};
+    for (int q = 0; q < 8; ++q)
         while (n % primes[q] == 0 && k < kMaxStages) { rad[k++] = primes[q]; n /= primes[q]; }
     *nst = k;
     return n == 1;
@@ -520,7 +530,7 @@ int bottlenect_launch(const specyolo_bottlenect_t* a, cudaStream_t stream) {
     p.pitch = a->W + 1;
     p.maxn = gc_scratch_len(a->H, a->W);
     SY_CHECK(gc_factor(a->W, p.rad_w, &p.nst_w) && gc_factor(a->H, p.rad_h, &p.nst_h), SPECYOLO_ERR_UNSUPPORTED,
-             "BottleNect: plane %d x %d has a prime factor above 7", a->H, a->W);
+             "BottleNect: plane %d x %d has a prime factor above 19", a->H, a->W);
     SY_CHECK(gc_fft_smem(a->H, a->W) <= 227 * 1024, SPECYOLO_ERR_UNSUPPORTED,
              "BottleNect: a %d x %d complex plane does not fit shared memory (up to 160 x 160, i.e. a 640 x 640 input)", a->H, a->W);
     const size_t plane_all = (size_t)a->B * a->C * p.HW;

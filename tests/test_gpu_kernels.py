@@ -476,7 +476,7 @@ def test_msc_spatial_attention(lib, B, c, H, W, window):
 
 @pytest.mark.parametrize("B,c,H,W,window", [(2, 32, 160, 160, False), (3, 32, 24, 32, True), (2, 16, 40, 56, False), (1, 32, 20, 12, False),
                                             (2, 32, 1, 1, False), (1, 16, 7, 15, True), (2, 32, 96, 128, False), (1, 16, 64, 192, False),
-                                            (1, 16, 32, 224, False), (1, 32, 32, 256, True)])
+                                            (1, 16, 32, 224, False), (1, 32, 32, 256, True), (1, 32, 104, 88, False), (1, 16, 152, 136, False)])
 def test_bottlenect_fgm(lib, B, c, H, W, window):
     """BottleNect + FGM (block.py:782-861) vs the oracle's restatement (torch.fft) on bf16-rounded inputs: the 160 x 160 x 32
     planes of the *_GC config at 640^2, every radix of the mixed-radix transform (4, 2, 3, 5, 7), an odd number of stages, every
