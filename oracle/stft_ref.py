@@ -14,7 +14,8 @@ affine map of [db_min, db_max] to [0,1] with clamping, then bilinear letterbox o
 padding value 114/255, three identical channels.
 
 Known-answer checks live in tests/test_stft_oracle.py (tone -> peak row, impulse -> flat spectrum,
-Parseval).
+Parseval) together with a cross-check of the STFT convention against torch.stft and scipy.fft on random samples
+(independent library implementations — not the reference, which has none: the header above stands).
 """
 from __future__ import annotations
 

@@ -42,3 +42,24 @@ def test_letterbox_layout_north_star_geometry():
     assert np.all(img[0, :, :240] == 114 / 255) and np.all(img[0, :, 400:] == 114 / 255)   # 160-row band
     assert np.array_equal(img[0, 0], img[0, 1]) and np.array_equal(img[0, 0], img[0, 2])
     assert 0.0 <= img[0, 0, 240:400].min() and img[0, 0, 240:400].max() <= 1.0
+
+
+def test_stft_power_matches_torch_and_scipy():
+    """The oracle's STFT convention (periodic Hann, hop 256, center=False, fftshift along frequency) against two independent
+    library implementations on the same samples: `torch.stft` and `scipy.signal.ShortTimeFFT`-free `scipy.fft` framing."""
+    import scipy.fft
+    import torch
+
+    rng = np.random.default_rng(5)
+    iq = (rng.standard_normal(9000) + 1j * rng.standard_normal(9000)).astype(np.complex64)
+    p = stft_ref.stft_power(iq)                                        # [1024, T]
+    T = 1 + (iq.size - 1024) // 256
+    assert p.shape == (1024, T)
+    w = torch.hann_window(1024, periodic=True, dtype=torch.float64)
+    X = torch.stft(torch.from_numpy(iq.astype(np.complex128)), n_fft=1024, hop_length=256, win_length=1024, window=w,
+                   center=False, onesided=False, return_complex=True)  # [1024, T], bins 0..1023
+    pt = torch.fft.fftshift(X.abs() ** 2, dim=0).numpy()
+    assert np.allclose(p, pt, rtol=1e-9, atol=1e-9 * pt.max())
+    frames = np.stack([iq[t * 256: t * 256 + 1024].astype(np.complex128) * w.numpy() for t in range(T)], 1)
+    ps = np.abs(scipy.fft.fftshift(scipy.fft.fft(frames, axis=0), axes=0)) ** 2
+    assert np.allclose(p, ps, rtol=1e-9, atol=1e-9 * ps.max())
